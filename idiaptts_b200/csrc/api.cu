@@ -1,0 +1,68 @@
+// Host-side plumbing of libb200world: error reporting, the shared twiddle table, scalar helpers.
+#include <stdarg.h>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace b2w {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+__global__ void twiddle_kernel(double2* tw) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < kTwN) {
+    double s, c;
+    sincospi(-2.0 * (double)k / (double)kTwN, &s, &c);
+    tw[k] = make_double2(c, s);
+  }
+}
+
+// One read-only table per device, built on first use (the only allocation the library ever makes).
+const double2* twiddle_table(cudaStream_t stream) {
+  static std::mutex mu;
+  static double2* tables[64] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!tables[dev]) {
+    double2* p = nullptr;
+    if (cudaMalloc(&p, sizeof(double2) * kTwN) != cudaSuccess) return nullptr;
+    twiddle_kernel<<<kTwN / 256, 256, 0, stream>>>(p);
+    // later launches may come from other streams: make the table globally visible once
+    if (cudaStreamSynchronize(stream) != cudaSuccess) {
+      cudaFree(p);
+      return nullptr;
+    }
+    tables[dev] = p;
+  }
+  return tables[dev];
+}
+
+}  // namespace b2w
+
+extern "C" int b2w_version(void) { return B2W_VERSION; }
+extern "C" const char* b2w_last_error(void) { return b2w::g_err; }
+
+extern "C" int32_t b2w_cheaptrick_fft_size(int32_t fs, double f0_floor) {
+  return (int32_t)pow(2.0, 1.0 + (int)(log(3.0 * fs / f0_floor + 1) / b2w::kLog2));
+}
+extern "C" int32_t b2w_num_aperiodicities(int32_t fs) { return b2w::num_aperiodicities(fs); }
+extern "C" int32_t b2w_d4c_fft_size(int32_t fs) {
+  return (int32_t)pow(2.0, 1.0 + (int)(log(4.0 * fs / b2w::kFloorF0D4C + 1) / b2w::kLog2));
+}

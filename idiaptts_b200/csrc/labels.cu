@@ -1,0 +1,239 @@
+// Label preparation around the vocoder kernels: lf0 / vuv with Merlin-style interpolation, np.gradient deltas, and the
+// corpus normalisation statistics.
+//
+// Replaces (reference paths under idiaptts/):
+//   src/data_preparation/world/WorldFeatLabelGen.py:798-802  lf0 = log(f0.clip(1e-10)) as float32, threshold, interpolate_lin
+//   misc/utils.py:40-86                                      interpolate_lin (pure-python double loop)
+//   misc/utils.py:103-105                                    compute_deltas = np.gradient(...).astype(float32)
+//   misc/normalisation/MeanStdDevExtractor.py:43-47          add_sample: N += T, sum x, sum x^2
+//   misc/normalisation/MeanCovarianceExtractor.py:44-48      add_sample: sum x, sum x^T x
+#include "common.cuh"
+
+namespace b2w {
+
+// One thread per utterance: the interpolation is a sequential scan in the reference and a few thousand frames long, so
+// the whole corpus is ~13k independent short scans - parallel across utterances, sequential inside (same float32
+// operation order as the reference, no fused multiply-add).
+__global__ void lf0_vuv_kernel(const double* __restrict__ f0, const int64_t* __restrict__ utt_frame_offset, int num_utts,
+                               float log_thr, float lf0_zero, float* __restrict__ lf0, float* __restrict__ vuv,
+                               int64_t stride) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= num_utts) return;
+  const int64_t beg = utt_frame_offset[u];
+  const int n = (int)(utt_frame_offset[u + 1] - beg);
+  float* d = lf0 + beg * stride;
+  float* v = vuv + beg * stride;
+  const double* f = f0 + beg;
+  // pass 1: thresholded log-F0 and the voicing flag (taken BEFORE interpolation, utils.py:50-52)
+  for (int i = 0; i < n; ++i) {
+    const float x = (float)fmax(f[i], 1e-10);  // np.log(..., dtype=float32) casts its input to float32 first
+    float l = (float)log((double)x);           // correctly rounded float32 logarithm
+    if (l <= log_thr) l = lf0_zero;
+    d[(int64_t)i * stride] = l;
+    v[(int64_t)i * stride] = l > 0.f ? 1.f : 0.f;
+  }
+  // pass 2: fill the unvoiced gaps
+  float last_value = 0.f;
+  int i = 0;
+  while (i < n) {
+    const float cur = d[(int64_t)i * stride];
+    if (cur <= 0.f) {
+      int j = i + 1;  // python leaves j = i + 1 when range(i + 1, n) is empty
+      for (int jj = i + 1; jj < n; ++jj) {
+        j = jj;
+        if (d[(int64_t)jj * stride] > 0.f) break;
+      }
+      if (j < n - 1) {
+        const float dj = d[(int64_t)j * stride];
+        if (last_value > 0.f) {
+          const float prev = d[(int64_t)(i - 1) * stride];
+          const float step = __fdiv_rn(__fsub_rn(dj, prev), (float)(j - i));
+          for (int k = i; k < j; ++k) d[(int64_t)k * stride] = __fadd_rn(prev, __fmul_rn(step, (float)(k - i + 1)));
+        } else {
+          for (int k = i; k < j; ++k) d[(int64_t)k * stride] = dj;
+        }
+        last_value = d[(int64_t)(j - 1) * stride];
+        i = j;
+      } else {
+        // "end of data": also taken when the next voiced frame is the LAST frame, which is then overwritten too
+        for (int k = i; k < n; ++k) d[(int64_t)k * stride] = last_value;
+        break;
+      }
+    } else {
+      last_value = cur;
+      ++i;
+    }
+  }
+}
+
+__device__ __forceinline__ int find_utt(const int64_t* __restrict__ off, int num_utts, int64_t frame) {
+  int lo = 0, hi = num_utts;  // off[lo] <= frame < off[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (off[mid] <= frame) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// np.gradient along time in float32: interior (x[i+1] - x[i-1]) / 2, one-sided differences at both ends
+__device__ __forceinline__ float grad_at(const float* __restrict__ col, int64_t stride, int i, int n) {
+  if (n < 2) return 0.f;
+  if (i == 0) return __fsub_rn(col[stride], col[0]);
+  if (i == n - 1) return __fsub_rn(col[(int64_t)(n - 1) * stride], col[(int64_t)(n - 2) * stride]);
+  return __fmul_rn(__fsub_rn(col[(int64_t)(i + 1) * stride], col[(int64_t)(i - 1) * stride]), 0.5f);
+}
+
+__global__ void deltas_kernel(const float* __restrict__ feats, int64_t fstride, int dim,
+                              const int64_t* __restrict__ utt_frame_offset, int num_utts, int64_t total_frames,
+                              float* __restrict__ deltas, float* __restrict__ ddeltas, int64_t ostride) {
+  const int64_t total = total_frames * dim;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t frame = e / dim;
+    const int c = (int)(e - frame * dim);
+    const int u = find_utt(utt_frame_offset, num_utts, frame);
+    const int64_t beg = utt_frame_offset[u];
+    const int n = (int)(utt_frame_offset[u + 1] - beg);
+    const int i = (int)(frame - beg);
+    const float* col = feats + beg * fstride + c;
+    const float d = grad_at(col, fstride, i, n);
+    if (deltas) deltas[frame * ostride + c] = d;
+    if (ddeltas) {
+      // gradient of the float32 deltas: recompute the neighbouring deltas (identical float32 values)
+      float dd = 0.f;
+      if (n >= 2) {
+        if (i == 0) dd = __fsub_rn(grad_at(col, fstride, 1, n), d);
+        else if (i == n - 1) dd = __fsub_rn(d, grad_at(col, fstride, n - 2, n));
+        else dd = __fmul_rn(__fsub_rn(grad_at(col, fstride, i + 1, n), grad_at(col, fstride, i - 1, n)), 0.5f);
+      }
+      ddeltas[frame * ostride + c] = dd;
+    }
+  }
+}
+
+// sums[c] += sum_t x[t][c]; sums[dim + c] += sum_t x[t][c]^2 (fp64).  blockDim.x = columns handled per pass (<= 256),
+// blockDim.y row lanes; one fp64 atomic per column and block.
+__global__ void stats_kernel(const float* __restrict__ feats, int64_t fstride, int dim, int64_t num_frames,
+                             int64_t rows_per_block, double* __restrict__ sums) {
+  extern __shared__ double sh[];  // [2][blockDim.y][blockDim.x]
+  const int64_t r0 = blockIdx.x * rows_per_block;
+  const int64_t r1 = min(num_frames, r0 + rows_per_block);
+  const int nx = blockDim.x, ny = blockDim.y;
+  for (int c0 = 0; c0 < dim; c0 += nx) {
+    const int c = c0 + threadIdx.x;
+    double s = 0.0, q = 0.0;
+    if (c < dim) {
+      for (int64_t r = r0 + threadIdx.y; r < r1; r += ny) {
+        const double x = (double)feats[r * fstride + c];
+        s += x;
+        q += x * x;
+      }
+    }
+    sh[(0 * ny + threadIdx.y) * nx + threadIdx.x] = s;
+    sh[(1 * ny + threadIdx.y) * nx + threadIdx.x] = q;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < dim) {
+      double ts = 0.0, tq = 0.0;
+      for (int y = 0; y < ny; ++y) {
+        ts += sh[(0 * ny + y) * nx + threadIdx.x];
+        tq += sh[(1 * ny + y) * nx + threadIdx.x];
+      }
+      atomicAdd(&sums[c], ts);
+      atomicAdd(&sums[dim + c], tq);
+    }
+    __syncthreads();
+  }
+}
+
+// gram[a][b] += sum_t x[t][a] x[t][b] (fp64).  blockIdx.y picks a 16 x 16 tile of (a, b) pairs (one pair per thread),
+// blockIdx.x a slab of rows; rows are staged 32 at a time in shared memory.  Only the add_deltas /
+// MeanCovarianceExtractor recipe needs it.
+constexpr int kGramRows = 32;
+__global__ void gram_kernel(const float* __restrict__ feats, int64_t fstride, int dim, int64_t num_frames,
+                            int64_t rows_per_block, double* __restrict__ gram) {
+  __shared__ float sa[kGramRows][17], sb[kGramRows][17];
+  const int tiles = (dim + 15) / 16;
+  const int a0 = (blockIdx.y / tiles) * 16, b0 = (blockIdx.y % tiles) * 16;
+  const int ta = threadIdx.x >> 4, tb = threadIdx.x & 15;
+  const int64_t r0 = blockIdx.x * rows_per_block;
+  const int64_t r1 = min(num_frames, r0 + rows_per_block);
+  double acc = 0.0;
+  for (int64_t rs = r0; rs < r1; rs += kGramRows) {
+    const int nr = (int)min((int64_t)kGramRows, r1 - rs);
+    __syncthreads();
+    for (int e = threadIdx.x; e < kGramRows * 16; e += blockDim.x) {
+      const int r = e >> 4, c = e & 15;
+      float va = 0.f, vb = 0.f;
+      if (r < nr) {
+        if (a0 + c < dim) va = feats[(rs + r) * fstride + a0 + c];
+        if (b0 + c < dim) vb = feats[(rs + r) * fstride + b0 + c];
+      }
+      sa[r][c] = va;
+      sb[r][c] = vb;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int r = 0; r < kGramRows; ++r) acc += (double)sa[r][ta] * (double)sb[r][tb];
+  }
+  if (a0 + ta < dim && b0 + tb < dim) atomicAdd(&gram[(int64_t)(a0 + ta) * dim + b0 + tb], acc);
+}
+
+}  // namespace b2w
+
+extern "C" int b2w_lf0_vuv(const double* f0, const int64_t* utt_frame_offset, int32_t num_utts, double f0_silence_threshold,
+                           double lf0_zero, float* lf0, float* vuv, int64_t out_stride, void* stream) {
+  using namespace b2w;
+  B2W_REQUIRE(f0 && utt_frame_offset && lf0 && vuv, "b2w_lf0_vuv: null argument");
+  B2W_REQUIRE(out_stride >= 1, "b2w_lf0_vuv: bad stride");
+  if (num_utts == 0) return 0;
+  const float log_thr = (float)log(f0_silence_threshold);
+  lf0_vuv_kernel<<<(num_utts + 63) / 64, 64, 0, (cudaStream_t)stream>>>(f0, utt_frame_offset, num_utts, log_thr,
+                                                                         (float)lf0_zero, lf0, vuv, out_stride);
+  return check_launch("lf0_vuv_kernel");
+}
+
+extern "C" int b2w_deltas(const float* feats, int64_t feat_stride, int32_t dim, const int64_t* utt_frame_offset,
+                          int32_t num_utts, int64_t num_frames, float* deltas, float* ddeltas, int64_t out_stride,
+                          void* stream) {
+  using namespace b2w;
+  B2W_REQUIRE(feats && utt_frame_offset && (deltas || ddeltas), "b2w_deltas: null argument");
+  B2W_REQUIRE(dim >= 1 && feat_stride >= dim && out_stride >= dim, "b2w_deltas: bad dim/stride");
+  if (num_utts == 0 || num_frames == 0) return 0;
+  const int64_t total = num_frames * dim;
+  int64_t g = (total + 255) / 256;
+  if (g > 148 * 32) g = 148 * 32;
+  deltas_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(feats, feat_stride, dim, utt_frame_offset, num_utts, num_frames,
+                                                               deltas, ddeltas, out_stride);
+  return check_launch("deltas_kernel");
+}
+
+extern "C" int b2w_stats_accumulate(const float* feats, int64_t feat_stride, int32_t dim, int64_t num_frames, double* sums,
+                                    double* gram, void* stream) {
+  using namespace b2w;
+  B2W_REQUIRE(feats && sums, "b2w_stats_accumulate: null argument");
+  B2W_REQUIRE(dim >= 1 && feat_stride >= dim, "b2w_stats_accumulate: bad dim/stride");
+  if (num_frames == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    int nx = ((dim + 31) / 32) * 32;
+    if (nx > 256) nx = 256;
+    const int ny = 256 / nx > 0 ? 256 / nx : 1;
+    int64_t nblk = 148 * 4;
+    int64_t rows = (num_frames + nblk - 1) / nblk;
+    if (rows < 64) rows = 64;
+    nblk = (num_frames + rows - 1) / rows;
+    stats_kernel<<<(unsigned)nblk, dim3(nx, ny), sizeof(double) * 2 * nx * ny, st>>>(feats, feat_stride, dim, num_frames, rows,
+                                                                                      sums);
+    int rc = check_launch("stats_kernel");
+    if (rc) return rc;
+  }
+  if (gram) {
+    const int tiles = (dim + 15) / 16;
+    int64_t nblk = 148;
+    int64_t rows = (num_frames + nblk - 1) / nblk;
+    if (rows < kGramRows) rows = kGramRows;
+    nblk = (num_frames + rows - 1) / rows;
+    gram_kernel<<<dim3((unsigned)nblk, tiles * tiles), 256, 0, st>>>(feats, feat_stride, dim, num_frames, rows, gram);
+    return check_launch("gram_kernel");
+  }
+  return 0;
+}

@@ -1,0 +1,578 @@
+// Mel-cepstral analysis (SPTK mcep, Newton-Raphson UELS) and synthesis-side mc -> spectrum, as dense contractions
+// against precomputed all-pass warping matrices.
+//
+// Replaces pysptk.mcep(amp_sp, order, alpha, eps=1e-8, etype=1, itype=3) called once per frame through
+// AudioProcessing.extract_mcep (idiaptts/src/data_preparation/audio/AudioProcessing.py:143-153) and
+// pysptk.mgc2sp(..., gamma=0) in mcep_to_amp_sp (:248-256).
+//
+// SPTK runs, per frame and per Newton iteration: freqt(mc -> N/2, -alpha), FFT, exp, IFFT, frqtr(-> 2m, alpha), and a
+// (Toeplitz + Hankel) solve.  freqt/frqtr are linear maps with constant coefficients and so are the real (I)FFTs, so
+// each pair collapses into one constant matrix (built in fp64 on the host by b2w_mcep_tables_host):
+//     C   = mc  . Cmat            [F x (m+1)] x [(m+1) x K]          (freqt + FFT)
+//     P   = per * exp(-2 C)                                           (elementwise)
+//     r~  = P   . M2^T            [F x K] x [K x (2m+1)]              (IFFT + frqtr)
+//     mc0 = log(per) . M0^T       [F x K] x [K x (m+2)]               (initial value, + start value s)
+// followed by a per-frame (m+1) x (m+1) SPD solve (blocked LDL^T, 4x4 register tiles, one warp per frame).
+// A CTA owns a tile of F frames and iterates until every frame of the tile has met SPTK's stopping rule.
+//
+// This file holds the fp32 CUDA-core version of the contractions (v1).
+#include <vector>
+
+#include "common.cuh"
+
+namespace b2w {
+
+constexpr int kMcThreads = 256;
+constexpr int kMcWarps = kMcThreads / 32;
+
+__host__ __device__ inline int pad4(int n) { return (n + 3) & ~3; }
+
+struct McepParams {
+  const void* in;
+  int in_is_power;
+  int64_t num_frames;
+  int K;       // fft_size/2 + 1
+  int KP;      // padded row length of the smem tile (multiple of 4)
+  int m;       // order
+  int MP;      // pad4(m + 1)
+  int NP0;     // pad4(m + 2): row stride of m0t
+  int NP2;     // pad4(2m + 1): row stride of m2t, and of the rt tile
+  int NBk;     // number of 4-wide blocks of the solve: ceil((m+1)/4)
+  int chol_floats;  // per-warp solve workspace in floats
+  int u_floats;     // size of the shared tile/workspace union in floats
+  int miniter, maxiter;
+  float threshold, eps;
+  float alpha;
+  const float* m0t;
+  const float* cmat;
+  const float* m2t;
+  void* mc_out;
+  int mc_dtype;
+  int64_t mc_stride;
+  int* iters;
+  int* status;
+};
+
+template <typename IT>
+__device__ __forceinline__ float load_per(const McepParams& p, int64_t frame, int j) {
+  const double v = (double)reinterpret_cast<const IT*>(p.in)[frame * p.K + j];
+  return (float)(p.in_is_power ? v + (double)p.eps : v * v + (double)p.eps);
+}
+
+// out[f][n] = sum_j tile[f][j] * mt[j][n], n < nout: thread (n = tid % NPAD, group = tid / NPAD) owns FG = F*NPAD/256
+// frames of one output column; the tile row is read as float4 broadcasts, the matrix column coalesced from L2.
+template <int F, int NPAD>
+__device__ __forceinline__ void gemm_tile_by_matrix(const float* __restrict__ tile, int KP, int K, const float* __restrict__ mt,
+                                                    int ldm, int nout, float* __restrict__ out, int ldo) {
+  constexpr int G = kMcThreads / NPAD;
+  constexpr int FG = F / G;
+  static_assert(FG >= 1, "tile too small for this mapping");
+  const int n = threadIdx.x % NPAD;
+  const int f0 = (threadIdx.x / NPAD) * FG;
+  if (n >= nout) return;
+  float acc[FG];
+#pragma unroll
+  for (int f = 0; f < FG; ++f) acc[f] = 0.f;
+  const int K4 = K & ~3;
+  for (int j = 0; j < K4; j += 4) {
+    const float w0 = __ldg(mt + (int64_t)(j + 0) * ldm + n);
+    const float w1 = __ldg(mt + (int64_t)(j + 1) * ldm + n);
+    const float w2 = __ldg(mt + (int64_t)(j + 2) * ldm + n);
+    const float w3 = __ldg(mt + (int64_t)(j + 3) * ldm + n);
+#pragma unroll
+    for (int f = 0; f < FG; ++f) {
+      const float4 p4 = *reinterpret_cast<const float4*>(tile + (f0 + f) * KP + j);
+      acc[f] = fmaf(p4.x, w0, acc[f]);
+      acc[f] = fmaf(p4.y, w1, acc[f]);
+      acc[f] = fmaf(p4.z, w2, acc[f]);
+      acc[f] = fmaf(p4.w, w3, acc[f]);
+    }
+  }
+  for (int j = K4; j < K; ++j) {
+    const float w = __ldg(mt + (int64_t)j * ldm + n);
+#pragma unroll
+    for (int f = 0; f < FG; ++f) acc[f] = fmaf(tile[(f0 + f) * KP + j], w, acc[f]);
+  }
+#pragma unroll
+  for (int f = 0; f < FG; ++f) out[(f0 + f) * ldo + n] = acc[f];
+}
+
+template <int F>
+__device__ __forceinline__ void gemm_tile_dispatch(const float* tile, int KP, int K, const float* mt, int ldm, int nout,
+                                                   float* out, int ldo) {
+  if (nout <= 32) gemm_tile_by_matrix<F, 32>(tile, KP, K, mt, ldm, nout, out, ldo);
+  else if (nout <= 64) gemm_tile_by_matrix<F, 64>(tile, KP, K, mt, ldm, nout, out, ldo);
+  else if (nout <= 128) gemm_tile_by_matrix<F, 128>(tile, KP, K, mt, ldm, nout, out, ldo);
+  else gemm_tile_by_matrix<F, 256>(tile, KP, K, mt, ldm, nout, out, ldo);
+}
+
+// C[f][j] = sum_k mc[f][k] * cmat[k][j] for one column j (all F frames in registers)
+template <int F>
+__device__ __forceinline__ void warp_column(const float* __restrict__ mc, int MP, const float* __restrict__ cmat, int K,
+                                            int j, float* acc) {
+#pragma unroll
+  for (int f = 0; f < F; ++f) acc[f] = 0.f;
+  for (int k = 0; k < MP; k += 4) {
+    // cmat is stored with pad4(m+1) rows (zero rows past m), mc rows are zero padded the same way
+    const float w0 = __ldg(cmat + (int64_t)(k + 0) * K + j);
+    const float w1 = __ldg(cmat + (int64_t)(k + 1) * K + j);
+    const float w2 = __ldg(cmat + (int64_t)(k + 2) * K + j);
+    const float w3 = __ldg(cmat + (int64_t)(k + 3) * K + j);
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+      const float4 m4 = *reinterpret_cast<const float4*>(mc + f * MP + k);
+      acc[f] = fmaf(m4.x, w0, acc[f]);
+      acc[f] = fmaf(m4.y, w1, acc[f]);
+      acc[f] = fmaf(m4.z, w2, acc[f]);
+      acc[f] = fmaf(m4.w, w3, acc[f]);
+    }
+  }
+}
+
+// ---- blocked LDL^T solve of the (m+1)x(m+1) system M d = b with M[i][k] = rt[|i-k|] + rt[i+k], one warp ---------------
+__device__ __forceinline__ int blk_index(int I, int Kb) { return (I * (I + 1) / 2 + Kb) * 16; }
+
+// returns false (warp-uniform) when a pivot is not positive
+__device__ __forceinline__ bool warp_ldl_solve(const float* __restrict__ rt, const float* __restrict__ al, int n, int NBk,
+                                              float* __restrict__ ws, float* __restrict__ x_out) {
+  const int lane = threadIdx.x & 31;
+  const int np = 4 * NBk;
+  float* A = ws;                                   // NBk(NBk+1)/2 blocks of 16
+  float* Wp = A + (NBk * (NBk + 1) / 2) * 16;      // NBk blocks of 16 (panel W = L D)
+  float* dv = Wp + NBk * 16;                       // np pivots
+  float* bv = dv + np;                             // np right-hand side / solution
+  // build
+  const int nblk = NBk * (NBk + 1) / 2;
+  for (int e = lane; e < nblk * 16; e += 32) {
+    const int bidx = e >> 4, r = (e >> 2) & 3, c = e & 3;
+    int I = 0, q = bidx;
+    while (q > I) { q -= I + 1; ++I; }
+    const int i = 4 * I + r, k = 4 * q + c;
+    float v;
+    if (i < n && k < n) v = rt[abs(i - k)] + rt[i + k];
+    else v = (i == k) ? 1.f : 0.f;
+    A[e] = v;
+  }
+  for (int i = lane; i < np; i += 32) bv[i] = (i < n) ? rt[i] - al[i] : 0.f;
+  __syncwarp();
+  bool ok = true;
+  for (int J = 0; J < NBk; ++J) {
+    // (a) diagonal block, redundantly in every lane
+    const float* a = A + blk_index(J, J);
+    const float a00 = a[0], a10 = a[4], a11 = a[5], a20 = a[8], a21 = a[9], a22 = a[10], a30 = a[12], a31 = a[13],
+                a32 = a[14], a33 = a[15];
+    const float d0 = a00;
+    const float l10 = a10 / d0, l20 = a20 / d0, l30 = a30 / d0;
+    const float d1 = a11 - l10 * l10 * d0;
+    const float l21 = (a21 - l20 * l10 * d0) / d1, l31 = (a31 - l30 * l10 * d0) / d1;
+    const float d2 = a22 - l20 * l20 * d0 - l21 * l21 * d1;
+    const float l32 = (a32 - l30 * l20 * d0 - l31 * l21 * d1) / d2;
+    const float d3 = a33 - l30 * l30 * d0 - l31 * l31 * d1 - l32 * l32 * d2;
+    if (!(d0 > 0.f && d1 > 0.f && d2 > 0.f && d3 > 0.f)) ok = false;
+    __syncwarp();
+    if (lane == 0) {
+      float* w = A + blk_index(J, J);
+      w[4] = l10; w[8] = l20; w[9] = l21; w[12] = l30; w[13] = l31; w[14] = l32;
+      dv[4 * J + 0] = d0; dv[4 * J + 1] = d1; dv[4 * J + 2] = d2; dv[4 * J + 3] = d3;
+    }
+    // (b) panel: L_IJ = A_IJ L_JJ^-T D^-1, W_IJ = L_IJ D
+    for (int I = J + 1 + lane; I < NBk; I += 32) {
+      float* X = A + blk_index(I, J);
+      float* W = Wp + I * 16;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float4 x = *reinterpret_cast<const float4*>(X + 4 * r);
+        const float w0 = x.x;
+        const float w1 = x.y - l10 * w0;
+        const float w2 = x.z - l20 * w0 - l21 * w1;
+        const float w3 = x.w - l30 * w0 - l31 * w1 - l32 * w2;
+        *reinterpret_cast<float4*>(W + 4 * r) = make_float4(w0, w1, w2, w3);
+        *reinterpret_cast<float4*>(X + 4 * r) = make_float4(w0 / d0, w1 / d1, w2 / d2, w3 / d3);
+      }
+    }
+    __syncwarp();
+    // (c) trailing update A_IK -= W_IJ L_KJ^T for J < Kb <= I
+    const int rr = NBk - 1 - J;
+    const int cnt = rr * (rr + 1) / 2;
+    for (int p = lane; p < cnt; p += 32) {
+      int a_ = 0, q = p;
+      while (q > a_) { q -= a_ + 1; ++a_; }
+      const int I = J + 1 + a_, Kb = J + 1 + q;
+      const float* W = Wp + I * 16;
+      const float* Lk = A + blk_index(Kb, J);
+      float* T = A + blk_index(I, Kb);
+      float4 lk[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) lk[c] = *reinterpret_cast<const float4*>(Lk + 4 * c);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float4 w = *reinterpret_cast<const float4*>(W + 4 * r);
+        float4 t = *reinterpret_cast<const float4*>(T + 4 * r);
+        t.x -= w.x * lk[0].x + w.y * lk[0].y + w.z * lk[0].z + w.w * lk[0].w;
+        t.y -= w.x * lk[1].x + w.y * lk[1].y + w.z * lk[1].z + w.w * lk[1].w;
+        t.z -= w.x * lk[2].x + w.y * lk[2].y + w.z * lk[2].z + w.w * lk[2].w;
+        t.w -= w.x * lk[3].x + w.y * lk[3].y + w.z * lk[3].z + w.w * lk[3].w;
+        *reinterpret_cast<float4*>(T + 4 * r) = t;
+      }
+    }
+    __syncwarp();
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  // forward substitution L y = b
+  for (int J = 0; J < NBk; ++J) {
+    const float* L = A + blk_index(J, J);
+    float y0 = bv[4 * J], y1 = bv[4 * J + 1], y2 = bv[4 * J + 2], y3 = bv[4 * J + 3];
+    y1 -= L[4] * y0;
+    y2 -= L[8] * y0 + L[9] * y1;
+    y3 -= L[12] * y0 + L[13] * y1 + L[14] * y2;
+    __syncwarp();
+    if (lane == 0) { bv[4 * J] = y0; bv[4 * J + 1] = y1; bv[4 * J + 2] = y2; bv[4 * J + 3] = y3; }
+    for (int I = J + 1 + lane; I < NBk; I += 32) {
+      const float* Li = A + blk_index(I, J);
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        bv[4 * I + r] -= Li[4 * r] * y0 + Li[4 * r + 1] * y1 + Li[4 * r + 2] * y2 + Li[4 * r + 3] * y3;
+    }
+    __syncwarp();
+  }
+  for (int i = lane; i < np; i += 32) bv[i] /= dv[i];
+  __syncwarp();
+  // backward substitution L^T x = z
+  for (int J = NBk - 1; J >= 0; --J) {
+    const float* L = A + blk_index(J, J);
+    float x0 = bv[4 * J], x1 = bv[4 * J + 1], x2 = bv[4 * J + 2], x3 = bv[4 * J + 3];
+    x2 -= L[14] * x3;
+    x1 -= L[9] * x2 + L[13] * x3;
+    x0 -= L[4] * x1 + L[8] * x2 + L[12] * x3;
+    __syncwarp();
+    if (lane == 0) { bv[4 * J] = x0; bv[4 * J + 1] = x1; bv[4 * J + 2] = x2; bv[4 * J + 3] = x3; }
+    for (int Kb = lane; Kb < J; Kb += 32) {
+      const float* Lj = A + blk_index(J, Kb);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        bv[4 * Kb + c] -= Lj[c] * x0 + Lj[4 + c] * x1 + Lj[8 + c] * x2 + Lj[12 + c] * x3;
+    }
+    __syncwarp();
+  }
+  for (int i = lane; i < n; i += 32) x_out[i] = bv[i];
+  __syncwarp();
+  return ok;
+}
+
+template <int F, typename IT>
+__global__ void __launch_bounds__(kMcThreads) mcep_kernel(McepParams p) {
+  extern __shared__ float smf[];
+  float* U = smf;                         // tile [F][KP] (log per / P), later aliased by the per-warp solve workspaces
+  float* mc = U + p.u_floats;             // [F][MP]
+  float* rt = mc + F * p.MP;              // [F][NP2]
+  float* al = rt + F * p.NP2;             // [MP]
+  float* sv = al + p.MP;                  // [F] start / previous r~[0]
+  int* act = reinterpret_cast<int*>(sv + F);  // [F] 1 = still iterating
+  int* itc = act + F;                         // [F] iteration count at exit
+  const int tid = threadIdx.x;
+  const int K = p.K, KP = p.KP, MP = p.MP, m = p.m;
+  const int64_t frame0 = (int64_t)blockIdx.x * F;
+  const int nvalid = (int)min((int64_t)F, p.num_frames - frame0);
+
+  // (-alpha)^k, zero padded
+  if (tid < MP) al[tid] = (tid <= m) ? powf(-p.alpha, (float)tid) : 0.f;
+  if (tid == 0) al[0] = 1.f;
+  for (int i = tid; i < F * MP; i += kMcThreads) mc[i] = 0.f;
+  // log periodogram tile
+  bool zero_per = false;
+  for (int f = 0; f < F; ++f) {
+    for (int j = tid; j < K; j += kMcThreads) {
+      float per = 1.f;
+      if (f < nvalid) per = load_per<IT>(p, frame0 + f, j);
+      if (!(per > 0.f)) zero_per = true;
+      U[f * KP + j] = logf(per);
+    }
+  }
+  if (zero_per) atomicOr(p.status, B2W_STATUS_ZERO_PERIODOGRAM);
+  __syncthreads();
+  // initial value: [mc | s] = log(per) . M0^T
+  gemm_tile_dispatch<F>(U, KP, K, p.m0t, p.NP0, m + 2, rt, p.NP2);
+  __syncthreads();
+  for (int i = tid; i < F * (m + 1); i += kMcThreads) {
+    const int f = i / (m + 1), k = i - f * (m + 1);
+    mc[f * MP + k] = rt[f * p.NP2 + k];
+  }
+  if (tid < F) {
+    sv[tid] = rt[tid * p.NP2 + m + 1];
+    act[tid] = tid < nvalid ? 1 : 0;
+    itc[tid] = 0;
+  }
+  __syncthreads();
+
+  for (int it = 1; it <= p.maxiter; ++it) {
+    // P = per * exp(-2 mc . Cmat)
+    {
+      float acc[F];
+      for (int j = tid; j + 1 < K; j += kMcThreads) {  // K - 1 is a multiple of 256 for every supported fft size
+        warp_column<F>(mc, MP, p.cmat, K, j, acc);
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+          float per = 1.f;
+          if (f < nvalid) per = load_per<IT>(p, frame0 + f, j);
+          U[f * KP + j] = per * expf(-2.f * acc[f]);
+        }
+      }
+      if (tid < F) {  // the Nyquist column, one frame per thread
+        float c = 0.f;
+        for (int k = 0; k <= m; ++k) c = fmaf(mc[tid * MP + k], __ldg(p.cmat + (int64_t)k * K + (K - 1)), c);
+        float per = 1.f;
+        if (tid < nvalid) per = load_per<IT>(p, frame0 + tid, K - 1);
+        U[tid * KP + K - 1] = per * expf(-2.f * c);
+      }
+    }
+    __syncthreads();
+    gemm_tile_dispatch<F>(U, KP, K, p.m2t, p.NP2, 2 * m + 1, rt, p.NP2);
+    __syncthreads();
+    // SPTK's stopping rule on r~[0]
+    if (tid < F && act[tid]) {
+      const float t = rt[tid * p.NP2];
+      if (it >= p.miniter) {
+        if (fabsf((t - sv[tid]) / t) < p.threshold) {
+          act[tid] = 0;
+          itc[tid] = it;
+        } else {
+          sv[tid] = t;
+        }
+      }
+    }
+    __syncthreads();
+    int any = 0;
+    if (tid < F) any = act[tid];
+    if (!__syncthreads_or(any)) break;
+    // Newton step for the frames still active: one warp per frame (the tile U is free now and holds the workspaces)
+    {
+      const int warp = tid >> 5, lane = tid & 31;
+      float* ws = U + warp * p.chol_floats;
+      for (int f = warp; f < F; f += kMcWarps) {
+        if (!act[f]) continue;
+        float* xo = ws + p.chol_floats - pad4(m + 1);  // tail of the workspace
+        const bool ok = warp_ldl_solve(rt + f * p.NP2, al, m + 1, p.NBk, ws, xo);
+        if (!ok) {
+          if (lane == 0) {
+            atomicOr(p.status, B2W_STATUS_SOLVE_FAILED);
+            act[f] = 0;
+            itc[f] = it;
+          }
+        } else {
+          for (int k = lane; k <= m; k += 32) mc[f * MP + k] += xo[k];
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+  }
+  // frames that ran out of iterations
+  if (tid < F && act[tid]) {
+    itc[tid] = p.maxiter;
+    atomicOr(p.status, B2W_STATUS_NOT_CONVERGED);
+  }
+  __syncthreads();
+  for (int i = tid; i < nvalid * (m + 1); i += kMcThreads) {
+    const int f = i / (m + 1), k = i - f * (m + 1);
+    const float v = mc[f * MP + k];
+    if (p.mc_dtype == B2W_F64) reinterpret_cast<double*>(p.mc_out)[(frame0 + f) * p.mc_stride + k] = (double)v;
+    else reinterpret_cast<float*>(p.mc_out)[(frame0 + f) * p.mc_stride + k] = v;
+  }
+  if (p.iters && tid < nvalid) p.iters[frame0 + tid] = itc[tid];
+}
+
+// out[f][j] = (exp?)(scale * sum_k mc[f][k] cmat[k][j])
+template <int F, typename MT, typename OT>
+__global__ void __launch_bounds__(kMcThreads) mc2sp_kernel(const MT* __restrict__ mcg, int64_t mc_stride, int64_t num_frames,
+                                                           int K, int m, const float* __restrict__ cmat, float scale,
+                                                           int do_exp, OT* __restrict__ out) {
+  extern __shared__ float smf[];
+  const int MP = pad4(m + 1);
+  float* mc = smf;  // [F][MP]
+  const int tid = threadIdx.x;
+  const int64_t frame0 = (int64_t)blockIdx.x * F;
+  const int nvalid = (int)min((int64_t)F, num_frames - frame0);
+  for (int i = tid; i < F * MP; i += kMcThreads) {
+    const int f = i / MP, k = i - f * MP;
+    mc[i] = (f < nvalid && k <= m) ? (float)mcg[(frame0 + f) * mc_stride + k] : 0.f;
+  }
+  __syncthreads();
+  float acc[F];
+  for (int j = tid; j < K; j += kMcThreads) {
+#pragma unroll
+    for (int f = 0; f < F; ++f) acc[f] = 0.f;
+    for (int k = 0; k <= m; ++k) {
+      const float w = __ldg(cmat + (int64_t)k * K + j);
+#pragma unroll
+      for (int f = 0; f < F; ++f) acc[f] = fmaf(mc[f * MP + k], w, acc[f]);
+    }
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+      if (f < nvalid) {
+        const float v = scale * acc[f];
+        out[(frame0 + f) * K + j] = (OT)(do_exp ? expf(v) : v);
+      }
+    }
+  }
+}
+
+// ---- host: fp64 construction of the warping matrices -------------------------------------------------------------------
+// freqt as a matrix: column p of the result is freqt(e_p); vectorised over the unit inputs.
+static void freqt_matrix_host(int m1, int m2, double a, bool is_frqtr, std::vector<double>& out /* [(m2+1) x (m1+1)] */) {
+  const int nin = m1 + 1, nout = m2 + 1;
+  const double b = 1.0 - a * a;
+  std::vector<double> g((size_t)nout * nin, 0.0), d((size_t)nout * nin, 0.0);
+  for (int i = -m1; i <= 0; ++i) {
+    d = g;
+    const int src = -i;
+    for (int p = 0; p < nin; ++p) {
+      const double e = (p == src) ? 1.0 : 0.0;
+      g[p] = is_frqtr ? e : e + a * d[p];
+    }
+    if (nout > 1) {
+      if (is_frqtr) {
+        for (int p = 0; p < nin; ++p) g[nin + p] = d[p] + a * (d[nin + p] - g[p]);
+      } else {
+        for (int p = 0; p < nin; ++p) g[nin + p] = b * d[p] + a * d[nin + p];
+      }
+    }
+    for (int j = 2; j < nout; ++j) {
+      double* gj = &g[(size_t)j * nin];
+      const double* gjm = &g[(size_t)(j - 1) * nin];
+      const double* dj = &d[(size_t)j * nin];
+      const double* djm = &d[(size_t)(j - 1) * nin];
+      for (int p = 0; p < nin; ++p) gj[p] = djm[p] + a * (dj[p] - gjm[p]);
+    }
+  }
+  out.swap(g);
+}
+
+}  // namespace b2w
+
+extern "C" int32_t b2w_mcep_pad(int32_t n) { return b2w::pad4(n); }
+
+extern "C" int b2w_mcep_tables_host(int32_t order, double alpha, int32_t fft_size, double* h_m0t, double* h_cmat,
+                                    double* h_m2t) {
+  using namespace b2w;
+  B2W_REQUIRE(order >= 1 && fft_size >= 8 && (fft_size & (fft_size - 1)) == 0, "b2w_mcep_tables_host: bad order/fft_size");
+  B2W_REQUIRE(h_m0t && h_cmat && h_m2t, "b2w_mcep_tables_host: null argument");
+  const int N = fft_size, f2 = N / 2, K = f2 + 1, m = order;
+  const int np0 = pad4(m + 2), np2 = pad4(2 * m + 1);
+  std::vector<double> A, Bm, R;
+  freqt_matrix_host(f2, m, alpha, false, A);       // [m+1][K]
+  freqt_matrix_host(m, f2, -alpha, false, Bm);     // [K][m+1]
+  freqt_matrix_host(f2, 2 * m, alpha, true, R);    // [2m+1][K]
+  std::vector<double> cosv(N);
+  for (int i = 0; i < N; ++i) cosv[i] = cos(2.0 * kPi * i / N);
+  // Fd[n][j] = D[n] * w_j cos(2 pi n j / N) / N   (real IFFT of the mirrored half spectrum, then c0/2, c[N/2]/2)
+  std::vector<double> Fm((size_t)K * K);
+  for (int n = 0; n < K; ++n)
+    for (int j = 0; j < K; ++j) {
+      const double w = (j == 0 || j == f2) ? 1.0 : 2.0;
+      Fm[(size_t)n * K + j] = w * cosv[(int)(((int64_t)n * j) % N)] / N;
+    }
+  for (int j = 0; j < K; ++j) {
+    double* row = h_m0t + (size_t)j * np0;
+    for (int k = 0; k < np0; ++k) row[k] = 0.0;
+    for (int k = 0; k <= m; ++k) {
+      double s = 0.0;
+      for (int n = 0; n < K; ++n) {
+        const double dn = (n == 0 || n == f2) ? 0.5 : 1.0;
+        s += A[(size_t)k * K + n] * dn * Fm[(size_t)n * K + j];
+      }
+      row[k] = s;
+    }
+    row[m + 1] = 0.5 * Fm[j];  // c[0] after halving: SPTK's start value s
+  }
+  for (int k = 0; k < pad4(m + 1); ++k)
+    for (int j = 0; j < K; ++j) {
+      double s = 0.0;
+      if (k <= m)
+        for (int n = 0; n < K; ++n) s += cosv[(int)(((int64_t)n * j) % N)] * Bm[(size_t)n * (m + 1) + k];
+      h_cmat[(size_t)k * K + j] = s;
+    }
+  for (int j = 0; j < K; ++j) {
+    double* row = h_m2t + (size_t)j * np2;
+    for (int r = 0; r < np2; ++r) row[r] = 0.0;
+    for (int r = 0; r <= 2 * m; ++r) {
+      double s = 0.0;
+      for (int n = 0; n < K; ++n) s += R[(size_t)r * K + n] * Fm[(size_t)n * K + j];
+      row[r] = s;
+    }
+  }
+  return 0;
+}
+
+extern "C" int b2w_mcep(const void* in, int32_t in_dtype, int32_t in_is_power, int64_t num_frames, int32_t fft_size,
+                        int32_t order, double alpha, int32_t miniter, int32_t maxiter, double threshold, double eps,
+                        const float* m0t, const float* cmat, const float* m2t, void* mc, int32_t mc_dtype, int64_t mc_stride,
+                        int32_t* iters, int32_t* status, void* stream) {
+  using namespace b2w;
+  B2W_REQUIRE(in && m0t && cmat && m2t && mc && status, "b2w_mcep: null argument");
+  B2W_REQUIRE(in_dtype == B2W_F64 || in_dtype == B2W_F32, "b2w_mcep: bad in_dtype %d", in_dtype);
+  B2W_REQUIRE(mc_dtype == B2W_F64 || mc_dtype == B2W_F32, "b2w_mcep: bad mc_dtype %d", mc_dtype);
+  B2W_REQUIRE(fft_size == 512 || fft_size == 1024 || fft_size == 2048 || fft_size == 4096,
+              "b2w_mcep: unsupported fft_size %d", fft_size);
+  B2W_REQUIRE(order >= 1 && 2 * order + 1 <= 256, "b2w_mcep: order %d out of range [1, 127]", order);
+  B2W_REQUIRE(mc_stride >= order + 1, "b2w_mcep: mc_stride too small");
+  B2W_REQUIRE(maxiter >= 1 && miniter >= 1, "b2w_mcep: bad iteration limits");
+  if (num_frames == 0) return 0;
+  McepParams p;
+  p.in = in; p.in_is_power = in_is_power; p.num_frames = num_frames;
+  p.K = fft_size / 2 + 1; p.KP = pad4(p.K); p.m = order; p.MP = pad4(order + 1);
+  p.NP0 = pad4(order + 2); p.NP2 = pad4(2 * order + 1);
+  p.NBk = (order + 1 + 3) / 4;
+  p.chol_floats = (p.NBk * (p.NBk + 1) / 2) * 16 + p.NBk * 16 + 8 * p.NBk + pad4(order + 1);
+  p.miniter = miniter; p.maxiter = maxiter; p.threshold = (float)threshold; p.eps = (float)eps; p.alpha = (float)alpha;
+  p.m0t = m0t; p.cmat = cmat; p.m2t = m2t; p.mc_out = mc; p.mc_dtype = mc_dtype; p.mc_stride = mc_stride;
+  p.iters = iters; p.status = status;
+  cudaStream_t st = (cudaStream_t)stream;
+  // tile height by fft size so the tile fits shared memory next to the small per-frame vectors
+  const int F = fft_size <= 1024 ? 32 : (fft_size == 2048 ? 16 : 8);
+  const int tile_floats = F * p.KP;
+  const int ws_floats = kMcWarps * p.chol_floats;
+  p.u_floats = tile_floats > ws_floats ? tile_floats : ws_floats;
+  const size_t smem = sizeof(float) * ((size_t)p.u_floats + (size_t)F * p.MP + (size_t)F * p.NP2 + p.MP + F) + sizeof(int) * 2 * F;
+  B2W_REQUIRE(smem <= 227 * 1024, "b2w_mcep: order %d needs %zu bytes of shared memory", order, smem);
+  const int64_t grid = (num_frames + F - 1) / F;
+  B2W_REQUIRE(grid < (int64_t)1 << 31, "b2w_mcep: too many frames in one call");
+#define B2W_MCEP_LAUNCH(FF, IT)                                                                          \
+  do {                                                                                                   \
+    cudaFuncSetAttribute(mcep_kernel<FF, IT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+    mcep_kernel<FF, IT><<<(unsigned)grid, kMcThreads, smem, st>>>(p);                                    \
+  } while (0)
+  if (in_dtype == B2W_F64) {
+    if (F == 32) B2W_MCEP_LAUNCH(32, double); else if (F == 16) B2W_MCEP_LAUNCH(16, double); else B2W_MCEP_LAUNCH(8, double);
+  } else {
+    if (F == 32) B2W_MCEP_LAUNCH(32, float); else if (F == 16) B2W_MCEP_LAUNCH(16, float); else B2W_MCEP_LAUNCH(8, float);
+  }
+#undef B2W_MCEP_LAUNCH
+  return check_launch("mcep_kernel");
+}
+
+extern "C" int b2w_mc2sp(const void* mc, int32_t mc_dtype, int64_t mc_stride, int64_t num_frames, int32_t fft_size,
+                         int32_t order, const float* cmat, double scale, int32_t do_exp, void* out, int32_t out_dtype,
+                         void* stream) {
+  using namespace b2w;
+  B2W_REQUIRE(mc && cmat && out, "b2w_mc2sp: null argument");
+  B2W_REQUIRE(mc_dtype == B2W_F64 || mc_dtype == B2W_F32, "b2w_mc2sp: bad mc_dtype %d", mc_dtype);
+  B2W_REQUIRE(out_dtype == B2W_F64 || out_dtype == B2W_F32, "b2w_mc2sp: bad out_dtype %d", out_dtype);
+  B2W_REQUIRE(order >= 0 && order < 512, "b2w_mc2sp: bad order %d", order);
+  if (num_frames == 0) return 0;
+  constexpr int F = 16;
+  const int K = fft_size / 2 + 1;
+  const size_t smem = sizeof(float) * F * pad4(order + 1);
+  const int64_t grid = (num_frames + F - 1) / F;
+  B2W_REQUIRE(grid < (int64_t)1 << 31, "b2w_mc2sp: too many frames in one call");
+  cudaStream_t st = (cudaStream_t)stream;
+#define B2W_MC2SP_LAUNCH(MT, OT)                                                                                      \
+  mc2sp_kernel<F, MT, OT><<<(unsigned)grid, kMcThreads, smem, st>>>((const MT*)mc, mc_stride, num_frames, K, order, cmat, \
+                                                                    (float)scale, do_exp, (OT*)out)
+  if (mc_dtype == B2W_F64) {
+    if (out_dtype == B2W_F64) B2W_MC2SP_LAUNCH(double, double); else B2W_MC2SP_LAUNCH(double, float);
+  } else {
+    if (out_dtype == B2W_F64) B2W_MC2SP_LAUNCH(float, double); else B2W_MC2SP_LAUNCH(float, float);
+  }
+#undef B2W_MC2SP_LAUNCH
+  return check_launch("mc2sp_kernel");
+}

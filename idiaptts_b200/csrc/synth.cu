@@ -1,0 +1,587 @@
+// WORLD synthesis on a ragged batch: pulse placement, per-pulse minimum-phase responses, atomic-free overlap-add.
+//
+// Replaces pyworld.synthesize(f0, sp, ap, fs) as called by WorldFeatLabelGen.world_features_to_raw
+// (idiaptts/src/data_preparation/world/WorldFeatLabelGen.py:943) inside Synthesiser.run_world_synth
+// (idiaptts/src/Synthesiser.py:51-65, a serial loop over utterances).  Algorithm: WORLD synthesis.cpp.
+//
+//   timebase     one CTA per utterance.  WORLD accumulates the phase of the sample-rate F0 contour sequentially over
+//                every sample; here each thread owns a contiguous run of samples and the running phase is a block-wide
+//                fp64 prefix sum (three sweeps: sums, pulse counts, pulse records).
+//   randn table  WORLD's randn() is xorshift128 (sum of 12 draws); Synthesis() reseeds it, and pulse p consumes exactly
+//                12 * (n_{p+1} - n_p) steps, so the noise of pulse p is the slice [n_p - n_0, n_{p+1} - n_0) of ONE fixed
+//                sequence.  The table kernel regenerates that sequence in parallel by GF(2) jump-ahead.
+//   render       one CTA per pulse: interpolated envelope / aperiodicity, two minimum-phase spectra (each two real
+//                FFTs), noise FFT, two inverse real FFTs, DC removal -> response[pulse][fft_size].
+//   overlap-add  gather: each output sample sums, in pulse order (= the order WORLD accumulates in), the <= fft_size /
+//                pulse-spacing responses that cover it.  No atomics, bit-reproducible.
+#include <mutex>
+
+#include "fft.cuh"
+
+namespace b2w {
+
+// ---- xorshift128 jump-ahead ------------------------------------------------------------------------------------------------
+constexpr int kRandChunk = 256;   // randn values per thread
+constexpr int kJumpLevels = 24;   // jump matrices T^(2^i), T = step^(12 * kRandChunk): up to 2^24 chunks
+struct JumpTables {
+  uint32_t col[kJumpLevels][128][4];  // column k of level i = image of state bit k
+};
+__device__ JumpTables g_jump;
+
+struct XsState { uint32_t x, y, z, w; };
+__host__ __device__ inline void xs_step(XsState& s) {
+  const uint32_t t = s.x ^ (s.x << 11);
+  s.x = s.y; s.y = s.z; s.z = s.w;
+  s.w = (s.w ^ (s.w >> 19)) ^ (t ^ (t >> 8));
+}
+
+typedef uint32_t BitMat[128][4];  // column-major: m[k] = M e_k packed as (x, y, z, w)
+static void bm_apply(const BitMat m, const uint32_t in[4], uint32_t out[4]) {
+  out[0] = out[1] = out[2] = out[3] = 0;
+  for (int k = 0; k < 128; ++k)
+    if ((in[k >> 5] >> (k & 31)) & 1u)
+      for (int q = 0; q < 4; ++q) out[q] ^= m[k][q];
+}
+static void bm_mul(const BitMat a, const BitMat b, BitMat c) {  // c = a * b
+  for (int k = 0; k < 128; ++k) bm_apply(a, b[k], c[k]);
+}
+
+static int ensure_jump_tables() {
+  static std::mutex mu;
+  static bool done[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+  std::lock_guard<std::mutex> lock(mu);
+  if (done[dev]) return 0;
+  static JumpTables host;
+  static bool built = false;
+  if (!built) {
+    static BitMat step, acc, tmp, sq;
+    for (int k = 0; k < 128; ++k) {
+      XsState s{0, 0, 0, 0};
+      (&s.x)[k >> 5] = 1u << (k & 31);
+      xs_step(s);
+      step[k][0] = s.x; step[k][1] = s.y; step[k][2] = s.z; step[k][3] = s.w;
+    }
+    // acc = step^(12 * kRandChunk) by square-and-multiply
+    for (int k = 0; k < 128; ++k)
+      for (int q = 0; q < 4; ++q) acc[k][q] = (q == (k >> 5)) ? (1u << (k & 31)) : 0u;  // identity
+    memcpy(sq, step, sizeof(BitMat));
+    for (unsigned e = 12u * kRandChunk; e; e >>= 1) {
+      if (e & 1u) { bm_mul(sq, acc, tmp); memcpy(acc, tmp, sizeof(BitMat)); }
+      bm_mul(sq, sq, tmp);
+      memcpy(sq, tmp, sizeof(BitMat));
+    }
+    for (int i = 0; i < kJumpLevels; ++i) {
+      memcpy(host.col[i], acc, sizeof(BitMat));
+      bm_mul(acc, acc, tmp);
+      memcpy(acc, tmp, sizeof(BitMat));
+    }
+    built = true;
+  }
+  if (cudaMemcpyToSymbol(g_jump, &host, sizeof(JumpTables)) != cudaSuccess) return -1;
+  done[dev] = true;
+  return 0;
+}
+
+__global__ void randn_table_kernel(double* __restrict__ table, int64_t n) {
+  const int64_t chunk = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t first = chunk * kRandChunk;
+  if (first >= n) return;
+  uint32_t s[4] = {123456789u, 362436069u, 521288629u, 88675123u};  // randn_reseed()
+  for (int lvl = 0; lvl < kJumpLevels; ++lvl) {
+    if ((chunk >> lvl) & 1) {
+      uint32_t o[4] = {0, 0, 0, 0};
+      for (int k = 0; k < 128; ++k) {
+        if ((s[k >> 5] >> (k & 31)) & 1u) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) o[q] ^= g_jump.col[lvl][k][q];
+        }
+      }
+      s[0] = o[0]; s[1] = o[1]; s[2] = o[2]; s[3] = o[3];
+    }
+  }
+  XsState st{s[0], s[1], s[2], s[3]};
+  const int64_t last = min(n, first + kRandChunk);
+  for (int64_t i = first; i < last; ++i) {
+    uint32_t tmp = 0;
+#pragma unroll
+    for (int r = 0; r < 12; ++r) {
+      xs_step(st);
+      tmp += st.w >> 4;
+    }
+    table[i] = (double)tmp / 268435456.0 - 6.0;
+  }
+}
+
+// ---- time base -----------------------------------------------------------------------------------------------------------------
+constexpr int kTbThreads = 256;
+
+struct TbFrame {  // WORLD interp1 of the coarse (frame-rate) F0 / VUV contours at one sample
+  double f0, vuv;
+};
+
+// coarse contour value i in [0, T]: index T is WORLD's linear extrapolation 2 c[T-1] - c[T-2]
+__device__ __forceinline__ void coarse_at(const double* __restrict__ f0, int T, double lowest_f0, int i, double& cf0, double& cv) {
+  if (i < T) {
+    const double v = f0[i];
+    cf0 = v < lowest_f0 ? 0.0 : v;
+    cv = cf0 == 0.0 ? 0.0 : 1.0;
+  } else {
+    double a0, v0, a1, v1;
+    coarse_at(f0, T, lowest_f0, T - 1, a1, v1);
+    if (T >= 2) coarse_at(f0, T, lowest_f0, T - 2, a0, v0); else { a0 = a1; v0 = v1; }
+    cf0 = __dsub_rn(__dmul_rn(a1, 2.0), a0);
+    cv = __dsub_rn(__dmul_rn(v1, 2.0), v0);
+  }
+}
+
+// per-sample F0 used for the phase (500 Hz where the interpolated VUV is <= 0.5) and the thresholded VUV
+__device__ __forceinline__ double sample_f0(const double* __restrict__ f0, int T, double lowest_f0, double fp, double fs, int n,
+                                            int& k, double& vuv_out) {
+  const double time = (double)n / fs;
+  while (k < T && time >= __dmul_rn((double)k, fp)) ++k;     // coarse_t[k-1] <= time < coarse_t[k], k in [1, T]
+  const double xl = __dmul_rn((double)(k - 1), fp), xr = __dmul_rn((double)k, fp);
+  const double s = __ddiv_rn(__dsub_rn(time, xl), __dsub_rn(xr, xl));
+  double fl, vl, fr, vr;
+  coarse_at(f0, T, lowest_f0, k - 1, fl, vl);
+  coarse_at(f0, T, lowest_f0, k, fr, vr);
+  const double if0 = __dadd_rn(fl, __dmul_rn(s, __dsub_rn(fr, fl)));
+  const double iv = __dadd_rn(vl, __dmul_rn(s, __dsub_rn(vr, vl)));
+  vuv_out = iv > 0.5 ? 1.0 : 0.0;
+  return vuv_out == 0.0 ? kDefaultF0 : if0;
+}
+
+__global__ void __launch_bounds__(kTbThreads)
+timebase_kernel(const double* __restrict__ f0_all, const int64_t* __restrict__ utt_frame_offset,
+                const int64_t* __restrict__ utt_out_offset, const int64_t* __restrict__ utt_pulse_offset, int fs_i,
+                double frame_period_ms, int fft_size, int* __restrict__ pulse_index, double* __restrict__ pulse_shift,
+                uint8_t* __restrict__ pulse_vuv, int* __restrict__ num_pulses, int* __restrict__ status) {
+  __shared__ double sh_d[kTbThreads / 32 + 1];
+  __shared__ int sh_i[kTbThreads / 32 + 1];
+  const int u = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double* f0 = f0_all + utt_frame_offset[u];
+  const int T = (int)(utt_frame_offset[u + 1] - utt_frame_offset[u]);
+  const int ylen = (int)(utt_out_offset[u + 1] - utt_out_offset[u]);
+  const int64_t poff = utt_pulse_offset[u];
+  const int cap = (int)(utt_pulse_offset[u + 1] - poff);
+  const double fs = (double)fs_i;
+  const double fp = frame_period_ms / 1000.0;
+  const double lowest_f0 = (double)(fs_i / fft_size) + 1.0;
+  const double two_pi = 2.0 * kPi;
+  if (T < 1 || ylen < 2) {
+    if (tid == 0) num_pulses[u] = 0;
+    return;
+  }
+  const int per = (ylen + kTbThreads - 1) / kTbThreads;
+  const int beg = min(ylen, tid * per), end = min(ylen, beg + per);
+  // sweep 1: phase advance of this thread's run
+  double run = 0.0;
+  {
+    int k = max(1, min(T, (int)((double)beg / fs / fp)));
+    while (k > 1 && (double)beg / fs < __dmul_rn((double)(k - 1), fp)) --k;
+    double v;
+    for (int n = beg; n < end; ++n) run = __dadd_rn(run, __ddiv_rn(__dmul_rn(two_pi, sample_f0(f0, T, lowest_f0, fp, fs, n, k, v)), fs));
+  }
+  // exclusive block scan of the runs
+  double incl = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) sh_d[warp] = incl;
+  __syncthreads();
+  double offset = incl - run;
+  for (int w = 0; w < warp; ++w) offset += sh_d[w];
+  // sweeps 2 and 3: count, then write, the pulses whose FIRST sample (index i of the jump i -> i+1) lies in this run.
+  // jump i -> i+1 is examined by the owner of sample i + 1.
+  int my_count = 0, my_base = 0;
+  for (int sweep = 0; sweep < 2; ++sweep) {
+    int k = max(1, min(T, (int)((double)beg / fs / fp)));
+    while (k > 1 && (double)beg / fs < __dmul_rn((double)(k - 1), fp)) --k;
+    double total = offset;
+    double prev_wrap = fmod(total, two_pi);  // wrap phase of sample beg - 1 (unused for beg == 0)
+    double prev_vuv = 0.0;
+    if (beg > 0 && beg < end) {  // vuv flag of sample beg - 1
+      int kk = max(1, k - 1);
+      while (kk > 1 && (double)(beg - 1) / fs < __dmul_rn((double)(kk - 1), fp)) --kk;
+      double v;
+      sample_f0(f0, T, lowest_f0, fp, fs, beg - 1, kk, v);
+      prev_vuv = v;
+    }
+    int cnt = 0;
+    for (int n = beg; n < end; ++n) {
+      double v;
+      const double f = sample_f0(f0, T, lowest_f0, fp, fs, n, k, v);
+      total = __dadd_rn(total, __ddiv_rn(__dmul_rn(two_pi, f), fs));
+      const double wrap = fmod(total, two_pi);
+      if (n > 0 && fabs(wrap - prev_wrap) > kPi) {
+        if (sweep == 1) {
+          const int slot = my_base + cnt;
+          if (slot < cap) {
+            const double y1 = prev_wrap - two_pi;
+            const double x = -y1 / (wrap - y1);
+            pulse_index[poff + slot] = n - 1;
+            pulse_shift[poff + slot] = x / fs;
+            pulse_vuv[poff + slot] = prev_vuv > 0.5 ? 1 : 0;
+          }
+        }
+        ++cnt;
+      }
+      prev_wrap = wrap;
+      prev_vuv = v;
+    }
+    if (sweep == 0) {
+      my_count = cnt;
+      int inc = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+      }
+      if (lane == 31) sh_i[warp] = inc;
+      __syncthreads();
+      my_base = inc - cnt;
+      for (int w = 0; w < warp; ++w) my_base += sh_i[w];
+      if (tid == kTbThreads - 1) {
+        const int totalp = my_base + my_count;
+        if (totalp > cap) atomicOr(status, B2W_STATUS_F0_TOO_HIGH);
+        num_pulses[u] = min(totalp, cap);
+      }
+    }
+  }
+}
+
+// ---- render -------------------------------------------------------------------------------------------------------------------
+template <int N>
+struct RenderSmem {
+  static constexpr int M = N / 2;
+  static constexpr int K = N / 2 + 1;
+  static constexpr int z_doubles = 2 * zp_size(M);
+  static constexpr int x_doubles = 2 * (K + 1);   // complex spectrum staging
+  static constexpr int env_doubles = K + 1;
+  static constexpr int ar_doubles = K + 1;
+  static constexpr int per_doubles = N;            // periodic response
+  static constexpr int zn_doubles = 2 * (K + 1);  // noise spectrum
+  static constexpr int red_doubles = 32;
+  static constexpr int total_bytes =
+      (z_doubles + x_doubles + env_doubles + ar_doubles + per_doubles + zn_doubles + red_doubles) * 8;
+};
+
+// WORLD GetMinimumPhaseSpectrum for the log-amplitude L[0..N/2] held in `logsp` -> X[0..N/2] (complex) in `X`.
+template <int N, int NT>
+__device__ __forceinline__ void minimum_phase(const double* logsp, double2* z, double2* X, const double2* __restrict__ tw,
+                                              int tid) {
+  constexpr int M = N / 2, H = N / 2, K = H + 1;
+  for (int k = tid; k < K; k += NT) {
+    const double v = logsp[k];
+    zreal<double>(z, k) = v;
+    if (k > 0 && k < H) zreal<double>(z, N - k) = v;
+  }
+  __syncthreads();
+  cfft<double, M, NT>(z, tw, tid);
+  // cepstrum (real for a symmetric input), folded: c[0], 2 c[1..N/2-1], c[N/2], zeros
+  for (int k = tid; k < K; k += NT) {
+    const double c = rfft_bin<double, N>(z, tw, k).x;
+    X[k].x = (k == 0 || k == H) ? c : 2.0 * c;
+  }
+  __syncthreads();
+  for (int n = tid; n < N; n += NT) zreal<double>(z, n) = (n <= H) ? X[n].x : 0.0;
+  __syncthreads();
+  cfft<double, M, NT>(z, tw, tid);
+  for (int k = tid; k < K; k += NT) {
+    const double2 s = rfft_bin<double, N>(z, tw, k);
+    const double mag = exp(s.x / N);
+    double sn, cs;
+    sincos(s.y / N, &sn, &cs);
+    X[k] = make_double2(mag * cs, mag * sn);
+  }
+  __syncthreads();
+}
+
+// Unnormalised inverse real FFT of the Hermitian half spectrum X[0..N/2], fft-shifted: out(j) = x[(j + N/2) mod N].
+template <int N, int NT, typename Emit>
+__device__ __forceinline__ void inverse_real_shifted(const double2* X, double2* z, const double2* __restrict__ tw, int tid,
+                                                     Emit emit) {
+  constexpr int M = N / 2;
+  for (int k = tid; k < M; k += NT) {
+    const double2 a = X[k];
+    const double2 bq = X[M - k];
+    const double2 b = make_double2(bq.x, -bq.y);                 // conj(X[M - k]) = X[k + M]
+    const double2 e = make_double2(a.x + b.x, a.y + b.y);
+    const double2 d = make_double2(a.x - b.x, a.y - b.y);
+    const double2 wq = __ldg(&tw[k * (kTwN / N)]);
+    const double2 wc = make_double2(wq.x, -wq.y);                // W^-k
+    const double2 o = cmul(d, wc);
+    // Y = e + i * o ; store conj(Y) so that a forward FFT followed by a conjugate gives the inverse transform
+    z[ZP(k)] = make_double2(e.x - o.y, -(e.y + o.x));
+  }
+  __syncthreads();
+  cfft<double, M, NT>(z, tw, tid);
+  for (int n = tid; n < M; n += NT) {
+    const double2 v = z[ZP(n)];
+    // x[2n] = Re, x[2n+1] = -Im ; shifted position j = (i + N/2) mod N
+    emit((2 * n + M) & (N - 1), v.x);
+    emit((2 * n + 1 + M) & (N - 1), -v.y);
+  }
+  __syncthreads();
+}
+
+template <typename PT>
+__device__ __forceinline__ double plane_at(const void* p, int64_t idx) { return (double)reinterpret_cast<const PT*>(p)[idx]; }
+
+template <int N, typename PT>
+__global__ void __launch_bounds__(N / 16)
+render_kernel(const void* __restrict__ sp, const void* __restrict__ ap, const int64_t* __restrict__ utt_frame_offset,
+              const int64_t* __restrict__ utt_pulse_offset, const int* __restrict__ num_pulses,
+              const int* __restrict__ pulse_index, const double* __restrict__ pulse_shift,
+              const uint8_t* __restrict__ pulse_vuv, const double* __restrict__ randn_table, int64_t randn_len, int fs_i,
+              double frame_period_ms, double* __restrict__ response, const double2* __restrict__ tw) {
+  constexpr int NT = N / 16;
+  constexpr int H = N / 2, K = H + 1;
+  const int u = blockIdx.y;
+  const int P = num_pulses[u];
+  const int p = blockIdx.x;
+  if (p >= P) return;
+  extern __shared__ double smem[];
+  double2* z = reinterpret_cast<double2*>(smem);
+  double2* X = reinterpret_cast<double2*>(smem + RenderSmem<N>::z_doubles);
+  double* env = smem + RenderSmem<N>::z_doubles + RenderSmem<N>::x_doubles;
+  double* ar = env + RenderSmem<N>::env_doubles;
+  double* periodic = ar + RenderSmem<N>::ar_doubles;
+  double2* Zn = reinterpret_cast<double2*>(periodic + RenderSmem<N>::per_doubles);
+  double* red = reinterpret_cast<double*>(Zn) + RenderSmem<N>::zn_doubles;
+  const int tid = threadIdx.x;
+  const double fs = (double)fs_i;
+  const double fp = frame_period_ms / 1000.0;
+  const int64_t poff = utt_pulse_offset[u];
+  const int64_t f_off = utt_frame_offset[u];
+  const int T = (int)(utt_frame_offset[u + 1] - f_off);
+  const int n_p = pulse_index[poff + p];
+  const int n_next = pulse_index[poff + min(P - 1, p + 1)];
+  const int n_first = pulse_index[poff];
+  const int noise_size = n_next - n_p;
+  const double cur_vuv = pulse_vuv[poff + p] ? 1.0 : 0.0;
+  const double cur_time = (double)n_p / fs;
+  const int fl = min(T - 1, (int)floor(cur_time / fp));
+  const int ce = min(T - 1, (int)ceil(cur_time / fp));
+  const double w = cur_time / fp - fl;
+  // interpolated spectral envelope and aperiodic ratio (WORLD GetSpectralEnvelope / GetAperiodicRatio)
+  for (int k = tid; k < K; k += NT) {
+    const double s0 = fabs(plane_at<PT>(sp, (f_off + fl) * K + k));
+    double a0 = plane_at<PT>(ap, (f_off + fl) * K + k);
+    a0 = fmax(0.001, fmin(0.999999999999, a0));
+    a0 *= a0;
+    if (fl == ce) {
+      env[k] = s0;
+      ar[k] = a0;
+    } else {
+      const double s1 = fabs(plane_at<PT>(sp, (f_off + ce) * K + k));
+      double a1 = plane_at<PT>(ap, (f_off + ce) * K + k);
+      a1 = fmax(0.001, fmin(0.999999999999, a1));
+      a1 *= a1;
+      env[k] = (1.0 - w) * s0 + w * s1;
+      ar[k] = (1.0 - w) * a0 + w * a1;
+    }
+  }
+  __syncthreads();
+  const bool has_periodic = !(cur_vuv <= 0.5 || ar[0] > 0.999);
+  if (has_periodic) {
+    double* L = periodic;  // log-spectrum staging shares the periodic buffer until the response is emitted
+    for (int k = tid; k < K; k += NT) L[k] = log(env[k] * (1.0 - ar[k]) + kMySafeGuardMinimum) / 2.0;
+    __syncthreads();
+    minimum_phase<N, NT>(L, z, X, tw, tid);
+    // fractional time shift: multiply bin k by (cos(c k) - i sqrt(1 - cos^2(c k)))
+    const double coef = 2.0 * kPi * pulse_shift[poff + p] * fs / N;
+    for (int k = tid; k < K; k += NT) {
+      const double2 v = X[k];
+      const double re2 = cos(coef * k);
+      const double im2 = sqrt(1.0 - re2 * re2);
+      X[k] = make_double2(v.x * re2 + v.y * im2, v.y * re2 - v.x * im2);
+    }
+    __syncthreads();
+    inverse_real_shifted<N, NT>(X, z, tw, tid, [&](int j, double v) { periodic[j] = v; });
+    // remove the DC component (WORLD RemoveDCComponent with GetDCRemover's Hann-shaped weights)
+    double dcs = 0.0, rs = 0.0;
+    for (int i = tid; i < H; i += NT) {
+      dcs += periodic[H + i];
+      rs += 2.0 * (0.5 - 0.5 * cos(2.0 * kPi * (i + 1.0) / (1.0 + N)));
+    }
+    block_sum2<NT>(dcs, rs, red);
+    for (int i = tid; i < H; i += NT) {
+      const double r = (0.5 - 0.5 * cos(2.0 * kPi * (i + 1.0) / (1.0 + N))) / rs;  // dc_remover[i] == dc_remover[N-1-i]
+      periodic[i] = -dcs * r;
+      periodic[N - 1 - i] -= dcs * r;
+    }
+    __syncthreads();
+  }
+  // noise spectrum of this pulse's slice of the randn stream (WORLD GetNoiseSpectrum)
+  {
+    const int64_t start = (int64_t)n_p - n_first;
+    double acc = 0.0;
+    for (int i = tid; i < noise_size; i += NT) acc += (start + i < randn_len) ? randn_table[start + i] : 0.0;
+    const double tot = block_sum<NT>(acc, red);
+    const double mean = noise_size > 0 ? tot / noise_size : 0.0;
+    for (int i = tid; i < N; i += NT) {
+      double v = 0.0;
+      if (i < noise_size && start + i < randn_len) v = randn_table[start + i] - mean;
+      zreal<double>(z, i) = v;
+    }
+    __syncthreads();
+    cfft<double, N / 2, NT>(z, tw, tid);
+    for (int k = tid; k < K; k += NT) Zn[k] = rfft_bin<double, N>(z, tw, k);
+  }
+  // aperiodic response: minimum phase of sqrt(env * ar) (voiced) or sqrt(env) (unvoiced), times the noise spectrum
+  for (int k = tid; k < K; k += NT) {
+    const double e = env[k];
+    env[k] = (cur_vuv != 0.0) ? log(e * ar[k]) / 2.0 : log(e) / 2.0;
+  }
+  __syncthreads();
+  minimum_phase<N, NT>(env, z, X, tw, tid);
+  for (int k = tid; k < K; k += NT) X[k] = cmul(X[k], Zn[k]);
+  __syncthreads();
+  const double sqrt_noise = sqrt((double)noise_size);
+  double* out = response + (poff + p) * (int64_t)N;
+  inverse_real_shifted<N, NT>(X, z, tw, tid, [&](int j, double v) {
+    const double per_v = has_periodic ? periodic[j] : 0.0;
+    out[j] = (per_v * sqrt_noise + v) / N;
+  });
+}
+
+// ---- overlap-add ---------------------------------------------------------------------------------------------------------------
+template <typename OT>
+__global__ void __launch_bounds__(256)
+overlap_add_kernel(const double* __restrict__ response, const int64_t* __restrict__ utt_out_offset,
+                   const int64_t* __restrict__ utt_pulse_offset, const int* __restrict__ num_pulses,
+                   const int* __restrict__ pulse_index, int fft_size, OT* __restrict__ y) {
+  const int u = blockIdx.y;
+  const int64_t yoff = utt_out_offset[u];
+  const int ylen = (int)(utt_out_offset[u + 1] - yoff);
+  const int n0 = blockIdx.x * 256;
+  if (n0 >= ylen) return;
+  const int n = n0 + threadIdx.x;
+  const int64_t poff = utt_pulse_offset[u];
+  const int P = num_pulses[u];
+  const int* idx = pulse_index + poff;
+  const int H = fft_size / 2;
+  // first pulse whose response can reach sample n0: n_p + H >= n0  <=>  n_p >= n0 - H
+  int lo = 0, hi = P;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (idx[mid] < n0 - H) lo = mid + 1; else hi = mid;
+  }
+  double acc = 0.0;
+  for (int p = lo; p < P; ++p) {
+    const int np = idx[p];
+    if (np - H + 1 > n0 + 255) break;          // response starts after this tile
+    const int j = n - (np - H + 1);
+    if (j >= 0 && j < fft_size) acc += response[(poff + p) * (int64_t)fft_size + j];
+  }
+  if (n < ylen) y[yoff + n] = (OT)acc;
+}
+
+// y[n] = x[n] + p y[n-1] (scipy.signal.lfilter([1], [1, -p])) on the float32-rounded waveform, one thread per utterance
+__global__ void deemphasis_kernel(const int64_t* __restrict__ utt_out_offset, int num_utts, double p, double* __restrict__ y) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= num_utts) return;
+  const int64_t b = utt_out_offset[u], e = utt_out_offset[u + 1];
+  double prev = 0.0;
+  for (int64_t i = b; i < e; ++i) {
+    prev = __dadd_rn((double)(float)y[i], __dmul_rn(p, prev));
+    y[i] = prev;
+  }
+}
+
+}  // namespace b2w
+
+extern "C" int64_t b2w_synth_max_pulses(int64_t y_length, int32_t fs) {
+  return (int64_t)((double)y_length * 1200.0 / (double)fs) + 64;
+}
+
+extern "C" int b2w_synth_randn_table(double* table, int64_t n, void* stream) {
+  using namespace b2w;
+  B2W_REQUIRE(table, "b2w_synth_randn_table: null argument");
+  if (n == 0) return 0;
+  B2W_REQUIRE(n / kRandChunk < ((int64_t)1 << kJumpLevels), "b2w_synth_randn_table: table too long");
+  B2W_REQUIRE(ensure_jump_tables() == 0, "b2w_synth_randn_table: cannot upload jump tables");
+  const int64_t chunks = (n + kRandChunk - 1) / kRandChunk;
+  randn_table_kernel<<<(unsigned)((chunks + 63) / 64), 64, 0, (cudaStream_t)stream>>>(table, n);
+  return check_launch("randn_table_kernel");
+}
+
+extern "C" int b2w_synth_timebase(const double* f0, const int64_t* utt_frame_offset, const int64_t* utt_out_offset,
+                                  const int64_t* utt_pulse_offset, int32_t num_utts, int32_t fs, double frame_period_ms,
+                                  int32_t fft_size, int32_t* pulse_index, double* pulse_shift, uint8_t* pulse_vuv,
+                                  int32_t* num_pulses, int32_t* status, void* stream) {
+  using namespace b2w;
+  B2W_REQUIRE(f0 && utt_frame_offset && utt_out_offset && utt_pulse_offset && pulse_index && pulse_shift && pulse_vuv &&
+                  num_pulses && status,
+              "b2w_synth_timebase: null argument");
+  if (num_utts == 0) return 0;
+  timebase_kernel<<<num_utts, kTbThreads, 0, (cudaStream_t)stream>>>(f0, utt_frame_offset, utt_out_offset, utt_pulse_offset,
+                                                                      fs, frame_period_ms, fft_size, pulse_index, pulse_shift,
+                                                                      pulse_vuv, num_pulses, status);
+  return check_launch("timebase_kernel");
+}
+
+extern "C" int b2w_synth_render(const void* sp, const void* ap, int32_t plane_dtype, const int64_t* utt_frame_offset,
+                                const int64_t* utt_pulse_offset, const int32_t* num_pulses, int32_t num_utts,
+                                const int32_t* pulse_index, const double* pulse_shift, const uint8_t* pulse_vuv,
+                                const double* randn_table, int64_t randn_table_len, int32_t fs, double frame_period_ms,
+                                int32_t fft_size, int64_t max_pulses_per_utt, double* response, void* stream) {
+  using namespace b2w;
+  B2W_REQUIRE(sp && ap && utt_frame_offset && utt_pulse_offset && num_pulses && pulse_index && pulse_shift && pulse_vuv &&
+                  randn_table && response,
+              "b2w_synth_render: null argument");
+  B2W_REQUIRE(plane_dtype == B2W_F64 || plane_dtype == B2W_F32, "b2w_synth_render: bad plane dtype %d", plane_dtype);
+  B2W_REQUIRE(num_utts <= 65535, "b2w_synth_render: at most 65535 utterances per call");
+  if (num_utts == 0 || max_pulses_per_utt == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const double2* tw = twiddle_table(st);
+  if (!tw) return check_launch("twiddle table");
+  dim3 grid((unsigned)max_pulses_per_utt, (unsigned)num_utts);
+#define B2W_RENDER_LAUNCH(NN, PT)                                                                                          \
+  do {                                                                                                                     \
+    const int smem = RenderSmem<NN>::total_bytes;                                                                          \
+    cudaFuncSetAttribute(render_kernel<NN, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                        \
+    render_kernel<NN, PT><<<grid, NN / 16, smem, st>>>(sp, ap, utt_frame_offset, utt_pulse_offset, num_pulses, pulse_index, \
+                                                       pulse_shift, pulse_vuv, randn_table, randn_table_len, fs,           \
+                                                       frame_period_ms, response, tw);                                     \
+  } while (0)
+  switch (fft_size) {
+    case 512: if (plane_dtype == B2W_F64) B2W_RENDER_LAUNCH(512, double); else B2W_RENDER_LAUNCH(512, float); break;
+    case 1024: if (plane_dtype == B2W_F64) B2W_RENDER_LAUNCH(1024, double); else B2W_RENDER_LAUNCH(1024, float); break;
+    case 2048: if (plane_dtype == B2W_F64) B2W_RENDER_LAUNCH(2048, double); else B2W_RENDER_LAUNCH(2048, float); break;
+    case 4096: if (plane_dtype == B2W_F64) B2W_RENDER_LAUNCH(4096, double); else B2W_RENDER_LAUNCH(4096, float); break;
+    default: set_error("b2w_synth_render: unsupported fft_size %d", fft_size); return -1;
+  }
+#undef B2W_RENDER_LAUNCH
+  return check_launch("render_kernel");
+}
+
+extern "C" int b2w_synth_overlap_add(const double* response, const int64_t* utt_out_offset, const int64_t* utt_pulse_offset,
+                                     const int32_t* num_pulses, int32_t num_utts, const int32_t* pulse_index, int32_t fft_size,
+                                     int64_t max_out_per_utt, double deemphasis, void* y, int32_t y_dtype, void* stream) {
+  using namespace b2w;
+  B2W_REQUIRE(response && utt_out_offset && utt_pulse_offset && num_pulses && pulse_index && y,
+              "b2w_synth_overlap_add: null argument");
+  B2W_REQUIRE(y_dtype == B2W_F64 || y_dtype == B2W_F32, "b2w_synth_overlap_add: bad y dtype %d", y_dtype);
+  B2W_REQUIRE(deemphasis == 0.0 || y_dtype == B2W_F64, "b2w_synth_overlap_add: de-emphasis needs a float64 output");
+  B2W_REQUIRE(num_utts <= 65535, "b2w_synth_overlap_add: at most 65535 utterances per call");
+  if (num_utts == 0 || max_out_per_utt == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)((max_out_per_utt + 255) / 256), (unsigned)num_utts);
+  if (y_dtype == B2W_F64)
+    overlap_add_kernel<double><<<grid, 256, 0, st>>>(response, utt_out_offset, utt_pulse_offset, num_pulses, pulse_index, fft_size, (double*)y);
+  else
+    overlap_add_kernel<float><<<grid, 256, 0, st>>>(response, utt_out_offset, utt_pulse_offset, num_pulses, pulse_index, fft_size, (float*)y);
+  int rc = check_launch("overlap_add_kernel");
+  if (rc) return rc;
+  if (deemphasis != 0.0) {
+    deemphasis_kernel<<<(num_utts + 63) / 64, 64, 0, st>>>(utt_out_offset, num_utts, deemphasis, (double*)y);
+    return check_launch("deemphasis_kernel");
+  }
+  return 0;
+}

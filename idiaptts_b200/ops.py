@@ -1,0 +1,463 @@
+"""Device-level operators: torch CUDA tensors in, torch CUDA tensors out, every computation done by
+libb200world.so through the C ABI (include/b200world.h).  torch is plumbing here (memory, streams), not compute.
+
+There is no CPU path: CPU tensors are rejected."""
+import math
+import threading
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import B2W_F32, B2W_F64, B2W_I16, check
+
+_DT = {torch.float64: B2W_F64, torch.float32: B2W_F32, torch.int16: B2W_I16}
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _need_cuda(*tensors):
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise ValueError("idiaptts_b200 operators need CUDA tensors (there is no CPU fallback)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise ValueError("all tensors must live on the same device")
+        if not t.is_contiguous():
+            raise ValueError("tensors must be contiguous")
+    return dev
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# scalar helpers (pure functions of the sampling rate; computed by the library so that both sides agree)
+# ----------------------------------------------------------------------------------------------------------------------
+def get_cheaptrick_fft_size(fs, f0_floor=71.0):
+    return int(_lib.load().b2w_cheaptrick_fft_size(int(fs), float(f0_floor)))
+
+
+def get_num_aperiodicities(fs):
+    return int(_lib.load().b2w_num_aperiodicities(int(fs)))
+
+
+def get_d4c_fft_size(fs):
+    return int(_lib.load().b2w_d4c_fft_size(int(fs)))
+
+
+def num_frames(num_samples, fs, frame_period=5.0):
+    """Frame count of pyworld.wav2world / dio (WORLD GetSamplesForDIO)."""
+    return int(1000.0 * num_samples / fs / frame_period) + 1
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# ragged batch
+# ----------------------------------------------------------------------------------------------------------------------
+class RaggedBatch:
+    """A set of utterances packed for the analysis kernels: waveform samples, cached F0 track, temporal positions.
+
+    x           packed samples (float64 | float32 | int16, int16 means value / 32768)
+    sample_off  int64 [U + 1]      frame_off  int64 [U + 1]
+    f0, t       float64 [F]        frame_utt  int32 [F]
+    """
+
+    def __init__(self, x, sample_off, f0, t, frame_off, frame_utt, fs, preemphasis=0.0):
+        self.device = _need_cuda(x, sample_off, f0, t, frame_off, frame_utt)
+        if x.dtype not in _DT:
+            raise ValueError("waveform dtype %s not supported" % x.dtype)
+        assert sample_off.dtype == torch.int64 and frame_off.dtype == torch.int64 and frame_utt.dtype == torch.int32
+        assert f0.dtype == torch.float64 and t.dtype == torch.float64
+        self.x, self.sample_off, self.f0, self.t = x, sample_off, f0, t
+        self.frame_off, self.frame_utt = frame_off, frame_utt
+        self.fs = int(fs)
+        self.preemphasis = float(preemphasis)
+        self.num_utts = sample_off.numel() - 1
+        self.num_frames = f0.numel()
+
+    @staticmethod
+    def from_host(waves, f0s, fs, frame_period=5.0, preemphasis=0.0, device="cuda", ts=None, pin=True):
+        """waves: list of 1-D numpy arrays (float64/float32/int16); f0s: list of float64 F0 tracks (Hz, 0 = unvoiced),
+        one value per frame.  ts: optional list of temporal positions; default i * frame_period / 1000."""
+        device = torch.device(device)
+        dt = waves[0].dtype
+        lens = np.array([len(w) for w in waves], np.int64)
+        flens = np.array([len(f) for f in f0s], np.int64)
+        sample_off = np.concatenate(([0], np.cumsum(lens)))
+        frame_off = np.concatenate(([0], np.cumsum(flens)))
+        x = np.concatenate([np.ascontiguousarray(w, dt) for w in waves]) if len(waves) > 1 else np.ascontiguousarray(waves[0])
+        f0 = np.concatenate([np.asarray(f, np.float64) for f in f0s])
+        if ts is None:
+            t = np.concatenate([np.arange(n) * frame_period / 1000.0 for n in flens])
+        else:
+            t = np.concatenate([np.asarray(v, np.float64) for v in ts])
+        frame_utt = np.repeat(np.arange(len(waves), dtype=np.int32), flens)
+
+        def up(a):
+            h = torch.from_numpy(np.ascontiguousarray(a))
+            if pin and h.numel() > 0:
+                h = h.pin_memory()
+            return h.to(device, non_blocking=True)
+
+        return RaggedBatch(up(x), up(sample_off), up(f0), up(t), up(frame_off), up(frame_utt), fs, preemphasis)
+
+    def c_struct(self, frame_lo=0, frame_hi=None):
+        """struct b2w_batch for frames [frame_lo, frame_hi) (chunking keeps the intermediate planes bounded)."""
+        if frame_hi is None:
+            frame_hi = self.num_frames
+        b = _lib.Batch()
+        b.x = self.x.data_ptr()
+        b.x_dtype = _DT[self.x.dtype]
+        b.num_utts = self.num_utts
+        b.preemphasis = self.preemphasis
+        b.utt_sample_offset = self.sample_off.data_ptr()
+        b.frame_utt = self.frame_utt.data_ptr() + 4 * frame_lo
+        b.f0 = self.f0.data_ptr() + 8 * frame_lo
+        b.t = self.t.data_ptr() + 8 * frame_lo
+        b.num_frames = frame_hi - frame_lo
+        b.fs = self.fs
+        return b
+
+
+def new_status(device):
+    return torch.zeros(1, dtype=torch.int32, device=device)
+
+
+def raise_for_status(status, what):
+    """Reads the device status word (synchronises) and raises like pyworld / pysptk would."""
+    s = int(status.item())
+    if s & _lib.STATUS_ZERO_PERIODOGRAM:
+        raise RuntimeError("%s: zero(s) are found in periodogram, use eps option to floor" % what)
+    if s & _lib.STATUS_SOLVE_FAILED:
+        raise RuntimeError("%s: failed to compute mcep; error occured in theq" % what)
+    if s & _lib.STATUS_F0_TOO_HIGH:
+        raise ValueError("%s: an F0 value is too high for the analysis window / pulse buffer" % what)
+    return s
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# analysis
+# ----------------------------------------------------------------------------------------------------------------------
+def cheaptrick(batch, fft_size=None, q1=-0.15, out_dtype=torch.float64, status=None, frame_lo=0, frame_hi=None, out=None):
+    """pyworld.cheaptrick on a ragged batch -> sp [F, fft_size/2+1] (power)."""
+    lib = _lib.load()
+    if fft_size is None:
+        fft_size = get_cheaptrick_fft_size(batch.fs)
+    if frame_hi is None:
+        frame_hi = batch.num_frames
+    nf = frame_hi - frame_lo
+    K = fft_size // 2 + 1
+    if out is None:
+        out = torch.empty((nf, K), dtype=out_dtype, device=batch.device)
+    if status is None:
+        status = new_status(batch.device)
+    b = batch.c_struct(frame_lo, frame_hi)
+    with torch.cuda.device(batch.device):
+        check(lib.b2w_cheaptrick(b, fft_size, float(q1), out.data_ptr(), _DT[out.dtype], status.data_ptr(),
+                                 _stream(batch.device)), "b2w_cheaptrick")
+    return out, status
+
+
+def d4c_coarse(batch, threshold=0.85, status=None, frame_lo=0, frame_hi=None):
+    """LoveTrain + D4C band aperiodicity -> (coarse_db [F, nap] f64, voiced [F] uint8)."""
+    lib = _lib.load()
+    if frame_hi is None:
+        frame_hi = batch.num_frames
+    nf = frame_hi - frame_lo
+    nap = get_num_aperiodicities(batch.fs)
+    coarse = torch.zeros((nf, max(nap, 1)), dtype=torch.float64, device=batch.device)
+    voiced = torch.zeros((nf,), dtype=torch.uint8, device=batch.device)
+    if status is None:
+        status = new_status(batch.device)
+    b = batch.c_struct(frame_lo, frame_hi)
+    with torch.cuda.device(batch.device):
+        check(lib.b2w_d4c_coarse(b, float(threshold), coarse.data_ptr(), voiced.data_ptr(), status.data_ptr(),
+                                 _stream(batch.device)), "b2w_d4c_coarse")
+    return coarse, voiced, status
+
+
+def d4c_expand(coarse, voiced, fs, fft_size):
+    lib = _lib.load()
+    dev = _need_cuda(coarse, voiced)
+    F = voiced.numel()
+    ap = torch.empty((F, fft_size // 2 + 1), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.b2w_d4c_expand(coarse.data_ptr(), voiced.data_ptr(), F, int(fs), int(fft_size), ap.data_ptr(), _stream(dev)),
+              "b2w_d4c_expand")
+    return ap
+
+
+def bap_from_coarse(coarse, voiced, fs, fft_size, out=None, out_stride=None):
+    """code_aperiodicity(d4c(...)) without the [F, K] plane.  out: float32 tensor written with row stride out_stride."""
+    lib = _lib.load()
+    dev = _need_cuda(coarse, voiced)
+    F = voiced.numel()
+    nap = get_num_aperiodicities(fs)
+    if out is None:
+        out = torch.empty((F, nap), dtype=torch.float32, device=dev)
+        out_stride = nap
+    with torch.cuda.device(dev):
+        check(lib.b2w_bap_from_coarse(coarse.data_ptr(), voiced.data_ptr(), F, int(fs), int(fft_size), out.data_ptr(),
+                                      int(out_stride), _stream(dev)), "b2w_bap_from_coarse")
+    return out
+
+
+def code_aperiodicity(ap, fs):
+    lib = _lib.load()
+    dev = _need_cuda(ap)
+    assert ap.dtype == torch.float64 and ap.dim() == 2
+    F, K = ap.shape
+    nap = get_num_aperiodicities(fs)
+    out = torch.empty((F, nap), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.b2w_code_aperiodicity(ap.data_ptr(), F, int(fs), 2 * (K - 1), out.data_ptr(), _stream(dev)),
+              "b2w_code_aperiodicity")
+    return out
+
+
+def decode_aperiodicity(bap, fs, fft_size):
+    lib = _lib.load()
+    dev = _need_cuda(bap)
+    assert bap.dtype == torch.float64 and bap.dim() == 2
+    nap = get_num_aperiodicities(fs)
+    if bap.shape[1] != nap:
+        raise ValueError("coded aperiodicity has %d bands, fs=%d needs %d" % (bap.shape[1], fs, nap))
+    F = bap.shape[0]
+    out = torch.empty((F, fft_size // 2 + 1), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.b2w_decode_aperiodicity(bap.data_ptr(), F, int(fs), int(fft_size), out.data_ptr(), _stream(dev)),
+              "b2w_decode_aperiodicity")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# mel-cepstrum
+# ----------------------------------------------------------------------------------------------------------------------
+class McepTables:
+    """The three precomputed all-pass warping matrices of (order, alpha, fft_size), float32 on one device."""
+    _cache = {}
+    _lock = threading.Lock()
+
+    def __init__(self, order, alpha, fft_size, device):
+        lib = _lib.load()
+        K = fft_size // 2 + 1
+        self.order, self.alpha, self.fft_size = int(order), float(alpha), int(fft_size)
+        np0, np2, mp = lib.b2w_mcep_pad(order + 2), lib.b2w_mcep_pad(2 * order + 1), lib.b2w_mcep_pad(order + 1)
+        m0t = np.empty((K, np0), np.float64)
+        cmat = np.empty((mp, K), np.float64)
+        m2t = np.empty((K, np2), np.float64)
+        check(lib.b2w_mcep_tables_host(self.order, self.alpha, self.fft_size, m0t.ctypes.data, cmat.ctypes.data,
+                                       m2t.ctypes.data), "b2w_mcep_tables_host")
+        self.host64 = (m0t, cmat, m2t)
+        self.m0t = torch.from_numpy(m0t.astype(np.float32)).to(device)
+        self.cmat = torch.from_numpy(cmat.astype(np.float32)).to(device)
+        self.m2t = torch.from_numpy(m2t.astype(np.float32)).to(device)
+
+    @classmethod
+    def get(cls, order, alpha, fft_size, device):
+        key = (int(order), float(alpha), int(fft_size), str(torch.device(device)))
+        with cls._lock:
+            tab = cls._cache.get(key)
+            if tab is None:
+                tab = cls(order, alpha, fft_size, device)
+                cls._cache[key] = tab
+            return tab
+
+
+def mcep(plane, order, alpha, is_power=False, miniter=2, maxiter=30, threshold=0.001, eps=1.0e-8, out=None,
+         out_stride=None, out_dtype=torch.float32, iters=None, status=None):
+    """pysptk.mcep(itype=3 (amplitude) or 4 (power), etype=1) on a [F, K] plane -> mc [F, order+1]."""
+    lib = _lib.load()
+    dev = _need_cuda(plane)
+    assert plane.dim() == 2 and plane.dtype in (torch.float32, torch.float64)
+    F, K = plane.shape
+    fft_size = 2 * (K - 1)
+    tab = McepTables.get(order, alpha, fft_size, dev)
+    if out is None:
+        out = torch.empty((F, order + 1), dtype=out_dtype, device=dev)
+        out_stride = order + 1
+    if status is None:
+        status = new_status(dev)
+    with torch.cuda.device(dev):
+        check(lib.b2w_mcep(plane.data_ptr(), _DT[plane.dtype], 1 if is_power else 0, F, fft_size, int(order), float(alpha),
+                           int(miniter), int(maxiter), float(threshold), float(eps), tab.m0t.data_ptr(), tab.cmat.data_ptr(),
+                           tab.m2t.data_ptr(), out.data_ptr(), _DT[out.dtype], int(out_stride), _ptr(iters),
+                           status.data_ptr(), _stream(dev)), "b2w_mcep")
+    return out, status
+
+
+def mc2sp(mc, alpha, fft_size, scale=1.0, do_exp=True, out_dtype=torch.float32, order=None, mc_stride=None):
+    """(exp of) scale * Re FFT(freqt(mc, fft_size/2, -alpha)): log-amplitude / amplitude / power spectrum from mel-cepstra."""
+    lib = _lib.load()
+    dev = _need_cuda(mc)
+    assert mc.dim() == 2 and mc.dtype in (torch.float32, torch.float64)
+    F = mc.shape[0]
+    if order is None:
+        order = mc.shape[1] - 1
+    if mc_stride is None:
+        mc_stride = mc.shape[1]
+    tab = McepTables.get(order, alpha, fft_size, dev)
+    out = torch.empty((F, fft_size // 2 + 1), dtype=out_dtype, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.b2w_mc2sp(mc.data_ptr(), _DT[mc.dtype], int(mc_stride), F, int(fft_size), int(order), tab.cmat.data_ptr(),
+                            float(scale), 1 if do_exp else 0, out.data_ptr(), _DT[out.dtype], _stream(dev)), "b2w_mc2sp")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# labels, deltas, statistics
+# ----------------------------------------------------------------------------------------------------------------------
+def lf0_vuv(f0, frame_off, f0_silence_threshold=30, lf0_zero=0, lf0_out=None, vuv_out=None, out_stride=1):
+    lib = _lib.load()
+    dev = _need_cuda(f0, frame_off)
+    F = f0.numel()
+    if lf0_out is None:
+        lf0_out = torch.empty((F, 1), dtype=torch.float32, device=dev)
+        vuv_out = torch.empty((F, 1), dtype=torch.float32, device=dev)
+        out_stride = 1
+    with torch.cuda.device(dev):
+        check(lib.b2w_lf0_vuv(f0.data_ptr(), frame_off.data_ptr(), frame_off.numel() - 1, float(f0_silence_threshold),
+                              float(lf0_zero), lf0_out.data_ptr(), vuv_out.data_ptr(), int(out_stride), _stream(dev)),
+              "b2w_lf0_vuv")
+    return lf0_out, vuv_out
+
+
+def deltas(feats, frame_off, want_double=True):
+    """np.gradient deltas (and double deltas) per utterance of a [F, D] float32 matrix."""
+    lib = _lib.load()
+    dev = _need_cuda(feats, frame_off)
+    assert feats.dtype == torch.float32 and feats.dim() == 2
+    F, D = feats.shape
+    d = torch.empty_like(feats)
+    dd = torch.empty_like(feats) if want_double else None
+    with torch.cuda.device(dev):
+        check(lib.b2w_deltas(feats.data_ptr(), D, D, frame_off.data_ptr(), frame_off.numel() - 1, F, d.data_ptr(), _ptr(dd), D,
+                             _stream(dev)), "b2w_deltas")
+    return d, dd
+
+
+def stats_accumulate(feats, sums, gram=None, dim=None, stride=None, num_frames=None, offset_elems=0):
+    """sums [2*dim] f64 += (sum x, sum x^2); gram [dim, dim] f64 += X^T X."""
+    lib = _lib.load()
+    dev = _need_cuda(feats, sums, gram)
+    assert feats.dtype == torch.float32 and sums.dtype == torch.float64
+    if dim is None:
+        num_frames, dim = feats.shape
+        stride = dim
+    with torch.cuda.device(dev):
+        check(lib.b2w_stats_accumulate(feats.data_ptr() + 4 * offset_elems, int(stride), int(dim), int(num_frames),
+                                       sums.data_ptr(), _ptr(gram), _stream(dev)), "b2w_stats_accumulate")
+    return sums
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# synthesis
+# ----------------------------------------------------------------------------------------------------------------------
+_randn_tables = {}
+_randn_lock = threading.Lock()
+
+
+def randn_table(n, device):
+    """WORLD's randn() stream after randn_reseed(), first n values (cached per device, grown on demand)."""
+    lib = _lib.load()
+    device = torch.device(device)
+    key = str(device)
+    with _randn_lock:
+        tab = _randn_tables.get(key)
+        if tab is None or tab.numel() < n:
+            size = max(int(n), 1 << 18)
+            tab = torch.empty(size, dtype=torch.float64, device=device)
+            with torch.cuda.device(device):
+                check(lib.b2w_synth_randn_table(tab.data_ptr(), size, _stream(device)), "b2w_synth_randn_table")
+            _randn_tables[key] = tab
+        return tab
+
+
+def synthesize(f0, sp, ap, frame_off, fs, frame_period=5.0, deemphasis=0.0, out_dtype=torch.float64, status=None):
+    """pyworld.synthesize on a ragged batch.  f0 [F] f64; sp, ap [F, K] (f64 or f32, same dtype); frame_off int64 [U+1]
+    (device) -> (y packed [sum y_len], out_off int64 [U+1] (host numpy))."""
+    lib = _lib.load()
+    dev = _need_cuda(f0, sp, ap, frame_off)
+    assert sp.dtype == ap.dtype and sp.dtype in (torch.float32, torch.float64) and f0.dtype == torch.float64
+    K = sp.shape[1]
+    fft_size = 2 * (K - 1)
+    foff = frame_off.cpu().numpy()
+    U = len(foff) - 1
+    T = np.diff(foff)
+    ylen = (T * frame_period * fs / 1000).astype(np.int64)  # int(T * frame_period * fs / 1000)
+    out_off = np.concatenate(([0], np.cumsum(ylen)))
+    caps = np.array([lib.b2w_synth_max_pulses(int(v), int(fs)) for v in ylen], np.int64)
+    pulse_off = np.concatenate(([0], np.cumsum(caps)))
+    d_out_off = torch.from_numpy(out_off).to(dev)
+    d_pulse_off = torch.from_numpy(pulse_off).to(dev)
+    total_cap = int(pulse_off[-1])
+    pulse_index = torch.empty(max(total_cap, 1), dtype=torch.int32, device=dev)
+    pulse_shift = torch.empty(max(total_cap, 1), dtype=torch.float64, device=dev)
+    pulse_vuv = torch.empty(max(total_cap, 1), dtype=torch.uint8, device=dev)
+    num_pulses = torch.zeros(max(U, 1), dtype=torch.int32, device=dev)
+    if status is None:
+        status = new_status(dev)
+    y = torch.empty(int(out_off[-1]), dtype=out_dtype, device=dev)
+    if U == 0 or out_off[-1] == 0:
+        return y, out_off, status
+    tab = randn_table(int(ylen.max()) + 1, dev)
+    st = _stream(dev)
+    with torch.cuda.device(dev):
+        check(lib.b2w_synth_timebase(f0.data_ptr(), frame_off.data_ptr(), d_out_off.data_ptr(), d_pulse_off.data_ptr(), U,
+                                     int(fs), float(frame_period), fft_size, pulse_index.data_ptr(), pulse_shift.data_ptr(),
+                                     pulse_vuv.data_ptr(), num_pulses.data_ptr(), status.data_ptr(), st),
+              "b2w_synth_timebase")
+        # the response buffer is sized by the ACTUAL pulse counts (one small D2H of U ints)
+        npul = num_pulses.cpu().numpy()[:U].astype(np.int64)
+        max_p = int(npul.max()) if U else 0
+        # responses are addressed by the slab offsets, so allocate slab-sized storage only up to the last used row
+        last_row = int((pulse_off[:-1] + npul).max()) if U else 0
+        response = torch.empty((max(last_row, 1), fft_size), dtype=torch.float64, device=dev)
+        if max_p > 0:
+            check(lib.b2w_synth_render(sp.data_ptr(), ap.data_ptr(), _DT[sp.dtype], frame_off.data_ptr(),
+                                       d_pulse_off.data_ptr(), num_pulses.data_ptr(), U, pulse_index.data_ptr(),
+                                       pulse_shift.data_ptr(), pulse_vuv.data_ptr(), tab.data_ptr(), tab.numel(), int(fs),
+                                       float(frame_period), fft_size, max_p, response.data_ptr(), st), "b2w_synth_render")
+        check(lib.b2w_synth_overlap_add(response.data_ptr(), d_out_off.data_ptr(), d_pulse_off.data_ptr(),
+                                        num_pulses.data_ptr(), U, pulse_index.data_ptr(), fft_size, int(ylen.max()),
+                                        float(deemphasis), y.data_ptr(), _DT[y.dtype], st), "b2w_synth_overlap_add")
+    return y, out_off, status
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Neural-VTLN all-pass warp
+# ----------------------------------------------------------------------------------------------------------------------
+def allpass_forward(x, alpha, n, mean=None, std_dev=None):
+    """x [rows, blocks*n] f32, alpha [rows] f32 -> y [rows, blocks*n]."""
+    lib = _lib.load()
+    dev = _need_cuda(x, alpha, mean, std_dev)
+    assert x.dtype == torch.float32 and alpha.dtype == torch.float32 and x.dim() == 2
+    rows, width = x.shape
+    assert width % n == 0 and alpha.numel() == rows
+    y = torch.empty_like(x)
+    with torch.cuda.device(dev):
+        check(lib.b2w_allpass_forward(x.data_ptr(), alpha.data_ptr(), rows, int(n), width // n, _ptr(mean), _ptr(std_dev),
+                                      y.data_ptr(), _stream(dev)), "b2w_allpass_forward")
+    return y
+
+
+def allpass_backward(grad_y, x, alpha, n, mean=None, std_dev=None):
+    lib = _lib.load()
+    dev = _need_cuda(grad_y, x, alpha, mean, std_dev)
+    rows, width = x.shape
+    blocks = width // n
+    gx = torch.empty_like(x)
+    ga = torch.empty_like(alpha)
+    ws = torch.empty(rows * blocks, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.b2w_allpass_backward(grad_y.data_ptr(), x.data_ptr(), alpha.data_ptr(), rows, int(n), blocks, _ptr(mean),
+                                       _ptr(std_dev), gx.data_ptr(), ga.data_ptr(), ws.data_ptr(), _stream(dev)),
+              "b2w_allpass_backward")
+    return gx, ga

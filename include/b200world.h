@@ -1,0 +1,184 @@
+/*
+ * b200world.h - C ABI of libb200world.so: the WORLD vocoder feature hot path of IdiapTTS as hand-written
+ * CUDA for sm_100a (B200).
+ *
+ * This is the drop-in boundary. Today the reference crosses into native code at the pyworld / pysptk Cython
+ * wrappers (single-threaded CPU C/C++, one utterance or one frame per call); every entry point below names the
+ * reference call site it replaces (paths relative to the reference repo root):
+ *
+ *   W  = idiaptts/src/data_preparation/world/WorldFeatLabelGen.py
+ *   A  = idiaptts/src/data_preparation/audio/AudioProcessing.py
+ *   U  = idiaptts/misc/utils.py
+ *   N  = idiaptts/misc/normalisation/MeanStdDevExtractor.py   (NC = MeanCovarianceExtractor.py)
+ *   L  = idiaptts/src/neural_networks/pytorch/layers/AllPassWarp.py   (LL = AllPassWarpLayer.py)
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer unless its name starts with h_ (host). The caller (PyTorch) owns all
+ *     memory; the library never allocates, frees or synchronises (exceptions are documented per call).
+ *   - Ragged batches: utterance u owns samples [utt_sample_offset[u], utt_sample_offset[u+1]) of the packed
+ *     waveform and frames [utt_frame_offset[u], utt_frame_offset[u+1]) of every per-frame array.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream). Calls are asynchronous.
+ *   - Return value: 0 ok; < 0 argument error (nothing launched); > 0 cudaError_t of the launch.
+ *     b2w_last_error() returns a thread-local message for the last non-zero return.
+ *   - `status` arrays (int32, device) receive per-call data-dependent error flags (see B2W_STATUS_*); the
+ *     caller reads them when it synchronises anyway.
+ *   - Re-entrant per (device, stream). No global mutable state.
+ */
+#ifndef B200WORLD_H_
+#define B200WORLD_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2W_VERSION 1
+
+#if defined(__GNUC__)
+#define B2W_API __attribute__((visibility("default")))
+#else
+#define B2W_API
+#endif
+
+/* element types of waveform / plane arguments */
+#define B2W_F64 0
+#define B2W_F32 1
+#define B2W_I16 2 /* waveform only: value / 32768 (what soundfile.read returns for PCM16, A:114) */
+
+/* bits of the device-side status word */
+#define B2W_STATUS_F0_TOO_HIGH 1   /* smoothing half-width exceeds the kernel's static bound (f0 > ~fs/8) */
+#define B2W_STATUS_ZERO_PERIODOGRAM 2 /* pysptk: "zero(s) are found in periodogram" (RuntimeError) */
+#define B2W_STATUS_SOLVE_FAILED 4  /* pysptk: "failed to compute mcep; error occured in theq" */
+#define B2W_STATUS_NOT_CONVERGED 8 /* informational: Newton loop hit maxiter (pysptk returns normally) */
+
+B2W_API int b2w_version(void);
+B2W_API const char* b2w_last_error(void);
+
+/* Ragged batch of utterances with a cached F0 track: the common input of the analysis kernels. */
+typedef struct {
+  const void* x;                    /* packed waveform, x_dtype */
+  int32_t x_dtype;                  /* B2W_F64 | B2W_F32 | B2W_I16 */
+  int32_t num_utts;
+  double preemphasis;               /* y[n] = x[n] - p*x[n-1], y[0] = x[0], per utterance, applied on load (A:117-118) */
+  const int64_t* utt_sample_offset; /* [num_utts + 1] */
+  const int32_t* frame_utt;         /* [num_frames] utterance index of every frame */
+  const double* f0;                 /* [num_frames] Hz, 0 = unvoiced */
+  const double* t;                  /* [num_frames] temporal positions in seconds (pyworld: i * frame_period / 1000) */
+  int64_t num_frames;
+  int32_t fs;
+  int32_t reserved;
+} b2w_batch;
+
+/* ---- CheapTrick: replaces pyworld.cheaptrick inside pyworld.wav2world (W:792). ------------------------------
+ * sp [num_frames, fft_size/2+1] power spectral envelope, sp_dtype B2W_F64 (pyworld-compatible) or B2W_F32
+ * (fused extract path). fft_size in {512, 1024, 2048, 4096}. status: 1 int32. */
+B2W_API int b2w_cheaptrick(const b2w_batch* b, int32_t fft_size, double q1, void* sp, int32_t sp_dtype, int32_t* status,
+                   void* stream);
+
+/* ---- D4C: replaces pyworld.d4c inside pyworld.wav2world (W:792). ------------------------------------------
+ * Stage 1 (the expensive one): LoveTrain voicing + per-band coarse aperiodicity.
+ *   coarse_db [num_frames, nap] dB (undefined where voiced == 0), voiced [num_frames] uint8.
+ *   nap = b2w_num_aperiodicities(fs); the D4C fft size is derived from fs as WORLD does. */
+B2W_API int b2w_d4c_coarse(const b2w_batch* b, double threshold, double* coarse_db, uint8_t* voiced, int32_t* status,
+                   void* stream);
+/* Stage 2a: expand to the pyworld.d4c result ap [num_frames, fft_size/2+1] f64 (1 - 1e-12 on unvoiced rows). */
+B2W_API int b2w_d4c_expand(const double* coarse_db, const uint8_t* voiced, int64_t num_frames, int32_t fs, int32_t fft_size,
+                   double* ap, void* stream);
+/* Stage 2b (fused extract): pyworld.code_aperiodicity(d4c(...)) (W:805) without materialising ap.
+ *   bap [num_frames, nap] f32 written with row stride bap_stride (elements). */
+B2W_API int b2w_bap_from_coarse(const double* coarse_db, const uint8_t* voiced, int64_t num_frames, int32_t fs,
+                        int32_t fft_size, float* bap, int64_t bap_stride, void* stream);
+
+/* ---- codec: pyworld.code_aperiodicity (W:805) / pyworld.decode_aperiodicity (W:940). ----------------------- */
+B2W_API int b2w_code_aperiodicity(const double* ap, int64_t num_frames, int32_t fs, int32_t fft_size, double* bap,
+                          void* stream);
+B2W_API int b2w_decode_aperiodicity(const double* bap, int64_t num_frames, int32_t fs, int32_t fft_size, double* ap,
+                            void* stream);
+
+/* ---- mel-cepstral analysis: replaces pysptk.mcep(itype=3|4, etype=1) (A:146). --------------------------------
+ * Host helper (runs on the CPU inside the call, fp64): builds the three precomputed all-pass warping matrices
+ * for (order, alpha, fft_size); K = fft_size/2+1, m = order:
+ *   h_m0t  [K, np0]  np0 = b2w_mcep_pad(m+2)  column n<=m: initial mel-cepstrum from log periodogram
+ *                                              (IFFT, c0/2, c[N/2]/2, freqt(alpha)); column m+1: c[0] (start value s)
+ *   h_cmat [b2w_mcep_pad(m+1), K]  C(w_j) = sum_k mc[k] * cmat[k][j]  (freqt(-alpha) to order N/2, then real FFT;
+ *                                              rows past m are zero)
+ *   h_m2t  [K, np2]  np2 = b2w_mcep_pad(2m+1)  r~[n] = sum_j m2t[j][n] * P[j]  (real IFFT, then frqtr(alpha) to 2m)
+ * The caller converts to float32 and uploads. */
+B2W_API int32_t b2w_mcep_pad(int32_t n);
+B2W_API int b2w_mcep_tables_host(int32_t order, double alpha, int32_t fft_size, double* h_m0t, double* h_cmat, double* h_m2t);
+/* in: spectrum plane [num_frames, K] (in_dtype F64|F32), in_is_power 0 = amplitude (x*x + eps), 1 = power (x + eps)
+ * out: mc [num_frames, order+1] (mc_dtype F64|F32) with row stride mc_stride elements; iters [num_frames] int32
+ * (may be NULL). Newton-Raphson UELS, miniter/maxiter/threshold as pysptk (2, 30, 1e-3). */
+B2W_API int b2w_mcep(const void* in, int32_t in_dtype, int32_t in_is_power, int64_t num_frames, int32_t fft_size,
+             int32_t order, double alpha, int32_t miniter, int32_t maxiter, double threshold, double eps,
+             const float* m0t, const float* cmat, const float* m2t, void* mc, int32_t mc_dtype, int64_t mc_stride,
+             int32_t* iters, int32_t* status, void* stream);
+/* log-amplitude spectrum from mel-cepstra: Re pysptk.mgc2sp(mc, alpha, gamma=0, fftlen) (A:252), optionally
+ * exponentiated (A:256 np.exp(...)) : out[f][j] = (do_exp ? exp : id)(scale * sum_k mc[f][k] cmat[k][j]).
+ * scale = 1 for mgc2sp / mcep_to_amp_sp, 2 (with do_exp) gives the power spectrum. */
+B2W_API int b2w_mc2sp(const void* mc, int32_t mc_dtype, int64_t mc_stride, int64_t num_frames, int32_t fft_size,
+              int32_t order, const float* cmat, double scale, int32_t do_exp, void* out, int32_t out_dtype,
+              void* stream);
+
+/* ---- label preparation: lf0 / vuv (W:798-802, U:40-86 interpolate_lin). -----------------------------------
+ * One ragged batch; float32 arithmetic identical to the reference. lf0/vuv written with element stride
+ * out_stride (so they can land directly in the packed [T, D] feature rows). */
+B2W_API int b2w_lf0_vuv(const double* f0, const int64_t* utt_frame_offset, int32_t num_utts, double f0_silence_threshold,
+                double lf0_zero, float* lf0, float* vuv, int64_t out_stride, void* stream);
+
+/* ---- deltas + normalisation statistics (U:103-105 np.gradient, N:43-47 add_sample, NC:44-48). -------------
+ * feats [num_frames, dim] f32 (row stride feat_stride); deltas/ddeltas may be NULL. */
+B2W_API int b2w_deltas(const float* feats, int64_t feat_stride, int32_t dim, const int64_t* utt_frame_offset,
+               int32_t num_utts, int64_t num_frames, float* deltas, float* ddeltas, int64_t out_stride, void* stream);
+/* sums [2*dim] f64 += (sum x, sum x^2) over all rows; gram [dim*dim] f64 += X^T X if not NULL.
+ * Accumulates (atomically, fp64) into the caller's buffers, which the caller zeroes once per corpus. */
+B2W_API int b2w_stats_accumulate(const float* feats, int64_t feat_stride, int32_t dim, int64_t num_frames, double* sums,
+                         double* gram, void* stream);
+
+/* ---- synthesis: replaces pyworld.synthesize (W:943) on a ragged batch. ---------------------------------------
+ * Inputs are the pyworld arguments per frame: f0 [F], sp [F, K] power, ap [F, K] (sp/ap dtype F64|F32).
+ * Stage 1 - time base: per utterance pulse placement (sequential fp64 phase accumulation, one thread per
+ *   utterance). pulse_index/pulse_shift/pulse_vuv: [capacity] per-utterance slabs at utt_pulse_offset[u]
+ *   (caller sizes them with b2w_synth_max_pulses); num_pulses [num_utts] int32 out.
+ * Stage 2 - render: one CTA per pulse builds the periodic + aperiodic minimum-phase responses and writes
+ *   response [total pulses, fft_size] f64.
+ * Stage 3 - overlap-add: atomic-free gather; every output sample sums, in pulse order, the responses covering it. */
+B2W_API int64_t b2w_synth_max_pulses(int64_t y_length, int32_t fs);
+B2W_API int b2w_synth_randn_table(double* table, int64_t n, void* stream); /* WORLD randn() stream after randn_reseed(): xorshift128 with GF(2) jump-ahead */
+B2W_API int b2w_synth_timebase(const double* f0, const int64_t* utt_frame_offset, const int64_t* utt_out_offset,
+                       const int64_t* utt_pulse_offset, int32_t num_utts, int32_t fs, double frame_period_ms,
+                       int32_t fft_size, int32_t* pulse_index, double* pulse_shift, uint8_t* pulse_vuv,
+                       int32_t* num_pulses, int32_t* status, void* stream);
+B2W_API int b2w_synth_render(const void* sp, const void* ap, int32_t plane_dtype, const int64_t* utt_frame_offset,
+                     const int64_t* utt_pulse_offset, const int32_t* num_pulses, int32_t num_utts,
+                     const int32_t* pulse_index, const double* pulse_shift, const uint8_t* pulse_vuv,
+                     const double* randn_table, int64_t randn_table_len, int32_t fs, double frame_period_ms,
+                     int32_t fft_size, int64_t max_pulses_per_utt, double* response, void* stream);
+B2W_API int b2w_synth_overlap_add(const double* response, const int64_t* utt_out_offset, const int64_t* utt_pulse_offset,
+                          const int32_t* num_pulses, int32_t num_utts, const int32_t* pulse_index, int32_t fft_size,
+                          int64_t max_out_per_utt, double deemphasis, void* y, int32_t y_dtype, void* stream);
+
+/* ---- Neural-VTLN all-pass warp: replaces AllPassWarp.forward's einsum+bmm (L:148-173, L:186-205). ------------
+ * x, y: [rows, blocks*n] f32; alpha [rows] f32 (already combined, L:176-184). Per n-block:
+ * x'[0] = x[0]/2, y = x' W(alpha), y[0] *= 2 with W(alpha) = freqt-matrix(n-1 -> n-1, alpha)^T evaluated by the
+ * fp64-free all-pass recursion in registers (never materialises the [rows, n, n] tensor).
+ * mean/std_dev (may be NULL, [blocks*n]) fold AllPassWarpLayer._denormalise/_normalise (LL:186-200) into the kernel. */
+B2W_API int b2w_allpass_forward(const float* x, const float* alpha, int64_t rows, int32_t n, int32_t blocks,
+                        const float* mean, const float* std_dev, float* y, void* stream);
+/* backward: grad_x [rows, blocks*n], grad_alpha [rows] from grad_y (and x, alpha): gx = S1 frqtr(S2 gy, -alpha)
+ * (A(alpha)^T == frqtr-matrix(-alpha)), galpha by the tangent of the forward recursion. */
+B2W_API int b2w_allpass_backward(const float* grad_y, const float* x, const float* alpha, int64_t rows, int32_t n,
+                         int32_t blocks, const float* mean, const float* std_dev, float* grad_x, float* grad_alpha,
+                         float* unit_workspace /* [rows * blocks] */, void* stream);
+
+/* ---- scalar helpers (host, pure functions): pyworld.get_cheaptrick_fft_size (A:60), get_num_aperiodicities
+ * (A:71), and the D4C transform size. */
+B2W_API int32_t b2w_cheaptrick_fft_size(int32_t fs, double f0_floor);
+B2W_API int32_t b2w_num_aperiodicities(int32_t fs);
+B2W_API int32_t b2w_d4c_fft_size(int32_t fs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200WORLD_H_ */
