@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Benchmark of the WORLD feature hot path (BASELINE.json metric: audio-seconds/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--utts U]
+
+Workload (config.workload = "ljspeech_extract"): BASELINE.json configs[1], the LJSpeech-shaped synthetic corpus
+(13,100 utterances x 6.5 s at 22.05 kHz, int16 PCM + cached F0 track) -> WorldFeatLabelGen-style features
+(mcep60, lf0, vuv, bap) + corpus normalisation statistics.  One step = one pass of the extraction over the corpus shard
+of every rank (weak scaling: every rank owns a full-size shard with its own seeds); ranks only exchange the
+statistics (one NCCL all-reduce per step, inside the timed region).
+
+value   : audio-seconds per second with the inputs resident in HBM (CUDA events, max over ranks).
+e2e     : the same pass through host buffers: pinned int16 wave + F0 host->device, extraction, features + statistics
+          device->host, all inside the timed region.
+roofline: the kernel with the largest share of the step, timed live with CUDA events on the launching stream.
+cpu_baseline / --impl reference: the CPU oracle (restated WORLD/SPTK algorithms; pyworld/pysptk are not installable here)
+          on all host cores over a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FS = 22050
+UTTS = 13100
+DUR = 6.5
+NUM_CODED_SPS = 60
+METRIC = "audio-seconds/s (WORLD analysis: CheapTrick + D4C + mcep60 + lf0/vuv/bap + stats, cached F0)"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        busy = [v for v in sm if v > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU oracle arm (cpu_baseline of the default run, and the whole of --impl reference)
+# ----------------------------------------------------------------------------------------------------------------------
+def _oracle_extract_one(args):
+    wave_i16, f0, fs, alpha = args
+    from oracle import glue_np, sptk_np, world_np
+    x = wave_i16.astype(np.float64) / 32768.0
+    T = len(f0)
+    t = world_np.temporal_positions(T)
+    sp = world_np.cheaptrick(x, f0, t, fs)
+    mc = sptk_np.mcep(np.sqrt(sp), order=NUM_CODED_SPS - 1, alpha=alpha, eps=1e-8, etype=1, itype=3).astype(np.float32)
+    ap = world_np.d4c(x, f0, t, fs)
+    bap = world_np.code_aperiodicity(ap, fs).astype(np.float32)
+    lf0, vuv = glue_np.interpolate_lin(glue_np.lf0_from_f0(f0))
+    feats = np.concatenate((mc, lf0.astype(np.float32), vuv.astype(np.float32), bap), axis=1)
+    return feats.sum(0, dtype=np.float64), (feats.astype(np.float64) ** 2).sum(0), len(x) / fs
+
+
+def cpu_oracle_throughput(waves, f0s, fs, alpha, cores, steps=1, warmup=0):
+    """audio-seconds/s of the CPU oracle over the given sample with a process pool of `cores` workers."""
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    jobs = [(np.ascontiguousarray(w), f, fs, alpha) for w, f in zip(waves, f0s)]
+    with ctx.Pool(cores) as pool:
+        for _ in range(warmup):
+            pool.map(_oracle_extract_one, jobs[:cores])
+        times = []
+        audio = 0.0
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            res = pool.map(_oracle_extract_one, jobs)
+            times.append(time.perf_counter() - t0)
+            audio = sum(r[2] for r in res)
+    return audio / (sum(times) / len(times)), sum(times) / len(times), audio
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch  # noqa: F401  (only for the synthetic generator, CPU)
+    from idiaptts_b200 import synthetic
+    from oracle import sptk_np
+    cores = len(os.sched_getaffinity(0))
+    alpha = float(sptk_np.mcepalpha(FS))
+    n_utts = max(cores, min(2 * cores, 64))  # bounded sample: about one or two 6.5 s utterances per core and step
+    waves, f0s = synthetic.make_corpus(n_utts, FS, seed=2, mean_dur=DUR, device="cpu")
+    waves = [w.numpy() for w in waves]
+    value, sec, audio = cpu_oracle_throughput(waves, f0s, FS, alpha, cores, steps=args.steps, warmup=min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "ljspeech_extract", "fs": FS, "utt_seconds": DUR, "num_coded_sps": NUM_CODED_SPS,
+                       "sample_utts": n_utts, "note": "CPU oracle = numpy restatement of WORLD/SPTK (pyworld/pysptk unavailable offline)"},
+            "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                             "sample": "%d utterances x %.1f s per step" % (n_utts, DUR)},
+            "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from idiaptts_b200 import ops, pipeline, synthetic
+    from idiaptts_b200.compat.pysptk import mcepalpha
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    alpha = float(mcepalpha(FS))
+    utts = args.utts
+    # every rank synthesises its own shard (weak scaling), distinct seeds
+    t0 = time.time()
+    waves, f0s = synthetic.make_corpus(utts, FS, seed=2, mean_dur=DUR, device=dev, batch=64, first_utt=rank * utts)
+    lens = np.array([w.numel() for w in waves], np.int64)
+    flens = np.array([len(f) for f in f0s], np.int64)
+    audio_s = float(lens.sum()) / FS
+    x_dev = torch.cat(waves)
+    del waves
+    f0_np = np.concatenate(f0s)
+    t_np = np.concatenate([np.arange(n) * 5.0 / 1000.0 for n in flens])
+    sample_off = np.concatenate(([0], np.cumsum(lens)))
+    frame_off = np.concatenate(([0], np.cumsum(flens)))
+    frame_utt = np.repeat(np.arange(utts, dtype=np.int32), flens)
+    gen_s = time.time() - t0
+    host = {"x": x_dev.cpu().pin_memory(), "f0": torch.from_numpy(f0_np).pin_memory(), "t": torch.from_numpy(t_np).pin_memory(),
+            "so": torch.from_numpy(sample_off).pin_memory(), "fo": torch.from_numpy(frame_off).pin_memory(),
+            "fu": torch.from_numpy(frame_utt).pin_memory()}
+
+    def to_dev():
+        return ops.RaggedBatch(host["x"].to(dev, non_blocking=True), host["so"].to(dev, non_blocking=True),
+                               host["f0"].to(dev, non_blocking=True), host["t"].to(dev, non_blocking=True),
+                               host["fo"].to(dev, non_blocking=True), host["fu"].to(dev, non_blocking=True), FS)
+
+    batch = to_dev()
+    F = batch.num_frames
+    an = pipeline.WorldAnalyzer(FS, NUM_CODED_SPS, alpha, device=dev, chunk_frames=args.chunk_frames)
+    feats = torch.empty((F, an.dim), dtype=torch.float32, device=dev)
+    stat_buf = torch.zeros(2 * an.dim + 1, dtype=torch.float64, device=dev)
+
+    def step(b, events=None):
+        stat_buf.zero_()
+        _, _, status = an.extract(b, feats=feats, sums=stat_buf[:2 * an.dim], events=events)
+        stat_buf[2 * an.dim] = float(F)
+        if world > 1:
+            dist.all_reduce(stat_buf)  # the path's only exchange step: corpus normalisation statistics
+        return status
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        status = step(batch)
+    barrier()
+    ops.raise_for_status(status, "extract")
+
+    # ---- timed region 1: inputs resident in HBM -----------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    events = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(batch, events)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_step = float(tmax.item()) / args.steps
+    value = audio_s * world / (ms_step / 1e3)
+    stats_host = stat_buf.cpu().numpy()
+
+    # per-kernel shares (rank 0's stream)
+    per = {}
+    for name, frames, a, b in events:
+        d = per.setdefault(name, [0.0, 0, 0])
+        d[0] += a.elapsed_time(b)
+        d[1] += 1
+        d[2] += frames
+    total_k = sum(v[0] for v in per.values())
+    top = max(per, key=lambda k: per[k][0])
+    H = FS * 0.005
+    K = an.n_fft // 2 + 1
+    alg_bytes_per_frame = {
+        "cheaptrick": 2 * H + 20 + 4 * K,              # int16 samples of one hop + f0/t/frame_utt in, float32 envelope row out
+        "mcep": 4 * K + 4 * NUM_CODED_SPS,             # float32 envelope row in, 60 float32 coefficients out
+        "d4c": 2 * H + 20 + 8 * an.nap + 1,            # samples + f0/t in, coarse aperiodicity + voiced flag out
+        "bap_from_coarse": 8 * an.nap + 1 + 4 * an.nap,
+        "lf0_vuv": 8 + 8,
+        "stats": 4 * an.dim,
+    }
+    peaks, peak_src = measured_peaks()
+    top_ms = per[top][0] / per[top][1]
+    top_frames = per[top][2] / per[top][1]
+    achieved = alg_bytes_per_frame[top] * top_frames / (top_ms / 1e3) / 1e9
+    roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                "share_of_step": per[top][0] / total_k,
+                "shares": {k: round(v[0] / total_k, 4) for k, v in per.items()},
+                "avg_launch_ms": {k: round(v[0] / v[1], 3) for k, v in per.items()},
+                "note": "compute-bound kernel (fp64 FFTs / fp32 contractions): the HBM fraction is reported because the "
+                        "metric asks for it, see DESIGN.md for the per-kernel bounds"}
+
+    # ---- timed region 2: end to end through host buffers ---------------------------------------------------------------
+    feats_host = torch.empty((F, an.dim), dtype=torch.float32).pin_memory()
+    stats_pinned = torch.empty(2 * an.dim + 1, dtype=torch.float64).pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = feats_host.numel() * 4 + stats_pinned.numel() * 8
+
+    def e2e_step():
+        b = to_dev()
+        step(b)
+        feats_host.copy_(feats, non_blocking=True)
+        stats_pinned.copy_(stat_buf, non_blocking=True)
+
+    e2e_step()
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    g1.record()
+    barrier()
+    t2 = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = audio_s * world / (float(t2.item()) / args.steps / 1e3)
+
+    if rank == 0:
+        # ---- CPU baseline on a bounded sample of the same workload (N = 1 only) -------------------------------------
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            # separate process: no fork of a CUDA-initialised interpreter
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                               capture_output=True, text=True)
+            try:
+                cpu = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
+            except Exception:
+                cpu = {"value": None, "unit": "audio-s/s", "cores": 0, "kind": "port", "sample": "failed: " + r.stderr[-300:]}
+        n = float(stats_host[2 * an.dim])
+        mean, std = pipeline.mean_std_from_sums(stats_host, n, an.dim)
+        line = {"metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+f32",
+                "data": "synthetic",
+                "config": {"workload": "ljspeech_extract", "utts_per_gpu": utts, "fs": FS, "utt_seconds": DUR,
+                           "frames_per_gpu": int(F), "audio_seconds_per_gpu": audio_s, "num_coded_sps": NUM_CODED_SPS,
+                           "mgc_alpha": alpha, "fft_size": an.n_fft, "num_bap": an.nap, "chunk_frames": an.chunk_frames,
+                           "l2": "inputs (%.2f GB int16) and outputs (%.2f GB) exceed the 126 MB L2" % (
+                               host["x"].numel() * 2 / 1e9, feats.numel() * 4 / 1e9),
+                           "corpus_gen_s": round(gen_s, 1), "mean_c0": float(mean[0]), "std_c0": float(std[0])},
+                "clocks": clocks, "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(h2d),
+                                          "d2h_bytes_per_step": int(d2h)},
+                "gpu_launches": int(args.steps * an.kernel_launches(F)), "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--utts", type=int, default=UTTS, help="utterances per GPU (default: the full LJSpeech-shaped corpus)")
+    ap.add_argument("--chunk-frames", type=int, default=1 << 18)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,136 @@
+"""Fused WORLD feature extraction / synthesis over ragged batches on one GPU (the engine behind WorldFeatLabelGen.gen_data
+and Synthesiser.run_world_synth).
+
+extract:   packed waveforms + cached F0  ->  [F, D] float32 rows  [coded_sp(num_coded_sps) | lf0 | vuv | bap(nap)]
+           (WorldFeatLabelGen.extract_features + convert_from_world_features, world/WorldFeatLabelGen.py:810-889, :765-776)
+           plus per-column sum / sum-of-squares in fp64 (MeanStdDevExtractor.add_sample, misc/normalisation/...:43-47).
+           Frames are processed in chunks so the only large intermediate (the float32 spectral-envelope plane of one
+           chunk) stays bounded; every kernel launch goes to the caller's current stream, nothing synchronises.
+synthesise: [F, D] rows -> packed waveforms (Synthesiser.run_world_synth, src/Synthesiser.py:39-80: convert_to_world_features,
+           decode_sp, world_features_to_raw)."""
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+class WorldAnalyzer:
+    def __init__(self, fs, num_coded_sps=60, mgc_alpha=None, hop_size_ms=5.0, n_fft=None, f0_silence_threshold=30,
+                 lf0_zero=0, chunk_frames=1 << 18, device="cuda"):
+        from .compat.pysptk import mcepalpha
+        self.fs = int(fs)
+        self.num_coded_sps = int(num_coded_sps)
+        self.alpha = float(mcepalpha(fs) if mgc_alpha is None else mgc_alpha)
+        self.hop_size_ms = float(hop_size_ms)
+        self.n_fft = int(n_fft) if n_fft is not None else ops.get_cheaptrick_fft_size(fs)
+        self.nap = ops.get_num_aperiodicities(fs)
+        self.f0_silence_threshold = f0_silence_threshold
+        self.lf0_zero = lf0_zero
+        self.chunk_frames = int(chunk_frames)
+        self.device = torch.device(device)
+        self.dim = self.num_coded_sps + 2 + self.nap
+        # upload the warping matrices once
+        ops.McepTables.get(self.num_coded_sps - 1, self.alpha, self.n_fft, self.device)
+        self._sp = None
+
+    def _sp_buffer(self, frames):
+        K = self.n_fft // 2 + 1
+        if self._sp is None or self._sp.shape[0] < frames:
+            self._sp = torch.empty((frames, K), dtype=torch.float32, device=self.device)
+        return self._sp
+
+    def extract(self, batch, feats=None, sums=None, status=None, events=None):
+        """batch: ops.RaggedBatch.  Returns (feats [F, dim] float32, sums [2*dim] float64, status int32[1]); `sums` is
+        accumulated into when given (corpus statistics over several calls).  events: optional list that receives
+        (kernel name, frames, start event, end event) per launch (bench.py's per-kernel timing)."""
+        def timed(name, frames, fn):
+            if events is None:
+                return fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn()
+            e1.record()
+            events.append((name, frames, e0, e1))
+            return r
+
+        F = batch.num_frames
+        D = self.num_coded_sps
+        if feats is None:
+            feats = torch.empty((F, self.dim), dtype=torch.float32, device=self.device)
+        if sums is None:
+            sums = torch.zeros(2 * self.dim, dtype=torch.float64, device=self.device)
+        if status is None:
+            status = ops.new_status(self.device)
+        flat = feats.view(-1)
+        # lf0 / vuv straight into their columns
+        timed("lf0_vuv", F, lambda: ops.lf0_vuv(batch.f0, batch.frame_off, self.f0_silence_threshold, self.lf0_zero,
+                                                lf0_out=flat[D:], vuv_out=flat[D + 1:], out_stride=self.dim))
+        chunk = min(self.chunk_frames, max(F, 1))
+        sp = self._sp_buffer(chunk)
+        for lo in range(0, F, chunk):
+            hi = min(F, lo + chunk)
+            spc = sp[:hi - lo]
+            nf = hi - lo
+            timed("cheaptrick", nf, lambda: ops.cheaptrick(batch, fft_size=self.n_fft, status=status, frame_lo=lo, frame_hi=hi,
+                                                           out=spc))
+            timed("mcep", nf, lambda: ops.mcep(spc, D - 1, self.alpha, is_power=True, out=flat[lo * self.dim:],
+                                               out_stride=self.dim, status=status))
+            coarse, voiced, _ = timed("d4c", nf, lambda: ops.d4c_coarse(batch, status=status, frame_lo=lo, frame_hi=hi))
+            timed("bap_from_coarse", nf, lambda: ops.bap_from_coarse(coarse, voiced, self.fs, self.n_fft,
+                                                                     out=flat[lo * self.dim + D + 2:], out_stride=self.dim))
+        timed("stats", F, lambda: ops.stats_accumulate(feats, sums))
+        return feats, sums, status
+
+    def kernel_launches(self, num_frames):
+        """Number of libb200world kernels one extract() call launches (for bench.py's gpu_launches)."""
+        chunks = max(1, math.ceil(num_frames / self.chunk_frames))
+        return 1 + 4 * chunks + 1
+
+
+def mean_std_from_sums(sums, n, dim):
+    """MeanStdDevExtractor.get_params / combine_mean_std (misc/normalisation/MeanStdDevExtractor.py:49-53, :230-241)."""
+    s = np.asarray(sums[:dim], np.float64)
+    q = np.asarray(sums[dim:2 * dim], np.float64)
+    mean = s / n
+    var = q / n - mean ** 2
+    var = np.where(var < 0, 0.0, var)
+    return mean, np.sqrt(var)
+
+
+class WorldSynthesizer:
+    def __init__(self, fs, num_coded_sps=60, mgc_alpha=None, hop_size_ms=5.0, n_fft=None, f0_silence_threshold=30, lf0_zero=0,
+                 device="cuda"):
+        from .compat.pysptk import mcepalpha
+        self.fs = int(fs)
+        self.num_coded_sps = int(num_coded_sps)
+        self.alpha = float(mcepalpha(fs) if mgc_alpha is None else mgc_alpha)
+        self.hop_size_ms = float(hop_size_ms)
+        self.n_fft = int(n_fft) if n_fft is not None else ops.get_cheaptrick_fft_size(fs)
+        self.nap = ops.get_num_aperiodicities(fs)
+        self.f0_silence_threshold = f0_silence_threshold
+        self.lf0_zero = lf0_zero
+        self.device = torch.device(device)
+        ops.McepTables.get(self.num_coded_sps - 1, self.alpha, self.n_fft, self.device)
+
+    def synthesize(self, feats, frame_off, preemphasis=0.0, out_dtype=torch.float32):
+        """feats [F, D + 2 + nap] float32 rows [coded_sp | lf0 | vuv | bap] on the device; frame_off int64 [U+1] on the device.
+        Returns (y packed, out_off numpy int64 [U+1], status)."""
+        D = self.num_coded_sps
+        assert feats.shape[1] == D + 2 + self.nap, "WORLD requires all features to be present."
+        # decode_sp: amp = exp(Re mgc2sp) as float32 (AudioProcessing.py:256), then pow_sp = amp^2 in float64 (W:924)
+        amp = ops.mc2sp(feats, self.alpha, self.n_fft, scale=1.0, do_exp=True, out_dtype=torch.float32, order=D - 1,
+                        mc_stride=feats.shape[1])
+        pow_sp = amp.double().square_()
+        lf0 = feats[:, D].double()
+        vuv = (feats[:, D + 1] >= 0.5)
+        f0 = torch.exp(lf0)
+        vuv = vuv & ~(f0 < self.f0_silence_threshold)
+        f0 = torch.where(vuv, f0, torch.full_like(f0, float(self.lf0_zero)))
+        bap = feats[:, D + 2:].double().contiguous()
+        ap = ops.decode_aperiodicity(bap, self.fs, self.n_fft)
+        de = float(preemphasis)
+        y, out_off, status = ops.synthesize(f0.contiguous(), pow_sp, ap, frame_off, self.fs, self.hop_size_ms, deemphasis=de,
+                                            out_dtype=torch.float64 if de != 0.0 else out_dtype)
+        return y, out_off, status
