@@ -1,0 +1,390 @@
+"""WorldFeatLabelGen with the reference's entry points (idiaptts/src/data_preparation/world/WorldFeatLabelGen.py), computed
+by libb200world.so on the GPU:
+
+    convert_to_world_features  :735-762      convert_from_world_features :765-776
+    world_extract_features     :779-807      extract_features            :810-889      trim_to_shortest :892-907
+    world_features_to_raw      :910-945      gen_data                    :947-1071     save_output      :1121-1172
+
+Scope: the vocoder path with a CACHED F0 track.  pyworld.wav2world's F0 stage (dio + stonemask) is not part of
+it, so every extraction entry point takes the F0 track (`f0=` / `f0_cache=`); calling without one raises.  The reader /
+normalisation protocol of NpzDataReader (load, __getitem__, postprocess) is host-side file IO outside the path.
+
+gen_data processes the whole id list as ONE ragged GPU batch (the reference loops over utterances, :996) and, when
+torch.distributed is initialised, takes this rank's shard of the list and all-reduces the normalisation statistics."""
+import glob
+import logging
+import math
+import os
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import distributed, ops, pipeline
+from .AudioProcessing import AudioProcessing
+from .MeanCovarianceExtractor import MeanCovarianceExtractor
+from .MeanStdDevExtractor import MeanStdDevExtractor
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("idiaptts_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class WorldFeatLabelGen(object):
+    """Create WORLD feature labels for .wav files."""
+
+    f0_silence_threshold = 30
+    lf0_zero = 0
+    preemphasis = 0.0
+    n_fft = None
+    win_length_ms = None
+
+    dir_lf0 = "lf0"
+    dir_vuv = "vuv"
+    dir_bap = "bap"
+    dir_deltas = "cmp"
+
+    ext_lf0 = "lf0"
+    ext_vuv = "vuv"
+    ext_bap = "bap"
+    ext_deltas = "cmp"
+
+    logger = logging.getLogger(__name__)
+
+    def __init__(self, dir_labels=None, add_deltas=False, preemphasis=0.0, n_fft=None, win_length_ms=None, num_coded_sps=60,
+                 num_bap=1, sp_type="mcep", hop_size_ms=5, load_sp=True, load_lf0=True, load_vuv=True, load_bap=True,
+                 f0_cache=None, mgc_alpha=None):
+        self.dir_labels = dir_labels
+        self.add_deltas = add_deltas
+        self.preemphasis = preemphasis
+        self.n_fft = n_fft
+        self.win_length_ms = win_length_ms
+        self.num_coded_sps = num_coded_sps
+        self.num_bap = num_bap
+        self.sp_type = sp_type
+        self.hop_size_ms = hop_size_ms
+        self.load_sp, self.load_lf0, self.load_vuv, self.load_bap = load_sp, load_lf0, load_vuv, load_bap
+        self.f0_cache = f0_cache
+        self.mgc_alpha = mgc_alpha
+        self.norm_params = None
+        self.dir_coded_sps = self.sp_type
+        if self.num_coded_sps != -1:
+            self.dir_coded_sps += str(self.num_coded_sps)
+        self.dir_deltas = WorldFeatLabelGen.dir_deltas + "_" + self.dir_coded_sps
+        if sp_type != "mcep":
+            raise NotImplementedError("only sp_type='mcep' is on the accelerated path (SURVEY.md 8f N3)")
+
+    # ---- layout conversion -------------------------------------------------------------------------------------------
+    @staticmethod
+    def convert_to_world_features(sample, contains_deltas=False, num_coded_sps=60, num_bap=1):
+        deltas_factor = 3 if contains_deltas else 1
+        num_expected_feats = (num_coded_sps + 1 + num_bap) * deltas_factor + 1
+        if sample.shape[1] != num_expected_feats:
+            num_expected_feats = (num_coded_sps + 1 + num_bap) * 3 + 1
+            if sample.shape[1] == num_expected_feats:  # deltas detected automatically
+                deltas_factor = 3
+            else:
+                raise ValueError("WORLD requires all features to be present.")
+        coded_sp = sample[:, :num_coded_sps]
+        lf0 = sample[:, num_coded_sps * deltas_factor]
+        vuv = np.copy(sample[:, num_coded_sps * deltas_factor + deltas_factor])
+        vuv[vuv < 0.5] = 0.0
+        vuv[vuv >= 0.5] = 1.0
+        if contains_deltas:
+            bap = sample[:, -num_bap * 3:-num_bap * 2]
+        else:
+            bap = sample[:, -num_bap:]
+        return coded_sp, lf0, vuv, bap
+
+    @staticmethod
+    def convert_from_world_features(coded_sp, lf0, vuv, bap):
+        if lf0.ndim < 2:
+            lf0 = lf0[:, None]
+        if vuv.ndim < 2:
+            vuv = vuv[:, None]
+        if bap.ndim < 2:
+            bap = bap[:, None]
+        return np.concatenate((coded_sp, lf0, vuv, bap), axis=1)
+
+    # ---- F0 cache ------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _lookup_f0(f0_cache, file_name):
+        """f0_cache: dict {id: f0 array} | directory holding <id>.npy (float64 Hz per 5 ms frame, 0 = unvoiced) | None."""
+        key = os.path.basename(file_name)
+        if f0_cache is None:
+            raise NotImplementedError(
+                "F0 estimation (pyworld dio/stonemask) is outside the accelerated WORLD path: pass the cached F0 track "
+                "(f0= / f0_cache=).  See DESIGN.md, out of scope.")
+        if isinstance(f0_cache, dict):
+            if key in f0_cache:
+                return np.asarray(f0_cache[key], np.float64)
+            if file_name in f0_cache:
+                return np.asarray(f0_cache[file_name], np.float64)
+            raise KeyError("no cached F0 for %s" % file_name)
+        path = os.path.join(f0_cache, key + ".npy")
+        return np.load(path).astype(np.float64)
+
+    # ---- analysis -------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def world_extract_features(raw, fs, hop_size_ms, f0_silence_threshold=None, lf0_zero=None, n_fft=None, f0=None):
+        """Returns (amp_sp [T, K] float64, lf0 [T, 1] float32, vuv [T, 1] float32, bap [T, nap] float32)."""
+        if f0_silence_threshold is None:
+            f0_silence_threshold = WorldFeatLabelGen.f0_silence_threshold
+        if lf0_zero is None:
+            lf0_zero = WorldFeatLabelGen.lf0_zero
+        if f0 is None:
+            WorldFeatLabelGen._lookup_f0(None, "")
+        raw = np.ascontiguousarray(raw)
+        if raw.dtype not in (np.float64, np.float32, np.int16):
+            raw = raw.astype(np.float64)
+        f0 = np.ascontiguousarray(f0, np.float64)
+        T = ops.num_frames(len(raw), fs, hop_size_ms)
+        if len(f0) != T:
+            raise ValueError("cached F0 has {} frames, the waveform gives {} at {} ms hop".format(len(f0), T, hop_size_ms))
+        dev = _device()
+        fft_size = n_fft if n_fft is not None else ops.get_cheaptrick_fft_size(fs)
+        batch = ops.RaggedBatch.from_host([raw], [f0], fs, frame_period=hop_size_ms, device=dev)
+        status = ops.new_status(dev)
+        sp, _ = ops.cheaptrick(batch, fft_size=fft_size, out_dtype=torch.float64, status=status)
+        amp_sp = torch.sqrt(sp)
+        coarse, voiced, _ = ops.d4c_coarse(batch, status=status)
+        bap = ops.bap_from_coarse(coarse, voiced, fs, fft_size)
+        lf0, vuv = ops.lf0_vuv(batch.f0, batch.frame_off, f0_silence_threshold, lf0_zero)
+        out = (amp_sp.cpu().numpy(), lf0.cpu().numpy(), vuv.cpu().numpy(), bap.cpu().numpy())
+        ops.raise_for_status(status, "world_extract_features")
+        return out
+
+    @staticmethod
+    def extract_features(dir_in, file_name, file_ext="wav", preemphasis=0.0, n_fft=None, win_length_ms=None, hop_size_ms=5,
+                         sp_type="mcep", num_coded_sps=40, load_sp=True, load_lf0=True, load_vuv=True, load_bap=True,
+                         f0_silence_threshold=None, lf0_zero=None, f0=None, f0_cache=None, mgc_alpha=None):
+        """Acoustic features of one audio file: (coded_sp, lf0, vuv, bap)."""
+        if sp_type != "mcep":
+            raise NotImplementedError("only sp_type='mcep' is on the accelerated path (SURVEY.md 8f N3)")
+        audio_name = os.path.join(dir_in, file_name + "." + file_ext)
+        raw, fs = AudioProcessing.get_raw(audio_name, preemphasis)
+        if f0 is None:
+            f0 = WorldFeatLabelGen._lookup_f0(f0_cache, file_name)
+        amp_sp, lf0, vuv, bap = WorldFeatLabelGen.world_extract_features(raw, fs, hop_size_ms, f0_silence_threshold, lf0_zero,
+                                                                         n_fft, f0=f0)
+        if load_vuv:
+            voiced_pct = vuv.sum() / len(vuv) * 100.0
+            if voiced_pct < 5.0:
+                logging.warning("Detected only {:.0f}% [{}/{}] unvoiced frames in {}.".format(voiced_pct, int(vuv.sum()),
+                                                                                              len(vuv), file_name))
+        coded_sp = None
+        if load_sp:
+            coded_sp = AudioProcessing.extract_mcep(amp_sp, num_coded_sps=num_coded_sps,
+                                                    mgc_alpha=AudioProcessing.fs_to_mgc_alpha(fs) if mgc_alpha is None else mgc_alpha)
+            assert len(coded_sp) == len(lf0), "Requires testing. Possibly trimming is a solution."
+        logging.info("Extracted features from {} at {} Hz with {} ms frame hop.".format(os.path.basename(file_name), fs, hop_size_ms))
+        coded_sp, lf0, vuv, bap = WorldFeatLabelGen.trim_to_shortest([coded_sp, lf0, vuv, bap])
+        return coded_sp, lf0, vuv, bap
+
+    @staticmethod
+    def trim_to_shortest(features):
+        len_shortest = min(map(len, [f for f in features if f is not None]))
+        for idx, feature in enumerate(features):
+            if feature is None:
+                continue
+            len_diff = len(feature) - len_shortest
+            if len_diff > 0:
+                trim_front = len_diff // 2
+                trim_end = len_diff - trim_front
+                features[idx] = feature[trim_front:len(feature) - trim_end]
+        return features
+
+    # ---- synthesis ------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def world_features_to_raw(amp_sp, lf0, vuv, bap, fs, n_fft=None, f0_silence_threshold=None, lf0_zero=None, preemphasis=0.0):
+        """WORLD synthesis of one utterance -> waveform (float32 values; float64 array as the reference returns after
+        scipy's lfilter)."""
+        if f0_silence_threshold is None:
+            f0_silence_threshold = WorldFeatLabelGen.f0_silence_threshold
+        if lf0_zero is None:
+            lf0_zero = WorldFeatLabelGen.lf0_zero
+        if n_fft is None:
+            n_fft = AudioProcessing.fs_to_frame_length(fs)
+        dev = _device()
+        pow_sp = np.square(amp_sp, dtype=np.float64)
+        f0 = np.exp(lf0, dtype=np.float64)
+        vuv = np.array(vuv, copy=True)
+        vuv[f0 < f0_silence_threshold] = 0
+        f0[vuv == 0] = lf0_zero
+        if f0.ndim > 1:
+            assert f0.shape[1:] == (1,) * (f0.ndim - 1), "F0 should have only one dimension at this stage."
+            f0 = f0.squeeze()
+        if bap.ndim < 2:
+            bap = bap.reshape(-1, 1)
+        ap = ops.decode_aperiodicity(torch.from_numpy(np.ascontiguousarray(bap, np.float64)).to(dev), fs, n_fft)
+        frame_off = torch.tensor([0, len(f0)], dtype=torch.int64, device=dev)
+        y, _, status = ops.synthesize(torch.from_numpy(np.ascontiguousarray(f0)).to(dev),
+                                      torch.from_numpy(np.ascontiguousarray(pow_sp)).to(dev), ap, frame_off, fs,
+                                      deemphasis=0.0, out_dtype=torch.float32)
+        raw = y.cpu().numpy()
+        ops.raise_for_status(status, "world_features_to_raw")
+        return AudioProcessing.depreemphasis(raw, preemphasis)
+
+    # ---- corpus extraction -------------------------------------------------------------------------------------------------
+    def gen_data(self, dir_in, dir_out=None, file_id_list="", file_ext="wav", id_list=None, return_dict=False, f0_cache=None):
+        """Prepare acoustic features of all utterances in id_list as ONE GPU batch; save them per feature / utterance as
+        .npz; return ([label_dict,] means, std_devs).  With torch.distributed initialised each rank extracts its shard
+        and the statistics are all-reduced (files are written by the owning rank, statistics by rank 0)."""
+        id_list, file_id_list_name = self._get_id_list(dir_in, file_id_list, id_list, file_ext)
+        f0_cache = f0_cache if f0_cache is not None else self.f0_cache
+        rank, world = distributed.world_info()
+        if dir_out is not None:
+            self._create_directories(dir_out)
+        dev = _device()
+
+        # read this rank's shard
+        headers = []
+        for name in id_list:
+            with __import__("wave").open(os.path.join(dir_in, name + "." + file_ext), "rb") as w:
+                headers.append((w.getnframes(), w.getframerate()))
+        if world > 1:
+            mine = distributed.shard_utterances([h[0] for h in headers], world)[rank]
+        else:
+            mine = np.arange(len(id_list))
+        my_ids = [id_list[i] for i in mine]
+        waves, f0s, fs = [], [], None
+        for name in my_ids:
+            x, cur_fs = AudioProcessing.read_wav(os.path.join(dir_in, name + "." + file_ext))
+            if fs is None:
+                fs = cur_fs
+            elif fs != cur_fs:
+                raise ValueError("mixed sampling rates in one gen_data call ({} vs {})".format(fs, cur_fs))
+            f0 = self._lookup_f0(f0_cache, name)
+            T = ops.num_frames(len(x), cur_fs, self.hop_size_ms)
+            if len(f0) != T:
+                raise ValueError("{}: cached F0 has {} frames, the waveform gives {}".format(name, len(f0), T))
+            waves.append(x)
+            f0s.append(f0)
+        if fs is None:
+            fs = headers[0][1] if headers else 16000
+        nap = ops.get_num_aperiodicities(fs)
+        D = self.num_coded_sps
+        dim = D + 2 + nap
+        alpha = self.mgc_alpha if self.mgc_alpha is not None else AudioProcessing.fs_to_mgc_alpha(fs)
+        stat = torch.zeros(1 + 2 * dim * (3 if self.add_deltas else 1) + (3 * dim) ** 2 * (1 if self.add_deltas else 0),
+                           dtype=torch.float64, device=dev)
+        feats_np, offs = None, None
+        if waves:
+            same = all(w.dtype == waves[0].dtype for w in waves)
+            if not same:
+                waves = [w.astype(np.float64) / 32768.0 if w.dtype == np.int16 else w.astype(np.float64) for w in waves]
+            batch = ops.RaggedBatch.from_host(waves, f0s, fs, frame_period=self.hop_size_ms, preemphasis=self.preemphasis, device=dev)
+            an = pipeline.WorldAnalyzer(fs, D, alpha, self.hop_size_ms, self.n_fft, WorldFeatLabelGen.f0_silence_threshold,
+                                        WorldFeatLabelGen.lf0_zero, device=dev)
+            feats, sums, status = an.extract(batch)
+            F = batch.num_frames
+            if self.add_deltas:
+                d, dd = ops.deltas(feats, batch.frame_off)
+                full = torch.cat((feats, d, dd), dim=1).contiguous()  # [F, 3*dim] = [static | delta | delta-delta]
+                sums3 = torch.zeros(2 * 3 * dim, dtype=torch.float64, device=dev)
+                gram = torch.zeros((3 * dim) ** 2, dtype=torch.float64, device=dev)
+                ops.stats_accumulate(full, sums3, gram)
+                stat[1:1 + 6 * dim] = sums3
+                stat[1 + 6 * dim:] = gram
+                feats_np = full.cpu().numpy()
+            else:
+                stat[1:1 + 2 * dim] = sums
+                feats_np = feats.cpu().numpy()
+            stat[0] = float(F)
+            offs = batch.frame_off.cpu().numpy()
+            ops.raise_for_status(status, "gen_data")
+        distributed.allreduce_stats(stat)
+        stat_np = stat.cpu().numpy()
+        n_total = int(round(stat_np[0]))
+
+        # per-feature column groups of the static block
+        groups = (("sp", self.load_sp, self.dir_coded_sps, self.sp_type, slice(0, D)),
+                  ("lf0", self.load_lf0, self.dir_lf0, self.ext_lf0, slice(D, D + 1)),
+                  ("vuv", self.load_vuv, self.dir_vuv, self.ext_vuv, slice(D + 1, D + 2)),
+                  ("bap", self.load_bap, self.dir_bap, self.ext_bap, slice(D + 2, D + 2 + nap)))
+
+        def cols(sl, block):  # columns of a feature in block 0 (static), 1 (delta), 2 (delta-delta)
+            return np.arange(sl.start, sl.stop) + block * dim
+
+        label_dict = OrderedDict()
+        if feats_np is not None:
+            for u, name in enumerate(my_ids):
+                rows = feats_np[offs[u]:offs[u + 1]]
+                out_parts = []
+                base = os.path.basename(name)
+                for key, load, fdir, fext, sl in groups:
+                    if not load:
+                        continue
+                    static = rows[:, cols(sl, 0)]
+                    if self.add_deltas and key != "vuv":
+                        dl, ddl = rows[:, cols(sl, 1)], rows[:, cols(sl, 2)]
+                        part = np.concatenate((static, dl, ddl), axis=1)
+                        if dir_out is not None:
+                            np.savez(os.path.join(dir_out, fdir, base), **{fext: static, fext + "_deltas": dl,
+                                                                          fext + "_double_deltas": ddl})
+                    else:
+                        part = static
+                        if dir_out is not None:
+                            np.savez(os.path.join(dir_out, fdir, base), **{fext: static})
+                    out_parts.append(part)
+                if return_dict:
+                    label_dict[name] = np.concatenate(out_parts, axis=1) if out_parts else None
+
+        # normalisation parameters from the (all-reduced) sums
+        output_means, output_std_dev = [], []
+        for key, load, fdir, fext, sl in groups:
+            if not load:
+                continue
+            if key == "vuv":
+                mean, std = np.atleast_1d(0.0), np.atleast_1d(1.0)
+                output_means.append(mean)
+                output_std_dev.append(std)
+                continue
+            if self.add_deltas:
+                c = np.concatenate([cols(sl, b) for b in range(3)])
+                ext = MeanCovarianceExtractor()
+                gram = stat_np[1 + 6 * dim:].reshape(3 * dim, 3 * dim)
+                ext.add_sums(n_total, stat_np[1:1 + 3 * dim][c][None, :], gram[np.ix_(c, c)])
+                mean, cov, std = ext.get_params()
+                output_means.append(mean)
+                output_std_dev.append(cov)
+            else:
+                ext = MeanStdDevExtractor()
+                ext.add_sums(n_total, stat_np[1:1 + dim][sl], stat_np[1 + dim:1 + 2 * dim][sl])
+                mean, std = ext.get_params()
+                output_means.append(mean)
+                output_std_dev.append(std)
+            if dir_out and rank == 0:
+                norm_file_path = os.path.join(dir_out, fdir, file_id_list_name)
+                if self.add_deltas:
+                    if file_id_list_name is not None and os.path.basename(file_id_list_name) != "":
+                        norm_file_path += "-"
+                    norm_file_path += "deltas"
+                self.logger.info("Write norm_prams to {}".format(norm_file_path))
+                ext.save(norm_file_path)
+        if not self.add_deltas:
+            if len(output_means) > 0:
+                output_means = np.concatenate(output_means, axis=0)
+                output_std_dev = np.concatenate(output_std_dev, axis=0)
+            else:
+                output_means, output_std_dev = None, None
+        self.norm_params = (output_means, output_std_dev)
+        if return_dict:
+            return label_dict, output_means, output_std_dev
+        return output_means, output_std_dev
+
+    def _get_id_list(self, dir_in, file_id_list, id_list, file_ext):
+        if id_list is None:
+            id_list = [os.path.splitext(os.path.basename(f))[0] for f in sorted(glob.glob(os.path.join(dir_in, "*" + file_ext)))]
+            file_id_list_name = "all"
+        else:
+            file_id_list_name = os.path.splitext(os.path.basename(file_id_list))[0]
+        return id_list, file_id_list_name
+
+    def _create_directories(self, dir_out):
+        for load, d in ((self.load_sp, self.dir_coded_sps), (self.load_lf0, self.dir_lf0), (self.load_vuv, self.dir_vuv),
+                        (self.load_bap, self.dir_bap)):
+            if load:
+                os.makedirs(os.path.join(dir_out, d), exist_ok=True)

@@ -4,9 +4,9 @@
 // (idiaptts/src/data_preparation/world/WorldFeatLabelGen.py:943) inside Synthesiser.run_world_synth
 // (idiaptts/src/Synthesiser.py:51-65, a serial loop over utterances).  Algorithm: WORLD synthesis.cpp.
 //
-//   timebase     one CTA per utterance.  WORLD accumulates the phase of the sample-rate F0 contour sequentially over
-//                every sample; here each thread owns a contiguous run of samples and the running phase is a block-wide
-//                fp64 prefix sum (three sweeps: sums, pulse counts, pulse records).
+//   timebase     three kernels: per-sample phase increments (parallel), the running phase (strictly sequential per
+//                utterance, as WORLD does it, because pulse positions are threshold decisions on its rounding), pulse
+//                detection + ordered compaction (one CTA per utterance).
 //   randn table  WORLD's randn() is xorshift128 (sum of 12 draws); Synthesis() reseeds it, and pulse p consumes exactly
 //                12 * (n_{p+1} - n_p) steps, so the noise of pulse p is the slice [n_p - n_0, n_{p+1} - n_0) of ONE fixed
 //                sequence.  The table kernel regenerates that sequence in parallel by GF(2) jump-ahead.
@@ -117,10 +117,6 @@ __global__ void randn_table_kernel(double* __restrict__ table, int64_t n) {
 // ---- time base -----------------------------------------------------------------------------------------------------------------
 constexpr int kTbThreads = 256;
 
-struct TbFrame {  // WORLD interp1 of the coarse (frame-rate) F0 / VUV contours at one sample
-  double f0, vuv;
-};
-
 // coarse contour value i in [0, T]: index T is WORLD's linear extrapolation 2 c[T-1] - c[T-2]
 __device__ __forceinline__ void coarse_at(const double* __restrict__ f0, int T, double lowest_f0, int i, double& cf0, double& cv) {
   if (i < T) {
@@ -152,18 +148,73 @@ __device__ __forceinline__ double sample_f0(const double* __restrict__ f0, int T
   return vuv_out == 0.0 ? kDefaultF0 : if0;
 }
 
+// (1) phase increment of every output sample, parallel: inc[n] = 2 pi f0(n) / fs
 __global__ void __launch_bounds__(kTbThreads)
-timebase_kernel(const double* __restrict__ f0_all, const int64_t* __restrict__ utt_frame_offset,
-                const int64_t* __restrict__ utt_out_offset, const int64_t* __restrict__ utt_pulse_offset, int fs_i,
-                double frame_period_ms, int fft_size, int* __restrict__ pulse_index, double* __restrict__ pulse_shift,
-                uint8_t* __restrict__ pulse_vuv, int* __restrict__ num_pulses, int* __restrict__ status) {
-  __shared__ double sh_d[kTbThreads / 32 + 1];
+phase_inc_kernel(const double* __restrict__ f0_all, const int64_t* __restrict__ utt_frame_offset,
+                 const int64_t* __restrict__ utt_out_offset, int fs_i, double frame_period_ms, int fft_size,
+                 double* __restrict__ phase) {
+  const int u = blockIdx.y;
+  const double* f0 = f0_all + utt_frame_offset[u];
+  const int T = (int)(utt_frame_offset[u + 1] - utt_frame_offset[u]);
+  const int64_t yoff = utt_out_offset[u];
+  const int ylen = (int)(utt_out_offset[u + 1] - yoff);
+  const int n = blockIdx.x * kTbThreads + threadIdx.x;
+  if (n >= ylen || T < 1) return;
+  const double fs = (double)fs_i;
+  const double fp = frame_period_ms / 1000.0;
+  const double lowest_f0 = (double)(fs_i / fft_size) + 1.0;
+  int k = max(1, min(T, (int)((double)n / fs / fp)));
+  while (k > 1 && (double)n / fs < __dmul_rn((double)(k - 1), fp)) --k;
+  double v;
+  const double f = sample_f0(f0, T, lowest_f0, fp, fs, n, k, v);
+  phase[yoff + n] = __ddiv_rn(__dmul_rn(2.0 * kPi, f), fs);
+}
+
+// (2) WORLD accumulates the phase sequentially (total[n] = total[n-1] + inc[n]); floating-point addition is not
+// associative and pulse positions are threshold decisions on fmod(total, 2 pi) - at 16 / 48 kHz the 500 Hz unvoiced
+// default even produces exact ties - so the running sum is kept strictly sequential: one warp per utterance stages
+// 1024 increments at a time in shared memory (coalesced), lane 0 runs the dependent DADD chain, the warp writes the
+// totals back (coalesced).  ~10 cycles per sample, all utterances in parallel.
+constexpr int kSeqChunk = 1024;
+__global__ void __launch_bounds__(32) phase_scan_kernel(const int64_t* __restrict__ utt_out_offset, double* __restrict__ phase) {
+  __shared__ double buf[kSeqChunk];
+  const int u = blockIdx.x;
+  const int lane = threadIdx.x;
+  const int64_t yoff = utt_out_offset[u];
+  const int ylen = (int)(utt_out_offset[u + 1] - yoff);
+  double total = 0.0;
+  for (int c0 = 0; c0 < ylen; c0 += kSeqChunk) {
+    const int cn = min(kSeqChunk, ylen - c0);
+    for (int i = lane; i < cn; i += 32) buf[i] = phase[yoff + c0 + i];
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll 8
+      for (int i = 0; i < cn; ++i) {
+        total = __dadd_rn(total, buf[i]);
+        buf[i] = total;
+      }
+    }
+    __syncwarp();
+    for (int i = lane; i < cn; i += 32) phase[yoff + c0 + i] = buf[i];
+    __syncwarp();
+  }
+}
+
+// (3) pulse detection and ordered compaction, one CTA per utterance: a pulse sits at sample i when
+// |wrap[i+1] - wrap[i]| > pi, wrap = fmod(total, 2 pi).
+__global__ void __launch_bounds__(kTbThreads)
+pulse_kernel(const double* __restrict__ f0_all, const int64_t* __restrict__ utt_frame_offset,
+             const int64_t* __restrict__ utt_out_offset, const int64_t* __restrict__ utt_pulse_offset, int fs_i,
+             double frame_period_ms, int fft_size, const double* __restrict__ phase, int* __restrict__ pulse_index,
+             double* __restrict__ pulse_shift, uint8_t* __restrict__ pulse_vuv, int* __restrict__ num_pulses,
+             int* __restrict__ status) {
   __shared__ int sh_i[kTbThreads / 32 + 1];
   const int u = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double* f0 = f0_all + utt_frame_offset[u];
   const int T = (int)(utt_frame_offset[u + 1] - utt_frame_offset[u]);
-  const int ylen = (int)(utt_out_offset[u + 1] - utt_out_offset[u]);
+  const int64_t yoff = utt_out_offset[u];
+  const int ylen = (int)(utt_out_offset[u + 1] - yoff);
   const int64_t poff = utt_pulse_offset[u];
   const int cap = (int)(utt_pulse_offset[u + 1] - poff);
   const double fs = (double)fs_i;
@@ -174,67 +225,37 @@ timebase_kernel(const double* __restrict__ f0_all, const int64_t* __restrict__ u
     if (tid == 0) num_pulses[u] = 0;
     return;
   }
-  const int per = (ylen + kTbThreads - 1) / kTbThreads;
-  const int beg = min(ylen, tid * per), end = min(ylen, beg + per);
-  // sweep 1: phase advance of this thread's run
-  double run = 0.0;
-  {
-    int k = max(1, min(T, (int)((double)beg / fs / fp)));
-    while (k > 1 && (double)beg / fs < __dmul_rn((double)(k - 1), fp)) --k;
-    double v;
-    for (int n = beg; n < end; ++n) run = __dadd_rn(run, __ddiv_rn(__dmul_rn(two_pi, sample_f0(f0, T, lowest_f0, fp, fs, n, k, v)), fs));
-  }
-  // exclusive block scan of the runs
-  double incl = run;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const double v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (lane == 31) sh_d[warp] = incl;
-  __syncthreads();
-  double offset = incl - run;
-  for (int w = 0; w < warp; ++w) offset += sh_d[w];
-  // sweeps 2 and 3: count, then write, the pulses whose FIRST sample (index i of the jump i -> i+1) lies in this run.
-  // jump i -> i+1 is examined by the owner of sample i + 1.
-  int my_count = 0, my_base = 0;
+  const double* tot = phase + yoff;
+  // this thread examines the jumps i -> i+1 for i in [beg, end)
+  const int njump = ylen - 1;
+  const int per = (njump + kTbThreads - 1) / kTbThreads;
+  const int beg = min(njump, tid * per), end = min(njump, beg + per);
+  int my_base = 0;
   for (int sweep = 0; sweep < 2; ++sweep) {
-    int k = max(1, min(T, (int)((double)beg / fs / fp)));
-    while (k > 1 && (double)beg / fs < __dmul_rn((double)(k - 1), fp)) --k;
-    double total = offset;
-    double prev_wrap = fmod(total, two_pi);  // wrap phase of sample beg - 1 (unused for beg == 0)
-    double prev_vuv = 0.0;
-    if (beg > 0 && beg < end) {  // vuv flag of sample beg - 1
-      int kk = max(1, k - 1);
-      while (kk > 1 && (double)(beg - 1) / fs < __dmul_rn((double)(kk - 1), fp)) --kk;
-      double v;
-      sample_f0(f0, T, lowest_f0, fp, fs, beg - 1, kk, v);
-      prev_vuv = v;
-    }
     int cnt = 0;
-    for (int n = beg; n < end; ++n) {
-      double v;
-      const double f = sample_f0(f0, T, lowest_f0, fp, fs, n, k, v);
-      total = __dadd_rn(total, __ddiv_rn(__dmul_rn(two_pi, f), fs));
-      const double wrap = fmod(total, two_pi);
-      if (n > 0 && fabs(wrap - prev_wrap) > kPi) {
+    double w0 = beg < end ? fmod(tot[beg], two_pi) : 0.0;
+    for (int i = beg; i < end; ++i) {
+      const double w1 = fmod(tot[i + 1], two_pi);
+      if (fabs(w1 - w0) > kPi) {
         if (sweep == 1) {
           const int slot = my_base + cnt;
           if (slot < cap) {
-            const double y1 = prev_wrap - two_pi;
-            const double x = -y1 / (wrap - y1);
-            pulse_index[poff + slot] = n - 1;
+            const double y1 = w0 - two_pi;
+            const double x = -y1 / (w1 - y1);
+            int k = max(1, min(T, (int)((double)i / fs / fp)));
+            while (k > 1 && (double)i / fs < __dmul_rn((double)(k - 1), fp)) --k;
+            double v;
+            sample_f0(f0, T, lowest_f0, fp, fs, i, k, v);
+            pulse_index[poff + slot] = i;
             pulse_shift[poff + slot] = x / fs;
-            pulse_vuv[poff + slot] = prev_vuv > 0.5 ? 1 : 0;
+            pulse_vuv[poff + slot] = v > 0.5 ? 1 : 0;
           }
         }
         ++cnt;
       }
-      prev_wrap = wrap;
-      prev_vuv = v;
+      w0 = w1;
     }
     if (sweep == 0) {
-      my_count = cnt;
       int inc = cnt;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -246,7 +267,7 @@ timebase_kernel(const double* __restrict__ f0_all, const int64_t* __restrict__ u
       my_base = inc - cnt;
       for (int w = 0; w < warp; ++w) my_base += sh_i[w];
       if (tid == kTbThreads - 1) {
-        const int totalp = my_base + my_count;
+        const int totalp = my_base + cnt;
         if (totalp > cap) atomicOr(status, B2W_STATUS_F0_TOO_HIGH);
         num_pulses[u] = min(totalp, cap);
       }
@@ -512,18 +533,26 @@ extern "C" int b2w_synth_randn_table(double* table, int64_t n, void* stream) {
 }
 
 extern "C" int b2w_synth_timebase(const double* f0, const int64_t* utt_frame_offset, const int64_t* utt_out_offset,
-                                  const int64_t* utt_pulse_offset, int32_t num_utts, int32_t fs, double frame_period_ms,
-                                  int32_t fft_size, int32_t* pulse_index, double* pulse_shift, uint8_t* pulse_vuv,
-                                  int32_t* num_pulses, int32_t* status, void* stream) {
+                                  const int64_t* utt_pulse_offset, int32_t num_utts, int64_t max_out_per_utt, int32_t fs,
+                                  double frame_period_ms, int32_t fft_size, double* phase_ws, int32_t* pulse_index,
+                                  double* pulse_shift, uint8_t* pulse_vuv, int32_t* num_pulses, int32_t* status, void* stream) {
   using namespace b2w;
-  B2W_REQUIRE(f0 && utt_frame_offset && utt_out_offset && utt_pulse_offset && pulse_index && pulse_shift && pulse_vuv &&
-                  num_pulses && status,
+  B2W_REQUIRE(f0 && utt_frame_offset && utt_out_offset && utt_pulse_offset && phase_ws && pulse_index && pulse_shift &&
+                  pulse_vuv && num_pulses && status,
               "b2w_synth_timebase: null argument");
-  if (num_utts == 0) return 0;
-  timebase_kernel<<<num_utts, kTbThreads, 0, (cudaStream_t)stream>>>(f0, utt_frame_offset, utt_out_offset, utt_pulse_offset,
-                                                                      fs, frame_period_ms, fft_size, pulse_index, pulse_shift,
-                                                                      pulse_vuv, num_pulses, status);
-  return check_launch("timebase_kernel");
+  B2W_REQUIRE(num_utts <= 65535, "b2w_synth_timebase: at most 65535 utterances per call");
+  if (num_utts == 0 || max_out_per_utt == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)((max_out_per_utt + kTbThreads - 1) / kTbThreads), (unsigned)num_utts);
+  phase_inc_kernel<<<grid, kTbThreads, 0, st>>>(f0, utt_frame_offset, utt_out_offset, fs, frame_period_ms, fft_size, phase_ws);
+  int rc = check_launch("phase_inc_kernel");
+  if (rc) return rc;
+  phase_scan_kernel<<<num_utts, 32, 0, st>>>(utt_out_offset, phase_ws);
+  rc = check_launch("phase_scan_kernel");
+  if (rc) return rc;
+  pulse_kernel<<<num_utts, kTbThreads, 0, st>>>(f0, utt_frame_offset, utt_out_offset, utt_pulse_offset, fs, frame_period_ms,
+                                                fft_size, phase_ws, pulse_index, pulse_shift, pulse_vuv, num_pulses, status);
+  return check_launch("pulse_kernel");
 }
 
 extern "C" int b2w_synth_render(const void* sp, const void* ap, int32_t plane_dtype, const int64_t* utt_frame_offset,

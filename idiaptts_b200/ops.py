@@ -410,10 +410,11 @@ def synthesize(f0, sp, ap, frame_off, fs, frame_period=5.0, deemphasis=0.0, out_
     tab = randn_table(int(ylen.max()) + 1, dev)
     st = _stream(dev)
     with torch.cuda.device(dev):
+        phase_ws = torch.empty(int(out_off[-1]), dtype=torch.float64, device=dev)
         check(lib.b2w_synth_timebase(f0.data_ptr(), frame_off.data_ptr(), d_out_off.data_ptr(), d_pulse_off.data_ptr(), U,
-                                     int(fs), float(frame_period), fft_size, pulse_index.data_ptr(), pulse_shift.data_ptr(),
-                                     pulse_vuv.data_ptr(), num_pulses.data_ptr(), status.data_ptr(), st),
-              "b2w_synth_timebase")
+                                     int(ylen.max()), int(fs), float(frame_period), fft_size, phase_ws.data_ptr(),
+                                     pulse_index.data_ptr(), pulse_shift.data_ptr(), pulse_vuv.data_ptr(),
+                                     num_pulses.data_ptr(), status.data_ptr(), st), "b2w_synth_timebase")
         # the response buffer is sized by the ACTUAL pulse counts (one small D2H of U ints)
         npul = num_pulses.cpu().numpy()[:U].astype(np.int64)
         max_p = int(npul.max()) if U else 0

@@ -69,9 +69,11 @@ def waveforms_from_f0(f0, fs, rngs, frame_period_ms=5.0, device="cpu", num_harmo
         amp = g / torch.clamp(fk / 500.0, min=1.0) * (fk < 0.45 * fs).float()
         x += amp * torch.sin((phase * k).remainder(2 * math.pi)).float()
     x = x * gate
+    noise = torch.empty((B, n), device=device, dtype=torch.float32)
     gen = torch.Generator(device=device)
-    gen.manual_seed(int(rngs[0].integers(0, 2 ** 31 - 1)))
-    noise = torch.randn((B, n), generator=gen, device=device, dtype=torch.float32)
+    for row, r in enumerate(rngs):  # one noise stream per utterance: an utterance does not depend on its batch
+        gen.manual_seed(int(r.integers(0, 2 ** 31 - 1)))
+        noise[row] = torch.randn(n, generator=gen, device=device, dtype=torch.float32)
     # one-pole tilt of the unvoiced noise, y[n] = x[n] + 0.7 y[n-1], as a short FIR (keeps it parallel)
     tilt = noise.clone()
     coef = 0.7

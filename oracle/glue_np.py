@@ -240,3 +240,45 @@ def allpass_warp_forward(x, alpha, n):
             y[0] *= 2.0
             out[i, b * n:(b + 1) * n] = y
     return out.reshape(x.shape)
+
+
+def freqt_with_tangent(x, alpha):
+    """freqt(x, len(x)-1, alpha) and its derivative w.r.t. alpha (fp64), by differentiating the recursion."""
+    n = len(x)
+    a = float(alpha)
+    b = 1.0 - a * a
+    g = np.zeros(n)
+    t = np.zeros(n)
+    for r in range(n - 1, -1, -1):
+        d, td = g.copy(), t.copy()
+        g[0] = x[r] + a * d[0]
+        t[0] = d[0] + a * td[0]
+        if n > 1:
+            g[1] = b * d[0] + a * d[1]
+            t[1] = -2.0 * a * d[0] + b * td[0] + d[1] + a * td[1]
+        for j in range(2, n):
+            g[j] = d[j - 1] + a * (d[j] - g[j - 1])
+            t[j] = td[j - 1] + (d[j] - g[j - 1]) + a * (td[j] - t[j - 1])
+    return g, t
+
+
+def allpass_warp_backward(grad_y, x, alpha, n):
+    """Gradients of allpass_warp_forward w.r.t. x and alpha (one alpha per row): (grad_x [rows, W], grad_alpha [rows])."""
+    x = np.asarray(x, np.float64)
+    gy = np.asarray(grad_y, np.float64)
+    al = np.asarray(alpha, np.float64).reshape(-1)
+    gx = np.zeros_like(x)
+    ga = np.zeros(x.shape[0])
+    S1 = np.ones(n)
+    S1[0] = 0.5
+    S2 = np.ones(n)
+    S2[0] = 2.0
+    for i in range(x.shape[0]):
+        A = sptk_np.freqt_matrix(n - 1, n - 1, float(al[i]))
+        J = (S2[:, None] * A) * S1[None, :]
+        for b in range(x.shape[1] // n):
+            sl = slice(b * n, (b + 1) * n)
+            gx[i, sl] = J.T @ gy[i, sl]
+            _, t = freqt_with_tangent(x[i, sl] * S1, float(al[i]))
+            ga[i] += np.dot(gy[i, sl] * S2, t)
+    return gx, ga

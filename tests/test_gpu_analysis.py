@@ -1,0 +1,179 @@
+"""Parity of the CUDA analysis kernels (through the C ABI) against the reference's golden vectors and the CPU oracle.
+
+Tolerances (BASELINE.json north_star): frame counts and vuv bit-exact; spectral envelope relative error <= 1e-4;
+mel-cepstral distortion < 0.01 dB; the tighter numbers asserted here are what the kernels actually deliver."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_utterance
+from oracle import glue_np, sptk_np, world_np
+
+pytestmark = pytest.mark.gpu
+
+IDS = ["LJ001-%04d" % i for i in range(1, 10)]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda", 0)
+
+
+@pytest.mark.parametrize("id_", ["LJ001-0002", "LJ001-0008"])
+def test_cheaptrick_vs_oracle(golden, id_):
+    from idiaptts_b200.compat import pyworld as pw
+    x, c, f0, fs = golden_utterance(golden, id_)
+    t = world_np.temporal_positions(len(f0))
+    ref = world_np.cheaptrick(x, f0, t, fs)
+    out = pw.cheaptrick(x, f0, t, fs)
+    assert out.shape == ref.shape and out.dtype == np.float64
+    assert (np.abs(out - ref) / ref).max() < 1e-6  # tolerance 1e-4
+
+
+@pytest.mark.parametrize("id_", IDS)
+def test_fused_analysis_reproduces_reference_cmp(golden, dev, id_):
+    """int16 wav + in-kernel pre-emphasis 0.97 -> CheapTrick (float32 plane) -> mcep20, D4C -> bap, against the reference's
+    own cmp_mcep20 fixtures (the same comparison that pins the oracle)."""
+    from idiaptts_b200 import ops
+    c = golden[id_ + "/cmp"]
+    f0 = np.where(c[:, 63] > 0, np.exp(c[:, 60].astype(np.float64)), 0.0)
+    wav = golden[id_ + "/wav"]
+    assert ops.num_frames(len(wav), 16000) == c.shape[0]  # frame count: bit-exact
+    batch = ops.RaggedBatch.from_host([wav], [f0], 16000, preemphasis=0.97, device=dev)
+    sp, status = ops.cheaptrick(batch, out_dtype=torch.float32)
+    mc, _ = ops.mcep(sp, 19, 0.58, is_power=True, status=status)
+    coarse, voiced, _ = ops.d4c_coarse(batch, status=status)
+    bap = ops.bap_from_coarse(coarse, voiced, 16000, 1024)
+    assert ops.raise_for_status(status, "analysis") & ~8 == 0
+    mc = mc.cpu().numpy()
+    assert np.abs(mc - c[:, :20]).max() < 2e-5
+    assert glue_np.mcd_db(c[:, :20], mc) < 1e-4  # tolerance 0.01 dB
+    bap = bap.cpu().numpy()
+    assert np.abs(bap[:, 0] - c[:, 64]).max() < 3e-5
+    assert np.all(bap[c[:, 63] == 0, 0] == np.float32(-8.685697e-12))
+
+
+def test_d4c_and_codec_vs_oracle(golden):
+    from idiaptts_b200.compat import pyworld as pw
+    x, c, f0, fs = golden_utterance(golden, "LJ001-0008")
+    t = world_np.temporal_positions(len(f0))
+    ap_ref = world_np.d4c(x, f0, t, fs)
+    ap = pw.d4c(x, f0, t, fs)
+    unv_ref = ap_ref[:, 0] > 0.99
+    assert np.array_equal(ap[:, 0] > 0.99, unv_ref)  # LoveTrain decisions identical
+    assert np.abs(ap - ap_ref).max() < 1e-9
+    bap = pw.code_aperiodicity(ap, fs)
+    np.testing.assert_allclose(bap, world_np.code_aperiodicity(ap_ref, fs), atol=1e-8)
+    np.testing.assert_allclose(pw.decode_aperiodicity(bap, fs, 1024), world_np.decode_aperiodicity(bap, fs, 1024), atol=1e-12)
+    with pytest.raises(ValueError):
+        pw.decode_aperiodicity(np.zeros((3, 2)), 16000, 1024)  # wrong band count for fs
+
+
+@pytest.mark.parametrize("order,alpha", [(19, 0.58), (59, 0.58), (59, 0.41), (79, 0.41)])
+def test_mcep_vs_oracle(golden, order, alpha):
+    from idiaptts_b200.compat import pysptk as ps
+    x, c, f0, fs = golden_utterance(golden, "LJ001-0008")
+    sp = world_np.cheaptrick(x, f0, world_np.temporal_positions(len(f0)), fs)
+    amp = np.sqrt(sp)
+    ref = [sptk_np.mcep_frame(a, order, alpha, eps=1e-8) for a in amp]
+    rm = np.stack([r[0] for r in ref])
+    out = ps.mcep(amp, order=order, alpha=alpha, eps=1.0e-8, min_det=0.0, etype=1, itype=3)
+    assert out.shape == rm.shape
+    assert np.abs(out - rm).max() < 2e-5
+    assert glue_np.mcd_db(rm, out) < 1e-4
+    one = ps.mcep(amp[40], order=order, alpha=alpha, eps=1.0e-8, etype=1, itype=3)  # 1-D input = one frame
+    np.testing.assert_allclose(one, out[40], atol=1e-6)
+    # power-spectrum input (itype=4) gives the same result as amplitude input
+    out4 = ps.mcep(sp, order=order, alpha=alpha, eps=1.0e-8, etype=1, itype=4)
+    assert np.abs(out4 - out).max() < 2e-5
+
+
+def test_mcep_iteration_counts_and_errors(golden, dev):
+    from idiaptts_b200 import ops
+    from idiaptts_b200.compat import pysptk as ps
+    x, c, f0, fs = golden_utterance(golden, "LJ001-0002")
+    sp = world_np.cheaptrick(x, f0, world_np.temporal_positions(len(f0)), fs)
+    ref_it = np.array([sptk_np.mcep_frame(np.sqrt(a), 59, 0.58, eps=1e-8)[1] for a in sp])
+    iters = torch.zeros(len(sp), dtype=torch.int32, device=dev)
+    ops.mcep(torch.from_numpy(sp).to(dev), 59, 0.58, is_power=True, iters=iters)
+    assert np.array_equal(iters.cpu().numpy(), ref_it)  # same Newton trajectory as SPTK
+    with pytest.raises(RuntimeError, match="periodogram"):
+        ps.mcep(np.zeros((2, 513)), order=19, alpha=0.4, etype=0, itype=3)  # pysptk raises on zeros without eps
+    with pytest.raises(ValueError):
+        ps.mcep(np.ones((2, 513)), order=19, alpha=0.4, etype=1, eps=-1.0, itype=3)
+
+
+def test_mc2sp_and_reference_reconstruction_threshold(golden):
+    """test_WorldFeatLabelGen.py:765-836: sum((world_amp - mcep80 -> amp)^2) < 100."""
+    from idiaptts_b200.AudioProcessing import AudioProcessing
+    from idiaptts_b200.compat import pysptk as ps
+    x, c, f0, fs = golden_utterance(golden, "LJ001-0008")
+    sp = world_np.cheaptrick(x, f0, world_np.temporal_positions(len(f0)), fs)
+    amp = np.sqrt(sp)
+    mc = AudioProcessing.extract_mcep(amp, 80, 0.41)
+    assert mc.dtype == np.float32 and mc.shape == (len(f0), 80)
+    rec = AudioProcessing.mcep_to_amp_sp(mc, fs, alpha=0.41)
+    assert ((amp - rec) ** 2).sum() < 100
+    ref = glue_np.mcep_to_amp_sp(mc, fs, alpha=0.41)
+    assert (np.abs(rec - ref) / ref).max() < 5e-5
+    mc60 = mc[:, :60].astype(np.float64)
+    np.testing.assert_allclose(ps.mgc2sp(mc60, 0.41, 0.0, 1024).real, sptk_np.mgc2sp(mc60, 0.41, 0.0, 1024).real, atol=2e-5)
+    p = ps.mc2sp(mc60, 0.41, 1024)
+    assert (np.abs(p - sptk_np.mc2sp(mc60, 0.41, 1024)) / p).max() < 1e-4
+
+
+def test_ragged_batch_equals_single_utterances_and_edge_cases(golden, dev):
+    from idiaptts_b200 import ops, pipeline
+    ids = ["LJ001-0002", "LJ001-0008", "LJ001-0004"]
+    waves = [golden[i + "/wav"] for i in ids]
+    f0s = [np.where(golden[i + "/cmp"][:, 63] > 0, np.exp(golden[i + "/cmp"][:, 60].astype(np.float64)), 0.0) for i in ids]
+    f0s[2] = np.zeros_like(f0s[2])       # an utterance without any voiced frame
+    f0s[1][10:14] = 20.0                 # below CheapTrick's floor -> treated with the 500 Hz default window
+    an = pipeline.WorldAnalyzer(16000, 60, 0.58, device=dev, chunk_frames=500)  # several chunks, chunk edge inside an utterance
+    batch = ops.RaggedBatch.from_host(waves, f0s, 16000, device=dev)
+    feats, sums, status = an.extract(batch)
+    ops.raise_for_status(status, "ragged")
+    feats = feats.cpu().numpy()
+    assert feats.shape == (sum(len(f) for f in f0s), 63) and np.isfinite(feats).all()
+    off = np.concatenate(([0], np.cumsum([len(f) for f in f0s])))
+    for u in range(3):
+        single, _, _ = pipeline.WorldAnalyzer(16000, 60, 0.58, device=dev).extract(
+            ops.RaggedBatch.from_host([waves[u]], [f0s[u]], 16000, device=dev))
+        assert np.array_equal(single.cpu().numpy(), feats[off[u]:off[u + 1]])  # batching does not change a single bit
+    assert np.all(feats[off[2]:off[3], 61] == 0) and np.all(feats[off[2]:off[3], 60] == 0)  # no voiced frame: lf0 stays 0
+    assert np.all(feats[off[2]:off[3], 62] == np.float32(-8.685697e-12))
+    s = sums.cpu().numpy()
+    np.testing.assert_allclose(s[:63], feats.astype(np.float64).sum(0), rtol=1e-9, atol=1e-6)
+    np.testing.assert_allclose(s[63:], (feats.astype(np.float64) ** 2).sum(0), rtol=1e-9, atol=1e-6)
+    # empty batch: no launch, empty outputs
+    eb = ops.RaggedBatch.from_host([np.zeros(0, np.int16)], [np.zeros(0)], 16000, device=dev)
+    ef, es, _ = an.extract(eb)
+    assert ef.shape == (0, 63) and float(es.abs().sum()) == 0.0
+    # an F0 far above the analysis range is reported, not silently mangled
+    bad = ops.RaggedBatch.from_host([waves[0]], [np.full(len(f0s[0]), 7000.0)], 16000, device=dev)
+    _, st = ops.cheaptrick(bad)
+    with pytest.raises(ValueError, match="F0"):
+        ops.raise_for_status(st, "cheaptrick")
+
+
+def test_22k_and_48k_sizes(dev):
+    """No reference goldens exist at these rates (smoke only in the reference, test_WorldFeatLabelGen.py:611-629): oracle parity."""
+    from idiaptts_b200 import ops, synthetic
+    for fs, n_fft, nap in ((22050, 1024, 2), (48000, 2048, 5)):
+        waves, f0s = synthetic.make_corpus(1, fs, seed=3, mean_dur=0.6)
+        w, f0 = waves[0].numpy(), f0s[0]
+        batch = ops.RaggedBatch.from_host([w], [f0], fs, device=dev)
+        sp, st = ops.cheaptrick(batch, out_dtype=torch.float64)
+        assert sp.shape[1] == n_fft // 2 + 1
+        x = w.astype(np.float64) / 32768.0
+        t = world_np.temporal_positions(len(f0))
+        ref = world_np.cheaptrick(x, f0, t, fs)
+        assert (np.abs(sp.cpu().numpy() - ref) / ref).max() < 1e-6
+        coarse, voiced, st = ops.d4c_coarse(batch, status=st)
+        v_ref, c_ref = world_np.d4c_coarse(x, f0, t, fs)
+        assert coarse.shape[1] == nap and np.array_equal(voiced.cpu().numpy().astype(bool), v_ref)
+        assert np.abs(coarse.cpu().numpy()[v_ref] - c_ref[v_ref]).max() < 1e-7
+        bap = ops.bap_from_coarse(coarse, voiced, fs, n_fft).cpu().numpy()
+        np.testing.assert_allclose(bap, world_np.code_aperiodicity(world_np.d4c(x, f0, t, fs), fs), atol=2e-5)
+        assert ops.raise_for_status(st, "sizes") == 0

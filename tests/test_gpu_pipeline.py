@@ -1,0 +1,175 @@
+"""End-to-end through the reference-facing entry points on the GPU: BASELINE config 1 (single synthetic 3 s 16 kHz utterance:
+extract mcep60 alpha 0.58 + lf0/vuv/bap + WORLD resynthesis) against the oracle; gen_data with files; run_world_synth; and
+size-independent properties at BASELINE-sized batches."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import glue_np, sptk_np, world_np
+
+pytestmark = pytest.mark.gpu
+
+
+def snr_db(ref, out):
+    return 10 * np.log10((ref ** 2).sum() / max(((out - ref) ** 2).sum(), 1e-300))
+
+
+def _write_corpus(tmp_path, n, fs, dur, seed):
+    from idiaptts_b200 import synthetic
+    from idiaptts_b200.Synthesiser import Synthesiser
+    waves, f0s = synthetic.make_corpus(n, fs, seed=seed, mean_dur=dur, std_dur=0.2)
+    ids, cache = [], {}
+    os.makedirs(tmp_path / "wav", exist_ok=True)
+    for u, (w, f) in enumerate(zip(waves, f0s)):
+        id_ = "utt%03d" % u
+        import wave
+        with wave.open(str(tmp_path / "wav" / (id_ + ".wav")), "wb") as wf:
+            wf.setnchannels(1)
+            wf.setsampwidth(2)
+            wf.setframerate(fs)
+            wf.writeframes(w.numpy().tobytes())
+        ids.append(id_)
+        cache[id_] = f
+    return ids, cache, waves, f0s
+
+
+def test_config1_extract_and_resynthesis(tmp_path):
+    """BASELINE.json configs[0]."""
+    from idiaptts_b200.WorldFeatLabelGen import WorldFeatLabelGen
+    from idiaptts_b200.AudioProcessing import AudioProcessing
+    fs = 16000
+    ids, cache, waves, f0s = _write_corpus(tmp_path, 1, fs, 3.0, seed=1)
+    f0 = f0s[0]
+    coded_sp, lf0, vuv, bap = WorldFeatLabelGen.extract_features(str(tmp_path / "wav"), ids[0], num_coded_sps=60, f0=f0, mgc_alpha=0.58)
+    x = waves[0].numpy().astype(np.float64) / 32768.0
+    T = world_np.num_frames(len(x), fs)
+    assert coded_sp.shape == (T, 60) and lf0.shape == (T, 1) and vuv.shape == (T, 1) and bap.shape == (T, 1)
+    assert coded_sp.dtype == lf0.dtype == vuv.dtype == bap.dtype == np.float32
+    amp_ref, lf0_ref, vuv_ref, bap_ref = glue_np.world_extract_features(x, fs, 5, f0)
+    mc_ref = glue_np.extract_mcep(amp_ref, 60, 0.58)
+    assert np.array_equal(vuv, vuv_ref)                                   # vuv: bit-exact
+    assert np.abs(lf0 - lf0_ref).max() < 1e-6
+    assert glue_np.mcd_db(mc_ref, coded_sp) < 1e-3                        # tolerance 0.01 dB
+    assert np.abs(bap - bap_ref).max() < 1e-4
+    amp, _, _, _ = WorldFeatLabelGen.world_extract_features(x, fs, 5, f0=f0)
+    assert amp.dtype == np.float64 and (np.abs(amp - amp_ref) / amp_ref).max() < 1e-6    # envelope tolerance 1e-4
+    # resynthesis from the coded features
+    amp_dec = AudioProcessing.decode_sp(coded_sp, "mcep", fs, alpha=0.58).astype(np.double)
+    y = WorldFeatLabelGen.world_features_to_raw(amp_dec, lf0[:, 0].copy(), vuv[:, 0].copy(), bap, fs)
+    y_ref = glue_np.world_features_to_raw(glue_np.mcep_to_amp_sp(coded_sp, fs, 0.58).astype(np.double), lf0[:, 0].copy(), vuv[:, 0].copy(), bap, fs)
+    assert len(y) == len(y_ref) and snr_db(y_ref, y) > 60
+
+
+@pytest.mark.parametrize("add_deltas", [False, True])
+def test_gen_data_files_and_statistics(tmp_path, add_deltas):
+    from idiaptts_b200.MeanStdDevExtractor import MeanStdDevExtractor
+    from idiaptts_b200.WorldFeatLabelGen import WorldFeatLabelGen
+    fs = 22050
+    ids, cache, waves, f0s = _write_corpus(tmp_path, 4, fs, 0.7, seed=6)
+    gen = WorldFeatLabelGen(str(tmp_path / "out"), add_deltas=add_deltas, num_coded_sps=60, num_bap=2, f0_cache=cache)
+    label_dict, means, stds = gen.gen_data(str(tmp_path / "wav"), str(tmp_path / "out"), file_id_list="train.txt", id_list=ids,
+                                           return_dict=True)
+    width = 3 * (60 + 1 + 2) + 1 if add_deltas else 64
+    for u, id_ in enumerate(ids):
+        T = world_np.num_frames(len(waves[u]), fs)
+        assert label_dict[id_].shape == (T, width)
+        for d, key in (("mcep60", "mcep"), ("lf0", "lf0"), ("vuv", "vuv"), ("bap", "bap")):
+            arch = np.load(str(tmp_path / "out" / d / (id_ + ".npz")))
+            assert key in arch.files and arch[key].shape[0] == T
+            if add_deltas and key != "vuv":
+                assert key + "_deltas" in arch.files and key + "_double_deltas" in arch.files
+                assert np.array_equal(arch[key + "_deltas"], glue_np.compute_deltas(arch[key]))
+                assert np.array_equal(arch[key + "_double_deltas"], glue_np.compute_deltas(arch[key + "_deltas"]))
+    # one utterance against the oracle
+    x = waves[1].numpy().astype(np.float64) / 32768.0
+    amp_ref, lf0_ref, vuv_ref, bap_ref = glue_np.world_extract_features(x, fs, 5, f0s[1])
+    mc_ref = glue_np.extract_mcep(amp_ref, 60, sptk_np.mcepalpha(fs))
+    mc = np.load(str(tmp_path / "out" / "mcep60" / (ids[1] + ".npz")))["mcep"]
+    assert glue_np.mcd_db(mc_ref, mc) < 1e-3
+    assert np.array_equal(np.load(str(tmp_path / "out" / "vuv" / (ids[1] + ".npz")))["vuv"], vuv_ref)
+    # statistics == reference extractor fed with the saved features
+    if not add_deltas:
+        assert means.shape == (64,) and stds.shape == (64,) and means[61] == 0.0 and stds[61] == 1.0
+        ext = MeanStdDevExtractor()
+        for id_ in ids:
+            ext.add_sample(np.load(str(tmp_path / "out" / "mcep60" / (id_ + ".npz")))["mcep"].astype(np.float64))
+        m, s = ext.get_params()
+        np.testing.assert_allclose(means[:60], m, rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(stds[:60], s, rtol=1e-5, atol=1e-7)
+        saved_m, saved_s = MeanStdDevExtractor.load(str(tmp_path / "out" / "mcep60" / "train-mean-std_dev.npz"))
+        np.testing.assert_allclose(saved_m, m, rtol=1e-5, atol=1e-6)
+        st = np.load(str(tmp_path / "out" / "lf0" / "train-stats.npz"))
+        assert int(st["sum_length"]) == sum(world_np.num_frames(len(w), fs) for w in waves)
+    else:
+        assert means[0].shape == (1, 180) and stds[0].shape == (180, 180)
+        full = np.concatenate([label_dict[i][:, :180] for i in ids]).astype(np.float64)
+        np.testing.assert_allclose(means[0][0], full.mean(0), rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(stds[0], np.cov(full.T, bias=True), rtol=1e-5, atol=1e-6)
+        assert os.path.exists(str(tmp_path / "out" / "mcep60" / "train-deltas-mean-covariance.npz"))
+    with pytest.raises(NotImplementedError, match="F0 estimation"):
+        WorldFeatLabelGen(str(tmp_path / "o2"), num_coded_sps=60, num_bap=2).gen_data(str(tmp_path / "wav"), None, id_list=ids)
+
+
+def test_run_world_synth_writes_reference_named_files(tmp_path):
+    from types import SimpleNamespace
+    from idiaptts_b200 import ops, pipeline, synthetic
+    from idiaptts_b200.AudioProcessing import AudioProcessing
+    from idiaptts_b200.Synthesiser import Synthesiser
+    dev = torch.device("cuda", 0)
+    fs = 16000
+    waves, f0s = synthetic.make_corpus(2, fs, seed=8, mean_dur=0.6)
+    an = pipeline.WorldAnalyzer(fs, 60, device=dev)
+    feats, _, _ = an.extract(ops.RaggedBatch.from_host([w.numpy() for w in waves], f0s, fs, device=dev))
+    off = np.concatenate(([0], np.cumsum([len(f) for f in f0s])))
+    fh = feats.cpu().numpy()
+    hp = SimpleNamespace(synth_fs=fs, num_coded_sps=60, num_bap=1, sp_type="mcep", do_post_filtering=False, synth_file_suffix="_t",
+                         synth_ext="wav", synth_dir=str(tmp_path / "synth"), preemphasis=0.0)
+    out = {"spk/a": fh[off[0]:off[1]], "b": fh[off[1]:off[2]]}
+    Synthesiser.run_world_synth(out, hp)
+    for name, rows in (("a", out["spk/a"]), ("b", out["b"])):
+        data, rfs = AudioProcessing.read_wav(str(tmp_path / "synth" / (name + "_t_60mcep_WORLD.wav")))
+        assert rfs == fs
+        assert abs(len(data) / fs / 0.005 - len(rows)) < 10  # test_AcousticModelTrainer.py:162-168
+
+
+def test_baseline_sized_batch_properties():
+    """BASELINE config 2 shape (6.5 s, 22.05 kHz utterances), a slice of 48 of them: properties that do not need the oracle."""
+    from idiaptts_b200 import ops, pipeline, synthetic
+    dev = torch.device("cuda", 0)
+    fs = 22050
+    waves, f0s = synthetic.make_corpus(48, fs, seed=2, mean_dur=6.5, device=dev)
+    x = torch.cat(waves)
+    lens = np.array([w.numel() for w in waves])
+    fl = np.array([len(f) for f in f0s])
+    assert np.all(fl == 1301) and np.all(lens == 143325)
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    batch = ops.RaggedBatch(x, up(np.concatenate(([0], np.cumsum(lens))).astype(np.int64)), up(np.concatenate(f0s)),
+                            up(np.concatenate([np.arange(n) * 5.0 / 1000.0 for n in fl])),
+                            up(np.concatenate(([0], np.cumsum(fl))).astype(np.int64)), up(np.repeat(np.arange(48, dtype=np.int32), fl)), fs)
+    an = pipeline.WorldAnalyzer(fs, 60, device=dev, chunk_frames=20000)
+    feats, sums, st = an.extract(batch)
+    assert ops.raise_for_status(st, "big") == 0
+    f = feats.cpu().numpy()
+    assert f.shape == (48 * 1301, 64) and np.isfinite(f).all()
+    # idempotence / determinism: a second pass gives identical bits
+    feats2, sums2, _ = an.extract(batch)
+    assert torch.equal(feats, feats2)
+    # statistics are the sums of what was written
+    np.testing.assert_allclose(sums.cpu().numpy()[:64], f.astype(np.float64).sum(0), rtol=1e-9, atol=1e-5)
+    # vuv column equals the F0 track's voicing, lf0 is continuous and positive wherever any voiced frame exists
+    assert np.array_equal(f[:, 61] > 0, np.concatenate(f0s) > 0)
+    assert np.all(f[:, 60] > 3.4)
+    # unvoiced frames carry the WORLD constant in every band; voiced frames have bap <= 0
+    unv = f[:, 61] == 0
+    assert np.all(f[unv][:, 62:] == np.float32(-8.685697e-12)) and np.all(f[:, 62:] <= 0)
+    # analysis -> synthesis round trip keeps the utterance energy within a few dB
+    syn = pipeline.WorldSynthesizer(fs, 60, device=dev)
+    y, out_off, st = syn.synthesize(feats[:4 * 1301].contiguous(), batch.frame_off[:5].contiguous())
+    assert ops.raise_for_status(st, "synth") == 0
+    y = y.cpu().numpy().astype(np.float64)
+    for u in range(4):
+        orig = waves[u].cpu().numpy().astype(np.float64) / 32768.0
+        got = y[out_off[u]:out_off[u + 1]]
+        assert abs(10 * np.log10((got ** 2).mean() / (orig ** 2).mean())) < 3.0

@@ -1,0 +1,49 @@
+"""Properties of the oracle's synthesis half (PARITY UNPINNED by reference goldens): the checks the
+reference itself makes (length, loose reconstruction error) plus internal consistency."""
+import numpy as np
+
+from conftest import golden_utterance
+from oracle import glue_np, world_np
+
+
+def test_reference_reconstruction_threshold(golden):
+    """test_WorldFeatLabelGen.py:704-763: after peak normalisation sum((orig - WORLD resynthesis)^2) < 10000."""
+    x, c, f0, fs = golden_utterance(golden, "LJ001-0008")
+    T = len(f0)
+    t = world_np.temporal_positions(T)
+    sp = world_np.cheaptrick(x, f0, t, fs)
+    ap = world_np.d4c(x, f0, t, fs)
+    y = world_np.synthesize(f0, sp, ap, fs)
+    assert len(y) == int(T * 5.0 * fs / 1000)
+    assert abs(len(y) / fs / 0.005 - T) < 10  # test_AcousticModelTrainer.py:162-168
+    n = min(len(x), len(y))
+    a, b = x[:n] / np.abs(x[:n]).max(), y[:n] / np.abs(y[:n]).max()
+    assert ((a - b) ** 2).sum() < 10000
+    # energy is preserved within a few dB in voiced speech
+    assert abs(10 * np.log10((y ** 2).sum() / (x[:n] ** 2).sum())) < 3.0
+
+
+def test_pulse_structure(golden):
+    x, c, f0, fs = golden_utterance(golden, "LJ001-0008")
+    idx, shift, vuv = world_np.synthesis_time_base(f0, fs, 0.005, int(len(f0) * 5.0 * fs / 1000), 1024)
+    assert np.all(np.diff(idx) > 0) and np.all((shift >= 0) & (shift <= 1.0 / fs + 1e-12))
+    # unvoiced stretches tick at 500 Hz: 32 samples at 16 kHz
+    d = np.diff(idx)
+    assert (d == 32).mean() > 0.2
+
+
+def test_codec_roundtrip_and_unvoiced_rule():
+    fs, n = 22050, 1024
+    bap = np.array([[-5.0, -2.0], [-0.3, -0.4], [-30.0, -10.0]])
+    ap = world_np.decode_aperiodicity(bap, fs, n)
+    assert np.all(ap[1] == 1.0 - 1e-12)  # mean(bap) > -0.5 -> unvoiced row
+    back = world_np.code_aperiodicity(ap, fs)
+    np.testing.assert_allclose(back[[0, 2]], bap[[0, 2]], atol=0.1)  # interpolation across the 3 kHz knot is not exact at 22.05 kHz
+    ap16 = world_np.decode_aperiodicity(bap[:, :1], 16000, n)
+    np.testing.assert_allclose(world_np.code_aperiodicity(ap16, 16000)[[0, 2]], bap[[0, 2], :1], atol=1e-9)
+
+
+def test_depreemphasis_inverts_preemphasis():
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(1000)
+    np.testing.assert_allclose(glue_np.depreemphasis(glue_np.preemphasis(x, 0.97), 0.97), x, atol=1e-9)
