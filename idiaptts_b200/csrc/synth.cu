@@ -328,8 +328,12 @@ __device__ __forceinline__ void inverse_real_shifted(const double2* X, double2* 
                                                      Emit emit) {
   constexpr int M = N / 2;
   for (int k = tid; k < M; k += NT) {
-    const double2 a = X[k];
-    const double2 bq = X[M - k];
+    double2 a = X[k];
+    double2 bq = X[M - k];
+    if (k == 0) {  // a c2r transform ignores the imaginary parts of the DC and Nyquist bins (WORLD / FFTW semantics);
+      a.y = 0.0;   // the fractional time shift makes the Nyquist bin complex
+      bq.y = 0.0;
+    }
     const double2 b = make_double2(bq.x, -bq.y);                 // conj(X[M - k]) = X[k + M]
     const double2 e = make_double2(a.x + b.x, a.y + b.y);
     const double2 d = make_double2(a.x - b.x, a.y - b.y);

@@ -380,7 +380,8 @@ def randn_table(n, device):
         return tab
 
 
-def synthesize(f0, sp, ap, frame_off, fs, frame_period=5.0, deemphasis=0.0, out_dtype=torch.float64, status=None):
+def synthesize(f0, sp, ap, frame_off, fs, frame_period=5.0, deemphasis=0.0, out_dtype=torch.float64, status=None,
+               debug=None):
     """pyworld.synthesize on a ragged batch.  f0 [F] f64; sp, ap [F, K] (f64 or f32, same dtype); frame_off int64 [U+1]
     (device) -> (y packed [sum y_len], out_off int64 [U+1] (host numpy))."""
     lib = _lib.load()
@@ -426,6 +427,9 @@ def synthesize(f0, sp, ap, frame_off, fs, frame_period=5.0, deemphasis=0.0, out_
                                        d_pulse_off.data_ptr(), num_pulses.data_ptr(), U, pulse_index.data_ptr(),
                                        pulse_shift.data_ptr(), pulse_vuv.data_ptr(), tab.data_ptr(), tab.numel(), int(fs),
                                        float(frame_period), fft_size, max_p, response.data_ptr(), st), "b2w_synth_render")
+        if debug is not None:  # diagnostics for the parity tests: the pulse table of every utterance
+            debug.update(pulse_off=pulse_off, num_pulses=npul, pulse_index=pulse_index, pulse_shift=pulse_shift,
+                         pulse_vuv=pulse_vuv, response=response)
         check(lib.b2w_synth_overlap_add(response.data_ptr(), d_out_off.data_ptr(), d_pulse_off.data_ptr(),
                                         num_pulses.data_ptr(), U, pulse_index.data_ptr(), fft_size, int(ylen.max()),
                                         float(deemphasis), y.data_ptr(), _DT[y.dtype], st), "b2w_synth_overlap_add")

@@ -63,6 +63,8 @@ class WorldAnalyzer:
             sums = torch.zeros(2 * self.dim, dtype=torch.float64, device=self.device)
         if status is None:
             status = ops.new_status(self.device)
+        if F == 0:  # nothing to launch
+            return feats, sums, status
         flat = feats.view(-1)
         # lf0 / vuv straight into their columns
         timed("lf0_vuv", F, lambda: ops.lf0_vuv(batch.f0, batch.frame_off, self.f0_silence_threshold, self.lf0_zero,

@@ -373,7 +373,7 @@ def synthesis_time_base(f0, fs, frame_period_s, y_length, fft_size):
     return idx, shift, ivuv
 
 
-def synthesize(f0, sp, ap, fs, frame_period=default_frame_period):
+def synthesize(f0, sp, ap, fs, frame_period=default_frame_period, responses=None):
     """pyworld.synthesize(f0, spectrogram, aperiodicity, fs, frame_period=5.0) -> y [int(T*frame_period*fs/1000)]."""
     f0 = np.ascontiguousarray(f0, np.float64)
     sp = np.ascontiguousarray(sp, np.float64)
@@ -438,6 +438,8 @@ def synthesize(f0, sp, ap, fs, frame_period=default_frame_period):
         wave = np.fft.irfft(X * Z, fft_size) * fft_size
         aperiodic = np.concatenate((wave[h:], wave[:h]))
         response = (periodic * math.sqrt(float(noise_size)) + aperiodic) / fft_size
+        if responses is not None:  # diagnostics for the parity tests
+            responses.append((periodic.copy(), aperiodic.copy(), response.copy()))
         offset = n_p - h + 1
         lo = max(0, -offset)
         hi = min(fft_size, y_length - offset)

@@ -32,7 +32,7 @@ def test_lf0_vuv_bit_exact():
     for u, tr in enumerate(tracks):
         ref_l, ref_v = glue_np.interpolate_lin(glue_np.lf0_from_f0(tr))
         assert np.array_equal(vuv[o[u]:o[u + 1]], ref_v.astype(np.float32)), tr  # vuv: bit-exact
-        np.testing.assert_allclose(lf0[o[u]:o[u + 1]], ref_l, rtol=0, atol=5e-7, err_msg=str(tr))  # 1 ulp of a float32 log
+        np.testing.assert_allclose(lf0[o[u]:o[u + 1]], ref_l, rtol=0, atol=1.5e-6, err_msg=str(tr))  # a few ulp of a float32 log (numpy's logf is not correctly rounded)
     # strided output (straight into packed feature rows)
     feats = torch.zeros((f0.numel(), 5), dtype=torch.float32, device=dev)
     flat = feats.view(-1)
