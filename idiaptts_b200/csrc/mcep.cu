@@ -59,135 +59,166 @@ __device__ __forceinline__ float load_per(const McepParams& p, int64_t frame, in
   return (float)(p.in_is_power ? v + (double)p.eps : v * v + (double)p.eps);
 }
 
-// out[f][n] = sum_j tile[f][j] * mt[j][n], n < nout: thread (n = tid % NPAD, group = tid / NPAD) owns FG = F*NPAD/256
-// frames of one output column; the tile row is read as float4 broadcasts, the matrix column coalesced from L2.
+// out[f][n] = sum_j tile[f][j] * mt[j][n], n < nout.  Thread (c = tid % (NPAD/2), group = tid / (NPAD/2)) owns the two
+// output columns c and c + NPAD/2 for FG = 2 F NPAD / 512... frames of its group: every float4 broadcast of a tile row
+// feeds 8 FMAs, the matrix columns are read coalesced from L2.
 template <int F, int NPAD>
 __device__ __forceinline__ void gemm_tile_by_matrix(const float* __restrict__ tile, int KP, int K, const float* __restrict__ mt,
                                                     int ldm, int nout, float* __restrict__ out, int ldo) {
-  constexpr int G = kMcThreads / NPAD;
-  constexpr int FG = F / G;
-  static_assert(FG >= 1, "tile too small for this mapping");
-  const int n = threadIdx.x % NPAD;
-  const int f0 = (threadIdx.x / NPAD) * FG;
-  if (n >= nout) return;
-  float acc[FG];
+  constexpr int HC = NPAD / 2;              // threads per frame group
+  constexpr int G = kMcThreads / HC;        // frame groups
+  constexpr int FG = F / G;                 // frames per thread
+  static_assert(FG >= 1 && FG * G == F, "tile height does not fit this mapping");
+  const int c0 = threadIdx.x % HC;
+  const int c1 = c0 + HC;
+  const int f0 = (threadIdx.x / HC) * FG;
+  const bool v0 = c0 < nout, v1 = c1 < nout;
+  if (!v0) return;
+  const int c1s = v1 ? c1 : c0;  // keep loads in bounds
+  float acc0[FG], acc1[FG];
 #pragma unroll
-  for (int f = 0; f < FG; ++f) acc[f] = 0.f;
+  for (int f = 0; f < FG; ++f) { acc0[f] = 0.f; acc1[f] = 0.f; }
   const int K4 = K & ~3;
   for (int j = 0; j < K4; j += 4) {
-    const float w0 = __ldg(mt + (int64_t)(j + 0) * ldm + n);
-    const float w1 = __ldg(mt + (int64_t)(j + 1) * ldm + n);
-    const float w2 = __ldg(mt + (int64_t)(j + 2) * ldm + n);
-    const float w3 = __ldg(mt + (int64_t)(j + 3) * ldm + n);
+    const float* r0 = mt + (int64_t)j * ldm;
+    const float a0 = __ldg(r0 + c0), a1 = __ldg(r0 + ldm + c0), a2 = __ldg(r0 + 2 * ldm + c0), a3 = __ldg(r0 + 3 * ldm + c0);
+    const float b0 = __ldg(r0 + c1s), b1 = __ldg(r0 + ldm + c1s), b2 = __ldg(r0 + 2 * ldm + c1s), b3 = __ldg(r0 + 3 * ldm + c1s);
 #pragma unroll
     for (int f = 0; f < FG; ++f) {
       const float4 p4 = *reinterpret_cast<const float4*>(tile + (f0 + f) * KP + j);
-      acc[f] = fmaf(p4.x, w0, acc[f]);
-      acc[f] = fmaf(p4.y, w1, acc[f]);
-      acc[f] = fmaf(p4.z, w2, acc[f]);
-      acc[f] = fmaf(p4.w, w3, acc[f]);
+      acc0[f] = fmaf(p4.x, a0, acc0[f]); acc1[f] = fmaf(p4.x, b0, acc1[f]);
+      acc0[f] = fmaf(p4.y, a1, acc0[f]); acc1[f] = fmaf(p4.y, b1, acc1[f]);
+      acc0[f] = fmaf(p4.z, a2, acc0[f]); acc1[f] = fmaf(p4.z, b2, acc1[f]);
+      acc0[f] = fmaf(p4.w, a3, acc0[f]); acc1[f] = fmaf(p4.w, b3, acc1[f]);
     }
   }
   for (int j = K4; j < K; ++j) {
-    const float w = __ldg(mt + (int64_t)j * ldm + n);
+    const float a = __ldg(mt + (int64_t)j * ldm + c0), b = __ldg(mt + (int64_t)j * ldm + c1s);
 #pragma unroll
-    for (int f = 0; f < FG; ++f) acc[f] = fmaf(tile[(f0 + f) * KP + j], w, acc[f]);
+    for (int f = 0; f < FG; ++f) {
+      const float t = tile[(f0 + f) * KP + j];
+      acc0[f] = fmaf(t, a, acc0[f]);
+      acc1[f] = fmaf(t, b, acc1[f]);
+    }
   }
 #pragma unroll
-  for (int f = 0; f < FG; ++f) out[(f0 + f) * ldo + n] = acc[f];
+  for (int f = 0; f < FG; ++f) {
+    out[(f0 + f) * ldo + c0] = acc0[f];
+    if (v1) out[(f0 + f) * ldo + c1] = acc1[f];
+  }
 }
 
 template <int F>
 __device__ __forceinline__ void gemm_tile_dispatch(const float* tile, int KP, int K, const float* mt, int ldm, int nout,
                                                    float* out, int ldo) {
-  if (nout <= 32) gemm_tile_by_matrix<F, 32>(tile, KP, K, mt, ldm, nout, out, ldo);
-  else if (nout <= 64) gemm_tile_by_matrix<F, 64>(tile, KP, K, mt, ldm, nout, out, ldo);
+  if (nout <= 64) gemm_tile_by_matrix<F, 64>(tile, KP, K, mt, ldm, nout, out, ldo);
   else if (nout <= 128) gemm_tile_by_matrix<F, 128>(tile, KP, K, mt, ldm, nout, out, ldo);
   else gemm_tile_by_matrix<F, 256>(tile, KP, K, mt, ldm, nout, out, ldo);
 }
 
-// C[f][j] = sum_k mc[f][k] * cmat[k][j] for one column j (all F frames in registers)
-template <int F>
-__device__ __forceinline__ void warp_column(const float* __restrict__ mc, int MP, const float* __restrict__ cmat, int K,
-                                            int j, float* acc) {
+// C[f][j] = sum_k mc[f][k] * cmat[k][j] for the two columns j0, j1 and FH frames starting at fbase (registers)
+template <int FH>
+__device__ __forceinline__ void two_columns(const float* __restrict__ mc, int MP, const float* __restrict__ cmat, int K, int j0,
+                                            int j1, int fbase, float* acc0, float* acc1) {
 #pragma unroll
-  for (int f = 0; f < F; ++f) acc[f] = 0.f;
+  for (int f = 0; f < FH; ++f) { acc0[f] = 0.f; acc1[f] = 0.f; }
   for (int k = 0; k < MP; k += 4) {
     // cmat is stored with pad4(m+1) rows (zero rows past m), mc rows are zero padded the same way
-    const float w0 = __ldg(cmat + (int64_t)(k + 0) * K + j);
-    const float w1 = __ldg(cmat + (int64_t)(k + 1) * K + j);
-    const float w2 = __ldg(cmat + (int64_t)(k + 2) * K + j);
-    const float w3 = __ldg(cmat + (int64_t)(k + 3) * K + j);
+    const float* r0 = cmat + (int64_t)k * K;
+    const float a0 = __ldg(r0 + j0), a1 = __ldg(r0 + K + j0), a2 = __ldg(r0 + 2 * K + j0), a3 = __ldg(r0 + 3 * K + j0);
+    const float b0 = __ldg(r0 + j1), b1 = __ldg(r0 + K + j1), b2 = __ldg(r0 + 2 * K + j1), b3 = __ldg(r0 + 3 * K + j1);
 #pragma unroll
-    for (int f = 0; f < F; ++f) {
-      const float4 m4 = *reinterpret_cast<const float4*>(mc + f * MP + k);
-      acc[f] = fmaf(m4.x, w0, acc[f]);
-      acc[f] = fmaf(m4.y, w1, acc[f]);
-      acc[f] = fmaf(m4.z, w2, acc[f]);
-      acc[f] = fmaf(m4.w, w3, acc[f]);
+    for (int f = 0; f < FH; ++f) {
+      const float4 m4 = *reinterpret_cast<const float4*>(mc + (fbase + f) * MP + k);
+      acc0[f] = fmaf(m4.x, a0, acc0[f]); acc1[f] = fmaf(m4.x, b0, acc1[f]);
+      acc0[f] = fmaf(m4.y, a1, acc0[f]); acc1[f] = fmaf(m4.y, b1, acc1[f]);
+      acc0[f] = fmaf(m4.z, a2, acc0[f]); acc1[f] = fmaf(m4.z, b2, acc1[f]);
+      acc0[f] = fmaf(m4.w, a3, acc0[f]); acc1[f] = fmaf(m4.w, b3, acc1[f]);
     }
   }
 }
 
-// ---- blocked LDL^T solve of the (m+1)x(m+1) system M d = b with M[i][k] = rt[|i-k|] + rt[i+k], one warp ---------------
-__device__ __forceinline__ int blk_index(int I, int Kb) { return (I * (I + 1) / 2 + Kb) * 16; }
+// ---- blocked LDL^T solve of the (m+1)x(m+1) system M d = b with M[i][k] = rt[|i-k|] + rt[i+k], one warp per frame ------
+// 4x4 blocks of the lower triangle, block (I, Kb <= I) at (I (I+1) / 2 + Kb) * kBlk floats; the 20-float stride keeps the
+// float4 accesses of lanes working on consecutive blocks on distinct banks.  The right-hand side rides along as an
+// extra column (forward substitution fused into the panel step); `tri` maps a flat pair index to (a, q), q <= a.
+constexpr int kBlk = 20;
+__device__ __forceinline__ int blk_index(int I, int Kb) { return (I * (I + 1) / 2 + Kb) * kBlk; }
 
 // returns false (warp-uniform) when a pivot is not positive
 __device__ __forceinline__ bool warp_ldl_solve(const float* __restrict__ rt, const float* __restrict__ al, int n, int NBk,
-                                              float* __restrict__ ws, float* __restrict__ x_out) {
+                                              const uint16_t* __restrict__ tri, float* __restrict__ ws,
+                                              float* __restrict__ x_out) {
   const int lane = threadIdx.x & 31;
   const int np = 4 * NBk;
-  float* A = ws;                                   // NBk(NBk+1)/2 blocks of 16
-  float* Wp = A + (NBk * (NBk + 1) / 2) * 16;      // NBk blocks of 16 (panel W = L D)
-  float* dv = Wp + NBk * 16;                       // np pivots
-  float* bv = dv + np;                             // np right-hand side / solution
-  // build
-  const int nblk = NBk * (NBk + 1) / 2;
-  for (int e = lane; e < nblk * 16; e += 32) {
-    const int bidx = e >> 4, r = (e >> 2) & 3, c = e & 3;
-    int I = 0, q = bidx;
-    while (q > I) { q -= I + 1; ++I; }
-    const int i = 4 * I + r, k = 4 * q + c;
-    float v;
-    if (i < n && k < n) v = rt[abs(i - k)] + rt[i + k];
-    else v = (i == k) ? 1.f : 0.f;
-    A[e] = v;
+  float* A = ws;                                     // NBk (NBk+1) / 2 blocks
+  float* Wp = A + (NBk * (NBk + 1) / 2) * kBlk;      // NBk blocks: panel W = L D
+  float* dv = Wp + NBk * kBlk;                       // np reciprocal pivots
+  float* bv = dv + np;                               // np right-hand side -> y -> solution
+  // build: one float4 (row r of block (I, Kb)) per lane and step
+  for (int I = 0; I < NBk; ++I) {
+    for (int e = lane; e < 4 * (I + 1); e += 32) {
+      const int Kb = e >> 2, r = e & 3;
+      const int i = 4 * I + r, k = 4 * Kb;
+      float4 v;
+      if (i < n && k + 3 < n) {
+        v.x = rt[abs(i - k)] + rt[i + k];
+        v.y = rt[abs(i - k - 1)] + rt[i + k + 1];
+        v.z = rt[abs(i - k - 2)] + rt[i + k + 2];
+        v.w = rt[abs(i - k - 3)] + rt[i + k + 3];
+      } else {
+        float t[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) t[c] = (i < n && k + c < n) ? rt[abs(i - k - c)] + rt[i + k + c] : (i == k + c ? 1.f : 0.f);
+        v = make_float4(t[0], t[1], t[2], t[3]);
+      }
+      *reinterpret_cast<float4*>(A + blk_index(I, Kb) + 4 * r) = v;
+    }
   }
   for (int i = lane; i < np; i += 32) bv[i] = (i < n) ? rt[i] - al[i] : 0.f;
   __syncwarp();
   bool ok = true;
   for (int J = 0; J < NBk; ++J) {
-    // (a) diagonal block, redundantly in every lane
+    // (a) diagonal block, redundantly in every lane (broadcast loads)
     const float* a = A + blk_index(J, J);
-    const float a00 = a[0], a10 = a[4], a11 = a[5], a20 = a[8], a21 = a[9], a22 = a[10], a30 = a[12], a31 = a[13],
-                a32 = a[14], a33 = a[15];
-    const float d0 = a00;
-    const float l10 = a10 / d0, l20 = a20 / d0, l30 = a30 / d0;
-    const float d1 = a11 - l10 * l10 * d0;
-    const float l21 = (a21 - l20 * l10 * d0) / d1, l31 = (a31 - l30 * l10 * d0) / d1;
-    const float d2 = a22 - l20 * l20 * d0 - l21 * l21 * d1;
-    const float l32 = (a32 - l30 * l20 * d0 - l31 * l21 * d1) / d2;
-    const float d3 = a33 - l30 * l30 * d0 - l31 * l31 * d1 - l32 * l32 * d2;
+    const float4 q0 = *reinterpret_cast<const float4*>(a), q1 = *reinterpret_cast<const float4*>(a + 4),
+                 q2 = *reinterpret_cast<const float4*>(a + 8), q3 = *reinterpret_cast<const float4*>(a + 12);
+    const float d0 = q0.x, r0 = 1.f / d0;
+    const float l10 = q1.x * r0, l20 = q2.x * r0, l30 = q3.x * r0;
+    const float d1 = q1.y - l10 * q1.x, r1 = 1.f / d1;
+    const float l21 = (q2.y - l20 * q1.x) * r1, l31 = (q3.y - l30 * q1.x) * r1;
+    const float d2 = q2.z - l20 * q2.x - l21 * (q2.y - l20 * q1.x), r2 = 1.f / d2;
+    const float l32 = (q3.z - l30 * q2.x - l31 * (q2.y - l20 * q1.x)) * r2;
+    const float d3 = q3.w - l30 * q3.x - l31 * (q3.y - l30 * q1.x) - l32 * (q3.z - l30 * q2.x - l31 * (q2.y - l20 * q1.x));
+    const float r3 = 1.f / d3;
     if (!(d0 > 0.f && d1 > 0.f && d2 > 0.f && d3 > 0.f)) ok = false;
+    // forward substitution inside the diagonal block: y_J = L_JJ^-1 b_J (b_J already holds b - sum_{K<J} L_JK y_K)
+    const float4 bj = *reinterpret_cast<const float4*>(bv + 4 * J);
+    const float y0 = bj.x;
+    const float y1 = bj.y - l10 * y0;
+    const float y2 = bj.z - l20 * y0 - l21 * y1;
+    const float y3 = bj.w - l30 * y0 - l31 * y1 - l32 * y2;
     __syncwarp();
     if (lane == 0) {
       float* w = A + blk_index(J, J);
       w[4] = l10; w[8] = l20; w[9] = l21; w[12] = l30; w[13] = l31; w[14] = l32;
-      dv[4 * J + 0] = d0; dv[4 * J + 1] = d1; dv[4 * J + 2] = d2; dv[4 * J + 3] = d3;
+      *reinterpret_cast<float4*>(dv + 4 * J) = make_float4(r0, r1, r2, r3);
+      *reinterpret_cast<float4*>(bv + 4 * J) = make_float4(y0, y1, y2, y3);
     }
-    // (b) panel: L_IJ = A_IJ L_JJ^-T D^-1, W_IJ = L_IJ D
-    for (int I = J + 1 + lane; I < NBk; I += 32) {
-      float* X = A + blk_index(I, J);
-      float* W = Wp + I * 16;
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const float4 x = *reinterpret_cast<const float4*>(X + 4 * r);
+    // (b) panel, one block row per lane: W = A_IJ L_JJ^-T, L_IJ = W D^-1, b_I -= L_IJ y_J
+    {
+      const int r = lane & 3;
+      for (int I = J + 1 + (lane >> 2); I < NBk; I += 8) {
+        float* X = A + blk_index(I, J) + 4 * r;
+        const float4 x = *reinterpret_cast<const float4*>(X);
         const float w0 = x.x;
         const float w1 = x.y - l10 * w0;
         const float w2 = x.z - l20 * w0 - l21 * w1;
         const float w3 = x.w - l30 * w0 - l31 * w1 - l32 * w2;
-        *reinterpret_cast<float4*>(W + 4 * r) = make_float4(w0, w1, w2, w3);
-        *reinterpret_cast<float4*>(X + 4 * r) = make_float4(w0 / d0, w1 / d1, w2 / d2, w3 / d3);
+        *reinterpret_cast<float4*>(Wp + I * kBlk + 4 * r) = make_float4(w0, w1, w2, w3);
+        const float4 l = make_float4(w0 * r0, w1 * r1, w2 * r2, w3 * r3);
+        *reinterpret_cast<float4*>(X) = l;
+        bv[4 * I + r] -= l.x * y0 + l.y * y1 + l.z * y2 + l.w * y3;
       }
     }
     __syncwarp();
@@ -195,10 +226,9 @@ __device__ __forceinline__ bool warp_ldl_solve(const float* __restrict__ rt, con
     const int rr = NBk - 1 - J;
     const int cnt = rr * (rr + 1) / 2;
     for (int p = lane; p < cnt; p += 32) {
-      int a_ = 0, q = p;
-      while (q > a_) { q -= a_ + 1; ++a_; }
-      const int I = J + 1 + a_, Kb = J + 1 + q;
-      const float* W = Wp + I * 16;
+      const int code = tri[p];
+      const int I = J + 1 + (code >> 8), Kb = J + 1 + (code & 255);
+      const float* W = Wp + I * kBlk;
       const float* Lk = A + blk_index(Kb, J);
       float* T = A + blk_index(I, Kb);
       float4 lk[4];
@@ -218,39 +248,25 @@ __device__ __forceinline__ bool warp_ldl_solve(const float* __restrict__ rt, con
     __syncwarp();
   }
   ok = __all_sync(0xffffffffu, ok);
-  // forward substitution L y = b
-  for (int J = 0; J < NBk; ++J) {
-    const float* L = A + blk_index(J, J);
-    float y0 = bv[4 * J], y1 = bv[4 * J + 1], y2 = bv[4 * J + 2], y3 = bv[4 * J + 3];
-    y1 -= L[4] * y0;
-    y2 -= L[8] * y0 + L[9] * y1;
-    y3 -= L[12] * y0 + L[13] * y1 + L[14] * y2;
-    __syncwarp();
-    if (lane == 0) { bv[4 * J] = y0; bv[4 * J + 1] = y1; bv[4 * J + 2] = y2; bv[4 * J + 3] = y3; }
-    for (int I = J + 1 + lane; I < NBk; I += 32) {
-      const float* Li = A + blk_index(I, J);
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-        bv[4 * I + r] -= Li[4 * r] * y0 + Li[4 * r + 1] * y1 + Li[4 * r + 2] * y2 + Li[4 * r + 3] * y3;
-    }
-    __syncwarp();
-  }
-  for (int i = lane; i < np; i += 32) bv[i] /= dv[i];
+  // z = D^-1 y
+  for (int i = lane; i < np; i += 32) bv[i] *= dv[i];
   __syncwarp();
   // backward substitution L^T x = z
   for (int J = NBk - 1; J >= 0; --J) {
     const float* L = A + blk_index(J, J);
-    float x0 = bv[4 * J], x1 = bv[4 * J + 1], x2 = bv[4 * J + 2], x3 = bv[4 * J + 3];
-    x2 -= L[14] * x3;
-    x1 -= L[9] * x2 + L[13] * x3;
-    x0 -= L[4] * x1 + L[8] * x2 + L[12] * x3;
+    const float4 zj = *reinterpret_cast<const float4*>(bv + 4 * J);
+    const float x3 = zj.w;
+    const float x2 = zj.z - L[14] * x3;
+    const float x1 = zj.y - L[9] * x2 - L[13] * x3;
+    const float x0 = zj.x - L[4] * x1 - L[8] * x2 - L[12] * x3;
     __syncwarp();
-    if (lane == 0) { bv[4 * J] = x0; bv[4 * J + 1] = x1; bv[4 * J + 2] = x2; bv[4 * J + 3] = x3; }
-    for (int Kb = lane; Kb < J; Kb += 32) {
-      const float* Lj = A + blk_index(J, Kb);
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
+    if (lane == 0) *reinterpret_cast<float4*>(bv + 4 * J) = make_float4(x0, x1, x2, x3);
+    {
+      const int c = lane & 3;
+      for (int Kb = lane >> 2; Kb < J; Kb += 8) {
+        const float* Lj = A + blk_index(J, Kb);
         bv[4 * Kb + c] -= Lj[c] * x0 + Lj[4 + c] * x1 + Lj[8 + c] * x2 + Lj[12 + c] * x3;
+      }
     }
     __syncwarp();
   }
@@ -269,11 +285,17 @@ __global__ void __launch_bounds__(kMcThreads) mcep_kernel(McepParams p) {
   float* sv = al + p.MP;                  // [F] start / previous r~[0]
   int* act = reinterpret_cast<int*>(sv + F);  // [F] 1 = still iterating
   int* itc = act + F;                         // [F] iteration count at exit
+  uint16_t* tri = reinterpret_cast<uint16_t*>(itc + F);  // [NBk (NBk-1) / 2] flat pair index -> (a << 8 | q), q <= a
   const int tid = threadIdx.x;
   const int K = p.K, KP = p.KP, MP = p.MP, m = p.m;
   const int64_t frame0 = (int64_t)blockIdx.x * F;
   const int nvalid = (int)min((int64_t)F, p.num_frames - frame0);
 
+  for (int pi = tid; pi < p.NBk * (p.NBk - 1) / 2; pi += kMcThreads) {
+    int a_ = 0, q = pi;
+    while (q > a_) { q -= a_ + 1; ++a_; }
+    tri[pi] = (uint16_t)((a_ << 8) | q);
+  }
   // (-alpha)^k, zero padded
   if (tid < MP) al[tid] = (tid <= m) ? powf(-p.alpha, (float)tid) : 0.f;
   if (tid == 0) al[0] = 1.f;
@@ -305,16 +327,27 @@ __global__ void __launch_bounds__(kMcThreads) mcep_kernel(McepParams p) {
   __syncthreads();
 
   for (int it = 1; it <= p.maxiter; ++it) {
-    // P = per * exp(-2 mc . Cmat)
+    // P = per * exp(-2 mc . Cmat): every thread owns the two columns tid and tid + 256 (and, for K - 1 = 1024 or 2048,
+    // further pairs), half of the tile's frames at a time
     {
-      float acc[F];
-      for (int j = tid; j + 1 < K; j += kMcThreads) {  // K - 1 is a multiple of 256 for every supported fft size
-        warp_column<F>(mc, MP, p.cmat, K, j, acc);
+      constexpr int FH = F >= 16 ? 16 : F;
+      float acc0[FH], acc1[FH];
+      for (int j0 = tid; j0 + 1 < K; j0 += 2 * kMcThreads) {  // K - 1 is a multiple of 256 for every supported fft size
+        const int j1 = j0 + kMcThreads;
+        const bool v1 = j1 + 1 < K;
+        const int j1s = v1 ? j1 : j0;
+        for (int fb = 0; fb < F; fb += FH) {
+          two_columns<FH>(mc, MP, p.cmat, K, j0, j1s, fb, acc0, acc1);
 #pragma unroll
-        for (int f = 0; f < F; ++f) {
-          float per = 1.f;
-          if (f < nvalid) per = load_per<IT>(p, frame0 + f, j);
-          U[f * KP + j] = per * expf(-2.f * acc[f]);
+          for (int f = 0; f < FH; ++f) {
+            float per0 = 1.f, per1 = 1.f;
+            if (fb + f < nvalid) {
+              per0 = load_per<IT>(p, frame0 + fb + f, j0);
+              per1 = load_per<IT>(p, frame0 + fb + f, j1s);
+            }
+            U[(fb + f) * KP + j0] = per0 * expf(-2.f * acc0[f]);
+            if (v1) U[(fb + f) * KP + j1] = per1 * expf(-2.f * acc1[f]);
+          }
         }
       }
       if (tid < F) {  // the Nyquist column, one frame per thread
@@ -351,7 +384,7 @@ __global__ void __launch_bounds__(kMcThreads) mcep_kernel(McepParams p) {
       for (int f = warp; f < F; f += kMcWarps) {
         if (!act[f]) continue;
         float* xo = ws + p.chol_floats - pad4(m + 1);  // tail of the workspace
-        const bool ok = warp_ldl_solve(rt + f * p.NP2, al, m + 1, p.NBk, ws, xo);
+        const bool ok = warp_ldl_solve(rt + f * p.NP2, al, m + 1, p.NBk, tri, ws, xo);
         if (!ok) {
           if (lane == 0) {
             atomicOr(p.status, B2W_STATUS_SOLVE_FAILED);
@@ -522,7 +555,7 @@ extern "C" int b2w_mcep(const void* in, int32_t in_dtype, int32_t in_is_power, i
   p.K = fft_size / 2 + 1; p.KP = pad4(p.K); p.m = order; p.MP = pad4(order + 1);
   p.NP0 = pad4(order + 2); p.NP2 = pad4(2 * order + 1);
   p.NBk = (order + 1 + 3) / 4;
-  p.chol_floats = (p.NBk * (p.NBk + 1) / 2) * 16 + p.NBk * 16 + 8 * p.NBk + pad4(order + 1);
+  p.chol_floats = (p.NBk * (p.NBk + 1) / 2) * kBlk + p.NBk * kBlk + 8 * p.NBk + pad4(order + 1);
   p.miniter = miniter; p.maxiter = maxiter; p.threshold = (float)threshold; p.eps = (float)eps; p.alpha = (float)alpha;
   p.m0t = m0t; p.cmat = cmat; p.m2t = m2t; p.mc_out = mc; p.mc_dtype = mc_dtype; p.mc_stride = mc_stride;
   p.iters = iters; p.status = status;
@@ -532,7 +565,8 @@ extern "C" int b2w_mcep(const void* in, int32_t in_dtype, int32_t in_is_power, i
   const int tile_floats = F * p.KP;
   const int ws_floats = kMcWarps * p.chol_floats;
   p.u_floats = tile_floats > ws_floats ? tile_floats : ws_floats;
-  const size_t smem = sizeof(float) * ((size_t)p.u_floats + (size_t)F * p.MP + (size_t)F * p.NP2 + p.MP + F) + sizeof(int) * 2 * F;
+  const size_t smem = sizeof(float) * ((size_t)p.u_floats + (size_t)F * p.MP + (size_t)F * p.NP2 + p.MP + F) + sizeof(int) * 2 * F +
+                      sizeof(uint16_t) * (size_t)(p.NBk * (p.NBk - 1) / 2 + 2);
   B2W_REQUIRE(smem <= 227 * 1024, "b2w_mcep: order %d needs %zu bytes of shared memory", order, smem);
   const int64_t grid = (num_frames + F - 1) / F;
   B2W_REQUIRE(grid < (int64_t)1 << 31, "b2w_mcep: too many frames in one call");

@@ -14,7 +14,8 @@ __device__ __forceinline__ void dc_correction(double* P, double* S, double f0, d
     if (tid == 0) atomicOr(status, B2W_STATUS_F0_TOO_HIGH);
     upper = K - 1;
   }
-  for (int i = tid; i < upper - 1; i += NT) S[i] = interp1q_at(f0, -fs / N, P, upper + 1, (double)i * fs / N);
+  const double inv_dx = -(double)N / fs;
+  for (int i = tid; i < upper - 1; i += NT) S[i] = interp1q_at(f0, inv_dx, P, upper + 1, (double)i * fs / N);
   __syncthreads();
   for (int i = tid; i < upper - 1; i += NT) P[i] += S[i];
   __syncthreads();
@@ -46,12 +47,13 @@ __device__ __forceinline__ void linear_smoothing(const double* in, double* S, do
   __syncthreads();
   block_scan_inclusive<NT>(S, L, red);
   const double origin_f = -(bnd - 0.5) * fs / N;
-  const double dfi = fs / N;
+  const double inv_dfi = (double)N / fs;
+  const double inv_width = 1.0 / width;
   for (int k = tid; k < K; k += NT) {
     const double fax = (double)k / N * fs - width / 2.0;
-    const double low = interp1q_at(origin_f, dfi, S, L, fax);
-    const double high = interp1q_at(origin_f, dfi, S, L, fax + width);
-    emit(k, (high - low) / width);
+    const double low = interp1q_at(origin_f, inv_dfi, S, L, fax);
+    const double high = interp1q_at(origin_f, inv_dfi, S, L, fax + width);
+    emit(k, (high - low) * inv_width);
   }
 }
 
