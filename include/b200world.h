@@ -174,6 +174,10 @@ B2W_API int b2w_allpass_backward(const float* grad_y, const float* x, const floa
                          int32_t blocks, const float* mean, const float* std_dev, float* grad_x, float* grad_alpha,
                          float* unit_workspace /* [rows * blocks] */, void* stream);
 
+/* ---- self-test of the tcgen05 (UMMA) building blocks used by the tensor-core mel-cepstrum kernel: one CTA computes
+ * d[128, n] = a[128, k] . bt[n, k]^T with the 3xTF32 split (n % 16 == 0, n <= 256, k % 8 == 0); b_tiled_ws: 2*n*k floats. */
+B2W_API int b2w_test_umma_gemm(const float* a, const float* bt, int32_t n, int32_t k, float* b_tiled_ws, float* d, void* stream);
+
 /* ---- scalar helpers (host, pure functions): pyworld.get_cheaptrick_fft_size (A:60), get_num_aperiodicities
  * (A:71), and the D4C transform size. */
 B2W_API int32_t b2w_cheaptrick_fft_size(int32_t fs, double f0_floor);
