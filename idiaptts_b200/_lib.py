@@ -38,6 +38,10 @@ _SIGNATURES = {
     "b2w_mcep": (c_int32, [c_void_p, c_int32, c_int32, c_int64, c_int32, c_int32, c_double, c_int32, c_int32, c_double,
                            c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p,
                            c_void_p]),
+    "b2w_mcep_tc_stream_floats": (c_int64, [c_int32]),
+    "b2w_mcep_tc_pretile": (c_int32, [c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b2w_mcep_tc": (c_int32, [c_void_p, c_int32, c_int32, c_int64, c_int32, c_int32, c_double, c_int32, c_int32, c_double,
+                              c_double, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_void_p]),
     "b2w_mc2sp": (c_int32, [c_void_p, c_int32, c_int64, c_int64, c_int32, c_int32, c_void_p, c_double, c_int32, c_void_p,
                             c_int32, c_void_p]),
     "b2w_lf0_vuv": (c_int32, [c_void_p, c_void_p, c_int32, c_double, c_double, c_void_p, c_void_p, c_int64, c_void_p]),

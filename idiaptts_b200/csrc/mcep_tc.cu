@@ -1,0 +1,429 @@
+// Mel-cepstral analysis (SPTK mcep Newton loop) with the dense all-pass-warp contractions on the 5th-generation tensor
+// cores: tcgen05.mma kind::tf32 with the 3xTF32 split (fp32-accurate), accumulators in tensor memory, constant matrices
+// streamed by 1-D bulk async copies (mbarrier completion) from a pre-tiled global stream.
+//
+// Same mathematics and the same reference call site as mcep.cu (pysptk.mcep, AudioProcessing.py:146); this is the
+// production path for order <= 63.  One CTA = 128 frames (the UMMA M dimension), 512 threads.
+//
+//   per Newton iteration, for each chunk of 16 frequency bins j0 .. j0+15 (33 chunks at K = 513):
+//     GEMM1   D1[128 x 16]   = mc[128 x 64] . Cmat[64 x 16 chunk]          24 MMAs (8 K-steps x 3 split products)
+//     epilogue (all threads)  P = per * exp(-2 D1)  -> hi/lo TF32 tiles in shared memory (A operand of GEMM2)
+//     GEMM2   D2[128 x 128] += P[128 x 16] . M2^T[16 chunk x 128]           6 MMAs
+//   then D2 row f = r~ of frame f: stopping rule on r~[0], and for the frames still iterating one warp each builds and
+//   solves the (m+1) x (m+1) Toeplitz-plus-Hankel system (mcep_solve.cuh) and updates mc (fp32, shared memory).
+//   Pass 0 (initial value) uses the same machinery: P = log(per), the stream holds M0^T instead of M2^T, GEMM1 is skipped.
+#include "common.cuh"
+#include "mcep_solve.cuh"
+#include "umma.cuh"
+
+namespace b2w {
+
+constexpr int kTcF = 128;        // frames per CTA = UMMA M
+constexpr int kTcThreads = 512;  // 16 warps: TMEM lane quarter q = warp & 3, column group g = warp >> 2
+constexpr int kTcBK = 16;        // bins per chunk
+constexpr int kTcMP = 64;        // padded cepstral dimension (K of GEMM1)
+constexpr int kTcN2 = 128;       // padded r~ length (N of GEMM2)
+constexpr int kTcKB = 16;        // block stride of the solve workspace
+constexpr uint32_t kB1Bytes = kTcBK * kTcMP * 4;   // one of hi / lo of the Cmat chunk   [N = 16 rows (bins)] x [K = 64]
+constexpr uint32_t kB2Bytes = kTcN2 * kTcBK * 4;   // one of hi / lo of the M2^T chunk   [N = 128 rows]       x [K = 16]
+constexpr uint32_t kStageBytes = 2 * kB1Bytes + 2 * kB2Bytes;  // 24 KB per chunk: [B1 hi | B1 lo | B2 hi | B2 lo]
+constexpr uint32_t kA1Bytes = kTcF * kTcMP * 4;    // 32 KB, one of hi / lo
+constexpr uint32_t kA2Bytes = kTcF * kTcBK * 4;    // 8 KB, one of hi / lo
+constexpr int kTmemCols = 256;                     // D1 at column 0 (16 used), D2 at column 32 (128 used)
+
+struct McepTcParams {
+  const void* in;
+  int in_is_power;
+  int64_t num_frames;
+  int K, m, NBk, nchunks;
+  int ws_floats;   // per-warp solve workspace
+  int miniter, maxiter;
+  float threshold, eps, alpha;
+  const float* stream0;  // pre-tiled [nchunks][kStageBytes]: pass 0 (M0^T in the B2 slots)
+  const float* stream1;  // pre-tiled [nchunks][kStageBytes]: Newton passes (Cmat chunk, M2^T chunk)
+  void* mc_out;
+  int mc_dtype;
+  int64_t mc_stride;
+  int* iters;
+  int* status;
+};
+
+// Builds both streams from the fp32 matrices of b2w_mcep_tables_host (m0t [K, np0], cmat [MP, K], m2t [K, np2]).
+__global__ void mcep_tc_pretile_kernel(const float* __restrict__ m0t, int np0, const float* __restrict__ cmat, const float* __restrict__ m2t,
+                                       int np2, int K, int m, int nchunks, float* __restrict__ stream0, float* __restrict__ stream1) {
+  const int stage_floats = kStageBytes / 4;
+  const int total = nchunks * stage_floats;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int c = e / stage_floats;
+    int o = e - c * stage_floats;
+    const int j0 = c * kTcBK;
+    float v0 = 0.f, v1 = 0.f;  // values for stream0 / stream1 at this slot BEFORE the hi/lo selection
+    bool lo;
+    if (o < 2 * (int)(kB1Bytes / 4)) {
+      // B1 tile: rows n = bin within chunk (16), K = cepstral index (64)
+      lo = o >= (int)(kB1Bytes / 4);
+      if (lo) o -= kB1Bytes / 4;
+      const int kc = o / (kTcBK * 4), rem = o - kc * (kTcBK * 4);   // chunk stride = R * 16 B = R * 4 floats
+      const int n = (rem >> 5) * 8 + ((rem >> 2) & 7), k = kc * 4 + (rem & 3);
+      const int j = j0 + n;
+      if (j < K && k <= m) v1 = cmat[(int64_t)k * K + j];
+    } else {
+      o -= 2 * (kB1Bytes / 4);
+      lo = o >= (int)(kB2Bytes / 4);
+      if (lo) o -= kB2Bytes / 4;
+      const int kc = o / (kTcN2 * 4), rem = o - kc * (kTcN2 * 4);
+      const int n = (rem >> 5) * 8 + ((rem >> 2) & 7), k = kc * 4 + (rem & 3);
+      const int j = j0 + k;
+      if (j < K) {
+        if (n <= 2 * m) v1 = m2t[(int64_t)j * np2 + n];
+        if (n <= m + 1) v0 = m0t[(int64_t)j * np0 + n];
+      }
+    }
+    float h0, l0, h1, l1;
+    umma::split_tf32(v0, h0, l0);
+    umma::split_tf32(v1, h1, l1);
+    stream0[e] = lo ? l0 : h0;
+    stream1[e] = lo ? l1 : h1;
+  }
+}
+
+template <typename IT>
+__device__ __forceinline__ float tc_load_per(const McepTcParams& p, int64_t frame, int j) {
+  const float v = (float)reinterpret_cast<const IT*>(p.in)[frame * p.K + j];
+  return p.in_is_power ? v + p.eps : fmaf(v, v, p.eps);
+}
+
+template <typename IT>
+__global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  // ---- shared memory map ----------------------------------------------------------------------------------------------
+  // GEMM phase:  [A1 hi 32K | A1 lo 32K | stage 0 24K | stage 1 24K | A2 hi 8K | A2 lo 8K]  = 128 KB
+  // solve phase: the same region holds the 16 per-warp workspaces
+  uint8_t* region = smem_raw;
+  float* a1_hi = reinterpret_cast<float*>(region);
+  float* a1_lo = reinterpret_cast<float*>(region + kA1Bytes);
+  uint8_t* stage_base = region + 2 * kA1Bytes;
+  float* a2_hi = reinterpret_cast<float*>(stage_base + 2 * kStageBytes);
+  float* a2_lo = reinterpret_cast<float*>(stage_base + 2 * kStageBytes + kA2Bytes);
+  const uint32_t gemm_bytes = 2 * kA1Bytes + 2 * kStageBytes + 2 * kA2Bytes;
+  const uint32_t ws_bytes = (uint32_t)(kTcThreads / 32) * (uint32_t)p.ws_floats * 4u;
+  const uint32_t region_bytes = gemm_bytes > ws_bytes ? gemm_bytes : ws_bytes;
+  float* mc = reinterpret_cast<float*>(region + region_bytes);  // [128][64] fp32
+  float* al = mc + kTcF * kTcMP;                                  // [64]
+  float* sv = al + kTcMP;                                         // [128]
+  int* act = reinterpret_cast<int*>(sv + kTcF);                   // [128]
+  int* itc = act + kTcF;                                          // [128]
+  int* qcnt = itc + kTcF;                                         // [4] work counters of the lane quarters
+  uint64_t* bars = reinterpret_cast<uint64_t*>(qcnt + 4);         // full[2], g1, g2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint16_t* tri = reinterpret_cast<uint16_t*>(tmem_slot + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, g = warp >> 2;
+  const int row = 32 * q + lane;  // this thread's TMEM lane = frame within the tile
+  const int K = p.K, m = p.m;
+  const int64_t frame0 = (int64_t)blockIdx.x * kTcF;
+  const int nvalid = (int)min((int64_t)kTcF, p.num_frames - frame0);
+  uint64_t* bar_full = bars;       // [2]
+  uint64_t* bar_g1 = bars + 2;
+  uint64_t* bar_g2 = bars + 3;
+
+  if (tid == 0) {
+    umma::mbar_init(&bar_full[0], 1);
+    umma::mbar_init(&bar_full[1], 1);
+    umma::mbar_init(bar_g1, 1);
+    umma::mbar_init(bar_g2, 1);
+    umma::mbar_fence_init();
+  }
+  if (warp == 0) umma::tmem_alloc(tmem_slot, kTmemCols);
+  for (int pi = tid; pi < p.NBk * (p.NBk - 1) / 2; pi += kTcThreads) {
+    int a_ = 0, qq = pi;
+    while (qq > a_) { qq -= a_ + 1; ++a_; }
+    tri[pi] = (uint16_t)((a_ << 8) | qq);
+  }
+  if (tid < kTcMP) al[tid] = (tid <= m) ? powf(-p.alpha, (float)tid) : 0.f;
+  if (tid == 0) al[0] = 1.f;
+  if (tid < kTcF) {
+    act[tid] = tid < nvalid ? 1 : 0;
+    itc[tid] = 0;
+    sv[tid] = 0.f;
+  }
+  for (int i = tid; i < kTcF * kTcMP; i += kTcThreads) mc[i] = 0.f;
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  umma::tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t t_d1 = tmem + ((uint32_t)(32 * q) << 16);        // D1: columns 0..15
+  const uint32_t t_d2 = tmem + ((uint32_t)(32 * q) << 16) + 32;   // D2: columns 32..159
+  const uint32_t idesc1 = umma::idesc_tf32(kTcF, kTcBK);
+  const uint32_t idesc2 = umma::idesc_tf32(kTcF, kTcN2);
+  uint32_t ph_full[2] = {0, 0}, ph_g1 = 0, ph_g2 = 0;  // parities, tracked identically by every thread
+  bool zero_per = false;
+
+  for (int pass = 0; pass <= p.maxiter; ++pass) {
+    const float* stream = pass == 0 ? p.stream0 : p.stream1;
+    // ---- A1 = hi/lo split of mc (Newton passes) ----------------------------------------------------------------------
+    if (pass > 0) {
+      for (int e = tid; e < kTcF * (kTcMP / 4); e += kTcThreads) {
+        const int r = e & (kTcF - 1), kc = e >> 7;  // consecutive threads -> consecutive rows: conflict-free 16 B stores
+        const float4 v = *reinterpret_cast<const float4*>(mc + r * kTcMP + 4 * kc);
+        float4 h, l;
+        umma::split_tf32(v.x, h.x, l.x);
+        umma::split_tf32(v.y, h.y, l.y);
+        umma::split_tf32(v.z, h.z, l.z);
+        umma::split_tf32(v.w, h.w, l.w);
+        const uint32_t off = umma::tile_off(kTcF, r, 4 * kc) / 4;
+        *reinterpret_cast<float4*>(a1_hi + off) = h;
+        *reinterpret_cast<float4*>(a1_lo + off) = l;
+      }
+      umma::fence_proxy_async();
+    }
+    __syncthreads();
+    if (tid == 0) {  // prefetch the first two chunks of this pass (both stages are drained at a pass boundary)
+      for (int s = 0; s < 2 && s < p.nchunks; ++s) {
+        umma::mbar_expect_tx(&bar_full[s], kStageBytes);
+        umma::bulk_g2s(stage_base + s * kStageBytes, reinterpret_cast<const uint8_t*>(stream) + (size_t)s * kStageBytes, kStageBytes,
+                       &bar_full[s]);
+      }
+    }
+    for (int c = 0; c < p.nchunks; ++c) {
+      const int s = c & 1;
+      const uint8_t* stg = stage_base + s * kStageBytes;
+      const int j0 = c * kTcBK;
+      if (tid == 0) {
+        umma::mbar_wait(&bar_full[s], ph_full[s]);
+        if (pass > 0) {
+          umma::tc_fence_after_sync();
+          const uint32_t b1h = umma::smem_u32(stg), b1l = b1h + kB1Bytes;
+          const uint32_t a_lbo = kTcF * 16, b_lbo = kTcBK * 16;
+#pragma unroll 1
+          for (int ks = 0; ks < kTcMP / 8; ++ks) {
+            const uint64_t ah = umma::smem_desc(umma::smem_u32(a1_hi) + 2 * ks * a_lbo, a_lbo, 128);
+            const uint64_t alo = umma::smem_desc(umma::smem_u32(a1_lo) + 2 * ks * a_lbo, a_lbo, 128);
+            const uint64_t bh = umma::smem_desc(b1h + 2 * ks * b_lbo, b_lbo, 128);
+            const uint64_t bl = umma::smem_desc(b1l + 2 * ks * b_lbo, b_lbo, 128);
+            umma::mma_tf32(tmem, alo, bh, idesc1, ks > 0);
+            umma::mma_tf32(tmem, ah, bl, idesc1, true);
+            umma::mma_tf32(tmem, ah, bh, idesc1, true);
+          }
+          umma::mma_commit(bar_g1);
+        }
+      }
+      ph_full[s] ^= 1;
+      // ---- epilogue: this thread owns row `row`, bins j0 + 4 g .. + 3 ------------------------------------------------
+      float cv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (pass > 0) {
+        umma::mbar_wait(bar_g1, ph_g1);
+        ph_g1 ^= 1;
+        umma::tc_fence_after_sync();
+        umma::tmem_ld4(t_d1 + 4 * g, cv);
+      }
+      float4 ph, pl;
+      {
+        float pv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int j = j0 + 4 * g + i;
+          float per = 1.f;
+          const bool inb = j < K;
+          if (inb && row < nvalid) per = tc_load_per<IT>(p, frame0 + row, j);
+          if (!(per > 0.f)) zero_per = true;
+          const float val = pass == 0 ? logf(per) : per * expf(-2.f * cv[i]);
+          pv[i] = inb ? val : 0.f;
+        }
+        umma::split_tf32(pv[0], ph.x, pl.x);
+        umma::split_tf32(pv[1], ph.y, pl.y);
+        umma::split_tf32(pv[2], ph.z, pl.z);
+        umma::split_tf32(pv[3], ph.w, pl.w);
+      }
+      if (c > 0) {  // A2 is single-buffered: the previous GEMM2 must have consumed it (pass boundaries are drained)
+        umma::mbar_wait(bar_g2, ph_g2);
+        ph_g2 ^= 1;
+      }
+      if (tid == 0 && c >= 1 && c + 1 < p.nchunks) {
+        // GEMM2(c-1) is complete: stage (c-1)&1 is free -> refill it with chunk c + 1
+        const int sn = (c + 1) & 1;
+        umma::mbar_expect_tx(&bar_full[sn], kStageBytes);
+        umma::bulk_g2s(stage_base + sn * kStageBytes, reinterpret_cast<const uint8_t*>(stream) + (size_t)(c + 1) * kStageBytes,
+                       kStageBytes, &bar_full[sn]);
+      }
+      {
+        const uint32_t off = umma::tile_off(kTcF, row, 4 * g) / 4;
+        *reinterpret_cast<float4*>(a2_hi + off) = ph;
+        *reinterpret_cast<float4*>(a2_lo + off) = pl;
+      }
+      umma::fence_proxy_async();
+      umma::tc_fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        umma::tc_fence_after_sync();
+        const uint32_t b2h = umma::smem_u32(stg) + 2 * kB1Bytes, b2l = b2h + kB2Bytes;
+        const uint32_t a_lbo = kTcF * 16, b_lbo = kTcN2 * 16;
+#pragma unroll
+        for (int ks = 0; ks < kTcBK / 8; ++ks) {
+          const uint64_t ah = umma::smem_desc(umma::smem_u32(a2_hi) + 2 * ks * a_lbo, a_lbo, 128);
+          const uint64_t alo = umma::smem_desc(umma::smem_u32(a2_lo) + 2 * ks * a_lbo, a_lbo, 128);
+          const uint64_t bh = umma::smem_desc(b2h + 2 * ks * b_lbo, b_lbo, 128);
+          const uint64_t bl = umma::smem_desc(b2l + 2 * ks * b_lbo, b_lbo, 128);
+          umma::mma_tf32(tmem + 32, alo, bh, idesc2, c > 0 || ks > 0);
+          umma::mma_tf32(tmem + 32, ah, bl, idesc2, true);
+          umma::mma_tf32(tmem + 32, ah, bh, idesc2, true);
+        }
+        umma::mma_commit(bar_g2);
+      }
+    }
+    // the last chunk's GEMM2 completes D2
+    umma::mbar_wait(bar_g2, ph_g2);
+    ph_g2 ^= 1;
+    umma::tc_fence_after_sync();
+
+    if (pass == 0) {
+      // D2[:, 0..m] = initial mel-cepstrum, D2[:, m+1] = SPTK's start value s
+      float v[16];
+      umma::tmem_ld16(t_d2 + 16 * g, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int k = 16 * g + i;
+        if (k <= m) mc[row * kTcMP + k] = v[i];
+        if (k == m + 1) sv[row] = v[i];
+      }
+      umma::tc_fence_before_sync();
+      __syncthreads();
+      continue;
+    }
+    // ---- stopping rule on r~[0] (one thread per frame) -----------------------------------------------------------
+    {
+      float v[4];
+      umma::tmem_ld4(t_d2, v);
+      if (g == 0 && act[row]) {
+        const float t = v[0];
+        if (pass >= p.miniter) {
+          if (fabsf((t - sv[row]) / t) < p.threshold) {
+            act[row] = 0;
+            itc[row] = pass;
+          } else {
+            sv[row] = t;
+          }
+        }
+      }
+      if (tid < 4) qcnt[tid] = 0;
+    }
+    __syncthreads();
+    int any = 0;
+    if (tid < kTcF) any = act[tid];
+    if (!__syncthreads_or(any)) break;
+    // ---- Newton step: the warps of a lane quarter share its 32 frames through a work counter -----------------------
+    {
+      float* ws = reinterpret_cast<float*>(region) + warp * p.ws_floats;
+      float* rtrow = ws + ldl_workspace_floats(p.NBk, kTcKB);   // [128]
+      float* xo = rtrow + kTcN2;                                // [64]
+      for (;;) {
+        int idx = 0;
+        if (lane == 0) idx = atomicAdd(&qcnt[q], 1);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= 32) break;
+        const int f = 32 * q + idx;
+        if (!act[f]) continue;
+        // pull row f of D2 out of tensor memory: every lane receives its own row, lane idx keeps it
+#pragma unroll
+        for (int cb = 0; cb < kTcN2 / 16; ++cb) {
+          float v[16];
+          umma::tmem_ld16(t_d2 + 16 * cb, v);
+          if (lane == idx) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(rtrow + 16 * cb + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          }
+        }
+        __syncwarp();
+        const bool ok = warp_ldl_solve<kTcKB>(rtrow, al, m + 1, p.NBk, tri, ws, xo);
+        if (!ok) {
+          if (lane == 0) {
+            atomicOr(p.status, B2W_STATUS_SOLVE_FAILED);
+            act[f] = 0;
+            itc[f] = pass;
+          }
+        } else {
+          for (int k = lane; k <= m; k += 32) mc[f * kTcMP + k] += xo[k];
+        }
+        __syncwarp();
+      }
+    }
+    umma::tc_fence_before_sync();
+    __syncthreads();
+  }
+  if (zero_per) atomicOr(p.status, B2W_STATUS_ZERO_PERIODOGRAM);
+  if (tid < kTcF && act[tid]) {
+    itc[tid] = p.maxiter;
+    atomicOr(p.status, B2W_STATUS_NOT_CONVERGED);
+  }
+  __syncthreads();
+  for (int i = tid; i < nvalid * (m + 1); i += kTcThreads) {
+    const int f = i / (m + 1), k = i - f * (m + 1);
+    const float v = mc[f * kTcMP + k];
+    if (p.mc_dtype == B2W_F64) reinterpret_cast<double*>(p.mc_out)[(frame0 + f) * p.mc_stride + k] = (double)v;
+    else reinterpret_cast<float*>(p.mc_out)[(frame0 + f) * p.mc_stride + k] = v;
+  }
+  if (p.iters && tid < nvalid) p.iters[frame0 + tid] = itc[tid];
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
+}
+
+}  // namespace b2w
+
+extern "C" int64_t b2w_mcep_tc_stream_floats(int32_t fft_size) {
+  const int K = fft_size / 2 + 1;
+  const int nchunks = (K + b2w::kTcBK - 1) / b2w::kTcBK;
+  return (int64_t)nchunks * (b2w::kStageBytes / 4);
+}
+
+extern "C" int b2w_mcep_tc_pretile(int32_t order, int32_t fft_size, const float* m0t, const float* cmat, const float* m2t,
+                                   float* stream0, float* stream1, void* stream) {
+  using namespace b2w;
+  B2W_REQUIRE(m0t && cmat && m2t && stream0 && stream1, "b2w_mcep_tc_pretile: null argument");
+  B2W_REQUIRE(order >= 1 && order <= 62, "b2w_mcep_tc_pretile: order %d out of range [1, 62]", order);
+  const int K = fft_size / 2 + 1;
+  const int nchunks = (K + kTcBK - 1) / kTcBK;
+  mcep_tc_pretile_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(m0t, pad4(order + 2), cmat, m2t, pad4(2 * order + 1), K, order, nchunks,
+                                                                 stream0, stream1);
+  return check_launch("mcep_tc_pretile_kernel");
+}
+
+extern "C" int b2w_mcep_tc(const void* in, int32_t in_dtype, int32_t in_is_power, int64_t num_frames, int32_t fft_size, int32_t order,
+                           double alpha, int32_t miniter, int32_t maxiter, double threshold, double eps, const float* stream0,
+                           const float* stream1, void* mc, int32_t mc_dtype, int64_t mc_stride, int32_t* iters, int32_t* status,
+                           void* stream) {
+  using namespace b2w;
+  B2W_REQUIRE(in && stream0 && stream1 && mc && status, "b2w_mcep_tc: null argument");
+  B2W_REQUIRE(in_dtype == B2W_F64 || in_dtype == B2W_F32, "b2w_mcep_tc: bad in_dtype %d", in_dtype);
+  B2W_REQUIRE(mc_dtype == B2W_F64 || mc_dtype == B2W_F32, "b2w_mcep_tc: bad mc_dtype %d", mc_dtype);
+  B2W_REQUIRE(order >= 1 && order <= 62, "b2w_mcep_tc: order %d out of range [1, 62] (use b2w_mcep)", order);
+  B2W_REQUIRE(fft_size >= 64 && (fft_size & (fft_size - 1)) == 0, "b2w_mcep_tc: bad fft_size %d", fft_size);
+  B2W_REQUIRE(mc_stride >= order + 1 && maxiter >= 1 && miniter >= 1, "b2w_mcep_tc: bad stride / iteration limits");
+  if (num_frames == 0) return 0;
+  McepTcParams p;
+  p.in = in; p.in_is_power = in_is_power; p.num_frames = num_frames;
+  p.K = fft_size / 2 + 1; p.m = order; p.NBk = (order + 1 + 3) / 4;
+  p.nchunks = (p.K + kTcBK - 1) / kTcBK;
+  p.ws_floats = ldl_workspace_floats(p.NBk, kTcKB) + kTcN2 + kTcMP;
+  p.miniter = miniter; p.maxiter = maxiter; p.threshold = (float)threshold; p.eps = (float)eps; p.alpha = (float)alpha;
+  p.stream0 = stream0; p.stream1 = stream1; p.mc_out = mc; p.mc_dtype = mc_dtype; p.mc_stride = mc_stride;
+  p.iters = iters; p.status = status;
+  const uint32_t gemm_bytes = 2 * kA1Bytes + 2 * kStageBytes + 2 * kA2Bytes;
+  const uint32_t ws_bytes = (uint32_t)(kTcThreads / 32) * (uint32_t)p.ws_floats * 4u;
+  const uint32_t region_bytes = gemm_bytes > ws_bytes ? gemm_bytes : ws_bytes;
+  const size_t smem = region_bytes + sizeof(float) * (kTcF * kTcMP + kTcMP + kTcF) + sizeof(int) * (2 * kTcF + 4) + 4 * 8 + 8 +
+                      sizeof(uint16_t) * (size_t)(p.NBk * (p.NBk - 1) / 2 + 2) + 16;
+  B2W_REQUIRE(smem <= 227 * 1024, "b2w_mcep_tc: %zu bytes of shared memory needed", smem);
+  const int64_t grid = (num_frames + kTcF - 1) / kTcF;
+  B2W_REQUIRE(grid < ((int64_t)1 << 31), "b2w_mcep_tc: too many frames in one call");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (in_dtype == B2W_F64) {
+    cudaFuncSetAttribute(mcep_tc_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    mcep_tc_kernel<double><<<(unsigned)grid, kTcThreads, smem, st>>>(p);
+  } else {
+    cudaFuncSetAttribute(mcep_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    mcep_tc_kernel<float><<<(unsigned)grid, kTcThreads, smem, st>>>(p);
+  }
+  return check_launch("mcep_tc_kernel");
+}

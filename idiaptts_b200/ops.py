@@ -259,6 +259,16 @@ class McepTables:
         self.m0t = torch.from_numpy(m0t.astype(np.float32)).to(device)
         self.cmat = torch.from_numpy(cmat.astype(np.float32)).to(device)
         self.m2t = torch.from_numpy(m2t.astype(np.float32)).to(device)
+        # pre-tiled hi/lo TF32 streams of the tensor-core kernel (order <= 62)
+        self.stream0 = self.stream1 = None
+        if self.order <= 62:
+            n = int(lib.b2w_mcep_tc_stream_floats(self.fft_size))
+            self.stream0 = torch.empty(n, dtype=torch.float32, device=device)
+            self.stream1 = torch.empty(n, dtype=torch.float32, device=device)
+            with torch.cuda.device(device):
+                check(lib.b2w_mcep_tc_pretile(self.order, self.fft_size, self.m0t.data_ptr(), self.cmat.data_ptr(), self.m2t.data_ptr(),
+                                              self.stream0.data_ptr(), self.stream1.data_ptr(), _stream(torch.device(device))),
+                      "b2w_mcep_tc_pretile")
 
     @classmethod
     def get(cls, order, alpha, fft_size, device):
@@ -272,8 +282,9 @@ class McepTables:
 
 
 def mcep(plane, order, alpha, is_power=False, miniter=2, maxiter=30, threshold=0.001, eps=1.0e-8, out=None,
-         out_stride=None, out_dtype=torch.float32, iters=None, status=None):
-    """pysptk.mcep(itype=3 (amplitude) or 4 (power), etype=1) on a [F, K] plane -> mc [F, order+1]."""
+         out_stride=None, out_dtype=torch.float32, iters=None, status=None, impl=None):
+    """pysptk.mcep(itype=3 (amplitude) or 4 (power), etype=1) on a [F, K] plane -> mc [F, order+1].
+    impl: "tc" = tcgen05 tensor-core kernel (default for order <= 62), "cc" = CUDA-core kernel (any order <= 127)."""
     lib = _lib.load()
     dev = _need_cuda(plane)
     assert plane.dim() == 2 and plane.dtype in (torch.float32, torch.float64)
@@ -285,6 +296,17 @@ def mcep(plane, order, alpha, is_power=False, miniter=2, maxiter=30, threshold=0
         out_stride = order + 1
     if status is None:
         status = new_status(dev)
+    if impl is None:
+        impl = "tc" if tab.stream0 is not None else "cc"
+    if impl == "tc":
+        if tab.stream0 is None:
+            raise ValueError("the tensor-core mcep kernel supports order <= 62")
+        with torch.cuda.device(dev):
+            check(lib.b2w_mcep_tc(plane.data_ptr(), _DT[plane.dtype], 1 if is_power else 0, F, fft_size, int(order), float(alpha),
+                                  int(miniter), int(maxiter), float(threshold), float(eps), tab.stream0.data_ptr(),
+                                  tab.stream1.data_ptr(), out.data_ptr(), _DT[out.dtype], int(out_stride), _ptr(iters),
+                                  status.data_ptr(), _stream(dev)), "b2w_mcep_tc")
+        return out, status
     with torch.cuda.device(dev):
         check(lib.b2w_mcep(plane.data_ptr(), _DT[plane.dtype], 1 if is_power else 0, F, fft_size, int(order), float(alpha),
                            int(miniter), int(maxiter), float(threshold), float(eps), tab.m0t.data_ptr(), tab.cmat.data_ptr(),
