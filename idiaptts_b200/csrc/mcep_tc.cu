@@ -23,7 +23,7 @@ constexpr int kTcThreads = 512;  // 16 warps: TMEM lane quarter q = warp & 3, co
 constexpr int kTcBK = 16;        // bins per chunk
 constexpr int kTcMP = 64;        // padded cepstral dimension (K of GEMM1)
 constexpr int kTcN2 = 128;       // padded r~ length (N of GEMM2)
-constexpr int kTcKB = 16;        // block stride of the solve workspace
+constexpr int kTcKB = 20;        // padded block stride of the solve workspace (bank-conflict free float4 accesses)
 constexpr uint32_t kB1Bytes = kTcBK * kTcMP * 4;   // one of hi / lo of the Cmat chunk   [N = 16 rows (bins)] x [K = 64]
 constexpr uint32_t kB2Bytes = kTcN2 * kTcBK * 4;   // one of hi / lo of the M2^T chunk   [N = 128 rows]       x [K = 16]
 constexpr uint32_t kStageBytes = 2 * kB1Bytes + 2 * kB2Bytes;  // 24 KB per chunk: [B1 hi | B1 lo | B2 hi | B2 lo]
