@@ -13,7 +13,7 @@ value   : audio-seconds per second with the inputs resident in HBM (CUDA events,
 e2e     : the same pass through host buffers: pinned int16 wave + F0 host->device, extraction, features + statistics
           device->host, all inside the timed region.
 roofline: the kernel with the largest share of the step, timed live with CUDA events on the launching stream.
-cpu_baseline / --impl reference: the CPU oracle (restated WORLD/SPTK algorithms; pyworld/pysptk are not installable here)
+cpu_baseline / --impl reference: the CPU oracle (C restatement of the WORLD/SPTK algorithms; pyworld/pysptk are not installable here)
           on all host cores over a bounded sample of the same workload.
 """
 import argparse
@@ -94,36 +94,29 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------------
 # CPU oracle arm (cpu_baseline of the default run, and the whole of --impl reference)
 # ----------------------------------------------------------------------------------------------------------------------
-def _oracle_extract_one(args):
-    wave_i16, f0, fs, alpha = args
-    from oracle import glue_np, sptk_np, world_np
-    x = wave_i16.astype(np.float64) / 32768.0
-    T = len(f0)
-    t = world_np.temporal_positions(T)
-    sp = world_np.cheaptrick(x, f0, t, fs)
-    mc = sptk_np.mcep(np.sqrt(sp), order=NUM_CODED_SPS - 1, alpha=alpha, eps=1e-8, etype=1, itype=3).astype(np.float32)
-    ap = world_np.d4c(x, f0, t, fs)
-    bap = world_np.code_aperiodicity(ap, fs).astype(np.float32)
-    lf0, vuv = glue_np.interpolate_lin(glue_np.lf0_from_f0(f0))
-    feats = np.concatenate((mc, lf0.astype(np.float32), vuv.astype(np.float32), bap), axis=1)
-    return feats.sum(0, dtype=np.float64), (feats.astype(np.float64) ** 2).sum(0), len(x) / fs
-
-
 def cpu_oracle_throughput(waves, f0s, fs, alpha, cores, steps=1, warmup=0):
-    """audio-seconds/s of the CPU oracle over the given sample with a process pool of `cores` workers."""
-    import multiprocessing as mp
-    ctx = mp.get_context("fork")
-    jobs = [(np.ascontiguousarray(w), f, fs, alpha) for w, f in zip(waves, f0s)]
-    with ctx.Pool(cores) as pool:
+    """audio-seconds/s of the CPU oracle (oracle/c/world_oracle.c: C restatement of WORLD / SPTK, one utterance per call,
+    the GIL is released inside) over the given sample with a pool of `cores` threads."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import world_c
+    world_c.lib()
+
+    def one(job):
+        w, f = job
+        feats = world_c.extract(w, fs, f, NUM_CODED_SPS, alpha)
+        return feats.sum(0, dtype=np.float64), len(w) / fs
+
+    jobs = [(np.ascontiguousarray(w), f) for w, f in zip(waves, f0s)]
+    with ThreadPoolExecutor(max_workers=cores) as pool:
         for _ in range(warmup):
-            pool.map(_oracle_extract_one, jobs[:cores])
+            list(pool.map(one, jobs[:cores]))
         times = []
         audio = 0.0
         for _ in range(steps):
             t0 = time.perf_counter()
-            res = pool.map(_oracle_extract_one, jobs)
+            res = list(pool.map(one, jobs))
             times.append(time.perf_counter() - t0)
-            audio = sum(r[2] for r in res)
+            audio = sum(r[1] for r in res)
     return audio / (sum(times) / len(times)), sum(times) / len(times), audio
 
 
@@ -144,7 +137,7 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "ljspeech_extract", "fs": FS, "utt_seconds": DUR, "num_coded_sps": NUM_CODED_SPS,
-                       "sample_utts": n_utts, "note": "CPU oracle = numpy restatement of WORLD/SPTK (pyworld/pysptk unavailable offline)"},
+                       "sample_utts": n_utts, "note": "CPU oracle = C restatement of WORLD/SPTK, gcc -O3 -march=native, one thread per utterance (pyworld/pysptk unavailable offline)"},
             "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port",
                              "sample": "%d utterances x %.1f s per step" % (n_utts, DUR)},
             "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
