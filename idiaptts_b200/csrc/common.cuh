@@ -111,7 +111,7 @@ template <int DT>
 __device__ __forceinline__ double raw_sample(const void* x, int64_t i) {
   if (DT == B2W_F64) return reinterpret_cast<const double*>(x)[i];
   if (DT == B2W_F32) return (double)reinterpret_cast<const float*>(x)[i];
-  return (double)reinterpret_cast<const int16_t*>(x)[i] / 32768.0;
+  return (double)reinterpret_cast<const int16_t*>(x)[i] * (1.0 / 32768.0);  // exact: power of two
 }
 template <int DT>
 __device__ __forceinline__ double emph_sample(const void* x, int64_t base, int idx, double p) {

@@ -269,6 +269,7 @@ class McepTables:
                 check(lib.b2w_mcep_tc_pretile(self.order, self.fft_size, self.m0t.data_ptr(), self.cmat.data_ptr(), self.m2t.data_ptr(),
                                               self.stream0.data_ptr(), self.stream1.data_ptr(), _stream(torch.device(device))),
                       "b2w_mcep_tc_pretile")
+            torch.cuda.current_stream(torch.device(device)).synchronize()  # tables are shared by every stream afterwards
 
     @classmethod
     def get(cls, order, alpha, fft_size, device):
