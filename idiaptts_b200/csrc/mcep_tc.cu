@@ -211,6 +211,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
       }
       ph_full[s] ^= 1;
       // ---- epilogue: this thread owns row `row`, bins j0 + 4 g .. + 3 ------------------------------------------------
+      // the periodogram values are requested BEFORE waiting for GEMM1, so their L2 latency overlaps the tensor work
+      float perv[4];
+      bool inb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = j0 + 4 * g + i;
+        inb[i] = j < K;
+        perv[i] = 1.f;
+        if (inb[i] && row < nvalid) perv[i] = tc_load_per<IT>(p, frame0 + row, j);
+      }
       float cv[4] = {0.f, 0.f, 0.f, 0.f};
       if (pass > 0) {
         umma::mbar_wait(bar_g1, ph_g1);
@@ -223,13 +233,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
         float pv[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int j = j0 + 4 * g + i;
-          float per = 1.f;
-          const bool inb = j < K;
-          if (inb && row < nvalid) per = tc_load_per<IT>(p, frame0 + row, j);
-          if (!(per > 0.f)) zero_per = true;
-          const float val = pass == 0 ? logf(per) : per * expf(-2.f * cv[i]);
-          pv[i] = inb ? val : 0.f;
+          if (!(perv[i] > 0.f)) zero_per = true;
+          const float val = pass == 0 ? logf(perv[i]) : perv[i] * expf(-2.f * cv[i]);
+          pv[i] = inb[i] ? val : 0.f;
         }
         umma::split_tf32(pv[0], ph.x, pl.x);
         umma::split_tf32(pv[1], ph.y, pl.y);
