@@ -190,6 +190,7 @@ def run_b200(args):
     batch = to_dev()
     F = batch.num_frames
     an = pipeline.WorldAnalyzer(FS, NUM_CODED_SPS, alpha, device=dev, chunk_frames=args.chunk_frames)
+    an.iters = torch.zeros(F, dtype=torch.int32, device=dev)
     feats = torch.empty((F, an.dim), dtype=torch.float32, device=dev)
     stat_buf = torch.zeros(2 * an.dim + 1, dtype=torch.float64, device=dev)
 
@@ -255,11 +256,24 @@ def run_b200(args):
     top_ms = per[top][0] / per[top][1]
     top_frames = per[top][2] / per[top][1]
     achieved = alg_bytes_per_frame[top] * top_frames / (top_ms / 1e3) / 1e9
+    # the tensor-core kernel of the step, for the record: algorithmic FLOPs of the warp contractions (initial value +
+    # mean Newton passes x (freqt+FFT and IFFT+frqtr as GEMMs)), not counting the 3x of the TF32 split nor the solves
+    mean_it = float(an.iters.float().mean().item())
+    m = NUM_CODED_SPS - 1
+    flops_frame = 2.0 * K * (m + 2) + mean_it * 2.0 * K * ((m + 1) + (2 * m + 1))
+    mcep_ms = per["mcep"][0] / per["mcep"][1]
+    mcep_frames = per["mcep"][2] / per["mcep"][1]
+    mcep_tflops = flops_frame * mcep_frames / (mcep_ms / 1e3) / 1e12
     roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
                 "share_of_step": per[top][0] / total_k,
                 "shares": {k: round(v[0] / total_k, 4) for k, v in per.items()},
                 "avg_launch_ms": {k: round(v[0] / v[1], 3) for k, v in per.items()},
+                "mcep_tensor": {"bound": "tensor", "achieved": mcep_tflops, "unit": "TFLOP/s (algorithmic, fp32-equivalent)",
+                                "peak": peaks.get("bf16_tflops_sustained"), "peak_unit": "TFLOP/s bf16 dense (measured)",
+                                "mean_newton_passes": mean_it,
+                                "note": "tcgen05 kind::tf32 with the 3xTF32 split; the kernel is bound by the per-frame 60x60 solves, "
+                                        "not by the tensor pipe"},
                 "note": "compute-bound kernel (fp64 FFTs / fp32 contractions): the HBM fraction is reported because the "
                         "metric asks for it, see DESIGN.md for the per-kernel bounds"}
 

@@ -5,10 +5,10 @@
 // Same mathematics and the same reference call site as mcep.cu (pysptk.mcep, AudioProcessing.py:146); this is the
 // production path for order <= 63.  One CTA = 128 frames (the UMMA M dimension), 512 threads.
 //
-//   per Newton iteration, for each chunk of 16 frequency bins j0 .. j0+15 (33 chunks at K = 513):
-//     GEMM1   D1[128 x 16]   = mc[128 x 64] . Cmat[64 x 16 chunk]          24 MMAs (8 K-steps x 3 split products)
+//   per Newton iteration, for each chunk of 32 frequency bins j0 .. j0+31 (17 chunks at K = 513):
+//     GEMM1   D1[128 x 32]   = mc[128 x 64] . Cmat[64 x 32 chunk]          24 MMAs (8 K-steps x 3 split products)
 //     epilogue (all threads)  P = per * exp(-2 D1)  -> hi/lo TF32 tiles in shared memory (A operand of GEMM2)
-//     GEMM2   D2[128 x 128] += P[128 x 16] . M2^T[16 chunk x 128]           6 MMAs
+//     GEMM2   D2[128 x 128] += P[128 x 32] . M2^T[32 chunk x 128]          12 MMAs
 //   then D2 row f = r~ of frame f: stopping rule on r~[0], and for the frames still iterating one warp each builds and
 //   solves the (m+1) x (m+1) Toeplitz-plus-Hankel system (mcep_solve.cuh) and updates mc (fp32, shared memory).
 //   Pass 0 (initial value) uses the same machinery: P = log(per), the stream holds M0^T instead of M2^T, GEMM1 is skipped.
@@ -20,16 +20,16 @@ namespace b2w {
 
 constexpr int kTcF = 128;        // frames per CTA = UMMA M
 constexpr int kTcThreads = 512;  // 16 warps: TMEM lane quarter q = warp & 3, column group g = warp >> 2
-constexpr int kTcBK = 16;        // bins per chunk
+constexpr int kTcBK = 32;        // bins per chunk
 constexpr int kTcMP = 64;        // padded cepstral dimension (K of GEMM1)
 constexpr int kTcN2 = 128;       // padded r~ length (N of GEMM2)
 constexpr int kTcKB = 20;        // padded block stride of the solve workspace (bank-conflict free float4 accesses)
 constexpr uint32_t kB1Bytes = kTcBK * kTcMP * 4;   // one of hi / lo of the Cmat chunk   [N = 16 rows (bins)] x [K = 64]
 constexpr uint32_t kB2Bytes = kTcN2 * kTcBK * 4;   // one of hi / lo of the M2^T chunk   [N = 128 rows]       x [K = 16]
-constexpr uint32_t kStageBytes = 2 * kB1Bytes + 2 * kB2Bytes;  // 24 KB per chunk: [B1 hi | B1 lo | B2 hi | B2 lo]
+constexpr uint32_t kStageBytes = 2 * kB1Bytes + 2 * kB2Bytes;  // 48 KB per chunk: [B1 hi | B1 lo | B2 hi | B2 lo]
 constexpr uint32_t kA1Bytes = kTcF * kTcMP * 4;    // 32 KB, one of hi / lo
-constexpr uint32_t kA2Bytes = kTcF * kTcBK * 4;    // 8 KB, one of hi / lo
-constexpr int kTmemCols = 256;                     // D1 at column 0 (16 used), D2 at column 32 (128 used)
+constexpr uint32_t kA2Bytes = kTcF * kTcBK * 4;    // 16 KB, one of hi / lo
+constexpr int kTmemCols = 256;                     // D1 at columns 0..31, D2 at columns 32..159
 
 struct McepTcParams {
   const void* in;
@@ -97,7 +97,7 @@ template <typename IT>
 __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   // ---- shared memory map ----------------------------------------------------------------------------------------------
-  // GEMM phase:  [A1 hi 32K | A1 lo 32K | stage 0 24K | stage 1 24K | A2 hi 8K | A2 lo 8K]  = 128 KB
+  // GEMM phase:  [A1 hi 32K | A1 lo 32K | stage 0 48K | stage 1 48K | A2 hi 16K | A2 lo 16K]  = 192 KB
   // solve phase: the same region holds the 16 per-warp workspaces
   uint8_t* region = smem_raw;
   float* a1_hi = reinterpret_cast<float*>(region);
@@ -210,37 +210,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
         }
       }
       ph_full[s] ^= 1;
-      // ---- epilogue: this thread owns row `row`, bins j0 + 4 g .. + 3 ------------------------------------------------
+      // ---- epilogue: this thread owns row `row`, bins j0 + 8 g .. + 7 ------------------------------------------------
       // the periodogram values are requested BEFORE waiting for GEMM1, so their L2 latency overlaps the tensor work
-      float perv[4];
-      bool inb[4];
+      constexpr int CPT = kTcBK / 4;  // columns per thread
+      float perv[CPT];
+      bool inb[CPT];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int j = j0 + 4 * g + i;
+      for (int i = 0; i < CPT; ++i) {
+        const int j = j0 + CPT * g + i;
         inb[i] = j < K;
         perv[i] = 1.f;
         if (inb[i] && row < nvalid) perv[i] = tc_load_per<IT>(p, frame0 + row, j);
       }
-      float cv[4] = {0.f, 0.f, 0.f, 0.f};
+      float cv[CPT];
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) cv[i] = 0.f;
       if (pass > 0) {
         umma::mbar_wait(bar_g1, ph_g1);
         ph_g1 ^= 1;
         umma::tc_fence_after_sync();
-        umma::tmem_ld4(t_d1 + 4 * g, cv);
+        umma::tmem_ld8(t_d1 + CPT * g, cv);
       }
-      float4 ph, pl;
-      {
-        float pv[4];
+      float ph[CPT], pl[CPT];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (!(perv[i] > 0.f)) zero_per = true;
-          const float val = pass == 0 ? logf(perv[i]) : perv[i] * expf(-2.f * cv[i]);
-          pv[i] = inb[i] ? val : 0.f;
-        }
-        umma::split_tf32(pv[0], ph.x, pl.x);
-        umma::split_tf32(pv[1], ph.y, pl.y);
-        umma::split_tf32(pv[2], ph.z, pl.z);
-        umma::split_tf32(pv[3], ph.w, pl.w);
+      for (int i = 0; i < CPT; ++i) {
+        if (!(perv[i] > 0.f)) zero_per = true;
+        const float val = pass == 0 ? logf(perv[i]) : perv[i] * expf(-2.f * cv[i]);
+        umma::split_tf32(inb[i] ? val : 0.f, ph[i], pl[i]);
       }
       if (c > 0) {  // A2 is single-buffered: the previous GEMM2 must have consumed it (pass boundaries are drained)
         umma::mbar_wait(bar_g2, ph_g2);
@@ -253,10 +249,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
         umma::bulk_g2s(stage_base + sn * kStageBytes, reinterpret_cast<const uint8_t*>(stream) + (size_t)(c + 1) * kStageBytes,
                        kStageBytes, &bar_full[sn]);
       }
-      {
-        const uint32_t off = umma::tile_off(kTcF, row, 4 * g) / 4;
-        *reinterpret_cast<float4*>(a2_hi + off) = ph;
-        *reinterpret_cast<float4*>(a2_lo + off) = pl;
+#pragma unroll
+      for (int h4 = 0; h4 < CPT / 4; ++h4) {
+        const uint32_t off = umma::tile_off(kTcF, row, CPT * g + 4 * h4) / 4;
+        *reinterpret_cast<float4*>(a2_hi + off) = make_float4(ph[4 * h4], ph[4 * h4 + 1], ph[4 * h4 + 2], ph[4 * h4 + 3]);
+        *reinterpret_cast<float4*>(a2_lo + off) = make_float4(pl[4 * h4], pl[4 * h4 + 1], pl[4 * h4 + 2], pl[4 * h4 + 3]);
       }
       umma::fence_proxy_async();
       umma::tc_fence_before_sync();

@@ -89,6 +89,17 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
   for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 8 consecutive columns (two 16-byte K-chunks)
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // ---- descriptors -------------------------------------------------------------------------------------------------------------
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, leading (K) and stride (M/N) byte offsets
 // in 16-byte units, version 1 (Blackwell), no swizzle

@@ -34,6 +34,7 @@ class WorldAnalyzer:
         # upload the warping matrices once
         ops.McepTables.get(self.num_coded_sps - 1, self.alpha, self.n_fft, self.device)
         self._sp = None
+        self.iters = None  # optional int32 [F] buffer: Newton iterations per frame (bench.py's FLOP accounting)
 
     def _sp_buffer(self, frames):
         K = self.n_fft // 2 + 1
@@ -77,8 +78,9 @@ class WorldAnalyzer:
             nf = hi - lo
             timed("cheaptrick", nf, lambda: ops.cheaptrick(batch, fft_size=self.n_fft, status=status, frame_lo=lo, frame_hi=hi,
                                                            out=spc))
+            it = None if self.iters is None else self.iters[lo:hi]
             timed("mcep", nf, lambda: ops.mcep(spc, D - 1, self.alpha, is_power=True, out=flat[lo * self.dim:],
-                                               out_stride=self.dim, status=status))
+                                               out_stride=self.dim, status=status, iters=it))
             coarse, voiced, _ = timed("d4c", nf, lambda: ops.d4c_coarse(batch, status=status, frame_lo=lo, frame_hi=hi))
             timed("bap_from_coarse", nf, lambda: ops.bap_from_coarse(coarse, voiced, self.fs, self.n_fft,
                                                                      out=flat[lo * self.dim + D + 2:], out_stride=self.dim))
