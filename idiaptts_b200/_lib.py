@@ -6,7 +6,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200world.so")
+# B2W_LIB selects another build of the same ABI (kernel-variant experiments, scripts/gpu_kbench.py)
+LIB_PATH = os.environ.get("B2W_LIB") or os.path.join(_HERE, "libb200world.so")
 
 B2W_F64, B2W_F32, B2W_I16 = 0, 1, 2
 STATUS_F0_TOO_HIGH = 1

@@ -138,6 +138,126 @@ __device__ __forceinline__ void cfft(typename Vec2<T>::type* z, const double2* _
   }
 }
 
+// ---- shared-memory twiddles ---------------------------------------------------------------------------------------------------
+// The FFT kernels are bound by the L1/LSU data pipe, and a gathered 16-byte global load costs one 32-byte sector per lane.
+// cfft_s therefore reads ONE twiddle per butterfly, w = exp(-2 pi i k / (Ns R)), from a small per-CTA shared-memory table
+// (contiguous in k: 4 wavefronts per warp) and forms w^2 .. w^(R-1) by multiplication (a few ulp, on the idle fp64 pipe).
+//   layout (complex entries):  [0, 8)    pass with Ns = 8      w(k),  k < 8
+//                              [8, 72)   pass with Ns = 64     w(k),  k < 64
+//                              [72, 136) pass with Ns >= 256   w(8 a), a < Ns / 8      (two-level: w(k) = w(8 a) w(b))
+//                              [136,144) pass with Ns >= 256   w(b),  b < 8
+constexpr int kFftTwEntries = 144;
+
+template <int M> struct FftPlan;  // radices of the passes, first to last
+template <> struct FftPlan<256> { static constexpr int n = 3; static constexpr int R[4] = {8, 8, 4, 1}; };
+template <> struct FftPlan<512> { static constexpr int n = 3; static constexpr int R[4] = {8, 8, 8, 1}; };
+template <> struct FftPlan<1024> { static constexpr int n = 4; static constexpr int R[4] = {8, 8, 4, 4}; };
+template <> struct FftPlan<2048> { static constexpr int n = 4; static constexpr int R[4] = {8, 8, 8, 4}; };
+template <> struct FftPlan<4096> { static constexpr int n = 4; static constexpr int R[4] = {8, 8, 8, 8}; };
+
+// Fills the table for cfft_s<T, M>; call once per CTA (all threads), followed by a __syncthreads() before the first FFT.
+template <typename T, int M, int NT>
+__device__ __forceinline__ void fft_tw_fill(typename Vec2<T>::type* tws, const double2* __restrict__ tw, int tid) {
+  using V = typename Vec2<T>::type;
+  using P = FftPlan<M>;
+  constexpr int R1 = P::R[1], R2 = P::R[2], R3 = P::R[3], Ns3 = P::R[0] * P::R[1] * P::R[2];
+  for (int e = tid; e < kFftTwEntries; e += NT) {
+    int idx = 0;  // index into the global table of kTwN-th roots
+    if (e < 8) idx = e * (kTwN / (8 * R1));
+    else if (e < 72) idx = (e - 8) * (kTwN / (64 * R2));
+    else if (P::n == 4) {
+      constexpr int step = kTwN / (Ns3 * R3);
+      idx = e < 136 ? ((e - 72) * 8 < Ns3 ? (e - 72) * 8 * step : 0) : (e - 136) * step;
+    }
+    tws[e] = tw_load<T, V>(tw, idx);
+  }
+}
+
+template <typename T, int R, int Ns, typename V>
+__device__ __forceinline__ V fft_tw_w1(const V* tws, int k) {
+  if (Ns == 8) return tws[k];
+  if (Ns == 64) return tws[8 + k];
+  return cmul(tws[72 + (k >> 3)], tws[136 + (k & 7)]);
+}
+
+template <typename T, int M, int NT, int R, int Ns>
+__device__ __forceinline__ void fft_pass_s(typename Vec2<T>::type* z, const typename Vec2<T>::type* tws, int tid) {
+  using V = typename Vec2<T>::type;
+  constexpr int NB = M / R;
+  constexpr int BPT = (NB + NT - 1) / NT;
+  V v[BPT][R];
+#pragma unroll
+  for (int b = 0; b < BPT; ++b) {
+    const int j = tid + b * NT;
+    if (NB % NT == 0 || j < NB) {
+#pragma unroll
+      for (int q = 0; q < R; ++q) v[b][q] = z[ZP(j + q * NB)];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int b = 0; b < BPT; ++b) {
+    const int j = tid + b * NT;
+    if (NB % NT == 0 || j < NB) {
+      const int k = j & (Ns - 1);
+      if (Ns > 1) {
+        const V w1 = fft_tw_w1<T, R, Ns, V>(tws, k);
+        const V w2 = cmul(w1, w1);
+        v[b][1] = cmul(v[b][1], w1);
+        v[b][2] = cmul(v[b][2], w2);
+        const V w3 = cmul(w2, w1);
+        v[b][3] = cmul(v[b][3], w3);
+        if (R == 8) {
+          const V w4 = cmul(w2, w2);
+          v[b][4] = cmul(v[b][4], w4);
+          v[b][5] = cmul(v[b][5], cmul(w4, w1));
+          v[b][6] = cmul(v[b][6], cmul(w3, w3));
+          v[b][7] = cmul(v[b][7], cmul(w4, w3));
+        }
+      }
+      dftR<T, R, V>(v[b]);
+      const int j0 = (j - k) * R + k;
+#pragma unroll
+      for (int q = 0; q < R; ++q) z[ZP(j0 + q * Ns)] = v[b][q];
+    }
+  }
+  __syncthreads();
+}
+
+// cfft with shared-memory twiddles (see above); same contract as cfft.
+template <typename T, int M, int NT>
+__device__ __forceinline__ void cfft_s(typename Vec2<T>::type* z, const typename Vec2<T>::type* tws, int tid) {
+  using P = FftPlan<M>;
+  constexpr int R0 = P::R[0], R1 = P::R[1], R2 = P::R[2], R3 = P::R[3];
+  fft_pass_s<T, M, NT, R0, 1>(z, tws, tid);
+  fft_pass_s<T, M, NT, R1, R0>(z, tws, tid);
+  fft_pass_s<T, M, NT, R2, R0 * R1>(z, tws, tid);
+  if constexpr (P::n == 4) fft_pass_s<T, M, NT, R3, R0 * R1 * R2>(z, tws, tid);
+}
+
+// Phasor pair for the real-FFT post-pass when bins are visited as k = tid, tid + NT, ...: w = exp(-2 pi i tid / N) and the
+// stride exp(-2 pi i NT / N); rfft_bin_w takes the running w, the caller advances it with cmul(w, step).
+template <typename T, int N, int NT>
+__device__ __forceinline__ void rfft_rot_init(const double2* __restrict__ tw, int tid, typename Vec2<T>::type& w0,
+                                              typename Vec2<T>::type& step) {
+  using V = typename Vec2<T>::type;
+  w0 = tw_load<T, V>(tw, tid * (kTwN / N));
+  step = tw_load<T, V>(tw, NT * (kTwN / N));
+}
+
+template <typename T, int N>
+__device__ __forceinline__ typename Vec2<T>::type rfft_bin_w(const typename Vec2<T>::type* z, int k,
+                                                             typename Vec2<T>::type w) {
+  using V = typename Vec2<T>::type;
+  constexpr int M = N / 2;
+  const V a = z[ZP(k & (M - 1))];
+  const V bq = z[ZP((M - k) & (M - 1))];
+  const V b = V{bq.x, -bq.y};
+  const V e = V{(T)0.5 * (a.x + b.x), (T)0.5 * (a.y + b.y)};
+  const V d = V{(T)0.5 * (a.x - b.x), (T)0.5 * (a.y - b.y)};
+  return cadd(e, cmul(w, cmul_mi(d)));
+}
+
 // Real sequence x[0..N) stored as N reals: real index n lives in complex slot n>>1 (component n&1) of the padded buffer.
 template <typename T>
 __device__ __forceinline__ T& zreal(typename Vec2<T>::type* z, int n) {
