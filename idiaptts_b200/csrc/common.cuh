@@ -79,6 +79,36 @@ __device__ __forceinline__ void block_sum2(double& a, double& b, double* scratch
   b = rb;
 }
 
+template <int NT>
+__device__ __forceinline__ void block_sum4(double& a, double& b, double& c, double& d, double* scratch /* >= 4*NT/32 */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+    d += __shfl_xor_sync(0xffffffffu, d, o);
+  }
+  if (NT == 32) return;
+  __syncthreads();
+  if (lane == 0) {
+    scratch[4 * warp] = a;
+    scratch[4 * warp + 1] = b;
+    scratch[4 * warp + 2] = c;
+    scratch[4 * warp + 3] = d;
+  }
+  __syncthreads();
+  double ra = 0.0, rb = 0.0, rc = 0.0, rd = 0.0;
+#pragma unroll
+  for (int w = 0; w < NT / 32; ++w) {
+    ra += scratch[4 * w];
+    rb += scratch[4 * w + 1];
+    rc += scratch[4 * w + 2];
+    rd += scratch[4 * w + 3];
+  }
+  a = ra; b = rb; c = rc; d = rd;
+}
+
 // In-place inclusive prefix sum of a[0..L) in shared memory (fp64). Each thread scans a contiguous chunk.
 template <int NT>
 __device__ __forceinline__ void block_scan_inclusive(double* a, int L, double* scratch /* >= NT/32 + 1 */) {

@@ -224,6 +224,30 @@ __device__ __forceinline__ void fft_pass_s(typename Vec2<T>::type* z, const type
   __syncthreads();
 }
 
+// First Stockham pass (Ns = 1) of an M-point FFT whose inputs are already in registers: v[q] = x[tid + q * NT] with
+// NT == M / R (one butterfly per thread).  Producers (windowing) therefore never stage the FFT input in shared memory and the
+// pass has no loads.  The caller guarantees that no thread still reads z (a __syncthreads() since the last read).
+template <typename T, int M, int NT>
+__device__ __forceinline__ void fft_first_pass_regs(typename Vec2<T>::type* z, typename Vec2<T>::type* v, int tid) {
+  using V = typename Vec2<T>::type;
+  constexpr int R = FftPlan<M>::R[0];
+  static_assert(M / R == NT, "one first-pass butterfly per thread");
+  dftR<T, R, V>(v);
+#pragma unroll
+  for (int q = 0; q < R; ++q) z[ZP(tid * R + q)] = v[q];
+  __syncthreads();
+}
+
+// Passes 2.. of cfft_s after fft_first_pass_regs.
+template <typename T, int M, int NT>
+__device__ __forceinline__ void cfft_s_tail(typename Vec2<T>::type* z, const typename Vec2<T>::type* tws, int tid) {
+  using P = FftPlan<M>;
+  constexpr int R0 = P::R[0], R1 = P::R[1], R2 = P::R[2], R3 = P::R[3];
+  fft_pass_s<T, M, NT, R1, R0>(z, tws, tid);
+  fft_pass_s<T, M, NT, R2, R0 * R1>(z, tws, tid);
+  if constexpr (P::n == 4) fft_pass_s<T, M, NT, R3, R0 * R1 * R2>(z, tws, tid);
+}
+
 // cfft with shared-memory twiddles (see above); same contract as cfft.
 template <typename T, int M, int NT>
 __device__ __forceinline__ void cfft_s(typename Vec2<T>::type* z, const typename Vec2<T>::type* tws, int tid) {
