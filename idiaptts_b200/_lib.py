@@ -28,7 +28,7 @@ class Batch(ctypes.Structure):
 _SIGNATURES = {
     "b2w_version": (c_int32, []),
     "b2w_last_error": (ctypes.c_char_p, []),
-    "b2w_cheaptrick": (c_int32, [ctypes.POINTER(Batch), c_int32, c_double, c_void_p, c_int32, c_void_p, c_void_p]),
+    "b2w_cheaptrick": (c_int32, [ctypes.POINTER(Batch), c_int32, c_double, c_void_p, c_int32, c_int64, c_void_p, c_void_p]),
     "b2w_d4c_coarse": (c_int32, [ctypes.POINTER(Batch), c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2w_d4c_expand": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "b2w_bap_from_coarse": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int64, c_void_p]),
@@ -41,7 +41,7 @@ _SIGNATURES = {
                            c_void_p]),
     "b2w_mcep_tc_stream_floats": (c_int64, [c_int32]),
     "b2w_mcep_tc_pretile": (c_int32, [c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "b2w_mcep_tc": (c_int32, [c_void_p, c_int32, c_int32, c_int64, c_int32, c_int32, c_double, c_int32, c_int32, c_double,
+    "b2w_mcep_tc": (c_int32, [c_void_p, c_int32, c_int32, c_int64, c_int64, c_int32, c_int32, c_double, c_int32, c_int32, c_double,
                               c_double, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_void_p]),
     "b2w_mc2sp": (c_int32, [c_void_p, c_int32, c_int64, c_int64, c_int32, c_int32, c_void_p, c_double, c_int32, c_void_p,
                             c_int32, c_void_p]),

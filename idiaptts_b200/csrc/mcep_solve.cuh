@@ -148,4 +148,137 @@ __device__ __forceinline__ bool warp_ldl_solve(const float* __restrict__ rt, con
 }
 
 
+// ---- register-resident LDL^T solve of the same system (compile-time size NS, NS % 4 == 0, NS <= 64) --------------------------------
+// The blocked solver above keeps the matrix in shared memory and is bound by dependent shared-memory round trips and by issue
+// slots (~7.6 k warp instructions for NS = 60).  Here lane l owns rows l and NS-1-l of the lower triangle IN REGISTERS
+// (l < NS/2; l + 1 and NS - l entries: balanced), the code is fully unrolled so every register index is static, and per pivot
+// column j the only exchange is: the UNSCALED column W[k][j] = A[k][j] is written once to shared memory (packed column-major,
+// kept for the back substitution) and read back as broadcast float4 vectors, while d_j and y_j travel by shuffle:
+//       A[i][k] -= (W[i][j] / d_j) W[k][j],   y_i -= (W[i][j] / d_j) y_j              (two f32x2 FMAs per float4 of column)
+// Entries of a lane's register rows beyond the row length hold garbage that is never read by valid data.
+// Back substitution runs in axpy form on the packed columns: lane c accumulates t_c = sum_i W[i][c] x_i for c = lane, lane + 32.
+__host__ __device__ constexpr int rr_col_start(int j) { return ((j + 1) / 4) * 4; }  // first stored row of column j
+// Packed column storage: row k >= rr_col_start(j) of column j lives at Wc[rr_col_base(NS, j) + k].  Column starts are float4
+// aligned and skewed so that base(j) = 4 j (mod 32): in the back substitution lane c reads column c, and the skew spreads the
+// 32 lanes' float4 loads over all banks (4 wavefronts per request, the minimum for 512 bytes).
+__host__ __device__ constexpr int rr_col_base(int NS, int j, bool want_end = false) {
+  int end = 0, base = 0;
+  for (int c = 0; c <= j; ++c) {
+    const int st = rr_col_start(c);
+    int off = end;
+    off += (((4 * c + st) % 32 - off % 32) + 32) % 32;
+    base = off - st;
+    end = off + (NS - st);
+  }
+  return want_end ? end : base;
+}
+__host__ __device__ constexpr int rr_workspace_floats(int NS) { return rr_col_base(NS, NS - 2, true) + 64 + 128; }
+
+__device__ __forceinline__ void ffma2(float2& c, const float2 a, const float2 b) {
+  unsigned long long cc = *reinterpret_cast<unsigned long long*>(&c);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;"
+      : "+l"(cc)
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+  c = *reinterpret_cast<float2*>(&cc);
+}
+
+// rt: r~[0 .. 2 NS - 2] with at least 64 readable floats BEFORE rt[0] (garbage allowed); al: (-alpha)^k; Wc: per-warp scratch of
+// rr_col_base(NS, NS - 2, true) floats.  On return lane l holds x[l] in x0 and x[l + 32] in x1.  Returns false (warp-uniform) when a
+// pivot is not positive.
+// colbase: shared-memory table of rr_col_base(NS, j), j < NS - 1 (filled once per CTA).
+template <int NS>
+__device__ __forceinline__ bool warp_rr_solve(const float* __restrict__ rt, const float* __restrict__ al, float* __restrict__ Wc,
+                                             const int* __restrict__ colbase, float& x0, float& x1) {
+  static_assert(NS % 4 == 0 && NS >= 8 && NS <= 64, "unsupported system size");
+  constexpr int H = NS / 2;            // lanes that own rows
+  constexpr int HP = (H + 3) & ~3;     // register row A, padded to whole float4 groups
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const bool act = lane < H;
+  const int iA = act ? lane : 0, iB = act ? NS - 1 - lane : NS - 1;  // idle lanes mirror lane 0 (they never store)
+  float2 a[HP / 2], b[NS / 2];
+  {
+    const float* rA = rt + iA;
+    const float* rB = rt + iB;
+#pragma unroll
+    for (int k = 0; k < HP; k += 2) a[k / 2] = make_float2(rA[-k] + rA[k], rA[-k - 1] + rA[k + 1]);
+#pragma unroll
+    for (int k = 0; k < NS; k += 2) b[k / 2] = make_float2(rB[-k] + rB[k], rB[-k - 1] + rB[k + 1]);
+  }
+  float yA = rt[iA] - al[iA], yB = rt[iB] - al[iB];
+  float rdk0 = 0.f, rdk1 = 0.f, zk0 = 0.f, zk1 = 0.f;  // 1 / d_c and z_c = y_c / d_c for c = lane, lane + 32
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < NS; ++j) {
+    // pivot and right-hand side of row j from their owner
+    const float dsrc = (j < H) ? ((j & 1) ? a[j / 2].y : a[j / 2].x) : ((j & 1) ? b[j / 2].y : b[j / 2].x);
+    const float ysrc = (j < H) ? yA : yB;
+    const int owner = (j < H) ? j : NS - 1 - j;
+    const float d = __shfl_sync(FULL, dsrc, owner);
+    const float yj = __shfl_sync(FULL, ysrc, owner);
+    ok = ok && (d > 0.f);
+    float rd = __fdividef(1.f, d);  // MUFU.RCP + one Newton step: correctly rounded up to the last bit or two
+    rd = fmaf(fmaf(-d, rd, 1.f), rd, rd);
+    if (lane == (j & 31)) {
+      if (j < 32) { rdk0 = rd; zk0 = yj * rd; }
+      else { rdk1 = rd; zk1 = yj * rd; }
+    }
+    if (j == NS - 1) break;
+    // this lane's entries of column j (0 where the row is not below the diagonal)
+    float wA = 0.f;
+    if (j < H) wA = (lane > j && act) ? ((j & 1) ? a[j / 2].y : a[j / 2].x) : 0.f;
+    const float wB = (iB > j && act) ? ((j & 1) ? b[j / 2].y : b[j / 2].x) : 0.f;
+    const int st = rr_col_start(j);
+    float* col = Wc + colbase[j];  // indexed by the absolute row
+    if (st < H) { if (act && iA >= st) col[iA] = wA; }
+    if (act && iB >= st) col[iB] = wB;
+    const float lA = wA * rd, lB = wB * rd;
+    yA -= lA * yj;
+    yB -= lB * yj;
+    const float2 nA = make_float2(-lA, -lA), nB = make_float2(-lB, -lB);
+    __syncwarp();
+#pragma unroll
+    for (int k4 = st; k4 < NS; k4 += 4) {
+      const float4 c = *reinterpret_cast<const float4*>(col + k4);
+      const float2 c01 = make_float2(c.x, c.y), c23 = make_float2(c.z, c.w);
+      if (k4 < H) {
+        ffma2(a[k4 / 2], nA, c01);
+        ffma2(a[k4 / 2 + 1], nA, c23);
+      }
+      ffma2(b[k4 / 2], nB, c01);
+      ffma2(b[k4 / 2 + 1], nB, c23);
+    }
+  }
+  ok = __all_sync(FULL, ok);
+  // backward substitution  x_c = z_c - (1 / d_c) sum_{i > c} W[i][c] x_i
+  const int c0i = lane < NS - 1 ? lane : 0, c1i = lane + 32 < NS - 1 ? lane + 32 : 0;
+  const float* c0 = Wc + colbase[c0i];
+  const float* c1 = Wc + colbase[c1i];
+  float t0 = 0.f, t1 = 0.f;
+  x0 = 0.f;
+  x1 = 0.f;
+  __syncwarp();
+  float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
+#pragma unroll
+  for (int i = NS - 1; i >= 0; --i) {
+    if ((i & 3) == 3) {  // rows i-3 .. i of this lane's two columns (rows above a column's start are other columns' data:
+      w0 = *reinterpret_cast<const float4*>(c0 + i - 3);  // they only reach accumulators that are already closed)
+      w1 = *reinterpret_cast<const float4*>(c1 + i - 3);
+    }
+    const float xv = (i < 32) ? zk0 - rdk0 * t0 : zk1 - rdk1 * t1;
+    const float xi = __shfl_sync(FULL, xv, i & 31);
+    if (lane == (i & 31)) {
+      if (i < 32) x0 = xi;
+      else x1 = xi;
+    }
+    if (i > 0) {  // contributions to the columns still open (c < i); closed accumulators collect garbage that is never read
+      const float e0 = (i & 3) == 3 ? w0.w : (i & 3) == 2 ? w0.z : (i & 3) == 1 ? w0.y : w0.x;
+      const float e1 = (i & 3) == 3 ? w1.w : (i & 3) == 2 ? w1.z : (i & 3) == 1 ? w1.y : w1.x;
+      t0 += e0 * xi;
+      t1 += e1 * xi;
+    }
+  }
+  return ok;
+}
+
 }  // namespace b2w

@@ -34,6 +34,8 @@ constexpr int kTmemCols = 256;                     // D1 at columns 0..31, D2 at
 struct McepTcParams {
   const void* in;
   int in_is_power;
+  int in_vec4;       // rows are 16-byte aligned fp32: read with float4 loads
+  int64_t in_stride; // elements
   int64_t num_frames;
   int K, m, NBk, nchunks;
   int ws_floats;   // per-warp solve workspace
@@ -87,13 +89,32 @@ __global__ void mcep_tc_pretile_kernel(const float* __restrict__ m0t, int np0, c
   }
 }
 
+// Periodogram values of row `frame`, bins jb .. jb + 7 (raw input; 1 where the bin is outside the spectrum so that log / the
+// zero check stay quiet).  Lanes hold different rows, so every load instruction costs one sector per lane: with padded rows
+// two float4 loads replace eight scalar ones.
 template <typename IT>
-__device__ __forceinline__ float tc_load_per(const McepTcParams& p, int64_t frame, int j) {
-  const float v = (float)reinterpret_cast<const IT*>(p.in)[frame * p.K + j];
-  return p.in_is_power ? v + p.eps : fmaf(v, v, p.eps);
+__device__ __forceinline__ void tc_load_raw8(const McepTcParams& p, int64_t frame, int jb, bool valid, float (&v)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = 1.f;
+  if (!valid) return;
+  const IT* rp = reinterpret_cast<const IT*>(p.in) + frame * p.in_stride + jb;
+  if (sizeof(IT) == 4 && p.in_vec4) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (jb + 4 * h < p.K) {  // the padded row covers the whole float4 (in_stride is a multiple of 4 >= K)
+        const float4 q4 = __ldg(reinterpret_cast<const float4*>(rp) + h);
+        v[4 * h] = q4.x; v[4 * h + 1] = q4.y; v[4 * h + 2] = q4.z; v[4 * h + 3] = q4.w;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (jb + i < p.K) v[i] = (float)rp[i];
+  }
 }
 
-template <typename IT>
+// NS = m + 1 when the register-resident solver is compiled for this order (mcep_solve.cuh), 0 = generic blocked solver
+template <typename IT, int NS>
 __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   // ---- shared memory map ----------------------------------------------------------------------------------------------
@@ -116,7 +137,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
   int* qcnt = itc + kTcF;                                         // [4] work counters of the lane quarters
   uint64_t* bars = reinterpret_cast<uint64_t*>(qcnt + 4);         // full[2], g1, g2
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
-  uint16_t* tri = reinterpret_cast<uint16_t*>(tmem_slot + 2);
+  int* colbase = reinterpret_cast<int*>(tmem_slot + 2);            // [64] packed-column offsets of the register-resident solver
+  uint16_t* tri = reinterpret_cast<uint16_t*>(colbase + 64);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, g = warp >> 2;
@@ -141,6 +163,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
     while (qq > a_) { qq -= a_ + 1; ++a_; }
     tri[pi] = (uint16_t)((a_ << 8) | qq);
   }
+  if (NS > 0 && tid < 64) colbase[tid] = rr_col_base(NS > 0 ? NS : 8, tid < NS - 1 ? tid : 0);
   if (tid < kTcMP) al[tid] = (tid <= m) ? powf(-p.alpha, (float)tid) : 0.f;
   if (tid == 0) al[0] = 1.f;
   if (tid < kTcF) {
@@ -186,6 +209,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
                        &bar_full[s]);
       }
     }
+    float pern[kTcBK / 4];  // raw periodogram values of the chunk about to be processed (prefetched one chunk ahead)
+    tc_load_raw8<IT>(p, frame0 + row, (kTcBK / 4) * g, row < nvalid, pern);
     for (int c = 0; c < p.nchunks; ++c) {
       const int s = c & 1;
       const uint8_t* stg = stage_base + s * kStageBytes;
@@ -213,15 +238,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
       // ---- epilogue: this thread owns row `row`, bins j0 + 8 g .. + 7 ------------------------------------------------
       // the periodogram values are requested BEFORE waiting for GEMM1, so their L2 latency overlaps the tensor work
       constexpr int CPT = kTcBK / 4;  // columns per thread
+      static_assert(CPT == 8, "tc_load_raw8 reads eight bins per thread");
       float perv[CPT];
       bool inb[CPT];
 #pragma unroll
       for (int i = 0; i < CPT; ++i) {
         const int j = j0 + CPT * g + i;
         inb[i] = j < K;
-        perv[i] = 1.f;
-        if (inb[i] && row < nvalid) perv[i] = tc_load_per<IT>(p, frame0 + row, j);
+        perv[i] = inb[i] ? (p.in_is_power ? pern[i] + p.eps : fmaf(pern[i], pern[i], p.eps)) : 1.f;
       }
+      // request the next chunk's values now: their latency hides behind this chunk's tensor work and epilogue
+      if (c + 1 < p.nchunks) tc_load_raw8<IT>(p, frame0 + row, j0 + kTcBK + CPT * g, row < nvalid, pern);
       float cv[CPT];
 #pragma unroll
       for (int i = 0; i < CPT; ++i) cv[i] = 0.f;
@@ -318,8 +345,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
     // ---- Newton step: the warps of a lane quarter share its 32 frames through a work counter -----------------------
     {
       float* ws = reinterpret_cast<float*>(region) + warp * p.ws_floats;
-      float* rtrow = ws + ldl_workspace_floats(p.NBk, kTcKB);   // [128]
-      float* xo = rtrow + kTcN2;                                // [64]
+      // generic: [blocked LDL^T workspace | r~ row 128 | x 64];  register-resident: [packed columns | 64 pad | r~ row 128]
+      float* rtrow = ws + (NS > 0 ? rr_workspace_floats(NS > 0 ? NS : 8) - kTcN2 : ldl_workspace_floats(p.NBk, kTcKB));
+      float* xo = rtrow + kTcN2;                                // [64] (generic solver only)
       for (;;) {
         int idx = 0;
         if (lane == 0) idx = atomicAdd(&qcnt[q], 1);
@@ -338,15 +366,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
           }
         }
         __syncwarp();
-        const bool ok = warp_ldl_solve<kTcKB>(rtrow, al, m + 1, p.NBk, tri, ws, xo);
-        if (!ok) {
-          if (lane == 0) {
-            atomicOr(p.status, B2W_STATUS_SOLVE_FAILED);
-            act[f] = 0;
-            itc[f] = pass;
+        bool ok;
+        if constexpr (NS > 0) {
+          float x0, x1;
+          ok = warp_rr_solve<NS>(rtrow, al, ws, colbase, x0, x1);
+          if (ok) {
+            if (lane < NS) mc[f * kTcMP + lane] += x0;
+            if (lane + 32 < NS) mc[f * kTcMP + lane + 32] += x1;
           }
         } else {
-          for (int k = lane; k <= m; k += 32) mc[f * kTcMP + k] += xo[k];
+          ok = warp_ldl_solve<kTcKB>(rtrow, al, m + 1, p.NBk, tri, ws, xo);
+          if (ok) {
+            for (int k = lane; k <= m; k += 32) mc[f * kTcMP + k] += xo[k];
+          }
+        }
+        if (!ok && lane == 0) {
+          atomicOr(p.status, B2W_STATUS_SOLVE_FAILED);
+          act[f] = 0;
+          itc[f] = pass;
         }
         __syncwarp();
       }
@@ -392,7 +429,8 @@ extern "C" int b2w_mcep_tc_pretile(int32_t order, int32_t fft_size, const float*
   return check_launch("mcep_tc_pretile_kernel");
 }
 
-extern "C" int b2w_mcep_tc(const void* in, int32_t in_dtype, int32_t in_is_power, int64_t num_frames, int32_t fft_size, int32_t order,
+extern "C" int b2w_mcep_tc(const void* in, int32_t in_dtype, int32_t in_is_power, int64_t in_stride, int64_t num_frames,
+                           int32_t fft_size, int32_t order,
                            double alpha, int32_t miniter, int32_t maxiter, double threshold, double eps, const float* stream0,
                            const float* stream1, void* mc, int32_t mc_dtype, int64_t mc_stride, int32_t* iters, int32_t* status,
                            void* stream) {
@@ -403,30 +441,43 @@ extern "C" int b2w_mcep_tc(const void* in, int32_t in_dtype, int32_t in_is_power
   B2W_REQUIRE(order >= 1 && order <= 62, "b2w_mcep_tc: order %d out of range [1, 62] (use b2w_mcep)", order);
   B2W_REQUIRE(fft_size >= 64 && (fft_size & (fft_size - 1)) == 0, "b2w_mcep_tc: bad fft_size %d", fft_size);
   B2W_REQUIRE(mc_stride >= order + 1 && maxiter >= 1 && miniter >= 1, "b2w_mcep_tc: bad stride / iteration limits");
+  B2W_REQUIRE(in_stride >= fft_size / 2 + 1, "b2w_mcep_tc: in_stride %lld < fft_size/2+1", (long long)in_stride);
   if (num_frames == 0) return 0;
   McepTcParams p;
   p.in = in; p.in_is_power = in_is_power; p.num_frames = num_frames;
+  p.in_stride = in_stride;
+  p.in_vec4 = (in_dtype == B2W_F32 && in_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0) ? 1 : 0;
   p.K = fft_size / 2 + 1; p.m = order; p.NBk = (order + 1 + 3) / 4;
   p.nchunks = (p.K + kTcBK - 1) / kTcBK;
   p.ws_floats = ldl_workspace_floats(p.NBk, kTcKB) + kTcN2 + kTcMP;
+  if (order + 1 == 20 || order + 1 == 40 || order + 1 == 60) p.ws_floats = max(p.ws_floats, rr_workspace_floats(order + 1));
   p.miniter = miniter; p.maxiter = maxiter; p.threshold = (float)threshold; p.eps = (float)eps; p.alpha = (float)alpha;
   p.stream0 = stream0; p.stream1 = stream1; p.mc_out = mc; p.mc_dtype = mc_dtype; p.mc_stride = mc_stride;
   p.iters = iters; p.status = status;
   const uint32_t gemm_bytes = 2 * kA1Bytes + 2 * kStageBytes + 2 * kA2Bytes;
   const uint32_t ws_bytes = (uint32_t)(kTcThreads / 32) * (uint32_t)p.ws_floats * 4u;
   const uint32_t region_bytes = gemm_bytes > ws_bytes ? gemm_bytes : ws_bytes;
-  const size_t smem = region_bytes + sizeof(float) * (kTcF * kTcMP + kTcMP + kTcF) + sizeof(int) * (2 * kTcF + 4) + 4 * 8 + 8 +
+  const size_t smem = region_bytes + sizeof(float) * (kTcF * kTcMP + kTcMP + kTcF) + sizeof(int) * (2 * kTcF + 4) + 4 * 8 + 8 + 64 * sizeof(int) +
                       sizeof(uint16_t) * (size_t)(p.NBk * (p.NBk - 1) / 2 + 2) + 16;
   B2W_REQUIRE(smem <= 227 * 1024, "b2w_mcep_tc: %zu bytes of shared memory needed", smem);
   const int64_t grid = (num_frames + kTcF - 1) / kTcF;
   B2W_REQUIRE(grid < ((int64_t)1 << 31), "b2w_mcep_tc: too many frames in one call");
   cudaStream_t st = (cudaStream_t)stream;
-  if (in_dtype == B2W_F64) {
-    cudaFuncSetAttribute(mcep_tc_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    mcep_tc_kernel<double><<<(unsigned)grid, kTcThreads, smem, st>>>(p);
-  } else {
-    cudaFuncSetAttribute(mcep_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    mcep_tc_kernel<float><<<(unsigned)grid, kTcThreads, smem, st>>>(p);
-  }
+#define B2W_TC_LAUNCH(IT, NS)                                                                                  \
+  do {                                                                                                         \
+    cudaFuncSetAttribute(mcep_tc_kernel<IT, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+    mcep_tc_kernel<IT, NS><<<(unsigned)grid, kTcThreads, smem, st>>>(p);                                       \
+  } while (0)
+#define B2W_TC_DISPATCH(IT)                        \
+  do {                                             \
+    if (order + 1 == 60) B2W_TC_LAUNCH(IT, 60);    \
+    else if (order + 1 == 40) B2W_TC_LAUNCH(IT, 40); \
+    else if (order + 1 == 20) B2W_TC_LAUNCH(IT, 20); \
+    else B2W_TC_LAUNCH(IT, 0);                     \
+  } while (0)
+  if (in_dtype == B2W_F64) B2W_TC_DISPATCH(double);
+  else B2W_TC_DISPATCH(float);
+#undef B2W_TC_DISPATCH
+#undef B2W_TC_LAUNCH
   return check_launch("mcep_tc_kernel");
 }

@@ -160,7 +160,8 @@ def cheaptrick(batch, fft_size=None, q1=-0.15, out_dtype=torch.float64, status=N
         status = new_status(batch.device)
     b = batch.c_struct(frame_lo, frame_hi)
     with torch.cuda.device(batch.device):
-        check(lib.b2w_cheaptrick(b, fft_size, float(q1), out.data_ptr(), _DT[out.dtype], status.data_ptr(),
+        assert out.dim() == 2 and out.shape[1] == K and out.stride(1) == 1 and out.shape[0] >= nf
+        check(lib.b2w_cheaptrick(b, fft_size, float(q1), out.data_ptr(), _DT[out.dtype], int(out.stride(0)), status.data_ptr(),
                                  _stream(batch.device)), "b2w_cheaptrick")
     return out, status
 
@@ -287,9 +288,14 @@ def mcep(plane, order, alpha, is_power=False, miniter=2, maxiter=30, threshold=0
     """pysptk.mcep(itype=3 (amplitude) or 4 (power), etype=1) on a [F, K] plane -> mc [F, order+1].
     impl: "tc" = tcgen05 tensor-core kernel (default for order <= 62), "cc" = CUDA-core kernel (any order <= 127)."""
     lib = _lib.load()
-    dev = _need_cuda(plane)
     assert plane.dim() == 2 and plane.dtype in (torch.float32, torch.float64)
     F, K = plane.shape
+    if plane.stride(1) != 1 or (F > 1 and plane.stride(0) < K):
+        plane = plane.contiguous()
+    in_stride = int(plane.stride(0)) if F > 1 else K  # rows may be padded (the stride of a single row is arbitrary in torch)
+    if not plane.is_cuda:
+        raise ValueError("idiaptts_b200 operators need CUDA tensors (there is no CPU fallback)")
+    dev = plane.device
     fft_size = 2 * (K - 1)
     tab = McepTables.get(order, alpha, fft_size, dev)
     if out is None:
@@ -303,11 +309,14 @@ def mcep(plane, order, alpha, is_power=False, miniter=2, maxiter=30, threshold=0
         if tab.stream0 is None:
             raise ValueError("the tensor-core mcep kernel supports order <= 62")
         with torch.cuda.device(dev):
-            check(lib.b2w_mcep_tc(plane.data_ptr(), _DT[plane.dtype], 1 if is_power else 0, F, fft_size, int(order), float(alpha),
+            check(lib.b2w_mcep_tc(plane.data_ptr(), _DT[plane.dtype], 1 if is_power else 0, in_stride, F, fft_size,
+                                  int(order), float(alpha),
                                   int(miniter), int(maxiter), float(threshold), float(eps), tab.stream0.data_ptr(),
                                   tab.stream1.data_ptr(), out.data_ptr(), _DT[out.dtype], int(out_stride), _ptr(iters),
                                   status.data_ptr(), _stream(dev)), "b2w_mcep_tc")
         return out, status
+    if in_stride != K:
+        plane = plane.contiguous()
     with torch.cuda.device(dev):
         check(lib.b2w_mcep(plane.data_ptr(), _DT[plane.dtype], 1 if is_power else 0, F, fft_size, int(order), float(alpha),
                            int(miniter), int(maxiter), float(threshold), float(eps), tab.m0t.data_ptr(), tab.cmat.data_ptr(),

@@ -39,8 +39,9 @@ class WorldAnalyzer:
     def _sp_buffer(self, frames):
         K = self.n_fft // 2 + 1
         if self._sp is None or self._sp.shape[0] < frames:
-            self._sp = torch.empty((frames, K), dtype=torch.float32, device=self.device)
-        return self._sp
+            # rows padded to a multiple of 8 floats: the mel-cepstrum kernel reads them with aligned 16-byte loads
+            self._sp = torch.empty((frames, (K + 7) // 8 * 8), dtype=torch.float32, device=self.device)
+        return self._sp[:, :K]
 
     def extract(self, batch, feats=None, sums=None, status=None, events=None):
         """batch: ops.RaggedBatch.  Returns (feats [F, dim] float32, sums [2*dim] float64, status int32[1]); `sums` is

@@ -72,9 +72,10 @@ typedef struct {
 
 /* ---- CheapTrick: replaces pyworld.cheaptrick inside pyworld.wav2world (W:792). ------------------------------
  * sp [num_frames, fft_size/2+1] power spectral envelope, sp_dtype B2W_F64 (pyworld-compatible) or B2W_F32
- * (fused extract path). fft_size in {512, 1024, 2048, 4096}. status: 1 int32. */
-B2W_API int b2w_cheaptrick(const b2w_batch* b, int32_t fft_size, double q1, void* sp, int32_t sp_dtype, int32_t* status,
-                   void* stream);
+ * (fused extract path), row stride sp_stride elements (>= fft_size/2+1; the fused path pads rows to a multiple of 8 floats so
+ * that b2w_mcep_tc can read them with aligned 16-byte loads). fft_size in {512, 1024, 2048, 4096}. status: 1 int32. */
+B2W_API int b2w_cheaptrick(const b2w_batch* b, int32_t fft_size, double q1, void* sp, int32_t sp_dtype, int64_t sp_stride,
+                   int32_t* status, void* stream);
 
 /* ---- D4C: replaces pyworld.d4c inside pyworld.wav2world (W:792). ------------------------------------------
  * Stage 1 (the expensive one): LoveTrain voicing + per-band coarse aperiodicity.
@@ -121,8 +122,9 @@ B2W_API int b2w_mcep(const void* in, int32_t in_dtype, int32_t in_is_power, int6
 B2W_API int64_t b2w_mcep_tc_stream_floats(int32_t fft_size);
 B2W_API int b2w_mcep_tc_pretile(int32_t order, int32_t fft_size, const float* m0t, const float* cmat, const float* m2t,
                                 float* stream0, float* stream1, void* stream);
-B2W_API int b2w_mcep_tc(const void* in, int32_t in_dtype, int32_t in_is_power, int64_t num_frames, int32_t fft_size,
-                        int32_t order, double alpha, int32_t miniter, int32_t maxiter, double threshold, double eps,
+/* in_stride: row stride of `in` in elements (>= K) */
+B2W_API int b2w_mcep_tc(const void* in, int32_t in_dtype, int32_t in_is_power, int64_t in_stride, int64_t num_frames,
+                        int32_t fft_size, int32_t order, double alpha, int32_t miniter, int32_t maxiter, double threshold, double eps,
                         const float* stream0, const float* stream1, void* mc, int32_t mc_dtype, int64_t mc_stride,
                         int32_t* iters, int32_t* status, void* stream);
 /* log-amplitude spectrum from mel-cepstra: Re pysptk.mgc2sp(mc, alpha, gamma=0, fftlen) (A:252), optionally

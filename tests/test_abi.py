@@ -76,7 +76,7 @@ def test_argument_errors_do_not_launch():
     st = ctypes.c_int32(0)
     b = _lib.Batch()
     b.x_dtype = 7
-    rc = lib.b2w_cheaptrick(b, 1024, -0.15, 0, 0, ctypes.addressof(st), 0)
+    rc = lib.b2w_cheaptrick(b, 1024, -0.15, 0, 0, 513, ctypes.addressof(st), 0)
     assert rc < 0 and b"b2w_cheaptrick" in lib.b2w_last_error()
     rc = lib.b2w_mcep(0, 0, 0, 10, 1024, 59, 0.5, 2, 30, 1e-3, 1e-8, 0, 0, 0, 0, 1, 60, 0, 0, 0)
     assert rc < 0 and b"null" in lib.b2w_last_error()
