@@ -18,6 +18,7 @@ cpu_baseline / --impl reference: the CPU oracle (C restatement of the WORLD/SPTK
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -150,7 +151,7 @@ def run_reference(args):
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from idiaptts_b200 import ops, pipeline, synthetic
+    from idiaptts_b200 import _lib, ops, pipeline, synthetic
     from idiaptts_b200.compat.pysptk import mcepalpha
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -264,8 +265,43 @@ def run_b200(args):
     mcep_ms = per["mcep"][0] / per["mcep"][1]
     mcep_frames = per["mcep"][2] / per["mcep"][1]
     mcep_tflops = flops_frame * mcep_frames / (mcep_ms / 1e3) / 1e12
+    # measured DRAM traffic of the dominant kernel (ncu --set full capture of this command, bytes per frame -> per launch)
+    traffic = None
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as f:
+            traffic = float(json.load(f)[top]["dram_bytes_per_frame"]) * top_frames
+    except Exception:
+        pass
+    # compute side of the dominant kernels: algorithmic fp64 FFT flops (5 N log2 N per complex FFT, nothing else counted)
+    # against the fp64 FMA rate measured right here with a pure-FMA probe kernel
+    probe = torch.zeros(8, dtype=torch.float64, device=dev)
+    lib = _lib.load()
+    lib.b2w_probe_fp64_fma(1 << 12, probe.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    nfma = lib.b2w_probe_fp64_fma(1 << 15, probe.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    p1.record()
+    torch.cuda.synchronize()
+    fp64_peak = 2.0 * nfma / (p0.elapsed_time(p1) / 1e3) / 1e12
+    n4 = 2048 if FS <= 24000 else 4096
+    lo_f, hi_f = 0, min(F, an.chunk_frames)
+    _, vflag, _ = ops.d4c_coarse(batch, frame_lo=lo_f, frame_hi=hi_f)
+    f0_pos = float((batch.f0[lo_f:hi_f] > 0).float().mean().item())     # frames that enter D4C (1 FFT: LoveTrain)
+    full = float(vflag.float().mean().item())                            # frames that run the whole of D4C
+    fft_flop = lambda n: 5.0 * n * math.log2(n)
+    d4c_flop_frame = f0_pos * fft_flop(n4) + full * (2 + (an.nap + 1) // 2) * fft_flop(n4)
+    ct_flop_frame = 3 * fft_flop(an.n_fft // 2)
+    def tfl(name, flop_frame):
+        return flop_frame * (per[name][2] / per[name][1]) / (per[name][0] / per[name][1] / 1e3) / 1e12
+    compute = {"fp64_fma_peak_tflops_measured": round(fp64_peak, 2),
+               "d4c": {"fft_tflops": round(tfl("d4c", d4c_flop_frame), 3), "frac_of_fp64_peak": round(tfl("d4c", d4c_flop_frame) / fp64_peak, 4),
+                       "frames_with_f0": round(f0_pos, 4), "frames_full_d4c": round(full, 4)},
+               "cheaptrick": {"fft_tflops": round(tfl("cheaptrick", ct_flop_frame), 3),
+                              "frac_of_fp64_peak": round(tfl("cheaptrick", ct_flop_frame) / fp64_peak, 4)},
+               "note": "FFT flops only (5 N log2 N per complex FFT); windows, smoothing, order statistics, log/exp are not counted. "
+                       "ncu (profiles/): these kernels are bound by the L1/shared-memory data pipe and the fp64 pipe together"}
     roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src, "compute": compute,
                 "share_of_step": per[top][0] / total_k,
                 "shares": {k: round(v[0] / total_k, 4) for k, v in per.items()},
                 "avg_launch_ms": {k: round(v[0] / v[1], 3) for k, v in per.items()},

@@ -54,7 +54,29 @@ const double2* twiddle_table(cudaStream_t stream) {
   return tables[dev];
 }
 
+// Peak-rate probe for bench.py's compute roofline: 8 independent fp64 FMA chains per thread, nothing else.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
+  double v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = a * (threadIdx.x + i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fma(v[i], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += v[i];
+  if (s == 123.456) out[0] = s;  // never true: keeps the chains alive
+}
+
 }  // namespace b2w
+
+extern "C" int64_t b2w_probe_fp64_fma(int32_t iters, double* scratch, void* stream) {
+  const int grid = 148 * 8, block = 256;
+  b2w::fp64_peak_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(scratch, iters, 0.999999, 1e-9);
+  if (b2w::check_launch("fp64_peak_kernel")) return -1;
+  return (int64_t)grid * block * 8 * (int64_t)iters;  // FMAs issued
+}
 
 extern "C" int b2w_version(void) { return B2W_VERSION; }
 extern "C" const char* b2w_last_error(void) { return b2w::g_err; }

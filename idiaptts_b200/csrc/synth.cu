@@ -287,14 +287,15 @@ struct RenderSmem {
   static constexpr int per_doubles = N;            // periodic response
   static constexpr int zn_doubles = 2 * (K + 1);  // noise spectrum
   static constexpr int red_doubles = 32;
+  static constexpr int tw_doubles = 2 * kFftTwEntries;  // shared-memory twiddles of cfft_s
   static constexpr int total_bytes =
-      (z_doubles + x_doubles + env_doubles + ar_doubles + per_doubles + zn_doubles + red_doubles) * 8;
+      (z_doubles + x_doubles + env_doubles + ar_doubles + per_doubles + zn_doubles + red_doubles + tw_doubles) * 8;
 };
 
 // WORLD GetMinimumPhaseSpectrum for the log-amplitude L[0..N/2] held in `logsp` -> X[0..N/2] (complex) in `X`.
 template <int N, int NT>
-__device__ __forceinline__ void minimum_phase(const double* logsp, double2* z, double2* X, const double2* __restrict__ tw,
-                                              int tid) {
+__device__ __forceinline__ void minimum_phase(const double* logsp, double2* z, double2* X, const double2* tws, double2 rw0,
+                                              double2 rstep, int tid) {
   constexpr int M = N / 2, H = N / 2, K = H + 1;
   for (int k = tid; k < K; k += NT) {
     const double v = logsp[k];
@@ -302,18 +303,24 @@ __device__ __forceinline__ void minimum_phase(const double* logsp, double2* z, d
     if (k > 0 && k < H) zreal<double>(z, N - k) = v;
   }
   __syncthreads();
-  cfft<double, M, NT>(z, tw, tid);
+  cfft_s<double, M, NT>(z, tws, tid);
   // cepstrum (real for a symmetric input), folded: c[0], 2 c[1..N/2-1], c[N/2], zeros
-  for (int k = tid; k < K; k += NT) {
-    const double c = rfft_bin<double, N>(z, tw, k).x;
-    X[k].x = (k == 0 || k == H) ? c : 2.0 * c;
+  {
+    double2 rw = rw0;
+    for (int k = tid; k < K; k += NT) {
+      const double c = rfft_bin_w<double, N>(z, k, rw).x;
+      rw = cmul(rw, rstep);
+      X[k].x = (k == 0 || k == H) ? c : 2.0 * c;
+    }
   }
   __syncthreads();
   for (int n = tid; n < N; n += NT) zreal<double>(z, n) = (n <= H) ? X[n].x : 0.0;
   __syncthreads();
-  cfft<double, M, NT>(z, tw, tid);
+  cfft_s<double, M, NT>(z, tws, tid);
+  double2 rw = rw0;
   for (int k = tid; k < K; k += NT) {
-    const double2 s = rfft_bin<double, N>(z, tw, k);
+    const double2 s = rfft_bin_w<double, N>(z, k, rw);
+    rw = cmul(rw, rstep);
     const double mag = exp(s.x / N);
     double sn, cs;
     sincos(s.y / N, &sn, &cs);
@@ -324,9 +331,10 @@ __device__ __forceinline__ void minimum_phase(const double* logsp, double2* z, d
 
 // Unnormalised inverse real FFT of the Hermitian half spectrum X[0..N/2], fft-shifted: out(j) = x[(j + N/2) mod N].
 template <int N, int NT, typename Emit>
-__device__ __forceinline__ void inverse_real_shifted(const double2* X, double2* z, const double2* __restrict__ tw, int tid,
-                                                     Emit emit) {
+__device__ __forceinline__ void inverse_real_shifted(const double2* X, double2* z, const double2* tws, double2 rw0, double2 rstep,
+                                                     int tid, Emit emit) {
   constexpr int M = N / 2;
+  double2 rw = rw0;
   for (int k = tid; k < M; k += NT) {
     double2 a = X[k];
     double2 bq = X[M - k];
@@ -337,14 +345,14 @@ __device__ __forceinline__ void inverse_real_shifted(const double2* X, double2* 
     const double2 b = make_double2(bq.x, -bq.y);                 // conj(X[M - k]) = X[k + M]
     const double2 e = make_double2(a.x + b.x, a.y + b.y);
     const double2 d = make_double2(a.x - b.x, a.y - b.y);
-    const double2 wq = __ldg(&tw[k * (kTwN / N)]);
-    const double2 wc = make_double2(wq.x, -wq.y);                // W^-k
+    const double2 wc = make_double2(rw.x, -rw.y);                // W^-k
+    rw = cmul(rw, rstep);
     const double2 o = cmul(d, wc);
     // Y = e + i * o ; store conj(Y) so that a forward FFT followed by a conjugate gives the inverse transform
     z[ZP(k)] = make_double2(e.x - o.y, -(e.y + o.x));
   }
   __syncthreads();
-  cfft<double, M, NT>(z, tw, tid);
+  cfft_s<double, M, NT>(z, tws, tid);
   for (int n = tid; n < M; n += NT) {
     const double2 v = z[ZP(n)];
     // x[2n] = Re, x[2n+1] = -Im ; shifted position j = (i + N/2) mod N
@@ -378,7 +386,11 @@ render_kernel(const void* __restrict__ sp, const void* __restrict__ ap, const in
   double* periodic = ar + RenderSmem<N>::ar_doubles;
   double2* Zn = reinterpret_cast<double2*>(periodic + RenderSmem<N>::per_doubles);
   double* red = reinterpret_cast<double*>(Zn) + RenderSmem<N>::zn_doubles;
+  double2* tws = reinterpret_cast<double2*>(red + RenderSmem<N>::red_doubles);
   const int tid = threadIdx.x;
+  fft_tw_fill<double, N / 2, NT>(tws, tw, tid);
+  double2 rw0, rstep;  // phasors of the real-FFT pre / post passes (bins tid, tid + NT, ...)
+  rfft_rot_init<double, N, NT>(tw, tid, rw0, rstep);
   const double fs = (double)fs_i;
   const double fp = frame_period_ms / 1000.0;
   const int64_t poff = utt_pulse_offset[u];
@@ -417,7 +429,7 @@ render_kernel(const void* __restrict__ sp, const void* __restrict__ ap, const in
     double* L = periodic;  // log-spectrum staging shares the periodic buffer until the response is emitted
     for (int k = tid; k < K; k += NT) L[k] = log(env[k] * (1.0 - ar[k]) + kMySafeGuardMinimum) / 2.0;
     __syncthreads();
-    minimum_phase<N, NT>(L, z, X, tw, tid);
+    minimum_phase<N, NT>(L, z, X, tws, rw0, rstep, tid);
     // fractional time shift: multiply bin k by (cos(c k) - i sqrt(1 - cos^2(c k)))
     const double coef = 2.0 * kPi * pulse_shift[poff + p] * fs / N;
     for (int k = tid; k < K; k += NT) {
@@ -427,7 +439,7 @@ render_kernel(const void* __restrict__ sp, const void* __restrict__ ap, const in
       X[k] = make_double2(v.x * re2 + v.y * im2, v.y * re2 - v.x * im2);
     }
     __syncthreads();
-    inverse_real_shifted<N, NT>(X, z, tw, tid, [&](int j, double v) { periodic[j] = v; });
+    inverse_real_shifted<N, NT>(X, z, tws, rw0, rstep, tid, [&](int j, double v) { periodic[j] = v; });
     // remove the DC component (WORLD RemoveDCComponent with GetDCRemover's Hann-shaped weights)
     double dcs = 0.0, rs = 0.0;
     for (int i = tid; i < H; i += NT) {
@@ -455,8 +467,12 @@ render_kernel(const void* __restrict__ sp, const void* __restrict__ ap, const in
       zreal<double>(z, i) = v;
     }
     __syncthreads();
-    cfft<double, N / 2, NT>(z, tw, tid);
-    for (int k = tid; k < K; k += NT) Zn[k] = rfft_bin<double, N>(z, tw, k);
+    cfft_s<double, N / 2, NT>(z, tws, tid);
+    double2 rw = rw0;
+    for (int k = tid; k < K; k += NT) {
+      Zn[k] = rfft_bin_w<double, N>(z, k, rw);
+      rw = cmul(rw, rstep);
+    }
   }
   // aperiodic response: minimum phase of sqrt(env * ar) (voiced) or sqrt(env) (unvoiced), times the noise spectrum
   for (int k = tid; k < K; k += NT) {
@@ -464,12 +480,12 @@ render_kernel(const void* __restrict__ sp, const void* __restrict__ ap, const in
     env[k] = (cur_vuv != 0.0) ? log(e * ar[k]) / 2.0 : log(e) / 2.0;
   }
   __syncthreads();
-  minimum_phase<N, NT>(env, z, X, tw, tid);
+  minimum_phase<N, NT>(env, z, X, tws, rw0, rstep, tid);
   for (int k = tid; k < K; k += NT) X[k] = cmul(X[k], Zn[k]);
   __syncthreads();
   const double sqrt_noise = sqrt((double)noise_size);
   double* out = response + (poff + p) * (int64_t)N;
-  inverse_real_shifted<N, NT>(X, z, tw, tid, [&](int j, double v) {
+  inverse_real_shifted<N, NT>(X, z, tws, rw0, rstep, tid, [&](int j, double v) {
     const double per_v = has_periodic ? periodic[j] : 0.0;
     out[j] = (per_v * sqrt_noise + v) / N;
   });

@@ -189,6 +189,8 @@ B2W_API int b2w_allpass_backward(const float* grad_y, const float* x, const floa
 
 /* ---- self-test of the tcgen05 (UMMA) building blocks used by the tensor-core mel-cepstrum kernel: one CTA computes
  * d[128, n] = a[128, k] . bt[n, k]^T with the 3xTF32 split (n % 16 == 0, n <= 256, k % 8 == 0); b_tiled_ws: 2*n*k floats. */
+/* measurement aid (bench.py): launches a pure fp64 FMA kernel, returns the number of FMAs it executes (or -1) */
+B2W_API int64_t b2w_probe_fp64_fma(int32_t iters, double* scratch, void* stream);
 B2W_API int b2w_test_umma_gemm(const float* a, const float* bt, int32_t n, int32_t k, float* b_tiled_ws, float* d, void* stream);
 
 /* ---- scalar helpers (host, pure functions): pyworld.get_cheaptrick_fft_size (A:60), get_num_aperiodicities
