@@ -319,10 +319,16 @@ def run_b200(args):
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     d2h = feats_host.numel() * 4 + stats_pinned.numel() * 8
 
+    e2e_state = {"buf": None}
+
     def e2e_step():
-        b = to_dev()
-        step(b)
-        feats_host.copy_(feats, non_blocking=True)
+        # the public end-to-end call: pinned host corpus in, pinned host features + statistics out, copies overlapped with
+        # the analysis of neighbouring frame chunks (pipeline.WorldAnalyzer.extract_from_host)
+        stat_buf.zero_()
+        _, _, _, e2e_state["buf"] = an.extract_from_host(host, feats_host, dev_buffers=e2e_state["buf"], sums=stat_buf[:2 * an.dim])
+        stat_buf[2 * an.dim] = float(F)
+        if world > 1:
+            dist.all_reduce(stat_buf)
         stats_pinned.copy_(stat_buf, non_blocking=True)
 
     e2e_step()

@@ -59,9 +59,14 @@ _SIGNATURES = {
                                         c_double, c_void_p, c_int32, c_void_p]),
     "b2w_allpass_forward": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                       c_void_p]),
+    "b2w_allpass_forward_tc": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p]),
+    "b2w_allpass_forward_masked": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                             c_void_p, c_void_p]),
     "b2w_allpass_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2w_probe_fp64_fma": (c_int64, [c_int32, c_void_p, c_void_p]),
+    "b2w_probe_umma": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "b2w_test_umma_gemm": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "b2w_cheaptrick_fft_size": (c_int32, [c_int32, c_double]),
     "b2w_num_aperiodicities": (c_int32, [c_int32]),

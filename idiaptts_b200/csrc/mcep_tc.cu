@@ -221,16 +221,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
           umma::tc_fence_after_sync();
           const uint32_t b1h = umma::smem_u32(stg), b1l = b1h + kB1Bytes;
           const uint32_t a_lbo = kTcF * 16, b_lbo = kTcBK * 16;
-#pragma unroll 1
-          for (int ks = 0; ks < kTcMP / 8; ++ks) {
-            const uint64_t ah = umma::smem_desc(umma::smem_u32(a1_hi) + 2 * ks * a_lbo, a_lbo, 128);
-            const uint64_t alo = umma::smem_desc(umma::smem_u32(a1_lo) + 2 * ks * a_lbo, a_lbo, 128);
-            const uint64_t bh = umma::smem_desc(b1h + 2 * ks * b_lbo, b_lbo, 128);
-            const uint64_t bl = umma::smem_desc(b1l + 2 * ks * b_lbo, b_lbo, 128);
-            umma::mma_tf32(tmem, alo, bh, idesc1, ks > 0);
-            umma::mma_tf32(tmem, ah, bl, idesc1, true);
-            umma::mma_tf32(tmem, ah, bh, idesc1, true);
-          }
+          umma::mma_3xtf32<kTcMP / 8>(tmem, umma::smem_desc(umma::smem_u32(a1_hi), a_lbo, 128),
+                                      umma::smem_desc(umma::smem_u32(a1_lo), a_lbo, 128), umma::smem_desc(b1h, b_lbo, 128),
+                                      umma::smem_desc(b1l, b_lbo, 128), 2 * a_lbo, 2 * b_lbo, idesc1, false);
           umma::mma_commit(bar_g1);
         }
       }
@@ -289,16 +282,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
         umma::tc_fence_after_sync();
         const uint32_t b2h = umma::smem_u32(stg) + 2 * kB1Bytes, b2l = b2h + kB2Bytes;
         const uint32_t a_lbo = kTcF * 16, b_lbo = kTcN2 * 16;
-#pragma unroll
-        for (int ks = 0; ks < kTcBK / 8; ++ks) {
-          const uint64_t ah = umma::smem_desc(umma::smem_u32(a2_hi) + 2 * ks * a_lbo, a_lbo, 128);
-          const uint64_t alo = umma::smem_desc(umma::smem_u32(a2_lo) + 2 * ks * a_lbo, a_lbo, 128);
-          const uint64_t bh = umma::smem_desc(b2h + 2 * ks * b_lbo, b_lbo, 128);
-          const uint64_t bl = umma::smem_desc(b2l + 2 * ks * b_lbo, b_lbo, 128);
-          umma::mma_tf32(tmem + 32, alo, bh, idesc2, c > 0 || ks > 0);
-          umma::mma_tf32(tmem + 32, ah, bl, idesc2, true);
-          umma::mma_tf32(tmem + 32, ah, bh, idesc2, true);
-        }
+        umma::mma_3xtf32<kTcBK / 8>(tmem + 32, umma::smem_desc(umma::smem_u32(a2_hi), a_lbo, 128),
+                                    umma::smem_desc(umma::smem_u32(a2_lo), a_lbo, 128), umma::smem_desc(b2h, b_lbo, 128),
+                                    umma::smem_desc(b2l, b_lbo, 128), 2 * a_lbo, 2 * b_lbo, idesc2, c > 0);
         umma::mma_commit(bar_g2);
       }
     }

@@ -126,6 +126,21 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
 }
+// The issuing thread is the bottleneck of short MMA sequences (measured: ~140 cycles per tcgen05.mma when every descriptor is
+// rebuilt in a rolled loop, scripts/gpu_umma_probe.py), so the K loop is unrolled over descriptors that advance by a constant:
+// the start-address field (16-byte units) sits in the low bits, adding (bytes >> 4) moves the operand window.
+// D (+)= A . B^T over KS K-steps of 8 with the 3xTF32 split (small products first); accumulate = false overwrites D.
+template <int KS>
+__device__ __forceinline__ void mma_3xtf32(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                           uint32_t a_step_bytes, uint32_t b_step_bytes, uint32_t idesc, bool accumulate) {
+  const uint64_t da = a_step_bytes >> 4, db = b_step_bytes >> 4;
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    mma_tf32(d_tmem, a_lo + ks * da, b_hi + ks * db, idesc, accumulate || ks > 0);
+    mma_tf32(d_tmem, a_hi + ks * da, b_lo + ks * db, idesc, true);
+    mma_tf32(d_tmem, a_hi + ks * da, b_hi + ks * db, idesc, true);
+  }
+}
 // all previously issued MMAs of this thread arrive on the mbarrier when they have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

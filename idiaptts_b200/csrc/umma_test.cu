@@ -89,7 +89,69 @@ __global__ void __launch_bounds__(128) umma_test_kernel(const float* __restrict_
   if (warp == 0) umma::tmem_dealloc(tmem, 256);
 }
 
+// Timing probe (scripts/gpu_umma_probe.py): cycles from the first tcgen05.mma to the commit's mbarrier arrival for `count`
+// MMAs of shape 128 x N x 8 (kind::tf32) spread round-robin over `nacc` independent accumulators (zeroed operands).
+__global__ void __launch_bounds__(128) umma_probe_kernel(int N, int count, int nacc, int M, int f16, long long* out) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  float* a = reinterpret_cast<float*>(smem);             // 128 x 64
+  float* b = a + 128 * 64;                                // 256 x 64 at most... only N x 64 used
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (128 * 64 + 128 * 64) * 4);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 2 * 128 * 64; i += 128) a[i] = 0.f;
+  if (tid == 0) { umma::mbar_init(bar, 1); umma::mbar_fence_init(); }
+  if (warp == 0) umma::tmem_alloc(slot, 512);
+  umma::fence_proxy_async();
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  umma::tc_fence_after_sync();
+  const uint32_t tmem = *slot;
+  uint32_t phase = 0;
+  for (int rep = 0; rep < 4; ++rep) {
+    long long t0 = 0;
+    if (tid == 0) {
+      // kind::f16 probe: bf16 operands (format 1), fp32 accumulate, K = 16 per instruction (same 32 bytes per row)
+      const uint32_t idesc = f16 ? ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24))
+                                 : umma::idesc_tf32(M, N);
+      const uint32_t a_lbo = (uint32_t)M * 16, b_lbo = (uint32_t)N * 16;
+      const uint64_t ad0 = umma::smem_desc(umma::smem_u32(a), a_lbo, 128), bd0 = umma::smem_desc(umma::smem_u32(b), b_lbo, 128);
+      t0 = clock64();
+      if (f16) {
+        for (int i = 0; i < count; ++i) {
+          const int ks = i & 7, acc = i % nacc;
+          const uint64_t ad = ad0 + ks * ((2 * a_lbo) >> 4), bd = bd0 + ks * ((2 * b_lbo) >> 4);
+          asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem + acc * N),
+                       "l"(ad), "l"(bd), "r"(idesc), "r"((uint32_t)(i >= nacc))
+                       : "memory");
+        }
+      } else {
+        // groups of 24 = one 3xTF32 product over K = 64 with unrolled, precomputed descriptors
+        for (int i = 0; i < count; i += 24)
+          umma::mma_3xtf32<8>(tmem + ((i / 24) % nacc) * N, ad0, ad0, bd0, bd0, 2 * a_lbo, 2 * b_lbo, idesc, i >= 24 * nacc);
+      }
+      umma::mma_commit(bar);
+    }
+    umma::mbar_wait(bar, phase);
+    phase ^= 1;
+    if (tid == 0) out[rep] = clock64() - t0;
+    umma::tc_fence_after_sync();
+    __syncthreads();
+  }
+  umma::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 512);
+}
+
 }  // namespace b2w
+
+extern "C" int b2w_probe_umma(int32_t n, int32_t count, int32_t nacc, int32_t m, int32_t f16, long long* out4, void* stream) {
+  using namespace b2w;
+  B2W_REQUIRE(out4 && n >= 16 && n <= 128 && n % 16 == 0 && nacc >= 1 && nacc * n <= 512 && (m == 64 || m == 128), "b2w_probe_umma: bad arguments");
+  const size_t smem = (size_t)(2 * 128 * 64) * 4 + 64;
+  cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(n, count, nacc, m, f16, out4);
+  return check_launch("umma_probe_kernel");
+}
 
 extern "C" int b2w_test_umma_gemm(const float* a, const float* bt, int32_t n, int32_t k, float* b_tiled_ws, float* d, void* stream) {
   using namespace b2w;

@@ -27,7 +27,9 @@ __device__ __forceinline__ void stage(float* __restrict__ sh, float* gl, int64_t
 template <int NMAX>
 __global__ void __launch_bounds__(kVtThreads)
 allpass_forward_kernel(const float* __restrict__ x, const float* __restrict__ alpha, int64_t rows, int n, int blocks,
-                       const float* __restrict__ mean, const float* __restrict__ std_dev, float* __restrict__ y) {
+                       const float* __restrict__ mean, const float* __restrict__ std_dev, float* __restrict__ y,
+                       const uint8_t* __restrict__ tile_mask) {
+  if (tile_mask && !tile_mask[blockIdx.x]) return;  // tile already done by the tensor-core kernel (vtln_tc.cu)
   extern __shared__ float sh[];  // [kVtThreads][n+1]
   const int64_t units = rows * blocks;
   const int64_t u0 = (int64_t)blockIdx.x * kVtThreads;
@@ -188,8 +190,15 @@ __global__ void reduce_blocks_kernel(const float* __restrict__ unit_vals, int64_
 
 }  // namespace b2w
 
+extern "C" int b2w_allpass_forward_masked(const float* x, const float* alpha, int64_t rows, int32_t n, int32_t blocks,
+                                          const float* mean, const float* std_dev, float* y, const uint8_t* tile_mask, void* stream);
 extern "C" int b2w_allpass_forward(const float* x, const float* alpha, int64_t rows, int32_t n, int32_t blocks,
                                    const float* mean, const float* std_dev, float* y, void* stream) {
+  return b2w_allpass_forward_masked(x, alpha, rows, n, blocks, mean, std_dev, y, nullptr, stream);
+}
+// tile_mask (may be NULL): one byte per tile of 128 (row, block) units; only tiles with a non-zero byte are computed
+extern "C" int b2w_allpass_forward_masked(const float* x, const float* alpha, int64_t rows, int32_t n, int32_t blocks,
+                                          const float* mean, const float* std_dev, float* y, const uint8_t* tile_mask, void* stream) {
   using namespace b2w;
   B2W_REQUIRE(x && alpha && y, "b2w_allpass_forward: null argument");
   B2W_REQUIRE(n >= 2 && n <= 128 && blocks >= 1, "b2w_allpass_forward: n %d (2..128) / blocks %d out of range", n, blocks);
@@ -202,7 +211,7 @@ extern "C" int b2w_allpass_forward(const float* x, const float* alpha, int64_t r
 #define B2W_VT_FWD(NMAX)                                                                                   \
   do {                                                                                                     \
     cudaFuncSetAttribute(allpass_forward_kernel<NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    allpass_forward_kernel<NMAX><<<(unsigned)grid, kVtThreads, smem, st>>>(x, alpha, rows, n, blocks, mean, std_dev, y); \
+    allpass_forward_kernel<NMAX><<<(unsigned)grid, kVtThreads, smem, st>>>(x, alpha, rows, n, blocks, mean, std_dev, y, tile_mask); \
   } while (0)
   if (n <= 32) B2W_VT_FWD(32); else if (n <= 64) B2W_VT_FWD(64); else B2W_VT_FWD(128);
 #undef B2W_VT_FWD

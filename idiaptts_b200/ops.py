@@ -471,14 +471,24 @@ def synthesize(f0, sp, ap, frame_off, fs, frame_period=5.0, deemphasis=0.0, out_
 # ----------------------------------------------------------------------------------------------------------------------
 # Neural-VTLN all-pass warp
 # ----------------------------------------------------------------------------------------------------------------------
-def allpass_forward(x, alpha, n, mean=None, std_dev=None):
-    """x [rows, blocks*n] f32, alpha [rows] f32 -> y [rows, blocks*n]."""
+def allpass_forward(x, alpha, n, mean=None, std_dev=None, impl=None):
+    """x [rows, blocks*n] f32, alpha [rows] f32 -> y [rows, blocks*n].
+    impl: "tc" = tensor-core GEMM for runs of rows that share alpha + recursion for the rest (default when n % 4 == 0, n <= 64),
+    "cc" = per-row recursion only."""
     lib = _lib.load()
     dev = _need_cuda(x, alpha, mean, std_dev)
     assert x.dtype == torch.float32 and alpha.dtype == torch.float32 and x.dim() == 2
     rows, width = x.shape
     assert width % n == 0 and alpha.numel() == rows
     y = torch.empty_like(x)
+    if impl is None:
+        impl = "tc" if (n % 4 == 0 and n <= 64 and x.data_ptr() % 16 == 0) else "cc"
+    if impl == "tc":
+        flags = torch.empty(((rows * (width // n) + 127) // 128,), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.b2w_allpass_forward_tc(x.data_ptr(), alpha.data_ptr(), rows, int(n), width // n, _ptr(mean), _ptr(std_dev),
+                                             y.data_ptr(), flags.data_ptr(), _stream(dev)), "b2w_allpass_forward_tc")
+        return y
     with torch.cuda.device(dev):
         check(lib.b2w_allpass_forward(x.data_ptr(), alpha.data_ptr(), rows, int(n), width // n, _ptr(mean), _ptr(std_dev),
                                       y.data_ptr(), _stream(dev)), "b2w_allpass_forward")

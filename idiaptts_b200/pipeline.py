@@ -43,10 +43,12 @@ class WorldAnalyzer:
             self._sp = torch.empty((frames, (K + 7) // 8 * 8), dtype=torch.float32, device=self.device)
         return self._sp[:, :K]
 
-    def extract(self, batch, feats=None, sums=None, status=None, events=None):
+    def extract(self, batch, feats=None, sums=None, status=None, events=None, pre_chunk=None, post_chunk=None):
         """batch: ops.RaggedBatch.  Returns (feats [F, dim] float32, sums [2*dim] float64, status int32[1]); `sums` is
         accumulated into when given (corpus statistics over several calls).  events: optional list that receives
-        (kernel name, frames, start event, end event) per launch (bench.py's per-kernel timing)."""
+        (kernel name, frames, start event, end event) per launch (bench.py's per-kernel timing).  pre_chunk / post_chunk:
+        optional callables (lo, hi) run before / after the launches of every frame chunk (extract_from_host uses them to
+        order the chunk behind its host-to-device copy and to start the device-to-host copy of its feature rows)."""
         def timed(name, frames, fn):
             if events is None:
                 return fn()
@@ -77,6 +79,8 @@ class WorldAnalyzer:
             hi = min(F, lo + chunk)
             spc = sp[:hi - lo]
             nf = hi - lo
+            if pre_chunk is not None:
+                pre_chunk(lo, hi)
             timed("cheaptrick", nf, lambda: ops.cheaptrick(batch, fft_size=self.n_fft, status=status, frame_lo=lo, frame_hi=hi,
                                                            out=spc))
             it = None if self.iters is None else self.iters[lo:hi]
@@ -85,8 +89,66 @@ class WorldAnalyzer:
             coarse, voiced, _ = timed("d4c", nf, lambda: ops.d4c_coarse(batch, status=status, frame_lo=lo, frame_hi=hi))
             timed("bap_from_coarse", nf, lambda: ops.bap_from_coarse(coarse, voiced, self.fs, self.n_fft,
                                                                      out=flat[lo * self.dim + D + 2:], out_stride=self.dim))
+            if post_chunk is not None:
+                post_chunk(lo, hi)
         timed("stats", F, lambda: ops.stats_accumulate(feats, sums))
         return feats, sums, status
+
+    def extract_from_host(self, host, feats_host, dev_buffers=None, sums=None):
+        """End-to-end extraction of a corpus shard that lives in pinned host memory: the packed waveform is copied in pieces
+        on a copy stream while earlier frame chunks are analysed, and every chunk's feature rows travel back to the pinned
+        `feats_host` [F, dim] on a second copy stream while the next chunk is analysed (gen_data's wav -> npz path without
+        the file IO).  host: dict of pinned CPU tensors x (int16 / float), so (sample offsets), f0, t, fo (frame offsets),
+        fu (frame -> utterance).  Returns (feats (device), sums, status, dev_buffers); pass dev_buffers back in to reuse
+        the device allocations.  Everything is asynchronous; synchronise the current stream before reading feats_host."""
+        dev = self.device
+        cur = torch.cuda.current_stream(dev)
+        if dev_buffers is None:
+            dev_buffers = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in host.items()}
+            dev_buffers["_in"] = torch.cuda.Stream(dev)
+            dev_buffers["_out"] = torch.cuda.Stream(dev)
+            dev_buffers["feats"] = torch.empty((host["f0"].numel(), self.dim), dtype=torch.float32, device=dev)
+        s_in, s_out = dev_buffers["_in"], dev_buffers["_out"]
+        d = dev_buffers
+        s_in.wait_stream(cur)   # earlier work on the current stream may still read the device buffers
+        s_out.wait_stream(cur)
+        so_np, fu_np = host["so"].numpy(), host["fu"].numpy()
+        F = host["f0"].numel()
+        with torch.cuda.stream(s_in):
+            for k in ("so", "fo", "f0", "t", "fu"):
+                d[k].copy_(host[k], non_blocking=True)
+            small_done = torch.cuda.Event()
+            small_done.record(s_in)
+        cur.wait_event(small_done)
+        batch = ops.RaggedBatch(d["x"], d["so"], d["f0"], d["t"], d["fo"], d["fu"], self.fs)
+        state = {"copied": 0, "out_events": []}
+        chunk = min(self.chunk_frames, max(F, 1))
+        # issue all waveform pieces up front on the copy stream, one event per frame chunk
+        piece_events = []
+        with torch.cuda.stream(s_in):
+            for lo in range(0, F, chunk):
+                hi = min(F, lo + chunk)
+                end = int(so_np[int(fu_np[hi - 1]) + 1])   # last sample the chunk's utterances can touch
+                if end > state["copied"]:
+                    d["x"][state["copied"]:end].copy_(host["x"][state["copied"]:end], non_blocking=True)
+                    state["copied"] = end
+                ev = torch.cuda.Event()
+                ev.record(s_in)
+                piece_events.append(ev)
+
+        def pre_chunk(lo, hi):
+            cur.wait_event(piece_events[lo // chunk])
+
+        def post_chunk(lo, hi):
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            s_out.wait_event(ev)
+            with torch.cuda.stream(s_out):
+                feats_host[lo:hi].copy_(d["feats"][lo:hi], non_blocking=True)
+
+        feats, sums, status = self.extract(batch, feats=d["feats"], sums=sums, pre_chunk=pre_chunk, post_chunk=post_chunk)
+        cur.wait_stream(s_out)
+        return feats, sums, status, dev_buffers
 
     def kernel_launches(self, num_frames):
         """Number of libb200world kernels one extract() call launches (for bench.py's gpu_launches)."""

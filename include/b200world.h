@@ -183,6 +183,13 @@ B2W_API int b2w_allpass_forward(const float* x, const float* alpha, int64_t rows
                         const float* mean, const float* std_dev, float* y, void* stream);
 /* backward: grad_x [rows, blocks*n], grad_alpha [rows] from grad_y (and x, alpha): gx = S1 frqtr(S2 gy, -alpha)
  * (A(alpha)^T == frqtr-matrix(-alpha)), galpha by the tangent of the forward recursion. */
+/* Tensor-core version of b2w_allpass_forward for n % 4 == 0, n <= 64: tiles of 128 consecutive (row, block) units that share
+ * one alpha run as a 3xTF32 tcgen05 GEMM against the warp matrix built on chip (HBM-bound); the other tiles are flagged in
+ * tile_flags [ceil(rows * blocks / 128)] bytes (workspace) and computed by the recursion kernel in a second launch. */
+B2W_API int b2w_allpass_forward_tc(const float* x, const float* alpha, int64_t rows, int32_t n, int32_t blocks, const float* mean,
+                                   const float* std_dev, float* y, uint8_t* tile_flags, void* stream);
+B2W_API int b2w_allpass_forward_masked(const float* x, const float* alpha, int64_t rows, int32_t n, int32_t blocks, const float* mean,
+                                       const float* std_dev, float* y, const uint8_t* tile_mask, void* stream);
 B2W_API int b2w_allpass_backward(const float* grad_y, const float* x, const float* alpha, int64_t rows, int32_t n,
                          int32_t blocks, const float* mean, const float* std_dev, float* grad_x, float* grad_alpha,
                          float* unit_workspace /* [rows * blocks] */, void* stream);
@@ -191,6 +198,7 @@ B2W_API int b2w_allpass_backward(const float* grad_y, const float* x, const floa
  * d[128, n] = a[128, k] . bt[n, k]^T with the 3xTF32 split (n % 16 == 0, n <= 256, k % 8 == 0); b_tiled_ws: 2*n*k floats. */
 /* measurement aid (bench.py): launches a pure fp64 FMA kernel, returns the number of FMAs it executes (or -1) */
 B2W_API int64_t b2w_probe_fp64_fma(int32_t iters, double* scratch, void* stream);
+B2W_API int b2w_probe_umma(int32_t n, int32_t count, int32_t nacc, int32_t m, int32_t f16, long long* out4, void* stream);
 B2W_API int b2w_test_umma_gemm(const float* a, const float* bt, int32_t n, int32_t k, float* b_tiled_ws, float* d, void* stream);
 
 /* ---- scalar helpers (host, pure functions): pyworld.get_cheaptrick_fft_size (A:60), get_num_aperiodicities

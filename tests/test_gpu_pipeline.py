@@ -173,3 +173,27 @@ def test_baseline_sized_batch_properties():
         orig = waves[u].cpu().numpy().astype(np.float64) / 32768.0
         got = y[out_off[u]:out_off[u + 1]]
         assert abs(10 * np.log10((got ** 2).mean() / (orig ** 2).mean())) < 3.0
+
+
+def test_extract_from_host_matches_resident_extract():
+    """The streamed host -> device -> host path (copies overlapped with the analysis of neighbouring chunks) returns exactly
+    the rows and statistics of the resident-input path, also when a chunk boundary falls inside an utterance."""
+    from idiaptts_b200 import ops, pipeline, synthetic
+    dev = torch.device("cuda", 0)
+    fs = 22050
+    waves, f0s = synthetic.make_corpus(7, fs, seed=11, mean_dur=1.2, std_dur=0.3)
+    batch = ops.RaggedBatch.from_host([w.numpy() for w in waves], f0s, fs, device=dev)
+    an = pipeline.WorldAnalyzer(fs, 60, device=dev, chunk_frames=500)   # 7 utterances of ~240 frames: ragged chunks
+    feats, sums, status = an.extract(batch)
+    ops.raise_for_status(status, "resident")
+    host = {"x": batch.x.cpu().pin_memory(), "so": batch.sample_off.cpu().pin_memory(), "f0": batch.f0.cpu().pin_memory(),
+            "t": batch.t.cpu().pin_memory(), "fo": batch.frame_off.cpu().pin_memory(), "fu": batch.frame_utt.cpu().pin_memory()}
+    out = torch.empty(feats.shape, dtype=torch.float32).pin_memory()
+    bufs = None
+    for _ in range(2):  # second call reuses the device buffers
+        out.zero_()
+        f2, s2, st2, bufs = an.extract_from_host(host, out, dev_buffers=bufs)
+        torch.cuda.synchronize()
+        ops.raise_for_status(st2, "streamed")
+        assert torch.equal(out, feats.cpu()) and torch.equal(f2, feats)
+        assert torch.allclose(s2, sums, rtol=1e-12, atol=0.0)  # fp64 atomics: summation order may differ in the last bits

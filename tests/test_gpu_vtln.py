@@ -82,3 +82,32 @@ def test_layer_module_interface():
     assert all(not b.requires_grad for b in layer.buffers())
     y2, _ = layer.forward_sample(np.random.randn(T, n).astype(np.float32), np.full((T, 1), 0.1, np.float32))
     assert y2.shape == (1, T, n)
+
+
+@pytest.mark.parametrize("n,blocks,norm", [(60, 1, False), (60, 1, True), (20, 1, True), (60, 3, False), (32, 1, False)])
+def test_tensor_core_forward_vs_fp64_oracle(n, blocks, norm):
+    """alpha constant over long runs of rows (one per speaker): tiles of 128 units that share alpha run on the tensor cores
+    (3xTF32), tiles that straddle a run boundary fall back to the recursion; both against the fp64 oracle, and the two
+    implementations against each other."""
+    from idiaptts_b200 import ops
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(100 + n + blocks)
+    runs = [300, 128, 5, 511, 77, 640]           # rows per speaker: boundaries fall inside and on tile edges
+    rows = sum(runs)
+    x = rng.standard_normal((rows, blocks * n)).astype(np.float32)
+    al = np.concatenate([np.full(r, rng.uniform(-0.2, 0.2), np.float32) for r in runs])
+    mean = rng.standard_normal(blocks * n).astype(np.float32) if norm else None
+    std = rng.uniform(0.5, 2.0, blocks * n).astype(np.float32) if norm else None
+    xd, ad = torch.from_numpy(x).to(dev), torch.from_numpy(al).to(dev)
+    md = torch.from_numpy(mean).to(dev) if norm else None
+    sd = torch.from_numpy(std).to(dev) if norm else None
+    y_tc = ops.allpass_forward(xd, ad, n, md, sd, impl="tc").cpu().numpy()
+    y_cc = ops.allpass_forward(xd, ad, n, md, sd, impl="cc").cpu().numpy()
+    xin = x.astype(np.float64) * std + mean if norm else x.astype(np.float64)
+    y_ref = glue_np.allpass_warp_forward(xin, al.astype(np.float64), n)
+    if norm:
+        y_ref = (y_ref - mean) / std
+    assert np.isfinite(y_tc).all()
+    assert np.abs(y_cc - y_ref).max() < 5e-5
+    assert np.abs(y_tc - y_ref).max() < 5e-5
+    assert np.abs(y_tc - y_cc).max() < 5e-5
