@@ -308,8 +308,8 @@ def run_b200(args):
                 "mcep_tensor": {"bound": "tensor", "achieved": mcep_tflops, "unit": "TFLOP/s (algorithmic, fp32-equivalent)",
                                 "peak": peaks.get("bf16_tflops_sustained"), "peak_unit": "TFLOP/s bf16 dense (measured)",
                                 "mean_newton_passes": mean_it,
-                                "note": "tcgen05 kind::tf32 with the 3xTF32 split; the kernel is bound by the per-frame 60x60 solves, "
-                                        "not by the tensor pipe"},
+                                "note": "tcgen05 kind::tf32 with the 3xTF32 split; the kernel is bound by issue slots / latency of the exp "
+                                        "epilogue and the per-frame 60x60 register-resident solves, not by the tensor pipe"},
                 "note": "compute-bound kernel (fp64 FFTs / fp32 contractions): the HBM fraction is reported because the "
                         "metric asks for it, see DESIGN.md for the per-kernel bounds"}
 
