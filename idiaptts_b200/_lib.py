@@ -63,6 +63,10 @@ _SIGNATURES = {
                                          c_void_p, c_void_p]),
     "b2w_allpass_forward_masked": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_void_p]),
+    "b2w_allpass_backward_tc": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b2w_allpass_backward_masked": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p,
+                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2w_allpass_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2w_probe_fp64_fma": (c_int64, [c_int32, c_void_p, c_void_p]),

@@ -84,7 +84,8 @@ template <int NMAX>
 __global__ void __launch_bounds__(kVtThreads)
 allpass_backward_kernel(const float* __restrict__ gy, const float* __restrict__ x, const float* __restrict__ alpha,
                         int64_t rows, int n, int blocks, const float* __restrict__ mean, const float* __restrict__ std_dev,
-                        float* __restrict__ gx, float* __restrict__ galpha_unit) {
+                        float* __restrict__ gx, float* __restrict__ galpha_unit, const uint8_t* __restrict__ tile_mask) {
+  if (tile_mask && !tile_mask[blockIdx.x]) return;  // tile already done by the tensor-core kernel (vtln_tc.cu)
   extern __shared__ float sh[];  // [2][kVtThreads][n+1]
   float* shx = sh;
   float* shg = sh + kVtThreads * (n + 1);
@@ -218,9 +219,17 @@ extern "C" int b2w_allpass_forward_masked(const float* x, const float* alpha, in
   return check_launch("allpass_forward_kernel");
 }
 
+extern "C" int b2w_allpass_backward_masked(const float* grad_y, const float* x, const float* alpha, int64_t rows, int32_t n, int32_t blocks,
+                                           const float* mean, const float* std_dev, float* grad_x, float* grad_alpha, float* unit_workspace,
+                                           const uint8_t* tile_mask, void* stream);
 extern "C" int b2w_allpass_backward(const float* grad_y, const float* x, const float* alpha, int64_t rows, int32_t n,
                                     int32_t blocks, const float* mean, const float* std_dev, float* grad_x, float* grad_alpha,
                                     float* unit_workspace, void* stream) {
+  return b2w_allpass_backward_masked(grad_y, x, alpha, rows, n, blocks, mean, std_dev, grad_x, grad_alpha, unit_workspace, nullptr, stream);
+}
+extern "C" int b2w_allpass_backward_masked(const float* grad_y, const float* x, const float* alpha, int64_t rows, int32_t n, int32_t blocks,
+                                           const float* mean, const float* std_dev, float* grad_x, float* grad_alpha, float* unit_workspace,
+                                           const uint8_t* tile_mask, void* stream) {
   using namespace b2w;
   B2W_REQUIRE(grad_y && x && alpha && grad_x && grad_alpha && unit_workspace, "b2w_allpass_backward: null argument");
   B2W_REQUIRE(n >= 2 && n <= 128 && blocks >= 1, "b2w_allpass_backward: n %d (2..128) / blocks %d out of range", n, blocks);
@@ -234,7 +243,7 @@ extern "C" int b2w_allpass_backward(const float* grad_y, const float* x, const f
   do {                                                                                                      \
     cudaFuncSetAttribute(allpass_backward_kernel<NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     allpass_backward_kernel<NMAX><<<(unsigned)grid, kVtThreads, smem, st>>>(grad_y, x, alpha, rows, n, blocks, mean, std_dev, \
-                                                                            grad_x, unit_workspace);          \
+                                                                            grad_x, unit_workspace, tile_mask); \
   } while (0)
   if (n <= 32) B2W_VT_BWD(32); else if (n <= 64) B2W_VT_BWD(64); else B2W_VT_BWD(128);
 #undef B2W_VT_BWD

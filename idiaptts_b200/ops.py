@@ -495,7 +495,8 @@ def allpass_forward(x, alpha, n, mean=None, std_dev=None, impl=None):
     return y
 
 
-def allpass_backward(grad_y, x, alpha, n, mean=None, std_dev=None):
+def allpass_backward(grad_y, x, alpha, n, mean=None, std_dev=None, impl=None):
+    """Gradients of allpass_forward w.r.t. x and alpha (impl as in allpass_forward)."""
     lib = _lib.load()
     dev = _need_cuda(grad_y, x, alpha, mean, std_dev)
     rows, width = x.shape
@@ -503,6 +504,15 @@ def allpass_backward(grad_y, x, alpha, n, mean=None, std_dev=None):
     gx = torch.empty_like(x)
     ga = torch.empty_like(alpha)
     ws = torch.empty(rows * blocks, dtype=torch.float32, device=dev)
+    if impl is None:
+        impl = "tc" if (n % 4 == 0 and n <= 64 and x.data_ptr() % 16 == 0 and grad_y.data_ptr() % 16 == 0) else "cc"
+    if impl == "tc":
+        flags = torch.empty(((rows * blocks + 127) // 128,), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.b2w_allpass_backward_tc(grad_y.data_ptr(), x.data_ptr(), alpha.data_ptr(), rows, int(n), blocks, _ptr(mean),
+                                              _ptr(std_dev), gx.data_ptr(), ga.data_ptr(), ws.data_ptr(), flags.data_ptr(),
+                                              _stream(dev)), "b2w_allpass_backward_tc")
+        return gx, ga
     with torch.cuda.device(dev):
         check(lib.b2w_allpass_backward(grad_y.data_ptr(), x.data_ptr(), alpha.data_ptr(), rows, int(n), blocks, _ptr(mean),
                                        _ptr(std_dev), gx.data_ptr(), ga.data_ptr(), ws.data_ptr(), _stream(dev)),

@@ -190,6 +190,15 @@ B2W_API int b2w_allpass_forward_tc(const float* x, const float* alpha, int64_t r
                                    const float* std_dev, float* y, uint8_t* tile_flags, void* stream);
 B2W_API int b2w_allpass_forward_masked(const float* x, const float* alpha, int64_t rows, int32_t n, int32_t blocks, const float* mean,
                                        const float* std_dev, float* y, const uint8_t* tile_mask, void* stream);
+/* Tensor-core backward for n % 4 == 0, n <= 64: per tile of 128 units that share alpha two 3xTF32 GEMMs (grad_x through the
+ * transposed warp matrix, d y / d alpha through the tangent matrix of the same wavefront recursion); other tiles are flagged in
+ * tile_flags and computed by the recursion kernel.  unit_workspace [rows * blocks] floats, tile_flags [ceil(rows*blocks/128)]. */
+B2W_API int b2w_allpass_backward_tc(const float* grad_y, const float* x, const float* alpha, int64_t rows, int32_t n, int32_t blocks,
+                                    const float* mean, const float* std_dev, float* grad_x, float* grad_alpha, float* unit_workspace,
+                                    uint8_t* tile_flags, void* stream);
+B2W_API int b2w_allpass_backward_masked(const float* grad_y, const float* x, const float* alpha, int64_t rows, int32_t n, int32_t blocks,
+                                        const float* mean, const float* std_dev, float* grad_x, float* grad_alpha, float* unit_workspace,
+                                        const uint8_t* tile_mask, void* stream);
 B2W_API int b2w_allpass_backward(const float* grad_y, const float* x, const float* alpha, int64_t rows, int32_t n,
                          int32_t blocks, const float* mean, const float* std_dev, float* grad_x, float* grad_alpha,
                          float* unit_workspace /* [rows * blocks] */, void* stream);

@@ -111,3 +111,34 @@ def test_tensor_core_forward_vs_fp64_oracle(n, blocks, norm):
     assert np.abs(y_cc - y_ref).max() < 5e-5
     assert np.abs(y_tc - y_ref).max() < 5e-5
     assert np.abs(y_tc - y_cc).max() < 5e-5
+
+
+@pytest.mark.parametrize("n,blocks,norm", [(60, 1, False), (60, 1, True), (20, 1, True), (60, 3, False)])
+def test_tensor_core_backward_vs_fp64_oracle(n, blocks, norm):
+    """Backward of the same configurations: grad_x through the transposed matrix, grad_alpha through the tangent matrix; tiles
+    with a run boundary take the recursion kernel."""
+    from idiaptts_b200 import ops
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(200 + n + blocks)
+    runs = [300, 128, 5, 511, 77, 640]
+    rows = sum(runs)
+    x = rng.standard_normal((rows, blocks * n)).astype(np.float32)
+    gy = rng.standard_normal((rows, blocks * n)).astype(np.float32)
+    al = np.concatenate([np.full(r, rng.uniform(-0.2, 0.2), np.float32) for r in runs])
+    mean = rng.standard_normal(blocks * n).astype(np.float32) if norm else None
+    std = rng.uniform(0.5, 2.0, blocks * n).astype(np.float32) if norm else None
+    xd, ad, gd = torch.from_numpy(x).to(dev), torch.from_numpy(al).to(dev), torch.from_numpy(gy).to(dev)
+    md = torch.from_numpy(mean).to(dev) if norm else None
+    sd = torch.from_numpy(std).to(dev) if norm else None
+    gx_tc, ga_tc = ops.allpass_backward(gd, xd, ad, n, md, sd, impl="tc")
+    gx_cc, ga_cc = ops.allpass_backward(gd, xd, ad, n, md, sd, impl="cc")
+    if norm:
+        gx_ref, ga_ref = glue_np.allpass_warp_backward(gy / std, x.astype(np.float64) * std + mean, al, n)
+        gx_ref = gx_ref * std
+    else:
+        gx_ref, ga_ref = glue_np.allpass_warp_backward(gy, x, al, n)
+    # grad_alpha is a 60-term dot product with large, cancelling terms (the tangent matrix grows with the cepstral index): the
+    # fp32 recursion and the 3xTF32 path both reach 0.6 - 1.5e-4 of (|ref| + 1) on the worst row
+    for (gx, ga), tol in (((gx_cc, ga_cc), 4e-4), ((gx_tc, ga_tc), 4e-4)):
+        assert np.abs(gx.cpu().numpy() - gx_ref).max() < 5e-5
+        assert (np.abs(ga.cpu().numpy() - ga_ref) / (np.abs(ga_ref) + 1.0)).max() < tol
