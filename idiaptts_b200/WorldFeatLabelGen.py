@@ -371,9 +371,54 @@ class WorldFeatLabelGen(object):
             else:
                 output_means, output_std_dev = None, None
         self.norm_params = (output_means, output_std_dev)
+        if self.add_deltas:  # covariance matrices per feature in the reference's indexing (coded_sp, lf0, vuv, bap)
+            self.covs = list(output_std_dev)
         if return_dict:
             return label_dict, output_means, output_std_dev
         return output_means, output_std_dev
+
+    # ---- after inference: [static | delta | delta-delta] network output -> WORLD features (MLPG) ------------------------------
+    def _postprocess_world(self, sample, norm_params=None, apply_mlpg=True):
+        """WorldFeatLabelGen._postprocess_world (world/WorldFeatLabelGen.py:357-415): with add_deltas the (already de-normalised)
+        sample [T, 3 D_sp + 3 + 1 + 3 nap] is reduced to [coded_sp | lf0 | vuv | bap] by MLPG per feature (self.covs[0], [1], [3]:
+        the covariance matrices gen_data returns with add_deltas) or, with apply_mlpg=False, by keeping the static columns;
+        vuv is thresholded at 0.5.  All features of the call go through the CUDA MLPG solver (idiaptts_b200.mlpg)."""
+        if not self.add_deltas:
+            return sample
+        from .mlpg import MLPG
+        mlpg = MLPG()
+        output_list = list()
+        num_processed_feats = 0
+        if self.load_sp:
+            coded_sp_full = sample[:, :self.num_coded_sps * 3]
+            num_processed_feats += self.num_coded_sps * 3
+            if apply_mlpg:
+                coded_sp = mlpg.generation(coded_sp_full, self.covs[0], self.covs[0].shape[0] // 3)
+            else:
+                coded_sp = coded_sp_full[:, :self.num_coded_sps]
+            output_list.append(coded_sp)
+        if self.load_lf0:
+            lf0_full = sample[:, num_processed_feats:num_processed_feats + 3]
+            num_processed_feats += 3
+            if apply_mlpg:
+                lf0 = mlpg.generation(lf0_full, self.covs[1], self.covs[1].shape[0] // 3)
+            else:
+                lf0 = lf0_full[:, 0:1]
+            output_list.append(lf0)
+        if self.load_vuv:
+            vuv = sample[:, num_processed_feats]
+            num_processed_feats += 1
+            vuv[vuv <= 0.5] = 0.0
+            vuv[vuv > 0.5] = 1.0
+            output_list.append(vuv[:, None])
+        if self.load_bap:
+            bap_full = sample[:, -self.num_bap * 3:]
+            if apply_mlpg:
+                bap = mlpg.generation(bap_full, self.covs[3], self.covs[3].shape[0] // 3)
+            else:
+                bap = bap_full[:, 0:self.num_bap]
+            output_list.append(bap)
+        return np.concatenate(output_list, axis=1)
 
     def _get_id_list(self, dir_in, file_id_list, id_list, file_ext):
         if id_list is None:

@@ -518,3 +518,25 @@ def allpass_backward(grad_y, x, alpha, n, mean=None, std_dev=None, impl=None):
                                        _ptr(std_dev), gx.data_ptr(), ga.data_ptr(), ws.data_ptr(), _stream(dev)),
               "b2w_allpass_backward")
     return gx, ga
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# MLPG
+# ----------------------------------------------------------------------------------------------------------------------
+def mlpg(feats, var3, frame_off, D):
+    """MLPG.generation on a ragged batch: feats [F, >= 3 D] rows [static | delta | delta-delta] (f32 / f64, last stride 1), var3
+    [3 D] f64 (diagonal of the covariance), frame_off int64 [U + 1] -> smoothed trajectories [F, D] f64."""
+    lib = _lib.load()
+    if not feats.is_cuda:
+        raise ValueError("idiaptts_b200 operators need CUDA tensors (there is no CPU fallback)")
+    dev = _need_cuda(var3, frame_off)
+    assert feats.dim() == 2 and feats.stride(1) == 1 and feats.shape[1] >= 3 * D and feats.dtype in (torch.float32, torch.float64)
+    assert var3.dtype == torch.float64 and var3.numel() == 3 * D and frame_off.dtype == torch.int64
+    F = feats.shape[0]
+    out = torch.empty((F, D), dtype=torch.float64, device=dev)
+    ws = torch.empty(int(lib.b2w_mlpg_workspace_doubles(F, int(D))), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.b2w_mlpg(feats.data_ptr(), _DT[feats.dtype], int(feats.stride(0)) if F > 1 else feats.shape[1], var3.data_ptr(),
+                           frame_off.data_ptr(), frame_off.numel() - 1, int(D), ws.data_ptr(), out.data_ptr(), int(D), _stream(dev)),
+              "b2w_mlpg")
+    return out

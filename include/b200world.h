@@ -205,6 +205,13 @@ B2W_API int b2w_allpass_backward(const float* grad_y, const float* x, const floa
 
 /* ---- self-test of the tcgen05 (UMMA) building blocks used by the tensor-core mel-cepstrum kernel: one CTA computes
  * d[128, n] = a[128, k] . bt[n, k]^T with the 3xTF32 split (n % 16 == 0, n <= 256, k % 8 == 0); b_tiled_ws: 2*n*k floats. */
+/* ---- MLPG: replaces MLPG.generation (idiaptts/misc/mlpg.py:94-127) as called from
+ * WorldFeatLabelGen._postprocess_world (W:357-415).  feats [F, >= 3 D] rows [static(D) | delta(D) | delta-delta(D)] (F64|F32, row stride
+ * feat_stride), var3 [3 D] = the diagonal of the covariance, frame_off [num_utts + 1]; out [F, D] fp64 (row stride out_stride);
+ * workspace: b2w_mlpg_workspace_doubles(F, D) doubles. */
+B2W_API int64_t b2w_mlpg_workspace_doubles(int64_t num_frames, int32_t D);
+B2W_API int b2w_mlpg(const void* feats, int32_t feats_dtype, int64_t feat_stride, const double* var3, const int64_t* frame_off,
+                     int32_t num_utts, int32_t D, double* workspace, double* out, int64_t out_stride, void* stream);
 /* measurement aid (bench.py): launches a pure fp64 FMA kernel, returns the number of FMAs it executes (or -1) */
 B2W_API int64_t b2w_probe_fp64_fma(int32_t iters, double* scratch, void* stream);
 B2W_API int b2w_probe_umma(int32_t n, int32_t count, int32_t nacc, int32_t m, int32_t f16, long long* out4, void* stream);

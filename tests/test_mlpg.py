@@ -1,0 +1,92 @@
+"""MLPG: the oracle's banded system against a dense solve of the same normal equations (CPU), and the CUDA
+pentadiagonal solver against the oracle (GPU)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mlpg_np
+
+
+def _case(rng, T, D):
+    f = rng.standard_normal((T, 3 * D))
+    cov = np.diag(rng.uniform(0.05, 3.0, 3 * D))
+    return f, cov
+
+
+@pytest.mark.parametrize("T,D", [(1, 2), (2, 1), (3, 2), (41, 3)])
+def test_oracle_banded_equals_dense(T, D):
+    f, cov = _case(np.random.default_rng(T * 10 + D), T, D)
+    if T == 1:  # a single frame: only the static expert (and the switched-off edge experts) act
+        x = mlpg_np.generation(f, cov, D)
+        assert np.allclose(x, mlpg_np.generation_dense(f, cov, D), atol=1e-12)
+        assert np.allclose(x[0], f[0, :D], atol=1e-9)
+        return
+    assert np.abs(mlpg_np.generation(f, cov, D) - mlpg_np.generation_dense(f, cov, D)).max() < 1e-10
+
+
+def test_oracle_constant_trajectory_is_a_fixed_point():
+    # static means constant, delta means zero: the smooth trajectory is the constant itself
+    T, D = 30, 2
+    f = np.zeros((T, 3 * D))
+    f[:, :D] = [1.5, -0.7]
+    x = mlpg_np.generation(f, np.eye(3 * D), D)
+    assert np.abs(x - f[:, :D]).max() < 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_gpu_mlpg_matches_oracle(dtype):
+    from idiaptts_b200 import ops
+    from idiaptts_b200.mlpg import MLPG
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(3)
+    D = 7
+    lens = [1, 2, 3, 57, 130, 4]
+    cov = np.diag(rng.uniform(0.05, 3.0, 3 * D))
+    feats = [rng.standard_normal((T, 3 * D)).astype(dtype) for T in lens]
+    ref = np.concatenate([mlpg_np.generation(f.astype(np.float64), cov, D) for f in feats])
+    off = torch.tensor(np.concatenate(([0], np.cumsum(lens))), dtype=torch.int64, device=dev)
+    out = ops.mlpg(torch.from_numpy(np.concatenate(feats)).to(dev), torch.from_numpy(np.diag(cov).copy()).to(dev), off, D)
+    assert out.dtype == torch.float64 and out.shape == (sum(lens), D)
+    assert np.abs(out.cpu().numpy() - ref).max() < 1e-9
+    # the reference-facing class (one utterance, numpy in / out, full covariance matrix)
+    x = MLPG().generation(feats[3], cov, D)
+    assert x.dtype == np.float64 and np.abs(x - mlpg_np.generation(feats[3].astype(np.float64), cov, D)).max() < 1e-9
+
+
+@pytest.mark.gpu
+def test_gpu_mlpg_world_shaped_batch():
+    """Acoustic-model-shaped output: 60 mel-cepstrum dimensions with deltas, 16 utterances; property check instead of the oracle
+    at full size: the solution satisfies the normal equations P x = b (residual) for a sampled dimension."""
+    from idiaptts_b200 import ops
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(4)
+    D, U, T = 60, 16, 1301
+    feats = rng.standard_normal((U * T, 3 * D)).astype(np.float32)
+    var = rng.uniform(0.1, 2.0, 3 * D)
+    off = torch.arange(U + 1, dtype=torch.int64, device=dev) * T
+    out = ops.mlpg(torch.from_numpy(feats).to(dev), torch.from_numpy(var).to(dev), off, D).cpu().numpy()
+    u, d = 5, 17
+    ref = mlpg_np.generation(feats[u * T:(u + 1) * T].astype(np.float64)[:, [d, D + d, 2 * D + d]], np.diag(var[[d, D + d, 2 * D + d]]), 1)
+    assert np.abs(out[u * T:(u + 1) * T, d] - ref[:, 0]).max() < 1e-9
+
+
+@pytest.mark.gpu
+def test_postprocess_world_applies_mlpg_per_feature():
+    """WorldFeatLabelGen._postprocess_world (reference :357-415) on a network-output-shaped sample with deltas."""
+    from idiaptts_b200.WorldFeatLabelGen import WorldFeatLabelGen
+    rng = np.random.default_rng(9)
+    D, nap, T = 20, 2, 83
+    gen = WorldFeatLabelGen(add_deltas=True, num_coded_sps=D, num_bap=nap)
+    gen.covs = [np.diag(rng.uniform(0.1, 2.0, 3 * D)), np.diag(rng.uniform(0.1, 2.0, 3)), np.atleast_1d(1.0),
+                np.diag(rng.uniform(0.1, 2.0, 3 * nap))]
+    sample = rng.standard_normal((T, 3 * D + 3 + 1 + 3 * nap))
+    sample[:, 3 * D + 3] = rng.uniform(0, 1, T)
+    out = gen._postprocess_world(sample.copy(), apply_mlpg=True)
+    assert out.shape == (T, D + 1 + 1 + nap)
+    assert np.abs(out[:, :D] - mlpg_np.generation(sample[:, :3 * D], gen.covs[0], D)).max() < 1e-9
+    assert np.abs(out[:, D:D + 1] - mlpg_np.generation(sample[:, 3 * D:3 * D + 3], gen.covs[1], 1)).max() < 1e-9
+    assert np.array_equal(out[:, D + 1], (sample[:, 3 * D + 3] > 0.5).astype(np.float64))
+    assert np.abs(out[:, D + 2:] - mlpg_np.generation(sample[:, -3 * nap:], gen.covs[3], nap)).max() < 1e-9
+    plain = gen._postprocess_world(sample.copy(), apply_mlpg=False)
+    assert np.array_equal(plain[:, :D], sample[:, :D]) and np.array_equal(plain[:, D + 2:], sample[:, -3 * nap:][:, :nap])
