@@ -377,6 +377,88 @@ class WorldFeatLabelGen(object):
             return label_dict, output_means, output_std_dev
         return output_means, output_std_dev
 
+    # ---- reading features back (the on-disk formats at the boundary) ----------------------------------------
+    @staticmethod
+    def load_sample(id_name, dir_out, add_deltas=False, num_coded_sps=60, num_bap=1, sp_type="mcep", load_sp=True, load_lf0=True,
+                    load_vuv=True, load_bap=True):
+        """WorldFeatLabelGen.load_sample (world/WorldFeatLabelGen.py:418-457): [T, len(coded_sp, lf0, vuv, bap)] float32 from
+        the per-feature npz files gen_data wrote (no pre-processing)."""
+        assert dir_out is not None, "dir_out cannot be None"
+        id_name = os.path.splitext(os.path.basename(id_name))[0]
+        reader = WorldFeatLabelGen(dir_labels=dir_out, add_deltas=add_deltas, num_coded_sps=num_coded_sps, num_bap=num_bap,
+                                   sp_type=sp_type, load_sp=load_sp, load_lf0=load_lf0, load_vuv=load_vuv, load_bap=load_bap)
+        return reader.load(id_name)
+
+    def load(self, id_name):
+        """:459-567: `<dir>/<feat>/<id>.npz` with keys <ext>[, <ext>_deltas, <ext>_double_deltas]; falls back to the legacy
+        raw-float32 files `<id>.<ext>` (no deltas) and `cmp_<sp><D>/<id>.cmp` (deltas)."""
+        f3 = 3 if self.add_deltas else 1
+        feats = (("sp", self.load_sp, self.dir_coded_sps, self.sp_type, self.num_coded_sps * f3),
+                 ("lf0", self.load_lf0, self.dir_lf0, self.ext_lf0, f3),
+                 ("vuv", self.load_vuv, self.dir_vuv, self.ext_vuv, 1),
+                 ("bap", self.load_bap, self.dir_bap, self.ext_bap, self.num_bap * f3))
+        out = []
+        try:
+            for key, load, fdir, fext, fdim in feats:
+                if not load:
+                    continue
+                path = os.path.join(self.dir_labels, fdir, id_name)
+                if os.path.exists(path + ".npz"):
+                    with np.load(path + ".npz") as arc:
+                        lab = arc[fext]
+                        if self.add_deltas and key != "vuv":
+                            lab = np.concatenate((lab, arc[fext + "_deltas"], arc[fext + "_double_deltas"]), axis=1)
+                elif not self.add_deltas:
+                    lab = np.fromfile(path + "." + fext, dtype=np.float32).reshape(-1, fdim)  # LEGACY raw float32
+                else:
+                    raise FileNotFoundError(path + ".npz")
+                out.append(lab)
+        except FileNotFoundError:
+            if not self.add_deltas:
+                raise
+            # LEGACY cmp file: [sp d dd | lf0 d dd | vuv | bap d dd]
+            D, nap = self.num_coded_sps, self.num_bap
+            path = os.path.join(self.dir_labels, "{}_{}{}".format(WorldFeatLabelGen.dir_deltas, self.sp_type, D),
+                                "{}.{}".format(id_name, WorldFeatLabelGen.ext_deltas))
+            lab = np.fromfile(path, dtype=np.float32).reshape(-1, 3 * (D + 1 + nap) + 1)
+            out = []
+            if self.load_sp:
+                out.append(lab[:, :3 * D])
+            if self.load_lf0:
+                out.append(lab[:, 3 * D:3 * D + 3])
+            if self.load_vuv:
+                out.append(lab[:, -3 * nap - 1:-3 * nap])
+            if self.load_bap:
+                out.append(lab[:, -3 * nap:])
+        return np.concatenate(out, axis=1)
+
+    def __getitem__(self, id_name):
+        """Load and normalise one sample (the reference's LabelGen protocol, legacy single-array form)."""
+        return self.preprocess_sample(self.load(os.path.splitext(os.path.basename(id_name))[0]))
+
+    def _flat_norm_params(self, norm_params=None):
+        mean, std = norm_params if norm_params is not None else (self.norm_params if self.norm_params is not None else (None, None))
+        if mean is None:
+            return None, None
+        if isinstance(mean, (list, tuple)):  # add_deltas: per-feature means / covariance matrices
+            mean = np.concatenate([np.atleast_1d(m).reshape(-1) for m in mean])
+            std = np.concatenate([np.sqrt(np.diag(c)) if np.ndim(c) == 2 else np.atleast_1d(c).reshape(-1) for c in std])
+        return np.asarray(mean, np.float32), np.asarray(std, np.float32)
+
+    def preprocess_sample(self, sample, norm_params=None):
+        """(sample - mean) / std_dev with the parameters of gen_data / get_normalisation_params (vuv: mean 0, std 1)."""
+        mean, std = self._flat_norm_params(norm_params)
+        if mean is None:
+            return sample
+        return np.float32((sample - mean) / std)
+
+    def postprocess_sample(self, sample, norm_params=None, apply_mlpg=True):
+        """:338-355: de-normalise, then _postprocess_world (MLPG per feature when the sample carries deltas)."""
+        mean, std = self._flat_norm_params(norm_params)
+        if mean is not None:
+            sample = np.copy((sample * std) + mean)
+        return self._postprocess_world(sample, apply_mlpg=apply_mlpg)
+
     # ---- after inference: [static | delta | delta-delta] network output -> WORLD features (MLPG) ------------------------------
     def _postprocess_world(self, sample, norm_params=None, apply_mlpg=True):
         """WorldFeatLabelGen._postprocess_world (world/WorldFeatLabelGen.py:357-415): with add_deltas the (already de-normalised)

@@ -104,10 +104,24 @@ def test_gen_data_files_and_statistics(tmp_path, add_deltas):
         assert int(st["sum_length"]) == sum(world_np.num_frames(len(w), fs) for w in waves)
     else:
         assert means[0].shape == (1, 180) and stds[0].shape == (180, 180)
+    # reader half: load_sample returns what gen_data wrote, __getitem__ normalises, postprocess_sample inverts (+ MLPG with deltas)
+    loaded = WorldFeatLabelGen.load_sample(ids[2], str(tmp_path / "out"), add_deltas=add_deltas, num_coded_sps=60, num_bap=2)
+    assert loaded.dtype == np.float32 and np.array_equal(loaded, label_dict[ids[2]])
+    norm = gen[ids[2]]
+    assert norm.shape == loaded.shape and np.isfinite(norm).all()
+    back = gen.postprocess_sample(norm, apply_mlpg=True)
+    assert back.shape == (loaded.shape[0], 64)
+    static = loaded[:, np.r_[0:60, 180:181, 183:184, 184:186]] if add_deltas else loaded
+    assert np.array_equal(back[:, 61], static[:, 61])                       # vuv survives exactly
+    if add_deltas:
+        # deltas computed from the statics are (nearly) consistent with them, so the maximum-probability trajectory stays close
+        assert np.abs(back[:, :60] - static[:, :60]).max() < 0.5 and np.abs(back[:, 60] - static[:, 60]).max() < 0.5
         full = np.concatenate([label_dict[i][:, :180] for i in ids]).astype(np.float64)
         np.testing.assert_allclose(means[0][0], full.mean(0), rtol=1e-6, atol=1e-7)
         np.testing.assert_allclose(stds[0], np.cov(full.T, bias=True), rtol=1e-5, atol=1e-6)
         assert os.path.exists(str(tmp_path / "out" / "mcep60" / "train-deltas-mean-covariance.npz"))
+    else:
+        np.testing.assert_allclose(back, static, rtol=1e-4, atol=1e-4)
     with pytest.raises(NotImplementedError, match="F0 estimation"):
         WorldFeatLabelGen(str(tmp_path / "o2"), num_coded_sps=60, num_bap=2).gen_data(str(tmp_path / "wav"), None, id_list=ids)
 
