@@ -9,6 +9,9 @@
 //     GEMM1   D1[128 x 32]   = mc[128 x 64] . Cmat[64 x 32 chunk]          24 MMAs (8 K-steps x 3 split products)
 //     epilogue (all threads)  P = per * exp(-2 D1)  -> hi/lo TF32 tiles in shared memory (A operand of GEMM2)
 //     GEMM2   D2[128 x 128] += P[128 x 32] . M2^T[32 chunk x 128]          12 MMAs
+//   The GEMM phase is warp specialised: thread 0 only streams the matrices and issues MMAs (GEMM1 of chunk c + 1 is in the tensor
+//   pipe while chunk c's epilogue runs: D1 is double buffered in tensor memory), warps 4-11 are the epilogue (one TMEM lane =
+//   one frame per thread, 16 bins each), everything is handed over through mbarriers -- no CTA barrier inside the chunk loop.
 //   then D2 row f = r~ of frame f: stopping rule on r~[0], and for the frames still iterating one warp each builds and
 //   solves the (m+1) x (m+1) Toeplitz-plus-Hankel system (mcep_solve.cuh) and updates mc (fp32, shared memory).
 //   Pass 0 (initial value) uses the same machinery: P = log(per), the stream holds M0^T instead of M2^T, GEMM1 is skipped.
@@ -29,7 +32,9 @@ constexpr uint32_t kB2Bytes = kTcN2 * kTcBK * 4;   // one of hi / lo of the M2^T
 constexpr uint32_t kStageBytes = 2 * kB1Bytes + 2 * kB2Bytes;  // 48 KB per chunk: [B1 hi | B1 lo | B2 hi | B2 lo]
 constexpr uint32_t kA1Bytes = kTcF * kTcMP * 4;    // 32 KB, one of hi / lo
 constexpr uint32_t kA2Bytes = kTcF * kTcBK * 4;    // 16 KB, one of hi / lo
-constexpr int kTmemCols = 256;                     // D1 at columns 0..31, D2 at columns 32..159
+constexpr int kTmemCols = 256;                     // D1[0] at columns 0..31, D2 at columns 32..159, D1[1] at columns 160..191
+constexpr int kTcEpiWarp0 = 4;                     // epilogue warps 4 .. 11 (two per TMEM lane quarter)
+constexpr int kTcEpiThreads = 256;
 
 struct McepTcParams {
   const void* in;
@@ -135,8 +140,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
   int* act = reinterpret_cast<int*>(sv + kTcF);                   // [128]
   int* itc = act + kTcF;                                          // [128]
   int* qcnt = itc + kTcF;                                         // [4] work counters of the lane quarters
-  uint64_t* bars = reinterpret_cast<uint64_t*>(qcnt + 4);         // full[2], g1, g2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(qcnt + 4);         // full[2], g1[2], d1_free[2], a2_full, g2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   int* colbase = reinterpret_cast<int*>(tmem_slot + 2);            // [64] packed-column offsets of the register-resident solver
   uint16_t* tri = reinterpret_cast<uint16_t*>(colbase + 64);
 
@@ -146,14 +151,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
   const int K = p.K, m = p.m;
   const int64_t frame0 = (int64_t)blockIdx.x * kTcF;
   const int nvalid = (int)min((int64_t)kTcF, p.num_frames - frame0);
-  uint64_t* bar_full = bars;       // [2]
-  uint64_t* bar_g1 = bars + 2;
-  uint64_t* bar_g2 = bars + 3;
+  uint64_t* bar_full = bars;        // [2] stage loaded (bytes)
+  uint64_t* bar_g1 = bars + 2;      // [2] GEMM1 into D1[slot] complete
+  uint64_t* bar_d1free = bars + 4;  // [2] every epilogue thread has read D1[slot]
+  uint64_t* bar_a2 = bars + 6;      //     every epilogue thread has written its part of A2
+  uint64_t* bar_g2 = bars + 7;      //     GEMM2 complete: A2 and the stage are free, D2 accumulated
 
   if (tid == 0) {
     umma::mbar_init(&bar_full[0], 1);
     umma::mbar_init(&bar_full[1], 1);
-    umma::mbar_init(bar_g1, 1);
+    umma::mbar_init(&bar_g1[0], 1);
+    umma::mbar_init(&bar_g1[1], 1);
+    umma::mbar_init(&bar_d1free[0], kTcEpiThreads);
+    umma::mbar_init(&bar_d1free[1], kTcEpiThreads);
+    umma::mbar_init(bar_a2, kTcEpiThreads);
     umma::mbar_init(bar_g2, 1);
     umma::mbar_fence_init();
   }
@@ -176,11 +187,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
   __syncthreads();
   umma::tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t t_d1 = tmem + ((uint32_t)(32 * q) << 16);        // D1: columns 0..15
   const uint32_t t_d2 = tmem + ((uint32_t)(32 * q) << 16) + 32;   // D2: columns 32..159
   const uint32_t idesc1 = umma::idesc_tf32(kTcF, kTcBK);
   const uint32_t idesc2 = umma::idesc_tf32(kTcF, kTcN2);
-  uint32_t ph_full[2] = {0, 0}, ph_g1 = 0, ph_g2 = 0;  // parities, tracked identically by every thread
+  // barrier parities: every completion of a barrier is consumed by exactly one wait of each role that uses it
+  uint32_t ph_full[2] = {0, 0}, ph_g1[2] = {0, 0}, ph_d1free[2] = {0, 0}, ph_a2 = 0, ph_g2 = 0;
+  const bool is_epi = warp >= kTcEpiWarp0 && warp < kTcEpiWarp0 + kTcEpiThreads / 32;
+  const int eh = (warp - kTcEpiWarp0) >> 2;  // epilogue column half: bins 16 eh .. 16 eh + 15 of the chunk
   bool zero_per = false;
 
   for (int pass = 0; pass <= p.maxiter; ++pass) {
@@ -202,95 +215,121 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
       umma::fence_proxy_async();
     }
     __syncthreads();
-    if (tid == 0) {  // prefetch the first two chunks of this pass (both stages are drained at a pass boundary)
-      for (int s = 0; s < 2 && s < p.nchunks; ++s) {
+    const int nch = p.nchunks;
+    if (tid == 0) {
+      // ---- issuer: stream the matrices, keep the tensor pipe fed ------------------------------------------------------------
+      auto load = [&](int c) {
+        const int s = c & 1;
         umma::mbar_expect_tx(&bar_full[s], kStageBytes);
-        umma::bulk_g2s(stage_base + s * kStageBytes, reinterpret_cast<const uint8_t*>(stream) + (size_t)s * kStageBytes, kStageBytes,
+        umma::bulk_g2s(stage_base + s * kStageBytes, reinterpret_cast<const uint8_t*>(stream) + (size_t)c * kStageBytes, kStageBytes,
                        &bar_full[s]);
+      };
+      const uint32_t a_lbo = kTcF * 16;
+      auto gemm1 = [&](int c) {  // D1[c & 1] = mc . Cmat chunk
+        const int s = c & 1;
+        const uint32_t b1h = umma::smem_u32(stage_base + s * kStageBytes), b1l = b1h + kB1Bytes, b_lbo = kTcBK * 16;
+        umma::mma_3xtf32<kTcMP / 8>(tmem + (s ? 160 : 0), umma::smem_desc(umma::smem_u32(a1_hi), a_lbo, 128),
+                                    umma::smem_desc(umma::smem_u32(a1_lo), a_lbo, 128), umma::smem_desc(b1h, b_lbo, 128),
+                                    umma::smem_desc(b1l, b_lbo, 128), 2 * a_lbo, 2 * b_lbo, idesc1, false);
+        umma::mma_commit(&bar_g1[s]);
+      };
+      for (int c = 0; c < 2 && c < nch; ++c) load(c);
+      if (pass > 0) {
+        umma::mbar_wait(&bar_full[0], ph_full[0]);
+        ph_full[0] ^= 1;
+        umma::tc_fence_after_sync();
+        gemm1(0);
       }
-    }
-    float pern[kTcBK / 4];  // raw periodogram values of the chunk about to be processed (prefetched one chunk ahead)
-    tc_load_raw8<IT>(p, frame0 + row, (kTcBK / 4) * g, row < nvalid, pern);
-    for (int c = 0; c < p.nchunks; ++c) {
-      const int s = c & 1;
-      const uint8_t* stg = stage_base + s * kStageBytes;
-      const int j0 = c * kTcBK;
-      if (tid == 0) {
-        umma::mbar_wait(&bar_full[s], ph_full[s]);
+      for (int c = 0; c < nch; ++c) {
+        const int s = c & 1;
         if (pass > 0) {
-          umma::tc_fence_after_sync();
-          const uint32_t b1h = umma::smem_u32(stg), b1l = b1h + kB1Bytes;
-          const uint32_t a_lbo = kTcF * 16, b_lbo = kTcBK * 16;
-          umma::mma_3xtf32<kTcMP / 8>(tmem, umma::smem_desc(umma::smem_u32(a1_hi), a_lbo, 128),
-                                      umma::smem_desc(umma::smem_u32(a1_lo), a_lbo, 128), umma::smem_desc(b1h, b_lbo, 128),
-                                      umma::smem_desc(b1l, b_lbo, 128), 2 * a_lbo, 2 * b_lbo, idesc1, false);
-          umma::mma_commit(bar_g1);
+          if (c + 1 < nch) {  // GEMM1 of the next chunk goes ahead of this chunk's GEMM2
+            const int sn = (c + 1) & 1;
+            umma::mbar_wait(&bar_full[sn], ph_full[sn]);
+            ph_full[sn] ^= 1;
+            if (c + 1 >= 2) {  // D1[sn] was last read by the epilogue of chunk c - 1
+              umma::mbar_wait(&bar_d1free[sn], ph_d1free[sn]);
+              ph_d1free[sn] ^= 1;
+            }
+            umma::tc_fence_after_sync();
+            gemm1(c + 1);
+          }
+        } else {
+          umma::mbar_wait(&bar_full[s], ph_full[s]);
+          ph_full[s] ^= 1;
+        }
+        umma::mbar_wait(bar_a2, ph_a2);  // the epilogue has written P of chunk c
+        ph_a2 ^= 1;
+        umma::tc_fence_after_sync();
+        {
+          const uint32_t b2h = umma::smem_u32(stage_base + s * kStageBytes) + 2 * kB1Bytes, b2l = b2h + kB2Bytes, b_lbo = kTcN2 * 16;
+          umma::mma_3xtf32<kTcBK / 8>(tmem + 32, umma::smem_desc(umma::smem_u32(a2_hi), a_lbo, 128),
+                                      umma::smem_desc(umma::smem_u32(a2_lo), a_lbo, 128), umma::smem_desc(b2h, b_lbo, 128),
+                                      umma::smem_desc(b2l, b_lbo, 128), 2 * a_lbo, 2 * b_lbo, idesc2, c > 0);
+          umma::mma_commit(bar_g2);
+        }
+        umma::mbar_wait(bar_g2, ph_g2);  // GEMM2(c) complete: stage s is free
+        ph_g2 ^= 1;
+        if (c + 2 < nch) load(c + 2);
+      }
+      if (pass > 0) {  // consume the D1 releases of the last two chunks (keeps the parities in step)
+        for (int c = (nch >= 2 ? nch - 2 : 0); c < nch; ++c) {
+          umma::mbar_wait(&bar_d1free[c & 1], ph_d1free[c & 1]);
+          ph_d1free[c & 1] ^= 1;
         }
       }
-      ph_full[s] ^= 1;
-      // ---- epilogue: this thread owns row `row`, bins j0 + 8 g .. + 7 ------------------------------------------------
-      // the periodogram values are requested BEFORE waiting for GEMM1, so their L2 latency overlaps the tensor work
-      constexpr int CPT = kTcBK / 4;  // columns per thread
-      static_assert(CPT == 8, "tc_load_raw8 reads eight bins per thread");
-      float perv[CPT];
-      bool inb[CPT];
+    } else if (is_epi) {
+      // ---- epilogue warps: P = per * exp(-2 D1) (pass 0: log per) -> hi / lo TF32 tiles of A2 ------------------------------------
+      constexpr int CPT = kTcBK / 2;  // 16 bins per thread
+      float pern[CPT];                // raw periodogram values, prefetched one chunk ahead
+      tc_load_raw8<IT>(p, frame0 + row, CPT * eh, row < nvalid, *reinterpret_cast<float(*)[8]>(pern));
+      tc_load_raw8<IT>(p, frame0 + row, CPT * eh + 8, row < nvalid, *reinterpret_cast<float(*)[8]>(pern + 8));
+      for (int c = 0; c < nch; ++c) {
+        const int s = c & 1;
+        const int j0 = c * kTcBK + CPT * eh;
+        float perv[CPT];
 #pragma unroll
-      for (int i = 0; i < CPT; ++i) {
-        const int j = j0 + CPT * g + i;
-        inb[i] = j < K;
-        perv[i] = inb[i] ? (p.in_is_power ? pern[i] + p.eps : fmaf(pern[i], pern[i], p.eps)) : 1.f;
-      }
-      // request the next chunk's values now: their latency hides behind this chunk's tensor work and epilogue
-      if (c + 1 < p.nchunks) tc_load_raw8<IT>(p, frame0 + row, j0 + kTcBK + CPT * g, row < nvalid, pern);
-      float cv[CPT];
+        for (int i = 0; i < CPT; ++i) perv[i] = (j0 + i < K) ? (p.in_is_power ? pern[i] + p.eps : fmaf(pern[i], pern[i], p.eps)) : 1.f;
+        if (c + 1 < nch) {
+          tc_load_raw8<IT>(p, frame0 + row, j0 + kTcBK, row < nvalid, *reinterpret_cast<float(*)[8]>(pern));
+          tc_load_raw8<IT>(p, frame0 + row, j0 + kTcBK + 8, row < nvalid, *reinterpret_cast<float(*)[8]>(pern + 8));
+        }
+        float cv[CPT];
 #pragma unroll
-      for (int i = 0; i < CPT; ++i) cv[i] = 0.f;
-      if (pass > 0) {
-        umma::mbar_wait(bar_g1, ph_g1);
-        ph_g1 ^= 1;
-        umma::tc_fence_after_sync();
-        umma::tmem_ld8(t_d1 + CPT * g, cv);
-      }
-      float ph[CPT], pl[CPT];
+        for (int i = 0; i < CPT; ++i) cv[i] = 0.f;
+        if (pass > 0) {
+          umma::mbar_wait(&bar_g1[s], ph_g1[s]);
+          ph_g1[s] ^= 1;
+          umma::tc_fence_after_sync();
+          umma::tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + (s ? 160 : 0) + CPT * eh, cv);
+          umma::tc_fence_before_sync();
+          umma::mbar_arrive(&bar_d1free[s]);
+        }
+        float ph[CPT], pl[CPT];
 #pragma unroll
-      for (int i = 0; i < CPT; ++i) {
-        if (!(perv[i] > 0.f)) zero_per = true;
-        const float val = pass == 0 ? logf(perv[i]) : perv[i] * expf(-2.f * cv[i]);
-        umma::split_tf32(inb[i] ? val : 0.f, ph[i], pl[i]);
-      }
-      if (c > 0) {  // A2 is single-buffered: the previous GEMM2 must have consumed it (pass boundaries are drained)
-        umma::mbar_wait(bar_g2, ph_g2);
-        ph_g2 ^= 1;
-      }
-      if (tid == 0 && c >= 1 && c + 1 < p.nchunks) {
-        // GEMM2(c-1) is complete: stage (c-1)&1 is free -> refill it with chunk c + 1
-        const int sn = (c + 1) & 1;
-        umma::mbar_expect_tx(&bar_full[sn], kStageBytes);
-        umma::bulk_g2s(stage_base + sn * kStageBytes, reinterpret_cast<const uint8_t*>(stream) + (size_t)(c + 1) * kStageBytes,
-                       kStageBytes, &bar_full[sn]);
-      }
+        for (int i = 0; i < CPT; ++i) {
+          if (!(perv[i] > 0.f)) zero_per = true;
+          const float val = pass == 0 ? logf(perv[i]) : perv[i] * expf(-2.f * cv[i]);
+          umma::split_tf32((j0 + i < K) ? val : 0.f, ph[i], pl[i]);
+        }
+        if (c > 0) {  // A2 is single-buffered: GEMM2 of the previous chunk must have consumed it
+          umma::mbar_wait(bar_g2, ph_g2);
+          ph_g2 ^= 1;
+        }
 #pragma unroll
-      for (int h4 = 0; h4 < CPT / 4; ++h4) {
-        const uint32_t off = umma::tile_off(kTcF, row, CPT * g + 4 * h4) / 4;
-        *reinterpret_cast<float4*>(a2_hi + off) = make_float4(ph[4 * h4], ph[4 * h4 + 1], ph[4 * h4 + 2], ph[4 * h4 + 3]);
-        *reinterpret_cast<float4*>(a2_lo + off) = make_float4(pl[4 * h4], pl[4 * h4 + 1], pl[4 * h4 + 2], pl[4 * h4 + 3]);
+        for (int h4 = 0; h4 < CPT / 4; ++h4) {
+          const uint32_t off = umma::tile_off(kTcF, row, CPT * eh + 4 * h4) / 4;
+          *reinterpret_cast<float4*>(a2_hi + off) = make_float4(ph[4 * h4], ph[4 * h4 + 1], ph[4 * h4 + 2], ph[4 * h4 + 3]);
+          *reinterpret_cast<float4*>(a2_lo + off) = make_float4(pl[4 * h4], pl[4 * h4 + 1], pl[4 * h4 + 2], pl[4 * h4 + 3]);
+        }
+        umma::fence_proxy_async();
+        umma::mbar_arrive(bar_a2);
       }
-      umma::fence_proxy_async();
-      umma::tc_fence_before_sync();
-      __syncthreads();
-      if (tid == 0) {
-        umma::tc_fence_after_sync();
-        const uint32_t b2h = umma::smem_u32(stg) + 2 * kB1Bytes, b2l = b2h + kB2Bytes;
-        const uint32_t a_lbo = kTcF * 16, b_lbo = kTcN2 * 16;
-        umma::mma_3xtf32<kTcBK / 8>(tmem + 32, umma::smem_desc(umma::smem_u32(a2_hi), a_lbo, 128),
-                                    umma::smem_desc(umma::smem_u32(a2_lo), a_lbo, 128), umma::smem_desc(b2h, b_lbo, 128),
-                                    umma::smem_desc(b2l, b_lbo, 128), 2 * a_lbo, 2 * b_lbo, idesc2, c > 0);
-        umma::mma_commit(bar_g2);
-      }
+      umma::mbar_wait(bar_g2, ph_g2);  // the last chunk's GEMM2 completes D2
+      ph_g2 ^= 1;
     }
-    // the last chunk's GEMM2 completes D2
-    umma::mbar_wait(bar_g2, ph_g2);
-    ph_g2 ^= 1;
+    umma::tc_fence_before_sync();
+    __syncthreads();  // D2 is complete (the epilogue warps and the issuer have waited for the last GEMM2)
     umma::tc_fence_after_sync();
 
     if (pass == 0) {
@@ -443,7 +482,7 @@ extern "C" int b2w_mcep_tc(const void* in, int32_t in_dtype, int32_t in_is_power
   const uint32_t gemm_bytes = 2 * kA1Bytes + 2 * kStageBytes + 2 * kA2Bytes;
   const uint32_t ws_bytes = (uint32_t)(kTcThreads / 32) * (uint32_t)p.ws_floats * 4u;
   const uint32_t region_bytes = gemm_bytes > ws_bytes ? gemm_bytes : ws_bytes;
-  const size_t smem = region_bytes + sizeof(float) * (kTcF * kTcMP + kTcMP + kTcF) + sizeof(int) * (2 * kTcF + 4) + 4 * 8 + 8 + 64 * sizeof(int) +
+  const size_t smem = region_bytes + sizeof(float) * (kTcF * kTcMP + kTcMP + kTcF) + sizeof(int) * (2 * kTcF + 4) + 8 * 8 + 8 + 64 * sizeof(int) +
                       sizeof(uint16_t) * (size_t)(p.NBk * (p.NBk - 1) / 2 + 2) + 16;
   B2W_REQUIRE(smem <= 227 * 1024, "b2w_mcep_tc: %zu bytes of shared memory needed", smem);
   const int64_t grid = (num_frames + kTcF - 1) / kTcF;
