@@ -36,6 +36,21 @@ constexpr int kTmemCols = 256;                     // D1[0] at columns 0..31, D2
 constexpr int kTcEpiWarp0 = 4;                     // epilogue warps 4 .. 11 (two per TMEM lane quarter)
 constexpr int kTcEpiThreads = 256;
 
+// Phase timing of CTA 0 (build with -DB2W_MCEP_PROF via scripts/build_variant.py; read with b2w_mcep_prof_read): slots 0-7 are
+// the issuer thread, 8-13 one epilogue thread, 14-15 the pass as seen by thread 32.
+__device__ long long g_mcep_prof[16];
+#ifdef B2W_MCEP_PROF
+#define PROF_DECL long long prof_t = 0, prof_acc[16] = {0}; const bool prof_on = blockIdx.x == 0 && (tid == 0 || tid == 128 || tid == 32)
+#define PROF_START() do { if (prof_on) prof_t = clock64(); } while (0)
+#define PROF_LAP(i) do { if (prof_on) { const long long n_ = clock64(); prof_acc[i] += n_ - prof_t; prof_t = n_; } } while (0)
+#define PROF_FLUSH(lo, hi) do { if (prof_on) { for (int i_ = lo; i_ < hi; ++i_) g_mcep_prof[i_] = prof_acc[i_]; } } while (0)
+#else
+#define PROF_DECL
+#define PROF_START()
+#define PROF_LAP(i)
+#define PROF_FLUSH(lo, hi)
+#endif
+
 struct McepTcParams {
   const void* in;
   int in_is_power;
@@ -195,6 +210,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
   const bool is_epi = warp >= kTcEpiWarp0 && warp < kTcEpiWarp0 + kTcEpiThreads / 32;
   const int eh = (warp - kTcEpiWarp0) >> 2;  // epilogue column half: bins 16 eh .. 16 eh + 15 of the chunk
   bool zero_per = false;
+  PROF_DECL;
+  PROF_START();
 
   for (int pass = 0; pass <= p.maxiter; ++pass) {
     const float* stream = pass == 0 ? p.stream0 : p.stream1;
@@ -233,6 +250,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
                                     umma::smem_desc(b1l, b_lbo, 128), 2 * a_lbo, 2 * b_lbo, idesc1, false);
         umma::mma_commit(&bar_g1[s]);
       };
+      PROF_LAP(0);  // outside the GEMM phase (A1 split, solves, barriers)
       for (int c = 0; c < 2 && c < nch; ++c) load(c);
       if (pass > 0) {
         umma::mbar_wait(&bar_full[0], ph_full[0]);
@@ -245,14 +263,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
         if (pass > 0) {
           if (c + 1 < nch) {  // GEMM1 of the next chunk goes ahead of this chunk's GEMM2
             const int sn = (c + 1) & 1;
+            PROF_LAP(1);
             umma::mbar_wait(&bar_full[sn], ph_full[sn]);
             ph_full[sn] ^= 1;
+            PROF_LAP(2);  // wait stage
             if (c + 1 >= 2) {  // D1[sn] was last read by the epilogue of chunk c - 1
               umma::mbar_wait(&bar_d1free[sn], ph_d1free[sn]);
               ph_d1free[sn] ^= 1;
             }
+            PROF_LAP(3);  // wait D1 free
             umma::tc_fence_after_sync();
             gemm1(c + 1);
+            PROF_LAP(4);  // GEMM1 issue
           }
         } else {
           umma::mbar_wait(&bar_full[s], ph_full[s]);
@@ -260,6 +282,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
         }
         umma::mbar_wait(bar_a2, ph_a2);  // the epilogue has written P of chunk c
         ph_a2 ^= 1;
+        PROF_LAP(5);  // wait A2
         umma::tc_fence_after_sync();
         {
           const uint32_t b2h = umma::smem_u32(stage_base + s * kStageBytes) + 2 * kB1Bytes, b2l = b2h + kB2Bytes, b_lbo = kTcN2 * 16;
@@ -268,8 +291,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
                                       umma::smem_desc(b2l, b_lbo, 128), 2 * a_lbo, 2 * b_lbo, idesc2, c > 0);
           umma::mma_commit(bar_g2);
         }
+        PROF_LAP(6);  // GEMM2 issue
         umma::mbar_wait(bar_g2, ph_g2);  // GEMM2(c) complete: stage s is free
         ph_g2 ^= 1;
+        PROF_LAP(7);  // wait GEMM2
         if (c + 2 < nch) load(c + 2);
       }
       if (pass > 0) {  // consume the D1 releases of the last two chunks (keeps the parities in step)
@@ -297,9 +322,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
         float cv[CPT];
 #pragma unroll
         for (int i = 0; i < CPT; ++i) cv[i] = 0.f;
+        PROF_LAP(8);  // epilogue: loads / prefetch issue (+ everything outside the GEMM phase)
         if (pass > 0) {
           umma::mbar_wait(&bar_g1[s], ph_g1[s]);
           ph_g1[s] ^= 1;
+          PROF_LAP(9);  // epilogue: wait GEMM1
           umma::tc_fence_after_sync();
           umma::tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + (s ? 160 : 0) + CPT * eh, cv);
           umma::tc_fence_before_sync();
@@ -312,10 +339,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
           const float val = pass == 0 ? logf(perv[i]) : perv[i] * expf(-2.f * cv[i]);
           umma::split_tf32((j0 + i < K) ? val : 0.f, ph[i], pl[i]);
         }
+        PROF_LAP(10);  // epilogue: tmem ld + exp + split
         if (c > 0) {  // A2 is single-buffered: GEMM2 of the previous chunk must have consumed it
           umma::mbar_wait(bar_g2, ph_g2);
           ph_g2 ^= 1;
         }
+        PROF_LAP(11);  // epilogue: wait A2 free (GEMM2 of the previous chunk)
 #pragma unroll
         for (int h4 = 0; h4 < CPT / 4; ++h4) {
           const uint32_t off = umma::tile_off(kTcF, row, CPT * eh + 4 * h4) / 4;
@@ -324,6 +353,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
         }
         umma::fence_proxy_async();
         umma::mbar_arrive(bar_a2);
+        PROF_LAP(12);  // epilogue: A2 stores + fence + arrive
       }
       umma::mbar_wait(bar_g2, ph_g2);  // the last chunk's GEMM2 completes D2
       ph_g2 ^= 1;
@@ -416,6 +446,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
     umma::tc_fence_before_sync();
     __syncthreads();
   }
+#ifdef B2W_MCEP_PROF
+  if (tid == 0) PROF_FLUSH(0, 8);
+  if (tid == 128) PROF_FLUSH(8, 14);
+#endif
   if (zero_per) atomicOr(p.status, B2W_STATUS_ZERO_PERIODOGRAM);
   if (tid < kTcF && act[tid]) {
     itc[tid] = p.maxiter;
@@ -435,6 +469,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
 }
 
 }  // namespace b2w
+
+extern "C" int b2w_mcep_prof_read(long long* out16) {
+  return (int)cudaMemcpyFromSymbol(out16, b2w::g_mcep_prof, sizeof(long long) * 16);
+}
 
 extern "C" int64_t b2w_mcep_tc_stream_floats(int32_t fft_size) {
   const int K = fft_size / 2 + 1;

@@ -214,6 +214,8 @@ B2W_API int b2w_mlpg(const void* feats, int32_t feats_dtype, int64_t feat_stride
                      int32_t num_utts, int32_t D, double* workspace, double* out, int64_t out_stride, void* stream);
 /* measurement aid (bench.py): launches a pure fp64 FMA kernel, returns the number of FMAs it executes (or -1) */
 B2W_API int64_t b2w_probe_fp64_fma(int32_t iters, double* scratch, void* stream);
+/* development aid: phase cycle counters of mcep_tc CTA 0 (non-zero only in a -DB2W_MCEP_PROF build) */
+B2W_API int b2w_mcep_prof_read(long long* out16);
 B2W_API int b2w_probe_umma(int32_t n, int32_t count, int32_t nacc, int32_t m, int32_t f16, long long* out4, void* stream);
 B2W_API int b2w_test_umma_gemm(const float* a, const float* bt, int32_t n, int32_t k, float* b_tiled_ws, float* d, void* stream);
 

@@ -56,3 +56,13 @@ if "d4c" in ks:
 print("status", int(status.item()))
 if a.dump:
     np.savez(a.dump, **res)
+
+if os.environ.get("B2W_LIB", "").find("mcepprof") >= 0:
+    import ctypes
+    buf = (ctypes.c_longlong * 16)()
+    _lib.load().b2w_mcep_prof_read(ctypes.cast(buf, ctypes.c_void_p))
+    names = ["issuer: outside GEMM phase", "issuer: loop overhead", "issuer: wait stage", "issuer: wait D1 free", "issuer: GEMM1 issue",
+             "issuer: wait A2", "issuer: GEMM2 issue", "issuer: wait GEMM2", "epi: loads (+ outside)", "epi: wait GEMM1",
+             "epi: tmem ld + exp + split", "epi: wait A2 free", "epi: A2 stores + arrive", "-", "-", "-"]
+    for n_, v in zip(names, buf):
+        print("  %-28s %10d cycles" % (n_, v))
