@@ -22,7 +22,18 @@
 namespace b2w {
 
 constexpr int kTcF = 128;        // frames per CTA = UMMA M
+#ifdef B2W_TC_ISSUER_WARP            // experiment: a 17th warp issues, all 16 others are epilogue warps (120 registers / thread)
+constexpr int kTcThreads = 544;
+constexpr int kTcIssuer = 512;
+constexpr int kTcEpiWarp0 = 0;
+constexpr int kTcEpiThreads = 512;
+#else
 constexpr int kTcThreads = 512;  // 16 warps: TMEM lane quarter q = warp & 3, column group g = warp >> 2
+constexpr int kTcIssuer = 0;     // the thread that streams the matrices and issues the MMAs
+constexpr int kTcEpiWarp0 = 4;   // epilogue warps 4 .. 11 (two per TMEM lane quarter)
+constexpr int kTcEpiThreads = 256;
+#endif
+constexpr int kTcSolveWarps = 16;
 constexpr int kTcBK = 32;        // bins per chunk
 constexpr int kTcMP = 64;        // padded cepstral dimension (K of GEMM1)
 constexpr int kTcN2 = 128;       // padded r~ length (N of GEMM2)
@@ -33,14 +44,12 @@ constexpr uint32_t kStageBytes = 2 * kB1Bytes + 2 * kB2Bytes;  // 48 KB per chun
 constexpr uint32_t kA1Bytes = kTcF * kTcMP * 4;    // 32 KB, one of hi / lo
 constexpr uint32_t kA2Bytes = kTcF * kTcBK * 4;    // 16 KB, one of hi / lo
 constexpr int kTmemCols = 256;                     // D1[0] at columns 0..31, D2 at columns 32..159, D1[1] at columns 160..191
-constexpr int kTcEpiWarp0 = 4;                     // epilogue warps 4 .. 11 (two per TMEM lane quarter)
-constexpr int kTcEpiThreads = 256;
 
 // Phase timing of CTA 0 (build with -DB2W_MCEP_PROF via scripts/build_variant.py; read with b2w_mcep_prof_read): slots 0-7 are
 // the issuer thread, 8-13 one epilogue thread, 14-15 the pass as seen by thread 32.
 __device__ long long g_mcep_prof[16];
 #ifdef B2W_MCEP_PROF
-#define PROF_DECL long long prof_t = 0, prof_acc[16] = {0}; const bool prof_on = blockIdx.x == 0 && (tid == 0 || tid == 128 || tid == 32)
+#define PROF_DECL long long prof_t = 0, prof_acc[16] = {0}; const bool prof_on = blockIdx.x == 0 && (tid == kTcIssuer || tid == 128)
 #define PROF_START() do { if (prof_on) prof_t = clock64(); } while (0)
 #define PROF_LAP(i) do { if (prof_on) { const long long n_ = clock64(); prof_acc[i] += n_ - prof_t; prof_t = n_; } } while (0)
 #define PROF_FLUSH(lo, hi) do { if (prof_on) { for (int i_ = lo; i_ < hi; ++i_) g_mcep_prof[i_] = prof_acc[i_]; } } while (0)
@@ -147,7 +156,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
   float* a2_hi = reinterpret_cast<float*>(stage_base + 2 * kStageBytes);
   float* a2_lo = reinterpret_cast<float*>(stage_base + 2 * kStageBytes + kA2Bytes);
   const uint32_t gemm_bytes = 2 * kA1Bytes + 2 * kStageBytes + 2 * kA2Bytes;
-  const uint32_t ws_bytes = (uint32_t)(kTcThreads / 32) * (uint32_t)p.ws_floats * 4u;
+  const uint32_t ws_bytes = (uint32_t)kTcSolveWarps * (uint32_t)p.ws_floats * 4u;
   const uint32_t region_bytes = gemm_bytes > ws_bytes ? gemm_bytes : ws_bytes;
   float* mc = reinterpret_cast<float*>(region + region_bytes);  // [128][64] fp32
   float* al = mc + kTcF * kTcMP;                                  // [64]
@@ -208,7 +217,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
   // barrier parities: every completion of a barrier is consumed by exactly one wait of each role that uses it
   uint32_t ph_full[2] = {0, 0}, ph_g1[2] = {0, 0}, ph_d1free[2] = {0, 0}, ph_a2 = 0, ph_g2 = 0;
   const bool is_epi = warp >= kTcEpiWarp0 && warp < kTcEpiWarp0 + kTcEpiThreads / 32;
-  const int eh = (warp - kTcEpiWarp0) >> 2;  // epilogue column half: bins 16 eh .. 16 eh + 15 of the chunk
+  const int eh = (warp - kTcEpiWarp0) >> 2;  // epilogue column group: bins CPT eh .. CPT eh + CPT - 1 of the chunk
   bool zero_per = false;
   PROF_DECL;
   PROF_START();
@@ -233,7 +242,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
     }
     __syncthreads();
     const int nch = p.nchunks;
-    if (tid == 0) {
+    if (tid == kTcIssuer) {
       // ---- issuer: stream the matrices, keep the tensor pipe fed ------------------------------------------------------------
       auto load = [&](int c) {
         const int s = c & 1;
@@ -305,10 +314,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
       }
     } else if (is_epi) {
       // ---- epilogue warps: P = per * exp(-2 D1) (pass 0: log per) -> hi / lo TF32 tiles of A2 ------------------------------------
-      constexpr int CPT = kTcBK / 2;  // 16 bins per thread
+      constexpr int CPT = kTcBK / (kTcEpiThreads / 128);  // bins per thread (16 with 8 epilogue warps)
       float pern[CPT];                // raw periodogram values, prefetched one chunk ahead
-      tc_load_raw8<IT>(p, frame0 + row, CPT * eh, row < nvalid, *reinterpret_cast<float(*)[8]>(pern));
-      tc_load_raw8<IT>(p, frame0 + row, CPT * eh + 8, row < nvalid, *reinterpret_cast<float(*)[8]>(pern + 8));
+#pragma unroll
+      for (int h = 0; h < CPT / 8; ++h)
+        tc_load_raw8<IT>(p, frame0 + row, CPT * eh + 8 * h, row < nvalid, *reinterpret_cast<float(*)[8]>(pern + 8 * h));
       for (int c = 0; c < nch; ++c) {
         const int s = c & 1;
         const int j0 = c * kTcBK + CPT * eh;
@@ -316,8 +326,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
 #pragma unroll
         for (int i = 0; i < CPT; ++i) perv[i] = (j0 + i < K) ? (p.in_is_power ? pern[i] + p.eps : fmaf(pern[i], pern[i], p.eps)) : 1.f;
         if (c + 1 < nch) {
-          tc_load_raw8<IT>(p, frame0 + row, j0 + kTcBK, row < nvalid, *reinterpret_cast<float(*)[8]>(pern));
-          tc_load_raw8<IT>(p, frame0 + row, j0 + kTcBK + 8, row < nvalid, *reinterpret_cast<float(*)[8]>(pern + 8));
+#pragma unroll
+          for (int h = 0; h < CPT / 8; ++h)
+            tc_load_raw8<IT>(p, frame0 + row, j0 + kTcBK + 8 * h, row < nvalid, *reinterpret_cast<float(*)[8]>(pern + 8 * h));
         }
         float cv[CPT];
 #pragma unroll
@@ -328,7 +339,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
           ph_g1[s] ^= 1;
           PROF_LAP(9);  // epilogue: wait GEMM1
           umma::tc_fence_after_sync();
-          umma::tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + (s ? 160 : 0) + CPT * eh, cv);
+          if constexpr (CPT == 16) umma::tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + (s ? 160 : 0) + CPT * eh, cv);
+          else umma::tmem_ld8(tmem + ((uint32_t)(32 * q) << 16) + (s ? 160 : 0) + CPT * eh, cv);
           umma::tc_fence_before_sync();
           umma::mbar_arrive(&bar_d1free[s]);
         }
@@ -398,7 +410,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
     if (tid < kTcF) any = act[tid];
     if (!__syncthreads_or(any)) break;
     // ---- Newton step: the warps of a lane quarter share its 32 frames through a work counter -----------------------
-    {
+    if (warp < kTcSolveWarps) {
       float* ws = reinterpret_cast<float*>(region) + warp * p.ws_floats;
       // generic: [blocked LDL^T workspace | r~ row 128 | x 64];  register-resident: [packed columns | 64 pad | r~ row 128]
       float* rtrow = ws + (NS > 0 ? rr_workspace_floats(NS > 0 ? NS : 8) - kTcN2 : ldl_workspace_floats(p.NBk, kTcKB));
@@ -447,7 +459,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
     __syncthreads();
   }
 #ifdef B2W_MCEP_PROF
-  if (tid == 0) PROF_FLUSH(0, 8);
+  if (tid == kTcIssuer) PROF_FLUSH(0, 8);
   if (tid == 128) PROF_FLUSH(8, 14);
 #endif
   if (zero_per) atomicOr(p.status, B2W_STATUS_ZERO_PERIODOGRAM);
@@ -518,7 +530,7 @@ extern "C" int b2w_mcep_tc(const void* in, int32_t in_dtype, int32_t in_is_power
   p.stream0 = stream0; p.stream1 = stream1; p.mc_out = mc; p.mc_dtype = mc_dtype; p.mc_stride = mc_stride;
   p.iters = iters; p.status = status;
   const uint32_t gemm_bytes = 2 * kA1Bytes + 2 * kStageBytes + 2 * kA2Bytes;
-  const uint32_t ws_bytes = (uint32_t)(kTcThreads / 32) * (uint32_t)p.ws_floats * 4u;
+  const uint32_t ws_bytes = (uint32_t)kTcSolveWarps * (uint32_t)p.ws_floats * 4u;
   const uint32_t region_bytes = gemm_bytes > ws_bytes ? gemm_bytes : ws_bytes;
   const size_t smem = region_bytes + sizeof(float) * (kTcF * kTcMP + kTcMP + kTcF) + sizeof(int) * (2 * kTcF + 4) + 8 * 8 + 8 + 64 * sizeof(int) +
                       sizeof(uint16_t) * (size_t)(p.NBk * (p.NBk - 1) / 2 + 2) + 16;
