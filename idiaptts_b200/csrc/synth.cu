@@ -285,11 +285,10 @@ struct RenderSmem {
   static constexpr int env_doubles = K + 1;
   static constexpr int ar_doubles = K + 1;
   static constexpr int per_doubles = N;            // periodic response
-  static constexpr int zn_doubles = 2 * (K + 1);  // noise spectrum
   static constexpr int red_doubles = 32;
   static constexpr int tw_doubles = 2 * kFftTwEntries;  // shared-memory twiddles of cfft_s
   static constexpr int total_bytes =
-      (z_doubles + x_doubles + env_doubles + ar_doubles + per_doubles + zn_doubles + red_doubles + tw_doubles) * 8;
+      (z_doubles + x_doubles + env_doubles + ar_doubles + per_doubles + red_doubles + tw_doubles) * 8;
 };
 
 // WORLD GetMinimumPhaseSpectrum for the log-amplitude L[0..N/2] held in `logsp` -> X[0..N/2] (complex) in `X`.
@@ -371,7 +370,7 @@ render_kernel(const void* __restrict__ sp, const void* __restrict__ ap, const in
               const int64_t* __restrict__ utt_pulse_offset, const int* __restrict__ num_pulses,
               const int* __restrict__ pulse_index, const double* __restrict__ pulse_shift,
               const uint8_t* __restrict__ pulse_vuv, const double* __restrict__ randn_table, int64_t randn_len, int fs_i,
-              double frame_period_ms, double* __restrict__ response, const double2* __restrict__ tw) {
+              double frame_period_ms, double* __restrict__ response, const double2* __restrict__ tw, double dc_rs) {
   constexpr int NT = N / 16;
   constexpr int H = N / 2, K = H + 1;
   const int u = blockIdx.y;
@@ -384,8 +383,7 @@ render_kernel(const void* __restrict__ sp, const void* __restrict__ ap, const in
   double* env = smem + RenderSmem<N>::z_doubles + RenderSmem<N>::x_doubles;
   double* ar = env + RenderSmem<N>::env_doubles;
   double* periodic = ar + RenderSmem<N>::ar_doubles;
-  double2* Zn = reinterpret_cast<double2*>(periodic + RenderSmem<N>::per_doubles);
-  double* red = reinterpret_cast<double*>(Zn) + RenderSmem<N>::zn_doubles;
+  double* red = periodic + RenderSmem<N>::per_doubles;
   double2* tws = reinterpret_cast<double2*>(red + RenderSmem<N>::red_doubles);
   const int tid = threadIdx.x;
   fft_tw_fill<double, N / 2, NT>(tws, tw, tid);
@@ -441,20 +439,36 @@ render_kernel(const void* __restrict__ sp, const void* __restrict__ ap, const in
     __syncthreads();
     inverse_real_shifted<N, NT>(X, z, tws, rw0, rstep, tid, [&](int j, double v) { periodic[j] = v; });
     // remove the DC component (WORLD RemoveDCComponent with GetDCRemover's Hann-shaped weights)
-    double dcs = 0.0, rs = 0.0;
-    for (int i = tid; i < H; i += NT) {
-      dcs += periodic[H + i];
-      rs += 2.0 * (0.5 - 0.5 * cos(2.0 * kPi * (i + 1.0) / (1.0 + N)));
-    }
-    block_sum2<NT>(dcs, rs, red);
-    for (int i = tid; i < H; i += NT) {
-      const double r = (0.5 - 0.5 * cos(2.0 * kPi * (i + 1.0) / (1.0 + N))) / rs;  // dc_remover[i] == dc_remover[N-1-i]
-      periodic[i] = -dcs * r;
-      periodic[N - 1 - i] -= dcs * r;
+    // dc_remover[i] = hann(i) / sum, hann(i) = 0.5 - 0.5 cos(2 pi (i + 1) / (1 + N)): the sum depends on N only (dc_rs, computed
+    // once on the host), the cosines of i = tid, tid + NT, ... come from a rotation recurrence instead of one cos() each
+    double dcs = 0.0;
+    for (int i = tid; i < H; i += NT) dcs += periodic[H + i];
+    dcs = block_sum<NT>(dcs, red);
+    {
+      double c, sn, cd, sd;
+      sincos(2.0 * kPi * (tid + 1.0) / (1.0 + N), &sn, &c);
+      sincos(2.0 * kPi * (double)NT / (1.0 + N), &sd, &cd);
+      const double scale = dcs / dc_rs;
+      for (int i = tid; i < H; i += NT) {
+        const double r = (0.5 - 0.5 * c) * scale;  // dc_remover[i] == dc_remover[N-1-i]
+        periodic[i] = -r;
+        periodic[N - 1 - i] -= r;
+        const double cn = c * cd - sn * sd;
+        sn = sn * cd + c * sd;
+        c = cn;
+      }
     }
     __syncthreads();
   }
-  // noise spectrum of this pulse's slice of the randn stream (WORLD GetNoiseSpectrum)
+  // aperiodic response: minimum phase of sqrt(env * ar) (voiced) or sqrt(env) (unvoiced) ...
+  for (int k = tid; k < K; k += NT) {
+    const double e = env[k];
+    env[k] = (cur_vuv != 0.0) ? log(e * ar[k]) / 2.0 : log(e) / 2.0;
+  }
+  __syncthreads();
+  minimum_phase<N, NT>(env, z, X, tws, rw0, rstep, tid);
+  // ... times the noise spectrum of this pulse's slice of the randn stream (WORLD GetNoiseSpectrum); the noise FFT reuses the
+  // FFT buffer after the minimum-phase spectrum is in X, and its bins are multiplied into X on the fly (no noise buffer)
   {
     const int64_t start = (int64_t)n_p - n_first;
     double acc = 0.0;
@@ -470,18 +484,10 @@ render_kernel(const void* __restrict__ sp, const void* __restrict__ ap, const in
     cfft_s<double, N / 2, NT>(z, tws, tid);
     double2 rw = rw0;
     for (int k = tid; k < K; k += NT) {
-      Zn[k] = rfft_bin_w<double, N>(z, k, rw);
+      X[k] = cmul(X[k], rfft_bin_w<double, N>(z, k, rw));
       rw = cmul(rw, rstep);
     }
   }
-  // aperiodic response: minimum phase of sqrt(env * ar) (voiced) or sqrt(env) (unvoiced), times the noise spectrum
-  for (int k = tid; k < K; k += NT) {
-    const double e = env[k];
-    env[k] = (cur_vuv != 0.0) ? log(e * ar[k]) / 2.0 : log(e) / 2.0;
-  }
-  __syncthreads();
-  minimum_phase<N, NT>(env, z, X, tws, rw0, rstep, tid);
-  for (int k = tid; k < K; k += NT) X[k] = cmul(X[k], Zn[k]);
   __syncthreads();
   const double sqrt_noise = sqrt((double)noise_size);
   double* out = response + (poff + p) * (int64_t)N;
@@ -591,13 +597,15 @@ extern "C" int b2w_synth_render(const void* sp, const void* ap, int32_t plane_dt
   const double2* tw = twiddle_table(st);
   if (!tw) return check_launch("twiddle table");
   dim3 grid((unsigned)max_pulses_per_utt, (unsigned)num_utts);
+  double dc_rs = 0.0;  // WORLD GetDCRemover: sum of the Hann-shaped weights (both halves), a constant of the fft size
+  for (int i = 0; i < fft_size / 2; ++i) dc_rs += 2.0 * (0.5 - 0.5 * cos(2.0 * kPi * (i + 1.0) / (1.0 + fft_size)));
 #define B2W_RENDER_LAUNCH(NN, PT)                                                                                          \
   do {                                                                                                                     \
     const int smem = RenderSmem<NN>::total_bytes;                                                                          \
     cudaFuncSetAttribute(render_kernel<NN, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                        \
     render_kernel<NN, PT><<<grid, NN / 16, smem, st>>>(sp, ap, utt_frame_offset, utt_pulse_offset, num_pulses, pulse_index, \
                                                        pulse_shift, pulse_vuv, randn_table, randn_table_len, fs,           \
-                                                       frame_period_ms, response, tw);                                     \
+                                                       frame_period_ms, response, tw, dc_rs);                              \
   } while (0)
   switch (fft_size) {
     case 512: if (plane_dtype == B2W_F64) B2W_RENDER_LAUNCH(512, double); else B2W_RENDER_LAUNCH(512, float); break;

@@ -1,0 +1,21 @@
+import json, os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from idiaptts_b200 import ops, pipeline, synthetic
+dev = torch.device("cuda", 0)
+fs, U = 22050, int(sys.argv[1]) if len(sys.argv) > 1 else 256
+waves, f0s = synthetic.make_corpus(U, fs, seed=4, mean_dur=6.5, device=dev)
+batch = ops.RaggedBatch.from_host([w.cpu().numpy() for w in waves], f0s, fs, device=dev)
+an = pipeline.WorldAnalyzer(fs, 60, device=dev)
+feats, _, _ = an.extract(batch)
+syn = pipeline.WorldSynthesizer(fs, 60, device=dev)
+y, out_off, st = syn.synthesize(feats, batch.frame_off)
+torch.cuda.synchronize()
+best = 1e9
+for _ in range(3):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); y, out_off, st = syn.synthesize(feats, batch.frame_off); e1.record(); torch.cuda.synchronize()
+    best = min(best, e0.elapsed_time(e1))
+audio = float(out_off[-1]) / fs
+print("synthesis of %d utts: %.3f ms, %.0f audio-s/s, checksum %.9e" % (U, best, audio / best * 1e3, y.double().abs().sum().item()))
