@@ -307,7 +307,9 @@ __global__ void __launch_bounds__(kMcThreads) mc2sp_kernel(const MT* __restrict_
     for (int f = 0; f < F; ++f) {
       if (f < nvalid) {
         const float v = scale * acc[f];
-        out[(frame0 + f) * K + j] = (OT)(do_exp ? expf(v) : v);
+        // do_exp 2: the power spectrum as world_features_to_raw builds it (W:924): float32 amplitude, squared in float64
+        const float a = do_exp ? expf(v) : v;
+        out[(frame0 + f) * K + j] = (do_exp == 2) ? (OT)((double)a * (double)a) : (OT)a;
       }
     }
   }

@@ -325,8 +325,9 @@ def mcep(plane, order, alpha, is_power=False, miniter=2, maxiter=30, threshold=0
     return out, status
 
 
-def mc2sp(mc, alpha, fft_size, scale=1.0, do_exp=True, out_dtype=torch.float32, order=None, mc_stride=None):
-    """(exp of) scale * Re FFT(freqt(mc, fft_size/2, -alpha)): log-amplitude / amplitude / power spectrum from mel-cepstra."""
+def mc2sp(mc, alpha, fft_size, scale=1.0, do_exp=True, out_dtype=torch.float32, order=None, mc_stride=None, square=False):
+    """(exp of) scale * Re FFT(freqt(mc, fft_size/2, -alpha)): log-amplitude / amplitude / power spectrum from mel-cepstra.
+    square=True (with do_exp, float64 output): the float32 amplitude squared in float64, i.e. world_features_to_raw's pow_sp."""
     lib = _lib.load()
     dev = _need_cuda(mc)
     assert mc.dim() == 2 and mc.dtype in (torch.float32, torch.float64)
@@ -339,7 +340,8 @@ def mc2sp(mc, alpha, fft_size, scale=1.0, do_exp=True, out_dtype=torch.float32, 
     out = torch.empty((F, fft_size // 2 + 1), dtype=out_dtype, device=dev)
     with torch.cuda.device(dev):
         check(lib.b2w_mc2sp(mc.data_ptr(), _DT[mc.dtype], int(mc_stride), F, int(fft_size), int(order), tab.cmat.data_ptr(),
-                            float(scale), 1 if do_exp else 0, out.data_ptr(), _DT[out.dtype], _stream(dev)), "b2w_mc2sp")
+                            float(scale), (2 if square else 1) if do_exp else 0, out.data_ptr(), _DT[out.dtype], _stream(dev)),
+              "b2w_mc2sp")
     return out
 
 

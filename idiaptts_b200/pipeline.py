@@ -187,9 +187,8 @@ class WorldSynthesizer:
         D = self.num_coded_sps
         assert feats.shape[1] == D + 2 + self.nap, "WORLD requires all features to be present."
         # decode_sp: amp = exp(Re mgc2sp) as float32 (AudioProcessing.py:256), then pow_sp = amp^2 in float64 (W:924)
-        amp = ops.mc2sp(feats, self.alpha, self.n_fft, scale=1.0, do_exp=True, out_dtype=torch.float32, order=D - 1,
-                        mc_stride=feats.shape[1])
-        pow_sp = amp.double().square_()
+        pow_sp = ops.mc2sp(feats, self.alpha, self.n_fft, scale=1.0, do_exp=True, out_dtype=torch.float64, order=D - 1,
+                           mc_stride=feats.shape[1], square=True)
         lf0 = feats[:, D].double()
         vuv = (feats[:, D + 1] >= 0.5)
         f0 = torch.exp(lf0)

@@ -129,7 +129,8 @@ B2W_API int b2w_mcep_tc(const void* in, int32_t in_dtype, int32_t in_is_power, i
                         int32_t* iters, int32_t* status, void* stream);
 /* log-amplitude spectrum from mel-cepstra: Re pysptk.mgc2sp(mc, alpha, gamma=0, fftlen) (A:252), optionally
  * exponentiated (A:256 np.exp(...)) : out[f][j] = (do_exp ? exp : id)(scale * sum_k mc[f][k] cmat[k][j]).
- * scale = 1 for mgc2sp / mcep_to_amp_sp, 2 (with do_exp) gives the power spectrum. */
+ * scale = 1 for mgc2sp / mcep_to_amp_sp, 2 (with do_exp) gives the power spectrum; do_exp = 2: the float32 amplitude squared in
+ * float64 (what world_features_to_raw feeds to synthesis, W:924). */
 B2W_API int b2w_mc2sp(const void* mc, int32_t mc_dtype, int64_t mc_stride, int64_t num_frames, int32_t fft_size,
               int32_t order, const float* cmat, double scale, int32_t do_exp, void* out, int32_t out_dtype,
               void* stream);
