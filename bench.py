@@ -344,6 +344,45 @@ def run_b200(args):
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = audio_s * world / (float(t2.item()) / args.steps / 1e3)
 
+    # ---- secondary measurements (rank 0): BASELINE.json configs[3] (batched synthesis of 256 utterances from the features just
+    # extracted) and configs[4] (Neural-VTLN warp forward + backward, VCTK-shaped) -- reported next to the headline, not part of it
+    secondary = None
+    if rank == 0 and not args.no_secondary:
+        def t_ms(fn, reps=3):
+            fn()
+            torch.cuda.synchronize()
+            best = 1e30
+            for _ in range(reps):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                torch.cuda.synchronize()
+                best = min(best, a.elapsed_time(b))
+            return best
+        nu = min(256, utts)
+        f_end = int(frame_off[nu])
+        syn = pipeline.WorldSynthesizer(FS, NUM_CODED_SPS, alpha, device=dev)
+        sub_feats, sub_off = feats[:f_end].contiguous(), batch.frame_off[:nu + 1].contiguous()
+        ms_syn = t_ms(lambda: syn.synthesize(sub_feats, sub_off))
+        syn_audio = f_end * 0.005
+        n_v, spk, utt_v, T_v = 60, 109, 4, 1301
+        rows_v = spk * utt_v * T_v
+        gen_v = torch.Generator(device=dev).manual_seed(5)
+        xv = torch.randn((rows_v, n_v), generator=gen_v, device=dev)
+        gv = torch.randn((rows_v, n_v), generator=gen_v, device=dev)
+        av = (torch.rand(spk, generator=gen_v, device=dev) * 0.4 - 0.2).repeat_interleave(utt_v * T_v).contiguous()
+        ms_vf = t_ms(lambda: ops.allpass_forward(xv, av, n_v), 5)
+        ms_vb = t_ms(lambda: ops.allpass_backward(gv, xv, av, n_v), 5)
+        secondary = {"synthesis": {"workload": "batched WORLD synthesis of %d utterances from mgc60+lf0+vuv+bap" % nu, "ms": round(ms_syn, 3),
+                                   "audio_s_per_s": syn_audio / (ms_syn / 1e3)},
+                     "analysis_plus_synthesis_audio_s_per_s": 1.0 / (1.0 / (audio_s / (ms_step / 1e3)) + 1.0 / (syn_audio / (ms_syn / 1e3))),
+                     "vtln": {"workload": "all-pass warp, 109 speakers x 4 utts x 1301 frames, n = 60, one alpha per speaker",
+                              "fwd_ms": round(ms_vf, 4), "bwd_ms": round(ms_vb, 4),
+                              "fwd_frac_of_hbm_peak": rows_v * (8 * n_v + 4) / (ms_vf / 1e3) / 1e9 / peaks["hbm_gbs"],
+                              "bwd_frac_of_hbm_peak": rows_v * (12 * n_v + 8) / (ms_vb / 1e3) / 1e9 / peaks["hbm_gbs"]}}
+        del xv, gv, av, sub_feats
+
     if rank == 0:
         # ---- CPU baseline on a bounded sample of the same workload (N = 1 only) -------------------------------------
         cpu = None
@@ -368,7 +407,8 @@ def run_b200(args):
                            "corpus_gen_s": round(gen_s, 1), "mean_c0": float(mean[0]), "std_c0": float(std[0])},
                 "clocks": clocks, "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(h2d),
                                           "d2h_bytes_per_step": int(d2h)},
-                "gpu_launches": int(args.steps * an.kernel_launches(F)), "roofline": roofline, "cpu_baseline": cpu}
+                "gpu_launches": int(args.steps * an.kernel_launches(F)), "roofline": roofline, "cpu_baseline": cpu,
+                "secondary": secondary}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -383,6 +423,7 @@ def main():
     ap.add_argument("--utts", type=int, default=UTTS, help="utterances per GPU (default: the full LJSpeech-shaped corpus)")
     ap.add_argument("--chunk-frames", type=int, default=1 << 18)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the synthesis / VTLN side measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
