@@ -177,3 +177,25 @@ def test_22k_and_48k_sizes(dev):
         bap = ops.bap_from_coarse(coarse, voiced, fs, n_fft).cpu().numpy()
         np.testing.assert_allclose(bap, world_np.code_aperiodicity(world_np.d4c(x, f0, t, fs), fs), atol=2e-5)
         assert ops.raise_for_status(st, "sizes") == 0
+
+
+def test_padded_planes_give_identical_results(golden, dev):
+    """The fused path pads envelope rows to a multiple of 8 floats (aligned 16-byte loads in the mel-cepstrum kernel): the row
+    stride of b2w_cheaptrick / b2w_mcep_tc must not change a single bit of the results."""
+    from idiaptts_b200 import ops
+    x, c, f0, fs = golden_utterance(golden, "LJ001-0003")
+    batch = ops.RaggedBatch.from_host([x], [f0], fs, device=dev, preemphasis=0.0)
+    K = 513
+    tight = torch.empty((len(f0), K), dtype=torch.float32, device=dev)
+    padded = torch.full((len(f0), 520), float("nan"), dtype=torch.float32, device=dev)
+    ops.cheaptrick(batch, fft_size=1024, out=tight)
+    ops.cheaptrick(batch, fft_size=1024, out=padded[:, :K])
+    assert torch.equal(tight, padded[:, :K]) and torch.isnan(padded[:, K:]).all()   # the padding is never written
+    it_a = torch.zeros(len(f0), dtype=torch.int32, device=dev)
+    it_b = torch.zeros_like(it_a)
+    mc_a, st_a = ops.mcep(tight, 59, 0.58, is_power=True, iters=it_a)
+    mc_b, st_b = ops.mcep(padded[:, :K], 59, 0.58, is_power=True, iters=it_b)                  # NaN padding must be ignored
+    assert int(st_a.item()) == 0 and int(st_b.item()) == 0
+    assert torch.equal(mc_a, mc_b) and torch.equal(it_a, it_b)
+    mc_c, _ = ops.mcep(tight.double(), 59, 0.58, is_power=True)                                 # float64 plane: scalar-load path
+    assert (mc_c - mc_a).abs().max().item() < 1e-5
