@@ -34,6 +34,19 @@ int check_launch(const char* what);
 constexpr int kTwN = 4096;
 const double2* twiddle_table(cudaStream_t stream);  // lazily built once per device (device code computes it with sincospi)
 
+// One out-of-line copy of the double-precision sincos: inlined it is ~250 instructions (with its large-argument path) per call
+// site, and the FFT kernels are instruction-fetch sensitive (ncu: 14-16 % "no instruction" stalls).
+#ifdef B2W_INLINE_SINCOS
+static __device__ __forceinline__ double2 sincos_ol(double x) {
+#else
+static __device__ __noinline__ double2 sincos_ol(double x) {
+#endif
+  double s, c;
+  sincos(x, &s, &c);
+  return make_double2(c, s);
+}
+#define B2W_SINCOS(ARG_, SPTR_, CPTR_) do { const double2 cs_ = b2w::sincos_ol(ARG_); *(CPTR_) = cs_.x; *(SPTR_) = cs_.y; } while (0)
+
 // device helpers --------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int mround_pos(double x) {  // WORLD matlab_round
   return x > 0 ? (int)(x + 0.5) : (int)(x - 0.5);

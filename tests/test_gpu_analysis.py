@@ -70,7 +70,7 @@ def test_d4c_and_codec_vs_oracle(golden):
         pw.decode_aperiodicity(np.zeros((3, 2)), 16000, 1024)  # wrong band count for fs
 
 
-@pytest.mark.parametrize("order,alpha", [(19, 0.58), (59, 0.58), (59, 0.41), (79, 0.41)])
+@pytest.mark.parametrize("order,alpha", [(19, 0.58), (59, 0.58), (59, 0.41), (79, 0.41), (39, 0.42), (24, 0.35)])
 def test_mcep_vs_oracle(golden, order, alpha):
     from idiaptts_b200.compat import pysptk as ps
     x, c, f0, fs = golden_utterance(golden, "LJ001-0008")
