@@ -71,6 +71,7 @@ _SIGNATURES = {
                                        c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2w_mlpg_workspace_doubles": (c_int64, [c_int64, c_int32]),
     "b2w_mlpg": (c_int32, [c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_void_p]),
+    "b2w_world_metrics": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "b2w_probe_fp64_fma": (c_int64, [c_int32, c_void_p, c_void_p]),
     "b2w_mcep_prof_read": (c_int32, [c_void_p]),
     "b2w_probe_umma": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),

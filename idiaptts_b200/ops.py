@@ -542,3 +542,18 @@ def mlpg(feats, var3, frame_off, D):
                            frame_off.data_ptr(), frame_off.numel() - 1, int(D), ws.data_ptr(), out.data_ptr(), int(D), _stream(dev)),
               "b2w_mlpg")
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# objective metrics
+# ----------------------------------------------------------------------------------------------------------------------
+def world_metrics(org, out, frame_utt, num_utts, num_coded_sps, num_bap):
+    """Per-utterance metric sums [num_utts, 8] f64 (see csrc/metrics.cu) of two float32 feature planes [F, D + 2 + nap]."""
+    lib = _lib.load()
+    dev = _need_cuda(org, out, frame_utt)
+    assert org.dtype == torch.float32 and out.dtype == torch.float32 and org.shape == out.shape and frame_utt.dtype == torch.int32
+    acc = torch.zeros((num_utts, 8), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.b2w_world_metrics(org.data_ptr(), out.data_ptr(), int(org.shape[1]), frame_utt.data_ptr(), int(org.shape[0]),
+                                    int(num_coded_sps), int(num_bap), acc.data_ptr(), _stream(dev)), "b2w_world_metrics")
+    return acc

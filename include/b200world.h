@@ -213,6 +213,12 @@ B2W_API int b2w_allpass_backward(const float* grad_y, const float* x, const floa
 B2W_API int64_t b2w_mlpg_workspace_doubles(int64_t num_frames, int32_t D);
 B2W_API int b2w_mlpg(const void* feats, int32_t feats_dtype, int64_t feat_stride, const double* var3, const int64_t* frame_off,
                      int32_t num_utts, int32_t D, double* workspace, double* out, int64_t out_stride, void* stream);
+/* ---- objective metrics: the sums behind Metrics.mcd_k / f0_rmse / gross_pitch_error / voicing_decision_error /
+ * f0_frame_error / aperiodicity_distortion (idiaptts/src/Metrics.py:84-164) for a ragged batch.  org / out: float32 rows
+ * [coded_sp(D) | lf0 | vuv | bap(nap)] with row stride `stride`; frame_utt [num_frames]; acc [num_utts][8] fp64, ZEROED by the caller
+ * (layout in csrc/metrics.cu). */
+B2W_API int b2w_world_metrics(const float* org, const float* out, int64_t stride, const int32_t* frame_utt, int64_t num_frames,
+                              int32_t num_coded_sps, int32_t num_bap, double* acc, void* stream);
 /* measurement aid (bench.py): launches a pure fp64 FMA kernel, returns the number of FMAs it executes (or -1) */
 B2W_API int64_t b2w_probe_fp64_fma(int32_t iters, double* scratch, void* stream);
 /* development aid: phase cycle counters of mcep_tc CTA 0 (non-zero only in a -DB2W_MCEP_PROF build) */

@@ -282,3 +282,24 @@ def allpass_warp_backward(grad_y, x, alpha, n):
             _, t = freqt_with_tangent(x[i, sl] * S1, float(al[i]))
             ga[i] += np.dot(gy[i, sl] * S2, t)
     return gx, ga
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Objective metrics (src/Metrics.py:84-164), restated for the parity test of idiaptts_b200/Metrics.py
+# ---------------------------------------------------------------------------------------------------------------
+def world_metrics(org_sp, org_lf0, org_vuv, org_bap, out_sp, out_lf0, out_vuv, out_bap):
+    T = len(out_sp)
+    org_sp, org_lf0, org_vuv, org_bap = (np.asarray(a, np.float64)[:T] for a in (org_sp, org_lf0, org_vuv, org_bap))
+    out_sp, out_lf0, out_vuv, out_bap = (np.asarray(a, np.float64) for a in (out_sp, out_lf0, out_vuv, out_bap))
+    res = {"MCD": mcd_db(org_sp, out_sp)}                                                                      # :84-92
+    res["F0 RMSE"] = math.sqrt((((np.exp(org_lf0) - np.exp(out_lf0)) ** 2) * org_vuv).sum() / org_vuv.sum())   # :94-106
+    err20 = np.abs(org_lf0 - out_lf0) > 0.2 * org_lf0
+    both = org_vuv * out_vuv
+    res["GPE"] = (err20 * both).sum() / both.sum()                                                            # :108-126
+    res["VDE"] = (org_vuv != out_vuv).sum() / len(out_vuv)                                                    # :150-155
+    res["FFE"] = (err20 * both).sum() / len(out_vuv) + res["VDE"]                                             # :128-148
+    if out_bap.ndim > 1 and out_bap.shape[1] > 1:                                                             # :157-164
+        res["BAP distortion"] = mcd_db(org_bap, out_bap)
+    else:
+        res["BAP distortion"] = math.sqrt(((org_bap - out_bap) ** 2).mean()) * (10.0 / math.log(10.0) * math.sqrt(2.0))
+    return res
