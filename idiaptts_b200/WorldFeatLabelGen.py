@@ -5,9 +5,9 @@ by libb200world.so on the GPU:
     world_extract_features     :779-807      extract_features            :810-889      trim_to_shortest :892-907
     world_features_to_raw      :910-945      gen_data                    :947-1071     save_output      :1121-1172
 
-Scope: the vocoder path with a CACHED F0 track.  pyworld.wav2world's F0 stage (dio + stonemask) is not part of
-it, so every extraction entry point takes the F0 track (`f0=` / `f0_cache=`); calling without one raises.  The reader /
-normalisation protocol of NpzDataReader (load, __getitem__, postprocess) is host-side file IO outside the path.
+F0: every extraction entry point takes an optional cached F0 track (`f0=` / `f0_cache=`, north_star); without one the F0
+half of pyworld.wav2world (DIO + StoneMask, :792) runs on the device too (ops.estimate_f0), as in the
+reference.
 
 gen_data processes the whole id list as ONE ragged GPU batch (the reference loops over utterances, :996) and, when
 torch.distributed is initialised, takes this rank's shard of the list and all-reduces the normalisation statistics."""
@@ -114,9 +114,7 @@ class WorldFeatLabelGen(object):
         """f0_cache: dict {id: f0 array} | directory holding <id>.npy (float64 Hz per 5 ms frame, 0 = unvoiced) | None."""
         key = os.path.basename(file_name)
         if f0_cache is None:
-            raise NotImplementedError(
-                "F0 estimation (pyworld dio/stonemask) is outside the accelerated WORLD path: pass the cached F0 track "
-                "(f0= / f0_cache=).  See DESIGN.md, out of scope.")
+            return None  # no cache: DIO + StoneMask on the device, as pyworld.wav2world does (:792)
         if isinstance(f0_cache, dict):
             if key in f0_cache:
                 return np.asarray(f0_cache[key], np.float64)
@@ -134,18 +132,19 @@ class WorldFeatLabelGen(object):
             f0_silence_threshold = WorldFeatLabelGen.f0_silence_threshold
         if lf0_zero is None:
             lf0_zero = WorldFeatLabelGen.lf0_zero
-        if f0 is None:
-            WorldFeatLabelGen._lookup_f0(None, "")
         raw = np.ascontiguousarray(raw)
         if raw.dtype not in (np.float64, np.float32, np.int16):
             raw = raw.astype(np.float64)
-        f0 = np.ascontiguousarray(f0, np.float64)
         T = ops.num_frames(len(raw), fs, hop_size_ms)
+        estimate = f0 is None
+        f0 = np.zeros(T) if estimate else np.ascontiguousarray(f0, np.float64)
         if len(f0) != T:
             raise ValueError("cached F0 has {} frames, the waveform gives {} at {} ms hop".format(len(f0), T, hop_size_ms))
         dev = _device()
         fft_size = n_fft if n_fft is not None else ops.get_cheaptrick_fft_size(fs)
         batch = ops.RaggedBatch.from_host([raw], [f0], fs, frame_period=hop_size_ms, device=dev)
+        if estimate:
+            ops.estimate_f0(batch, frame_period=hop_size_ms)
         status = ops.new_status(dev)
         sp, _ = ops.cheaptrick(batch, fft_size=fft_size, out_dtype=torch.float64, status=status)
         amp_sp = torch.sqrt(sp)
@@ -258,6 +257,8 @@ class WorldFeatLabelGen(object):
                 raise ValueError("mixed sampling rates in one gen_data call ({} vs {})".format(fs, cur_fs))
             f0 = self._lookup_f0(f0_cache, name)
             T = ops.num_frames(len(x), cur_fs, self.hop_size_ms)
+            if f0 is None:
+                f0 = np.zeros(T)
             if len(f0) != T:
                 raise ValueError("{}: cached F0 has {} frames, the waveform gives {}".format(name, len(f0), T))
             waves.append(x)
@@ -276,6 +277,8 @@ class WorldFeatLabelGen(object):
             if not same:
                 waves = [w.astype(np.float64) / 32768.0 if w.dtype == np.int16 else w.astype(np.float64) for w in waves]
             batch = ops.RaggedBatch.from_host(waves, f0s, fs, frame_period=self.hop_size_ms, preemphasis=self.preemphasis, device=dev)
+            if f0_cache is None:
+                ops.estimate_f0(batch, frame_period=self.hop_size_ms)
             an = pipeline.WorldAnalyzer(fs, D, alpha, self.hop_size_ms, self.n_fft, WorldFeatLabelGen.f0_silence_threshold,
                                         WorldFeatLabelGen.lf0_zero, device=dev)
             feats, sums, status = an.extract(batch)

@@ -5,8 +5,8 @@ Reference call sites (idiaptts/src/...): data_preparation/world/WorldFeatLabelGe
 (code_aperiodicity), :940 (decode_aperiodicity), :943 (synthesize); data_preparation/audio/AudioProcessing.py:60
 (get_cheaptrick_fft_size), :71 (get_num_aperiodicities); Synthesiser.py:47.
 
-Scope note: F0 estimation (dio / stonemask) is outside the accelerated path (north_star: cached F0), so `wav2world`
-takes the F0 track as an extra argument instead of estimating it."""
+F0: `dio` (speed = 1) and `stonemask` run on the device too; `wav2world` estimates the F0 track exactly as
+pyworld does unless a cached track is passed as `f0=` (north_star: cached F0)."""
 import numpy as np
 import torch
 
@@ -59,8 +59,32 @@ def d4c(x, f0, temporal_positions, fs, threshold=0.85, fft_size=None):
     return ap
 
 
-def wav2world(x, fs, f0, fft_size=None, frame_period=default_frame_period):
-    """pyworld.wav2world with the F0 track supplied (cached F0) -> f0, sp, ap."""
+def dio(x, fs, f0_floor=default_f0_floor, f0_ceil=default_f0_ceil, channels_in_octave=2.0, frame_period=default_frame_period,
+        speed=1, allowed_range=0.1):
+    """pyworld.dio -> (f0 [T], temporal_positions [T]) float64.  Only speed = 1 (pyworld's default, no decimation)."""
+    if speed != 1:
+        raise ValueError("only speed = 1 (pyworld's default) is implemented")
+    x = np.ascontiguousarray(x, np.float64)
+    if x.ndim != 1:
+        raise ValueError("x must be 1-D")
+    T = ops.num_frames(len(x), fs, frame_period)
+    t = np.arange(T) * frame_period / 1000.0
+    batch = ops.RaggedBatch.from_host([x], [np.zeros(T)], fs, ts=[t], device=_device())
+    f0 = ops.dio(batch, f0_floor, f0_ceil, channels_in_octave, frame_period, allowed_range)
+    return f0.cpu().numpy(), t
+
+
+def stonemask(x, f0, temporal_positions, fs):
+    """pyworld.stonemask -> refined f0 [T] float64."""
+    batch = _batch(x, f0, temporal_positions, fs)
+    return ops.stonemask(batch).cpu().numpy()
+
+
+def wav2world(x, fs, fft_size=None, frame_period=default_frame_period, f0=None):
+    """pyworld.wav2world -> f0, sp, ap.  f0 = None: DIO + StoneMask as pyworld; else the supplied (cached) track is used."""
+    if f0 is None:
+        _f0, t = dio(x, fs, frame_period=frame_period)
+        f0 = stonemask(x, _f0, t, fs)
     f0 = np.ascontiguousarray(f0, np.float64)
     t = np.arange(len(f0)) * frame_period / 1000.0
     return f0, cheaptrick(x, f0, t, fs, fft_size=fft_size), d4c(x, f0, t, fs, fft_size=fft_size)

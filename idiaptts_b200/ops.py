@@ -143,6 +143,101 @@ def raise_for_status(status, what):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# F0 estimation: DIO + StoneMask
+# ----------------------------------------------------------------------------------------------------------------------
+DIO_MAX_CHUNK_SAMPLES = 48 * 1024 * 1024  # the event lists cost ~120 bytes of workspace per sample: 48 M samples ~ 6 GB
+
+
+def _utt_chunks(sample_off_host, max_samples):
+    """Utterance ranges [u0, u1) whose sample counts stay below max_samples (a single longer utterance forms its own chunk)."""
+    U = len(sample_off_host) - 1
+    u0 = 0
+    while u0 < U:
+        u1 = u0 + 1
+        while u1 < U and sample_off_host[u1 + 1] - sample_off_host[u0] <= max_samples:
+            u1 += 1
+        yield u0, u1
+        u0 = u1
+
+
+def _sub_batch(batch, u0, u1, s_off, f_off, f0):
+    """struct b2w_batch + frame offsets of utterances [u0, u1) (offsets rebased; the tensors are kept alive by the caller)."""
+    so = (batch.sample_off[u0:u1 + 1] - int(s_off[u0])).contiguous()
+    fo = (batch.frame_off[u0:u1 + 1] - int(f_off[u0])).contiguous()
+    fu = (batch.frame_utt[int(f_off[u0]):int(f_off[u1])] - u0).contiguous()
+    b = _lib.Batch()
+    b.x = batch.x.data_ptr() + int(s_off[u0]) * batch.x.element_size()
+    b.x_dtype = _DT[batch.x.dtype]
+    b.num_utts = u1 - u0
+    b.preemphasis = batch.preemphasis
+    b.utt_sample_offset = so.data_ptr()
+    b.frame_utt = fu.data_ptr()
+    b.f0 = 0 if f0 is None else f0.data_ptr() + 8 * int(f_off[u0])
+    b.t = batch.t.data_ptr() + 8 * int(f_off[u0])
+    b.num_frames = int(f_off[u1] - f_off[u0])
+    b.fs = batch.fs
+    return b, (so, fo, fu)
+
+
+def dio(batch, f0_floor=71.0, f0_ceil=800.0, channels_in_octave=2.0, frame_period=5.0, allowed_range=0.1, step2="erosion",
+        max_chunk_samples=None):
+    """pyworld.dio (speed = 1) on a ragged batch -> f0 [F] float64 (batch.f0 is ignored; batch.t must be i * frame_period / 1000).
+
+    step2: "erosion" reproduces the reference's fixtures (oracle/dio_np.py), "sections" is the later WORLD variant."""
+    if step2 not in ("erosion", "sections"):
+        raise ValueError("step2 must be 'erosion' or 'sections'")
+    lib = _lib.load()
+    dev = batch.device
+    if lib.b2w_dio_num_bands(float(f0_floor), float(f0_ceil), float(channels_in_octave)) < 1:
+        raise ValueError("bad f0_floor / f0_ceil / channels_in_octave")
+    out = torch.empty(batch.num_frames, dtype=torch.float64, device=dev)
+    if batch.num_frames == 0:
+        return out
+    s_off = batch.sample_off.cpu().numpy()
+    f_off = batch.frame_off.cpu().numpy()
+    with torch.cuda.device(dev):
+        for u0, u1 in _utt_chunks(s_off, max_chunk_samples or DIO_MAX_CHUNK_SAMPLES):
+            S = int(s_off[u1] - s_off[u0])
+            F = int(f_off[u1] - f_off[u0])
+            if F == 0:
+                continue
+            nbytes = int(lib.b2w_dio_workspace_bytes(S, u1 - u0, F, batch.fs, float(f0_floor), float(f0_ceil), float(channels_in_octave)))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            b, keep = _sub_batch(batch, u0, u1, s_off, f_off, None)
+            check(lib.b2w_dio(b, S, keep[1].data_ptr(), float(f0_floor), float(f0_ceil), float(channels_in_octave), float(frame_period),
+                              float(allowed_range), 1 if step2 == "sections" else 0, ws.data_ptr(),
+                              out.data_ptr() + 8 * int(f_off[u0]), _stream(dev)), "b2w_dio")
+            ws.record_stream(torch.cuda.current_stream(dev))
+            for k in keep:
+                k.record_stream(torch.cuda.current_stream(dev))
+    return out
+
+
+def stonemask(batch, f0=None):
+    """pyworld.stonemask on a ragged batch: refines f0 (default batch.f0) -> [F] float64."""
+    lib = _lib.load()
+    dev = batch.device
+    f0 = batch.f0 if f0 is None else f0
+    _need_cuda(f0)
+    assert f0.dtype == torch.float64 and f0.numel() == batch.num_frames
+    out = torch.empty(batch.num_frames, dtype=torch.float64, device=dev)
+    if batch.num_frames == 0:
+        return out
+    b = batch.c_struct()
+    b.f0 = f0.data_ptr()
+    with torch.cuda.device(dev):
+        check(lib.b2w_stonemask(b, out.data_ptr(), _stream(dev)), "b2w_stonemask")
+    return out
+
+
+def estimate_f0(batch, frame_period=5.0, **dio_args):
+    """The F0 half of pyworld.wav2world (WorldFeatLabelGen.py:792): dio + stonemask; also stores the result in batch.f0."""
+    f0 = stonemask(batch, dio(batch, frame_period=frame_period, **dio_args))
+    batch.f0 = f0
+    return f0
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # analysis
 # ----------------------------------------------------------------------------------------------------------------------
 def cheaptrick(batch, fft_size=None, q1=-0.15, out_dtype=torch.float64, status=None, frame_lo=0, frame_hi=None, out=None):

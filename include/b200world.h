@@ -213,6 +213,22 @@ B2W_API int b2w_allpass_backward(const float* grad_y, const float* x, const floa
 B2W_API int64_t b2w_mlpg_workspace_doubles(int64_t num_frames, int32_t D);
 B2W_API int b2w_mlpg(const void* feats, int32_t feats_dtype, int64_t feat_stride, const double* var3, const int64_t* frame_off,
                      int32_t num_utts, int32_t D, double* workspace, double* out, int64_t out_stride, void* stream);
+/* ---- F0 estimation: pyworld.dio (speed = 1) and pyworld.stonemask, the F0 half of pyworld.wav2world
+ * (W:792; world/LF0LabelGen.py:263-264).  b->f0 is ignored by b2w_dio and is the initial track for b2w_stonemask; b->t holds
+ * i * frame_period / 1000 per utterance (as pyworld.dio returns).  num_samples = utt_sample_offset[num_utts] (the host knows
+ * it; the library never reads device memory on the host).  utt_frame_offset [num_utts + 1].
+ * DIO's two filters run as direct linear convolutions (WORLD sizes its FFT so that the circular convolution never wraps).
+ * step2_sections: 0 = FixF0Contour step 2 as the reference's fixtures were produced (erosion by voice_range_minimum frames),
+ * 1 = the later WORLD variant (drop voiced sections shorter than voice_range_minimum).
+ * workspace: b2w_dio_workspace_bytes(...) bytes (~ 8 + 112 * num_bands / 7 bytes per sample: chunk long corpora). */
+B2W_API int32_t b2w_dio_num_bands(double f0_floor, double f0_ceil, double channels_in_octave);
+B2W_API int64_t b2w_dio_workspace_bytes(int64_t num_samples, int32_t num_utts, int64_t num_frames, int32_t fs, double f0_floor,
+                                        double f0_ceil, double channels_in_octave);
+B2W_API int b2w_dio(const b2w_batch* b, int64_t num_samples, const int64_t* utt_frame_offset, double f0_floor, double f0_ceil,
+                    double channels_in_octave, double frame_period, double allowed_range, int32_t step2_sections,
+                    void* workspace, double* f0_out, void* stream);
+B2W_API int b2w_stonemask(const b2w_batch* b, double* refined_f0, void* stream);
+
 /* ---- objective metrics: the sums behind Metrics.mcd_k / f0_rmse / gross_pitch_error / voicing_decision_error /
  * f0_frame_error / aperiodicity_distortion (idiaptts/src/Metrics.py:84-164) for a ragged batch.  org / out: float32 rows
  * [coded_sp(D) | lf0 | vuv | bap(nap)] with row stride `stride`; frame_utt [num_frames]; acc [num_utts][8] fp64, ZEROED by the caller

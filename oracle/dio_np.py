@@ -217,8 +217,9 @@ def _fix_f0(power, numer, fft_size, fs, initial_f0, nharm):
     num = den = 0.0
     for i in range(nharm):
         idx = mround(initial_f0 * fft_size / fs * (i + 1))
-        inst = 0.0 if power[idx] == 0.0 else idx * fs / fft_size + numer[idx] / power[idx] * fs / 2.0 / math.pi
-        amp = math.sqrt(power[idx])
+        k = idx % fft_size  # WORLD reads past fft_size / 2 when 6 * f0 > fs / 2 (undefined there); the spectrum is periodic
+        inst = 0.0 if power[k] == 0.0 else idx * fs / fft_size + numer[k] / power[k] * fs / 2.0 / math.pi
+        amp = math.sqrt(power[k])
         num += amp * inst
         den += amp * (i + 1.0)
     return num / (den + kMySafeGuardMinimum)
@@ -239,8 +240,8 @@ def stonemask_frame(x, fs, pos, initial_f0):
     dw[1:-1] = -(w[2:] - w[:-2]) / 2.0
     dw[-1] = w[-2] / 2.0
     seg = x[np.clip(index_raw - 1, 0, len(x) - 1)]
-    main = np.fft.rfft(seg * w, fft_size)
-    diff = np.fft.rfft(seg * dw, fft_size)
+    main = np.fft.fft(seg * w, fft_size)
+    diff = np.fft.fft(seg * dw, fft_size)
     power = main.real ** 2 + main.imag ** 2
     numer = main.real * diff.imag - main.imag * diff.real
     tentative = _fix_f0(power, numer, fft_size, fs, initial_f0, 2)

@@ -1,0 +1,117 @@
+"""GPU parity of the F0 stage: b2w_dio + b2w_stonemask against the reference's golden vectors (the lf0 / vuv
+columns of fixtures/WORLD/cmp_mcep20/*.cmp, produced by pyworld.wav2world) and against the numpy oracle (oracle/dio_np.py)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_utterance
+from oracle import dio_np, glue_np, world_np
+
+pytestmark = pytest.mark.gpu
+
+IDS = ["LJ001-%04d" % i for i in range(1, 10)]
+
+
+def _batch(waves, fs, preemphasis=0.0, frame_period=5.0):
+    from idiaptts_b200 import ops
+    f0s = [np.zeros(world_np.num_frames(len(w), fs, frame_period)) for w in waves]
+    return ops.RaggedBatch.from_host(waves, f0s, fs, frame_period=frame_period, preemphasis=preemphasis, device="cuda")
+
+
+def test_f0_reproduces_reference_fixtures(golden):
+    """All 9 reference utterances as one ragged int16 batch, pre-emphasis applied on load: vuv bit-exact, lf0 to float32 round-off."""
+    from idiaptts_b200 import ops
+    waves = [golden[i + "/wav"] for i in IDS]
+    batch = _batch(waves, 16000, preemphasis=0.97)
+    f0 = ops.estimate_f0(batch).cpu().numpy()
+    off = batch.frame_off.cpu().numpy()
+    total = 0
+    for u, id_ in enumerate(IDS):
+        c = golden[id_ + "/cmp"]
+        f = f0[off[u]:off[u + 1]]
+        assert len(f) == c.shape[0]
+        assert np.array_equal(f > 0, c[:, 63] > 0), id_
+        v = f > 0
+        assert np.abs(np.log(f[v]).astype(np.float32) - c[v, 60]).max() < 1e-6, id_
+        total += len(f)
+    assert total == 11579
+    # ... and the label columns the pipeline derives from it (interpolate_lin, WorldFeatLabelGen.py:798-802)
+    lf0, vuv = ops.lf0_vuv(batch.f0, batch.frame_off)
+    lf0, vuv = lf0.cpu().numpy(), vuv.cpu().numpy()
+    for u, id_ in enumerate(IDS):
+        c = golden[id_ + "/cmp"]
+        assert np.array_equal(vuv[off[u]:off[u + 1], 0], c[:, 63])
+        assert np.abs(lf0[off[u]:off[u + 1], 0] - c[:, 60]).max() < 2e-6
+
+
+@pytest.mark.parametrize("fs,step2", [(22050, "erosion"), (22050, "sections"), (48000, "erosion"), (16000, "erosion")])
+def test_dio_and_stonemask_match_oracle(fs, step2):
+    from idiaptts_b200 import ops, synthetic
+    waves, _ = synthetic.make_corpus(3, fs, seed=31 + fs % 7, mean_dur=1.2, device="cpu")
+    waves = [w.numpy() for w in waves]
+    batch = _batch(waves, fs)
+    f0_dio = ops.dio(batch, step2=step2).cpu().numpy()
+    off = batch.frame_off.cpu().numpy()
+    refs = []
+    for u, w in enumerate(waves):
+        x = w.astype(np.float64) / 32768.0
+        T = off[u + 1] - off[u]
+        t = np.arange(T) * 5.0 / 1000.0  # WORLD: i * frame_period / 1000 (not i * 0.005: StoneMask rounds (t + dt) * fs to samples)
+        cands, scores = dio_np.dio_candidates(x, fs, t)
+        ref = dio_np.fix_f0_contour(5.0, cands, dio_np.best_f0_contour(cands, scores), 71.0, 0.1, step2=step2)
+        got = f0_dio[off[u]:off[u + 1]]
+        assert np.array_equal(got > 0, ref > 0)
+        np.testing.assert_allclose(got, ref, rtol=1e-9, atol=0)
+        refs.append(dio_np.stonemask(x, ref, t, fs))
+    assert (f0_dio > 0).mean() > 0.2  # the synthetic corpus is ~65 % voiced
+    f0 = ops.stonemask(batch, torch.from_numpy(f0_dio).cuda()).cpu().numpy()
+    ref = np.concatenate(refs)
+    assert np.array_equal(f0 > 0, ref > 0)
+    np.testing.assert_allclose(f0, ref, rtol=1e-9, atol=0)
+
+
+def test_dio_chunking_short_and_empty_utterances():
+    from idiaptts_b200 import ops, synthetic
+    fs = 16000
+    waves, _ = synthetic.make_corpus(4, fs, seed=5, mean_dur=0.9, device="cpu")
+    waves = [w.numpy() for w in waves]
+    waves.insert(1, np.zeros(400, np.int16))          # 6 frames <= voice_range_minimum: FixF0Contour leaves it unvoiced
+    waves.insert(3, np.zeros(3000, np.int16))         # digital silence: no zero crossings at all
+    batch = _batch(waves, fs)
+    a = ops.estimate_f0(batch).cpu().numpy()
+    b = ops.stonemask(batch, ops.dio(batch, max_chunk_samples=20000)).cpu().numpy()  # every utterance its own chunk
+    assert np.array_equal(a, b)
+    off = batch.frame_off.cpu().numpy()
+    assert not a[off[1]:off[2]].any() and not a[off[3]:off[4]].any()
+    for u in (0, 2, 5):
+        x = waves[u].astype(np.float64) / 32768.0
+        ref, _ = dio_np.wav2world_f0(x, fs)
+        assert np.array_equal(a[off[u]:off[u + 1]] > 0, ref > 0)
+        np.testing.assert_allclose(a[off[u]:off[u + 1]], ref, rtol=1e-9)
+
+
+def test_pyworld_compatible_f0_calls(golden):
+    from idiaptts_b200.compat import pyworld
+    x, c, _, fs = golden_utterance(golden, "LJ001-0002")
+    _f0, t = pyworld.dio(x, fs)
+    assert _f0.dtype == np.float64 and t.dtype == np.float64 and len(_f0) == len(t) == c.shape[0]
+    assert np.array_equal(t, np.arange(len(t)) * 5.0 / 1000.0)
+    f0 = pyworld.stonemask(x, _f0, t, fs)
+    assert np.array_equal(f0 > 0, c[:, 63] > 0)
+    f0b, sp, ap = pyworld.wav2world(x, fs)
+    assert np.array_equal(f0, f0b) and sp.shape == (len(f0), 513) and ap.shape == sp.shape
+    with pytest.raises(ValueError):
+        pyworld.dio(x, fs, speed=4)
+
+
+def test_world_extract_features_without_cached_f0(golden):
+    """The reference's call (WorldFeatLabelGen.world_extract_features(raw, fs, hop), :779-807) with no F0 supplied."""
+    from idiaptts_b200.WorldFeatLabelGen import WorldFeatLabelGen
+    x, c, f0g, fs = golden_utterance(golden, "LJ001-0008")
+    amp_sp, lf0, vuv, bap = WorldFeatLabelGen.world_extract_features(x, fs, 5)
+    assert np.array_equal(vuv[:, 0], c[:, 63])
+    assert np.abs(lf0[:, 0] - c[:, 60]).max() < 2e-6
+    assert np.abs(bap[:, 0] - c[:, 64]).max() < 3e-5
+    from idiaptts_b200.AudioProcessing import AudioProcessing
+    mc = AudioProcessing.extract_mcep(amp_sp, num_coded_sps=20, mgc_alpha=0.58)
+    assert glue_np.mcd_db(c[:, :20], mc) < 1e-3

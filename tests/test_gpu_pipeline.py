@@ -122,8 +122,10 @@ def test_gen_data_files_and_statistics(tmp_path, add_deltas):
         assert os.path.exists(str(tmp_path / "out" / "mcep60" / "train-deltas-mean-covariance.npz"))
     else:
         np.testing.assert_allclose(back, static, rtol=1e-4, atol=1e-4)
-    with pytest.raises(NotImplementedError, match="F0 estimation"):
-        WorldFeatLabelGen(str(tmp_path / "o2"), num_coded_sps=60, num_bap=2).gen_data(str(tmp_path / "wav"), None, id_list=ids)
+    # without an F0 cache the F0 stage of pyworld.wav2world (DIO + StoneMask) runs on the device
+    ld2, _, _ = WorldFeatLabelGen(str(tmp_path / "o2"), num_coded_sps=60, num_bap=2).gen_data(str(tmp_path / "wav"), None, id_list=ids,
+                                                                                            return_dict=True)
+    assert [ld2[i].shape[0] for i in ids] == [label_dict[i].shape[0] for i in ids]
 
 
 def test_run_world_synth_writes_reference_named_files(tmp_path):

@@ -143,8 +143,9 @@ def test_scalar_mappings_and_out_of_scope_errors():
         AudioProcessing.extract_mgc(None)
     with pytest.raises(NotImplementedError):
         AudioProcessing.decode_sp(np.zeros((2, 60)), "mgc", 16000)
-    with pytest.raises(NotImplementedError, match="F0 estimation"):
-        WorldFeatLabelGen.world_extract_features(np.zeros(1600), 16000, 5)
+    if not torch.cuda.is_available():  # no cached F0 -> DIO + StoneMask on the device: without a GPU this fails loudly
+        with pytest.raises(RuntimeError):
+            WorldFeatLabelGen.world_extract_features(np.zeros(1600), 16000, 5)
     with pytest.raises(NotImplementedError):
         WorldFeatLabelGen(sp_type="mgc")
 
