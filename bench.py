@@ -381,7 +381,23 @@ def run_b200(args):
                               "fwd_ms": round(ms_vf, 4), "bwd_ms": round(ms_vb, 4),
                               "fwd_frac_of_hbm_peak": rows_v * (8 * n_v + 4) / (ms_vf / 1e3) / 1e9 / peaks["hbm_gbs"],
                               "bwd_frac_of_hbm_peak": rows_v * (12 * n_v + 8) / (ms_vb / 1e3) / 1e9 / peaks["hbm_gbs"]}}
-        del xv, gv, av, sub_feats
+        # F0 stage (not part of the headline, which is quoted with cached F0): DIO + StoneMask over the first 512
+        # utterances, and what the un-cached pyworld.wav2world path would run at
+        nf0 = min(512, utts)
+        sub = ops.RaggedBatch(batch.x[:int(sample_off[nf0])], batch.sample_off[:nf0 + 1].contiguous(), batch.f0[:int(frame_off[nf0])],
+                              batch.t[:int(frame_off[nf0])], batch.frame_off[:nf0 + 1].contiguous(),
+                              batch.frame_utt[:int(frame_off[nf0])], FS)
+        ms_dio = t_ms(lambda: ops.dio(sub), 2)
+        f0_dio = ops.dio(sub)
+        ms_sm = t_ms(lambda: ops.stonemask(sub, f0_dio), 2)
+        f0_audio = int(sample_off[nf0]) / FS
+        f0_rate = f0_audio / ((ms_dio + ms_sm) / 1e3)
+        dio_dfma = 2.0 * int(sample_off[nf0]) * ops.dio_fir_taps(FS)   # flop of the two FIR stages
+        secondary["f0_stage"] = {"workload": "DIO + StoneMask (pyworld.wav2world's F0 half), %d utterances" % nf0,
+                                 "dio_ms": round(ms_dio, 3), "stonemask_ms": round(ms_sm, 3), "audio_s_per_s": f0_rate,
+                                 "dio_fir_tflops_fp64": dio_dfma / (ms_dio / 1e3) / 1e12,
+                                 "analysis_with_f0_estimation_audio_s_per_s": 1.0 / (1.0 / (audio_s / (ms_step / 1e3)) + 1.0 / f0_rate)}
+        del xv, gv, av, sub_feats, sub, f0_dio
 
     if rank == 0:
         # ---- CPU baseline on a bounded sample of the same workload (N = 1 only) -------------------------------------

@@ -298,10 +298,20 @@ __global__ void __launch_bounds__(kMcThreads) mc2sp_kernel(const MT* __restrict_
   for (int j = tid; j < K; j += kMcThreads) {
 #pragma unroll
     for (int f = 0; f < F; ++f) acc[f] = 0.f;
-    for (int k = 0; k <= m; ++k) {
-      const float w = __ldg(cmat + (int64_t)k * K + j);
+    // four coefficients per step: one 16-byte broadcast shared-memory load feeds four FMAs (one scalar load per FMA made the
+    // kernel LSU-bound); rows of mc are zero-padded to MP = pad4(m + 1), the summation order over k is unchanged
+    for (int k = 0; k < MP; k += 4) {
+      float w[4];
 #pragma unroll
-      for (int f = 0; f < F; ++f) acc[f] = fmaf(mc[f * MP + k], w, acc[f]);
+      for (int q = 0; q < 4; ++q) w[q] = (k + q <= m) ? __ldg(cmat + (int64_t)(k + q) * K + j) : 0.f;
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        const float4 c4 = *reinterpret_cast<const float4*>(mc + f * MP + k);
+        acc[f] = fmaf(c4.x, w[0], acc[f]);
+        acc[f] = fmaf(c4.y, w[1], acc[f]);
+        acc[f] = fmaf(c4.z, w[2], acc[f]);
+        acc[f] = fmaf(c4.w, w[3], acc[f]);
+      }
     }
 #pragma unroll
     for (int f = 0; f < F; ++f) {

@@ -213,6 +213,16 @@ def dio(batch, f0_floor=71.0, f0_ceil=800.0, channels_in_octave=2.0, frame_perio
     return out
 
 
+def dio_fir_taps(fs, f0_floor=71.0, f0_ceil=800.0, channels_in_octave=2.0):
+    """Taps per sample of DIO's two FIR stages (low cut + all bands): the kernel's algorithmic DFMA count per sample."""
+    nb = 1 + int(math.log(f0_ceil / f0_floor) / math.log(2.0) * channels_in_octave)
+    rnd = lambda v: int(v + 0.5)
+    taps = 2 * rnd(fs / 50.0) + 1
+    for i in range(nb):
+        taps += 4 * rnd(fs / (f0_floor * 2.0 ** ((i + 1) / channels_in_octave)) / 2.0)
+    return taps
+
+
 def stonemask(batch, f0=None):
     """pyworld.stonemask on a ragged batch: refines f0 (default batch.f0) -> [F] float64."""
     lib = _lib.load()

@@ -1,5 +1,7 @@
 """GPU parity of the F0 stage: b2w_dio + b2w_stonemask against the reference's golden vectors (the lf0 / vuv
 columns of fixtures/WORLD/cmp_mcep20/*.cmp, produced by pyworld.wav2world) and against the numpy oracle (oracle/dio_np.py)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -115,3 +117,44 @@ def test_world_extract_features_without_cached_f0(golden):
     from idiaptts_b200.AudioProcessing import AudioProcessing
     mc = AudioProcessing.extract_mcep(amp_sp, num_coded_sps=20, mgc_alpha=0.58)
     assert glue_np.mcd_db(c[:, :20], mc) < 1e-3
+
+
+@pytest.mark.parametrize("add_deltas", [False, True])
+def test_lf0labelgen_gen_data(tmp_path, golden, add_deltas):
+    """LF0LabelGen.gen_data (LF0LabelGen.py:212-321) on three reference utterances against the oracle path of the same code."""
+    import wave
+    from idiaptts_b200.LF0LabelGen import LF0LabelGen
+    ids = IDS[1:2] + IDS[7:9]
+    os.makedirs(str(tmp_path / "wav"))
+    for i in ids:
+        with wave.open(str(tmp_path / "wav" / (i + ".wav")), "wb") as w:
+            w.setnchannels(1); w.setsampwidth(2); w.setframerate(16000)
+            w.writeframes(golden[i + "/wav"].astype(np.int16).tobytes())
+    gen = LF0LabelGen(str(tmp_path / "out"), add_deltas=add_deltas)
+    label_dict, mean, std = gen.gen_data(str(tmp_path / "wav"), str(tmp_path / "out"), file_id_list="train.txt", id_list=ids,
+                                         add_deltas=add_deltas, return_dict=True)
+    allrows = []
+    for i in ids:
+        x = golden[i + "/wav"].astype(np.float64) / 32768.0   # no pre-emphasis here (soundfile.read, :262)
+        f0, _ = dio_np.wav2world_f0(x, 16000)
+        lf0, vuv = glue_np.interpolate_lin(glue_np.lf0_from_f0(f0, f0_silence_threshold=20))
+        got = label_dict[i]
+        assert got.shape == (len(f0), 4 if add_deltas else 2)
+        assert np.array_equal(got[:, -1], vuv[:, 0])
+        assert np.abs(got[:, 0] - lf0[:, 0]).max() < 2e-6
+        if add_deltas:
+            assert np.array_equal(got[:, 1:2], glue_np.compute_deltas(got[:, 0:1]))
+            assert np.array_equal(got[:, 2:3], glue_np.compute_deltas(got[:, 1:2]))
+        if add_deltas:  # the reference writes all four columns into <id>.lf0_deltas (:285)
+            raw = np.fromfile(str(tmp_path / "out" / "lf0" / (i + ".lf0_deltas")), dtype=np.float32).reshape(-1, 4)
+            assert np.array_equal(raw, got)
+        else:
+            assert np.array_equal(LF0LabelGen.load_sample(i, str(tmp_path / "out")), got)
+        allrows.append(got)
+    allrows = np.concatenate(allrows).astype(np.float64)
+    np.testing.assert_allclose(mean[0], allrows[:, 0].mean(), rtol=1e-5)
+    assert mean[-1] == 0.0 and abs(std[-1] - 1.0) < 1e-12
+    params = gen.get_normalisation_params(str(tmp_path / "out"), "train")
+    assert params[0].shape[-1] == (4 if add_deltas else 2)
+    norm = gen.preprocess_sample(label_dict[ids[0]])
+    np.testing.assert_allclose(gen.postprocess_sample(norm), label_dict[ids[0]], atol=1e-5)
