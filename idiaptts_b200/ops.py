@@ -328,7 +328,7 @@ def code_aperiodicity(ap, fs):
     return out
 
 
-def decode_aperiodicity(bap, fs, fft_size):
+def decode_aperiodicity(bap, fs, fft_size, out=None):
     lib = _lib.load()
     dev = _need_cuda(bap)
     assert bap.dtype == torch.float64 and bap.dim() == 2
@@ -336,7 +336,9 @@ def decode_aperiodicity(bap, fs, fft_size):
     if bap.shape[1] != nap:
         raise ValueError("coded aperiodicity has %d bands, fs=%d needs %d" % (bap.shape[1], fs, nap))
     F = bap.shape[0]
-    out = torch.empty((F, fft_size // 2 + 1), dtype=torch.float64, device=dev)
+    if out is None:
+        out = torch.empty((F, fft_size // 2 + 1), dtype=torch.float64, device=dev)
+    assert out.dtype == torch.float64 and out.shape == (F, fft_size // 2 + 1) and out.is_contiguous()
     with torch.cuda.device(dev):
         check(lib.b2w_decode_aperiodicity(bap.data_ptr(), F, int(fs), int(fft_size), out.data_ptr(), _stream(dev)),
               "b2w_decode_aperiodicity")
@@ -430,7 +432,7 @@ def mcep(plane, order, alpha, is_power=False, miniter=2, maxiter=30, threshold=0
     return out, status
 
 
-def mc2sp(mc, alpha, fft_size, scale=1.0, do_exp=True, out_dtype=torch.float32, order=None, mc_stride=None, square=False):
+def mc2sp(mc, alpha, fft_size, scale=1.0, do_exp=True, out_dtype=torch.float32, order=None, mc_stride=None, square=False, out=None):
     """(exp of) scale * Re FFT(freqt(mc, fft_size/2, -alpha)): log-amplitude / amplitude / power spectrum from mel-cepstra.
     square=True (with do_exp, float64 output): the float32 amplitude squared in float64, i.e. world_features_to_raw's pow_sp."""
     lib = _lib.load()
@@ -442,7 +444,9 @@ def mc2sp(mc, alpha, fft_size, scale=1.0, do_exp=True, out_dtype=torch.float32, 
     if mc_stride is None:
         mc_stride = mc.shape[1]
     tab = McepTables.get(order, alpha, fft_size, dev)
-    out = torch.empty((F, fft_size // 2 + 1), dtype=out_dtype, device=dev)
+    if out is None:
+        out = torch.empty((F, fft_size // 2 + 1), dtype=out_dtype, device=dev)
+    assert out.dtype == out_dtype and out.shape == (F, fft_size // 2 + 1) and out.is_contiguous()
     with torch.cuda.device(dev):
         check(lib.b2w_mc2sp(mc.data_ptr(), _DT[mc.dtype], int(mc_stride), F, int(fft_size), int(order), tab.cmat.data_ptr(),
                             float(scale), (2 if square else 1) if do_exp else 0, out.data_ptr(), _DT[out.dtype], _stream(dev)),
@@ -519,34 +523,87 @@ def randn_table(n, device):
         return tab
 
 
+class SynthPlan:
+    """Pulse table of a ragged batch (WORLD GetTimeBase / GetPulseLocationsForTimeBase), launched asynchronously by
+    synth_timebase; synth_render turns it into waveforms once the spectral planes exist."""
+    pass
+
+
+def synth_timebase(f0, frame_off, fs, fft_size, frame_period=5.0, status=None):
+    """Launches the pulse-placement kernels (sequential per utterance, a few hundred threads: they overlap well with other
+    work on a second stream).  f0 [F] f64, frame_off int64 [U+1] (device).  Returns a SynthPlan; nothing is synchronised."""
+    lib = _lib.load()
+    dev = _need_cuda(f0, frame_off)
+    assert f0.dtype == torch.float64
+    p = SynthPlan()
+    foff = frame_off.cpu().numpy()
+    p.U = U = len(foff) - 1
+    T = np.diff(foff)
+    p.ylen = ylen = (T * frame_period * fs / 1000).astype(np.int64)  # int(T * frame_period * fs / 1000)
+    p.out_off = out_off = np.concatenate(([0], np.cumsum(ylen)))
+    caps = np.array([lib.b2w_synth_max_pulses(int(v), int(fs)) for v in ylen], np.int64)
+    p.pulse_off = pulse_off = np.concatenate(([0], np.cumsum(caps)))
+    p.d_out_off = torch.from_numpy(out_off).to(dev)
+    p.d_pulse_off = torch.from_numpy(pulse_off).to(dev)
+    total_cap = int(pulse_off[-1])
+    p.pulse_index = torch.empty(max(total_cap, 1), dtype=torch.int32, device=dev)
+    p.pulse_shift = torch.empty(max(total_cap, 1), dtype=torch.float64, device=dev)
+    p.pulse_vuv = torch.empty(max(total_cap, 1), dtype=torch.uint8, device=dev)
+    p.num_pulses = torch.zeros(max(U, 1), dtype=torch.int32, device=dev)
+    p.status = new_status(dev) if status is None else status
+    p.fs, p.frame_period, p.fft_size, p.frame_off, p.device = int(fs), float(frame_period), int(fft_size), frame_off, dev
+    p.empty = U == 0 or out_off[-1] == 0
+    if p.empty:
+        return p
+    p.tab = randn_table(int(ylen.max()) + 1, dev)
+    with torch.cuda.device(dev):
+        phase_ws = torch.empty(int(out_off[-1]), dtype=torch.float64, device=dev)
+        check(lib.b2w_synth_timebase(f0.data_ptr(), frame_off.data_ptr(), p.d_out_off.data_ptr(), p.d_pulse_off.data_ptr(), U,
+                                     int(ylen.max()), int(fs), float(frame_period), fft_size, phase_ws.data_ptr(),
+                                     p.pulse_index.data_ptr(), p.pulse_shift.data_ptr(), p.pulse_vuv.data_ptr(),
+                                     p.num_pulses.data_ptr(), p.status.data_ptr(), _stream(dev)), "b2w_synth_timebase")
+    return p
+
+
+def synth_render(p, sp, ap, deemphasis=0.0, out_dtype=torch.float64, debug=None):
+    """Minimum-phase responses of every pulse of the plan + overlap-add.  sp, ap [F, K] (f64 or f32, same dtype)."""
+    lib = _lib.load()
+    dev = _need_cuda(sp, ap)
+    assert sp.dtype == ap.dtype and sp.dtype in (torch.float32, torch.float64)
+    assert 2 * (sp.shape[1] - 1) == p.fft_size
+    U, fft_size, out_off, pulse_off = p.U, p.fft_size, p.out_off, p.pulse_off
+    y = torch.empty(int(out_off[-1]), dtype=out_dtype, device=dev)
+    if p.empty:
+        return y, out_off, p.status
+    st = _stream(dev)
+    with torch.cuda.device(dev):
+        # the response buffer is sized by the ACTUAL pulse counts (one small D2H of U ints)
+        npul = p.num_pulses.cpu().numpy()[:U].astype(np.int64)
+        max_p = int(npul.max()) if U else 0
+        # responses are addressed by the slab offsets, so allocate slab-sized storage only up to the last used row
+        last_row = int((pulse_off[:-1] + npul).max()) if U else 0
+        response = torch.empty((max(last_row, 1), fft_size), dtype=torch.float64, device=dev)
+        if max_p > 0:
+            check(lib.b2w_synth_render(sp.data_ptr(), ap.data_ptr(), _DT[sp.dtype], p.frame_off.data_ptr(),
+                                       p.d_pulse_off.data_ptr(), p.num_pulses.data_ptr(), U, p.pulse_index.data_ptr(),
+                                       p.pulse_shift.data_ptr(), p.pulse_vuv.data_ptr(), p.tab.data_ptr(), p.tab.numel(), p.fs,
+                                       p.frame_period, fft_size, max_p, response.data_ptr(), st), "b2w_synth_render")
+        if debug is not None:  # diagnostics for the parity tests: the pulse table of every utterance
+            debug.update(pulse_off=pulse_off, num_pulses=npul, pulse_index=p.pulse_index, pulse_shift=p.pulse_shift,
+                         pulse_vuv=p.pulse_vuv, response=response)
+        check(lib.b2w_synth_overlap_add(response.data_ptr(), p.d_out_off.data_ptr(), p.d_pulse_off.data_ptr(),
+                                        p.num_pulses.data_ptr(), U, p.pulse_index.data_ptr(), fft_size, int(p.ylen.max()),
+                                        float(deemphasis), y.data_ptr(), _DT[y.dtype], st), "b2w_synth_overlap_add")
+    return y, out_off, p.status
+
+
 def synthesize(f0, sp, ap, frame_off, fs, frame_period=5.0, deemphasis=0.0, out_dtype=torch.float64, status=None,
                debug=None):
     """pyworld.synthesize on a ragged batch.  f0 [F] f64; sp, ap [F, K] (f64 or f32, same dtype); frame_off int64 [U+1]
     (device) -> (y packed [sum y_len], out_off int64 [U+1] (host numpy))."""
-    lib = _lib.load()
-    dev = _need_cuda(f0, sp, ap, frame_off)
-    assert sp.dtype == ap.dtype and sp.dtype in (torch.float32, torch.float64) and f0.dtype == torch.float64
-    K = sp.shape[1]
-    fft_size = 2 * (K - 1)
-    foff = frame_off.cpu().numpy()
-    U = len(foff) - 1
-    T = np.diff(foff)
-    ylen = (T * frame_period * fs / 1000).astype(np.int64)  # int(T * frame_period * fs / 1000)
-    out_off = np.concatenate(([0], np.cumsum(ylen)))
-    caps = np.array([lib.b2w_synth_max_pulses(int(v), int(fs)) for v in ylen], np.int64)
-    pulse_off = np.concatenate(([0], np.cumsum(caps)))
-    d_out_off = torch.from_numpy(out_off).to(dev)
-    d_pulse_off = torch.from_numpy(pulse_off).to(dev)
-    total_cap = int(pulse_off[-1])
-    pulse_index = torch.empty(max(total_cap, 1), dtype=torch.int32, device=dev)
-    pulse_shift = torch.empty(max(total_cap, 1), dtype=torch.float64, device=dev)
-    pulse_vuv = torch.empty(max(total_cap, 1), dtype=torch.uint8, device=dev)
-    num_pulses = torch.zeros(max(U, 1), dtype=torch.int32, device=dev)
-    if status is None:
-        status = new_status(dev)
-    y = torch.empty(int(out_off[-1]), dtype=out_dtype, device=dev)
-    if U == 0 or out_off[-1] == 0:
-        return y, out_off, status
+    _need_cuda(f0, sp, ap, frame_off)
+    plan = synth_timebase(f0, frame_off, fs, 2 * (sp.shape[1] - 1), frame_period, status)
+    return synth_render(plan, sp, ap, deemphasis, out_dtype, debug)
     tab = randn_table(int(ylen.max()) + 1, dev)
     st = _stream(dev)
     with torch.cuda.device(dev):

@@ -186,17 +186,19 @@ class WorldSynthesizer:
         Returns (y packed, out_off numpy int64 [U+1], status)."""
         D = self.num_coded_sps
         assert feats.shape[1] == D + 2 + self.nap, "WORLD requires all features to be present."
-        # decode_sp: amp = exp(Re mgc2sp) as float32 (AudioProcessing.py:256), then pow_sp = amp^2 in float64 (W:924)
-        pow_sp = ops.mc2sp(feats, self.alpha, self.n_fft, scale=1.0, do_exp=True, out_dtype=torch.float64, order=D - 1,
-                           mc_stride=feats.shape[1], square=True)
         lf0 = feats[:, D].double()
         vuv = (feats[:, D + 1] >= 0.5)
         f0 = torch.exp(lf0)
         vuv = vuv & ~(f0 < self.f0_silence_threshold)
         f0 = torch.where(vuv, f0, torch.full_like(f0, float(self.lf0_zero)))
+        # decode_sp: amp = exp(Re mgc2sp) as float32 (AudioProcessing.py:256), then pow_sp = amp^2 in float64 (W:924)
+        pow_sp = ops.mc2sp(feats, self.alpha, self.n_fft, scale=1.0, do_exp=True, out_dtype=torch.float64, order=D - 1,
+                           mc_stride=feats.shape[1], square=True)
         bap = feats[:, D + 2:].double().contiguous()
         ap = ops.decode_aperiodicity(bap, self.fs, self.n_fft)
+        # (Measured: decoding the two planes on a side stream while the sequential pulse placement runs on this one is SLOWER,
+        # 23.2 ms against 19.8 ms for 256 utterances -- scripts/gpu_synth_phases.py -- so the stages stay in one stream.)
+        plan = ops.synth_timebase(f0.contiguous(), frame_off, self.fs, self.n_fft, self.hop_size_ms)
         de = float(preemphasis)
-        y, out_off, status = ops.synthesize(f0.contiguous(), pow_sp, ap, frame_off, self.fs, self.hop_size_ms, deemphasis=de,
-                                            out_dtype=torch.float64 if de != 0.0 else out_dtype)
+        y, out_off, status = ops.synth_render(plan, pow_sp, ap, deemphasis=de, out_dtype=torch.float64 if de != 0.0 else out_dtype)
         return y, out_off, status
