@@ -140,7 +140,22 @@ allpass_tc_forward_kernel(const float* __restrict__ x, const float* __restrict__
   // the staging buffer (which aliases the A tiles: every MMA reading A must be complete) and leave with coalesced stores;
   // the rare two-run tiles write rows [lo, hi) straight to global memory because their A tile is needed by a second GEMM.
   auto emit_rows = [&](bool direct, int lo, int hi, float* ydst) {
-    if (warp < 4) {
+    if (!direct) {
+      // all eight warps: warp w reads TMEM lane quarter w & 3 (its rows) and column half w >> 2
+      const int row = 32 * (warp & 3) + lane;
+      const int c0 = 32 * (warp >> 2);
+      const uint32_t taddr = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + c0;
+      float v[16];
+#pragma unroll
+      for (int cb = 0; cb < 2; ++cb) {
+        umma::tmem_ld16(taddr + 16 * cb, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int c = c0 + 16 * cb + i;
+          stage[row * kVtcStageStride + c] = (v[i] - vmean[c]) * vrstd[c];
+        }
+      }
+    } else if (warp < 4) {
       const int row = 32 * warp + lane;
       const uint32_t taddr = tmem + ((uint32_t)(32 * warp) << 16);
       float v[16];
@@ -171,22 +186,30 @@ allpass_tc_forward_kernel(const float* __restrict__ x, const float* __restrict__
     const float a1 = alpha[(u0 + nun - 1) / blocks];
     const int blk0 = (int)(u0 - row0 * blocks);
     const bool norm_ok = blocks == 1 || (mean == nullptr && std_dev == nullptr);
-    const int s0 = __syncthreads_count(tid < nun && pre_alpha == a0);   // length of the first run if the tile is well formed
-    bool fine = true;
-    if (tid < nun) fine = (tid < s0) ? (pre_alpha == a0) : (pre_alpha == a1);
-    const bool ok = __syncthreads_and(fine) && norm_ok;
+    int s0 = nun;   // length of the first run if the tile is well formed
+    bool ok = norm_ok;
+    if (!__syncthreads_and(tid >= nun || pre_alpha == a0)) {  // not one alpha for the whole tile (rare): look for two runs
+      s0 = __syncthreads_count(tid < nun && pre_alpha == a0);
+      bool fine = true;
+      if (tid < nun) fine = (tid < s0) ? (pre_alpha == a0) : (pre_alpha == a1);
+      ok = __syncthreads_and(fine) && norm_ok;
+    }
     if (tid == 0) tile_mixed[t] = ok ? 0 : 1;
     if (!ok) {
       if (t + 1 < t_end) prefetch(t + 1);
       continue;
     }
     // ---- normalisation vectors of this tile's block -----------------------------------------------------------------------
-    if (cached_blk != blk0 && tid < kVtcNP) {
-      const bool in = tid < n;
-      vmean[tid] = (in && mean) ? mean[blk0 * n + tid] : 0.f;
-      const float sd = (in && std_dev) ? std_dev[blk0 * n + tid] : 1.f;
-      vstd[tid] = sd;
-      vrstd[tid] = 1.f / sd;
+    bool rewritten = false;
+    if (cached_blk != blk0) {
+      if (tid < kVtcNP) {
+        const bool in = tid < n;
+        vmean[tid] = (in && mean) ? mean[blk0 * n + tid] : 0.f;
+        const float sd = (in && std_dev) ? std_dev[blk0 * n + tid] : 1.f;
+        vstd[tid] = sd;
+        vrstd[tid] = 1.f / sd;
+      }
+      rewritten = true;
     }
     cached_blk = blk0;
     // ---- matrix of the first run --------------------------------------------------------------------------------------------
@@ -194,8 +217,9 @@ allpass_tc_forward_kernel(const float* __restrict__ x, const float* __restrict__
       if (warp == 0) vtc_build_matrix(b_hi, b_lo, a0, n);
       cached_alpha = a0;
       have_matrix = true;
+      rewritten = true;
     }
-    __syncthreads();  // vectors + matrix visible
+    if (rewritten) __syncthreads();  // vectors + matrix visible (block-uniform condition)
     // ---- A = hi / lo split of the de-normalised tile ----------------------------------------------------------------------------
     {
 #pragma unroll
@@ -345,6 +369,7 @@ allpass_tc_backward_kernel(const float* __restrict__ gy, const float* __restrict
   float* vmean = reinterpret_cast<float*>(smem + VtcBwdSmem::vec);
   float* vstd = vmean + kVtcNP;
   float* vrstd = vstd + kVtcNP;
+  __shared__ float ga_half[kVtcF];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + VtcBwdSmem::misc);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -415,20 +440,25 @@ allpass_tc_backward_kernel(const float* __restrict__ gy, const float* __restrict
       if (t + 1 < t_end) prefetch(t + 1);
       continue;
     }
-    if (cached_blk != blk0 && tid < kVtcNP) {
-      const bool in = tid < n;
-      vmean[tid] = (in && mean) ? mean[blk0 * n + tid] : 0.f;
-      const float sd = (in && std_dev) ? std_dev[blk0 * n + tid] : 1.f;
-      vstd[tid] = sd;
-      vrstd[tid] = 1.f / sd;
+    bool rewritten = false;
+    if (cached_blk != blk0) {
+      if (tid < kVtcNP) {
+        const bool in = tid < n;
+        vmean[tid] = (in && mean) ? mean[blk0 * n + tid] : 0.f;
+        const float sd = (in && std_dev) ? std_dev[blk0 * n + tid] : 1.f;
+        vstd[tid] = sd;
+        vrstd[tid] = 1.f / sd;
+      }
+      rewritten = true;
     }
     cached_blk = blk0;
     if (!have_matrix || a0 != cached_alpha) {
       if (warp == 0) vtc_build_matrices_bwd(bb_hi, bb_lo, bt_hi, bt_lo, a0, n);
       cached_alpha = a0;
       have_matrix = true;
+      rewritten = true;
     }
-    __syncthreads();
+    if (rewritten) __syncthreads();  // block-uniform condition
 #pragma unroll
     for (int i = 0; i < kPre; ++i) {
       const int item = warp + 8 * i;
@@ -472,20 +502,23 @@ allpass_tc_backward_kernel(const float* __restrict__ gy, const float* __restrict
     umma::mbar_wait(bar, phase);
     phase ^= 1;
     umma::tc_fence_after_sync();
-    if (warp < 4) {
-      const int row = 32 * warp + lane;
-      const uint32_t taddr = tmem + ((uint32_t)(32 * warp) << 16);
+    {
+      // all eight warps: warp w owns TMEM lane quarter w & 3 (its rows) and column half w >> 2; the two halves of a row's
+      // d alpha dot product meet in shared memory
+      const int row = 32 * (warp & 3) + lane;
+      const int c0 = 32 * (warp >> 2);
+      const uint32_t taddr = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + c0;
       float v[16];
       float ga = 0.f;
 #pragma unroll
-      for (int cb = 0; cb < kVtcNP / 16; ++cb) {
+      for (int cb = 0; cb < 2; ++cb) {
         umma::tmem_ld16(taddr + 16 * cb, v);  // D1: gradient w.r.t. the de-normalised input
 #pragma unroll
-        for (int i = 0; i < 16; ++i) stage[row * kVtcStageStride + 16 * cb + i] = v[i] * vstd[16 * cb + i];
+        for (int i = 0; i < 16; ++i) stage[row * kVtcStageStride + c0 + 16 * cb + i] = v[i] * vstd[c0 + 16 * cb + i];
         umma::tmem_ld16(taddr + 64 + 16 * cb, v);  // D2: d y / d alpha
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
-          const uint32_t off = umma::tile_off(kVtcF, row, 16 * cb + i) / 4;
+          const uint32_t off = umma::tile_off(kVtcF, row, c0 + 16 * cb + i) / 4;
           const float4 gh = *reinterpret_cast<const float4*>(g_hi + off), gl = *reinterpret_cast<const float4*>(g_lo + off);
           ga = fmaf(gh.x + gl.x, v[i], ga);
           ga = fmaf(gh.y + gl.y, v[i + 1], ga);
@@ -493,10 +526,11 @@ allpass_tc_backward_kernel(const float* __restrict__ gy, const float* __restrict
           ga = fmaf(gh.w + gl.w, v[i + 3], ga);
         }
       }
-      if (row < nun) galpha_unit[u0 + row] = ga;
+      if (warp >= 4) ga_half[row] = ga;
+      umma::tc_fence_before_sync();
+      __syncthreads();
+      if (warp < 4 && row < nun) galpha_unit[u0 + row] = ga + ga_half[row];
     }
-    umma::tc_fence_before_sync();
-    __syncthreads();
     {
       float4* dst = reinterpret_cast<float4*>(gx + u0 * n);
 #pragma unroll

@@ -24,7 +24,7 @@ if os.path.exists(lf):
         except ValueError: continue
         k = r[ki].split("(")[0][:60]
         agg[k][0] += 1; agg[k][1] += v
-    mine = {k: v for k, v in agg.items() if any(s in k for s in ("cheaptrick", "d4c", "mcep", "lf0_vuv", "bap_from", "stats_kernel"))}
+    mine = {k: v for k, v in agg.items() if any(s in k for s in ("cheaptrick", "d4c", "mcep", "lf0_vuv", "bap_from", "stats_kernel", "dio_", "stonemask"))}
     tot = sum(v[1] for v in mine.values())
     with open(os.path.join(P, "%s_launch_summary.txt" % tag), "w") as o:
         o.write("ncu launch list (gpu__time_duration.sum, --clock-control none): bench.py --utts 1024 --steps 1 --warmup 1 (warm-up + timed + e2e passes)\n")
