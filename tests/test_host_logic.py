@@ -159,3 +159,27 @@ def test_product_path_fails_loudly_without_gpu():
         pysptk.mcep(np.ones((3, 513)), 59, 0.58, etype=1, eps=1e-8, itype=3)
     with pytest.raises(RuntimeError, match="CUDA"):
         WorldFeatLabelGen.world_extract_features(np.zeros(1600), 16000, 5, f0=np.zeros(21))
+
+
+def test_f0_stage_host_helpers():
+    """Host-side pieces of the DIO / StoneMask path (no GPU): chunking, band geometry and workspace size through the C ABI."""
+    from idiaptts_b200 import _lib, ops
+    from oracle import dio_np
+    off = np.array([0, 10, 30, 35, 100, 101])
+    assert list(ops._utt_chunks(off, 30)) == [(0, 2), (2, 3), (3, 4), (4, 5)]   # a longer utterance forms its own chunk
+    assert list(ops._utt_chunks(off, 1000)) == [(0, 5)]
+    assert list(ops._utt_chunks(np.array([0]), 10)) == []
+    lib = _lib.load()
+    assert lib.b2w_dio_num_bands(71.0, 800.0, 2.0) == len(dio_np.dio_bands(16000)) == 7
+    assert lib.b2w_dio_num_bands(800.0, 71.0, 2.0) < 0
+    for fs in (16000, 22050, 48000):
+        bands = dio_np.dio_bands(fs)
+        taps = 2 * dio_np.mround(fs / 50.0) + 1 + sum(4 * dio_np.mround(fs / b / 2.0) for b in bands)
+        assert ops.dio_fir_taps(fs) == taps
+        small = lib.b2w_dio_workspace_bytes(100000, 4, 500, fs, 71.0, 800.0, 2.0)
+        big = lib.b2w_dio_workspace_bytes(200000, 4, 500, fs, 71.0, 800.0, 2.0)
+        assert 0 < small < big and (big - small) <= 100000 * (8 + 16 * 7 + 1)
+    # WORLD sizes DIO's FFT so that the circular convolution never wraps: the premise of the direct (linear) FIR kernels
+    for n, fs in ((48000, 16000), (143325, 22050), (480000, 48000)):
+        h0 = dio_np.mround(fs / bands[0] / 2.0)
+        assert dio_np.dio_fft_size(n, fs) >= (n + 1) + 2 * dio_np.mround(fs / 50.0) + 1 + 4 * h0
