@@ -207,9 +207,7 @@ def dio(batch, f0_floor=71.0, f0_ceil=800.0, channels_in_octave=2.0, frame_perio
             check(lib.b2w_dio(b, S, keep[1].data_ptr(), float(f0_floor), float(f0_ceil), float(channels_in_octave), float(frame_period),
                               float(allowed_range), 1 if step2 == "sections" else 0, ws.data_ptr(),
                               out.data_ptr() + 8 * int(f_off[u0]), _stream(dev)), "b2w_dio")
-            ws.record_stream(torch.cuda.current_stream(dev))
-            for k in keep:
-                k.record_stream(torch.cuda.current_stream(dev))
+            del ws, keep  # allocated and used on the current stream: the caching allocator's stream-ordered reuse is safe
     return out
 
 
