@@ -158,3 +158,23 @@ def test_lf0labelgen_gen_data(tmp_path, golden, add_deltas):
     assert params[0].shape[-1] == (4 if add_deltas else 2)
     norm = gen.preprocess_sample(label_dict[ids[0]])
     np.testing.assert_allclose(gen.postprocess_sample(norm), label_dict[ids[0]], atol=1e-5)
+
+
+def test_f0_scale_invariance_at_corpus_scale():
+    """Size-independent property at the benchmark's utterance shape (6.5 s @ 22.05 kHz): every DIO / StoneMask decision is
+    homogeneous in the waveform, and scaling by a power of two is exact in IEEE arithmetic, so DIO(x / 4) == DIO(x) bit for bit."""
+    from idiaptts_b200 import ops, synthetic
+    fs = 22050
+    waves, _ = synthetic.make_corpus(48, fs, seed=77, mean_dur=6.5, device="cpu")
+    xs = [w.numpy().astype(np.float64) / 32768.0 for w in waves]
+    ba, bb = _batch(xs, fs), _batch([x * 0.25 for x in xs], fs)
+    da, db = ops.dio(ba), ops.dio(bb)
+    assert torch.equal(da, db)                      # DIO: exactly homogeneous
+    a, b = ops.stonemask(ba, da).cpu().numpy(), ops.stonemask(bb, db).cpu().numpy()
+    assert np.array_equal(a > 0, b > 0)             # StoneMask adds 1e-12 to an amplitude sum (FixF0): homogeneous to ~1e-12
+    np.testing.assert_allclose(a, b, rtol=1e-9)
+    assert 0.3 < (a > 0).mean() < 0.9
+    # ... and an utterance's track does not depend on what else is in the batch
+    c = ops.estimate_f0(_batch(xs[5:6], fs)).cpu().numpy()
+    off = np.concatenate(([0], np.cumsum([world_np.num_frames(len(x), fs) for x in xs])))
+    assert np.array_equal(c, a[off[5]:off[6]])
