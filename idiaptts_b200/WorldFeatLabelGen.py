@@ -455,6 +455,25 @@ class WorldFeatLabelGen(object):
             return sample
         return np.float32((sample - mean) / std)
 
+    def prepare_batch_device(self, feats, frame_off, batch_first=False, norm_params=None, min_frames=None):
+        """Device-side form of `preprocess_sample` on every utterance + `ModularModelHandlerPyTorch.prepare_batch` (:389-499) for
+        feature rows that are already on the GPU (e.g. straight out of pipeline.WorldAnalyzer.extract): ragged [F, W] float32 +
+        frame offsets -> (padded [T_max, B, W] | [B, T_max, W], mask, lengths).  One HBM pass (ops.pad_normalise)."""
+        mean, std = self._flat_norm_params(norm_params)
+        dev = feats.device
+        m = None if mean is None else torch.from_numpy(np.ascontiguousarray(mean.reshape(-1))).to(dev)
+        sd = None if std is None else torch.from_numpy(np.ascontiguousarray(std.reshape(-1))).to(dev)
+        return ops.pad_normalise(feats, frame_off, m, sd, batch_first=batch_first, min_frames=min_frames)
+
+    def unprepare_batch_device(self, padded, frame_off, frame_utt, batch_first=False, norm_params=None):
+        """Network output [T_max, B, W] | [B, T_max, W] -> de-normalised ragged rows [F, W] on the device (the first half of
+        `postprocess_sample`, :338-355; MLPG / synthesis continue from there without leaving the GPU)."""
+        mean, std = self._flat_norm_params(norm_params)
+        dev = padded.device
+        m = None if mean is None else torch.from_numpy(np.ascontiguousarray(mean.reshape(-1))).to(dev)
+        sd = None if std is None else torch.from_numpy(np.ascontiguousarray(std.reshape(-1))).to(dev)
+        return ops.unpad_denormalise(padded, frame_off, frame_utt, m, sd, batch_first=batch_first)
+
     def postprocess_sample(self, sample, norm_params=None, apply_mlpg=True):
         """:338-355: de-normalise, then _postprocess_world (MLPG per feature when the sample carries deltas)."""
         mean, std = self._flat_norm_params(norm_params)

@@ -72,6 +72,10 @@ _SIGNATURES = {
     "b2w_mlpg_workspace_doubles": (c_int64, [c_int64, c_int32]),
     "b2w_mlpg": (c_int32, [c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_void_p]),
     "b2w_world_metrics": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
+    "b2w_pad_normalise": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p,
+                                    c_void_p, c_void_p]),
+    "b2w_unpad_denormalise": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p,
+                                        c_int32, c_void_p, c_int64, c_void_p]),
     "b2w_dio_num_bands": (c_int32, [c_double, c_double, c_double]),
     "b2w_dio_workspace_bytes": (c_int64, [c_int64, c_int32, c_int64, c_int32, c_double, c_double, c_double]),
     "b2w_dio": (c_int32, [ctypes.POINTER(Batch), c_int64, c_void_p, c_double, c_double, c_double, c_double, c_double, c_int32,

@@ -179,6 +179,200 @@ __global__ void gram_kernel(const float* __restrict__ feats, int64_t fstride, in
 
 }  // namespace b2w
 
+// ---- trainer-facing batch ---------------------------------------------------------------------------------------
+// Ragged feature rows -> the padded, normalised tensor a trainer consumes, in one pass: WorldFeatLabelGen.preprocess_sample
+// ((x - mean) / std_dev in float32, world/WorldFeatLabelGen.py:279-336) followed by ModularModelHandlerPyTorch.prepare_batch
+// (pad_sequence with zeros to the longest utterance + sequence_mask, :389-499).  One warp per (t, b) row, lanes over the
+// feature columns: coalesced reads and writes, the kernel is HBM-bound.  Separate subtract / divide (and multiply / add in the
+// inverse): bit-identical to numpy's float32 arithmetic.
+namespace b2w {
+__global__ void __launch_bounds__(256) pad_normalise_kernel(const float* __restrict__ feats, int64_t feat_stride, int width,
+                                                            const int64_t* __restrict__ foff, int U, int t_max,
+                                                            const float* __restrict__ mean, const float* __restrict__ std_dev,
+                                                            int batch_first, float* __restrict__ out, float* __restrict__ mask) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t rows = (int64_t)t_max * U;
+  for (int64_t r = warp0; r < rows; r += nwarps) {
+    // r enumerates the OUTPUT rows in memory order
+    const int b = batch_first ? (int)(r / t_max) : (int)(r % U);
+    const int t = batch_first ? (int)(r % t_max) : (int)(r / U);
+    const int64_t f0 = foff[b];
+    const bool valid = t < (int)(foff[b + 1] - f0);
+    float* o = out + r * width;
+    if (valid) {
+      const float* x = feats + (f0 + t) * feat_stride;
+      for (int w = lane; w < width; w += 32) {
+        const float m = mean ? mean[w] : 0.f, sd = std_dev ? std_dev[w] : 1.f;
+        o[w] = __fdiv_rn(__fsub_rn(x[w], m), sd);
+      }
+    } else {
+      for (int w = lane; w < width; w += 32) o[w] = 0.f;
+    }
+    if (mask && lane == 0) mask[r] = valid ? 1.f : 0.f;
+  }
+}
+
+// float4 variants (width, strides and pointers multiples of 4 floats): one thread per 16-byte chunk, two chunks in flight
+__device__ __forceinline__ float4 norm4(float4 x, float4 m, float4 sd) {
+  return make_float4(__fdiv_rn(__fsub_rn(x.x, m.x), sd.x), __fdiv_rn(__fsub_rn(x.y, m.y), sd.y), __fdiv_rn(__fsub_rn(x.z, m.z), sd.z),
+                     __fdiv_rn(__fsub_rn(x.w, m.w), sd.w));
+}
+__device__ __forceinline__ float4 denorm4(float4 x, float4 m, float4 sd) {
+  return make_float4(__fadd_rn(__fmul_rn(x.x, sd.x), m.x), __fadd_rn(__fmul_rn(x.y, sd.y), m.y), __fadd_rn(__fmul_rn(x.z, sd.z), m.z),
+                     __fadd_rn(__fmul_rn(x.w, sd.w), m.w));
+}
+
+__global__ void __launch_bounds__(256) pad_normalise4_kernel(const float4* __restrict__ feats, int64_t stride4, int w4,
+                                                             const int64_t* __restrict__ foff, int U, int t_max,
+                                                             const float4* __restrict__ mean, const float4* __restrict__ std_dev,
+                                                             int batch_first, float4* __restrict__ out, float* __restrict__ mask) {
+  const int64_t total = (int64_t)t_max * U * w4;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f), one = make_float4(1.f, 1.f, 1.f, 1.f);
+  for (int64_t q0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q0 < total; q0 += 2 * step) {
+    float4 x[2];
+    int c[2];
+    bool valid[2], live[2];
+    int64_t r[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int64_t q = q0 + k * step;
+      live[k] = q < total;
+      valid[k] = false;
+      x[k] = zero;
+      c[k] = 0;
+      r[k] = 0;
+      if (live[k]) {
+        r[k] = q / w4;
+        c[k] = (int)(q - r[k] * w4);
+        const int b = batch_first ? (int)(r[k] / t_max) : (int)(r[k] % U);
+        const int t = batch_first ? (int)(r[k] % t_max) : (int)(r[k] / U);
+        const int64_t f0 = foff[b];
+        valid[k] = t < (int)(foff[b + 1] - f0);
+        if (valid[k]) x[k] = __ldcs(feats + (f0 + t) * stride4 + c[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (!live[k]) continue;
+      float4 v = zero;
+      if (valid[k]) v = norm4(x[k], mean ? mean[c[k]] : zero, std_dev ? std_dev[c[k]] : one);
+      __stcs(out + r[k] * w4 + c[k], v);
+      if (mask && c[k] == 0) mask[r[k]] = valid[k] ? 1.f : 0.f;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) unpad_denormalise4_kernel(const float4* __restrict__ padded, int w4,
+                                                                 const int64_t* __restrict__ foff, const int32_t* __restrict__ frame_utt,
+                                                                 int64_t F, int U, int t_max, const float4* __restrict__ mean,
+                                                                 const float4* __restrict__ std_dev, int batch_first,
+                                                                 float4* __restrict__ feats, int64_t stride4) {
+  const int64_t total = F * w4;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f), one = make_float4(1.f, 1.f, 1.f, 1.f);
+  for (int64_t q0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q0 < total; q0 += 2 * step) {
+    float4 x[2];
+    int c[2];
+    int64_t f[2];
+    bool live[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int64_t q = q0 + k * step;
+      live[k] = q < total;
+      x[k] = zero;
+      c[k] = 0;
+      f[k] = 0;
+      if (live[k]) {
+        f[k] = q / w4;
+        c[k] = (int)(q - f[k] * w4);
+        const int b = frame_utt[f[k]];
+        const int t = (int)(f[k] - foff[b]);
+        const int64_t r = batch_first ? (int64_t)b * t_max + t : (int64_t)t * U + b;
+        x[k] = __ldcs(padded + r * w4 + c[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+      if (live[k]) __stcs(feats + f[k] * stride4 + c[k], denorm4(x[k], mean ? mean[c[k]] : zero, std_dev ? std_dev[c[k]] : one));
+  }
+}
+
+__global__ void __launch_bounds__(256) unpad_denormalise_kernel(const float* __restrict__ padded, int width,
+                                                                const int64_t* __restrict__ foff, const int32_t* __restrict__ frame_utt,
+                                                                int64_t F, int U, int t_max, const float* __restrict__ mean,
+                                                                const float* __restrict__ std_dev, int batch_first,
+                                                                float* __restrict__ feats, int64_t feat_stride) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t f = warp0; f < F; f += nwarps) {
+    const int b = frame_utt[f];
+    const int t = (int)(f - foff[b]);
+    const int64_t r = batch_first ? (int64_t)b * t_max + t : (int64_t)t * U + b;
+    const float* x = padded + r * width;
+    float* o = feats + f * feat_stride;
+    for (int w = lane; w < width; w += 32) {
+      const float m = mean ? mean[w] : 0.f, sd = std_dev ? std_dev[w] : 1.f;
+      o[w] = __fadd_rn(__fmul_rn(x[w], sd), m);
+    }
+  }
+}
+}  // namespace b2w
+
+extern "C" int b2w_pad_normalise(const float* feats, int64_t feat_stride, int32_t width, const int64_t* utt_frame_offset,
+                                 int32_t num_utts, int32_t t_max, const float* mean, const float* std_dev, int32_t batch_first,
+                                 float* out, float* mask, void* stream) {
+  using namespace b2w;
+  B2W_REQUIRE(feats && utt_frame_offset && out, "b2w_pad_normalise: null argument");
+  B2W_REQUIRE(width >= 1 && feat_stride >= width && t_max >= 0, "b2w_pad_normalise: bad width %d / stride / t_max", width);
+  const int64_t rows = (int64_t)t_max * num_utts;
+  if (num_utts <= 0 || rows == 0) return 0;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (width % 4 == 0 && feat_stride % 4 == 0 && al16(feats) && al16(out) && al16(mean) && al16(std_dev)) {
+    const int64_t quads = rows * (width / 4);
+    int64_t g4 = (quads + 511) / 512;
+    if (g4 > 148 * 16) g4 = 148 * 16;
+    pad_normalise4_kernel<<<(unsigned)g4, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(feats), feat_stride / 4, width / 4, utt_frame_offset, num_utts, t_max,
+        reinterpret_cast<const float4*>(mean), reinterpret_cast<const float4*>(std_dev), batch_first, reinterpret_cast<float4*>(out), mask);
+    return check_launch("pad_normalise4_kernel");
+  }
+  int64_t g = (rows + 7) / 8;
+  if (g > 148 * 32) g = 148 * 32;
+  pad_normalise_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(feats, feat_stride, width, utt_frame_offset, num_utts, t_max,
+                                                                     mean, std_dev, batch_first, out, mask);
+  return check_launch("pad_normalise_kernel");
+}
+
+extern "C" int b2w_unpad_denormalise(const float* padded, int32_t width, const int64_t* utt_frame_offset, const int32_t* frame_utt,
+                                     int64_t num_frames, int32_t num_utts, int32_t t_max, const float* mean, const float* std_dev,
+                                     int32_t batch_first, float* feats, int64_t feat_stride, void* stream) {
+  using namespace b2w;
+  B2W_REQUIRE(padded && utt_frame_offset && frame_utt && feats, "b2w_unpad_denormalise: null argument");
+  B2W_REQUIRE(width >= 1 && feat_stride >= width && t_max >= 0, "b2w_unpad_denormalise: bad width %d / stride / t_max", width);
+  if (num_utts <= 0 || num_frames <= 0) return 0;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (width % 4 == 0 && feat_stride % 4 == 0 && al16(feats) && al16(padded) && al16(mean) && al16(std_dev)) {
+    const int64_t quads = num_frames * (width / 4);
+    int64_t g4 = (quads + 511) / 512;
+    if (g4 > 148 * 16) g4 = 148 * 16;
+    unpad_denormalise4_kernel<<<(unsigned)g4, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(padded), width / 4, utt_frame_offset, frame_utt, num_frames, num_utts, t_max,
+        reinterpret_cast<const float4*>(mean), reinterpret_cast<const float4*>(std_dev), batch_first, reinterpret_cast<float4*>(feats),
+        feat_stride / 4);
+    return check_launch("unpad_denormalise4_kernel");
+  }
+  int64_t g = (num_frames + 7) / 8;
+  if (g > 148 * 32) g = 148 * 32;
+  unpad_denormalise_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(padded, width, utt_frame_offset, frame_utt, num_frames,
+                                                                         num_utts, t_max, mean, std_dev, batch_first, feats,
+                                                                         feat_stride);
+  return check_launch("unpad_denormalise_kernel");
+}
+
 extern "C" int b2w_lf0_vuv(const double* f0, const int64_t* utt_frame_offset, int32_t num_utts, double f0_silence_threshold,
                            double lf0_zero, float* lf0, float* vuv, int64_t out_stride, void* stream) {
   using namespace b2w;

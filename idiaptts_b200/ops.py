@@ -499,6 +499,55 @@ def stats_accumulate(feats, sums, gram=None, dim=None, stride=None, num_frames=N
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# trainer-facing batch
+# ----------------------------------------------------------------------------------------------------------------------
+def pad_normalise(feats, frame_off, mean=None, std_dev=None, batch_first=False, min_frames=None, want_mask=True, lengths=None):
+    """Ragged rows [F, W] f32 -> (padded [T_max, U, W] (or [U, T_max, W]), mask [T_max, U, 1] (or [U, T_max, 1]) | None,
+    lengths int64 [U] (host numpy)): preprocess_sample + prepare_batch of the reference in one HBM pass."""
+    lib = _lib.load()
+    if not feats.is_cuda:
+        raise ValueError("idiaptts_b200 operators need CUDA tensors (there is no CPU fallback)")
+    dev = _need_cuda(frame_off, mean, std_dev)
+    assert feats.dim() == 2 and feats.dtype == torch.float32 and feats.stride(1) == 1 and frame_off.dtype == torch.int64
+    W = feats.shape[1]
+    for v in (mean, std_dev):
+        assert v is None or (v.dtype == torch.float32 and v.numel() == W)
+    if lengths is None:  # one small device-to-host read; pass the host copy of the utterance lengths to stay asynchronous
+        lengths = np.diff(frame_off.cpu().numpy())
+    U = len(lengths)
+    assert U == frame_off.numel() - 1
+    t_max = int(lengths.max()) if U else 0
+    if min_frames is not None:
+        t_max = max(t_max, int(min_frames))
+    shape = (U, t_max, W) if batch_first else (t_max, U, W)
+    out = torch.empty(shape, dtype=torch.float32, device=dev)
+    mask = torch.empty(shape[:2] + (1,), dtype=torch.float32, device=dev) if want_mask else None
+    with torch.cuda.device(dev):
+        check(lib.b2w_pad_normalise(feats.data_ptr(), int(feats.stride(0)) if feats.shape[0] > 1 else W, W, frame_off.data_ptr(), U,
+                                    t_max, _ptr(mean), _ptr(std_dev), 1 if batch_first else 0, out.data_ptr(), _ptr(mask),
+                                    _stream(dev)), "b2w_pad_normalise")
+    return out, mask, lengths
+
+
+def unpad_denormalise(padded, frame_off, frame_utt, mean=None, std_dev=None, batch_first=False):
+    """Inverse of pad_normalise for network outputs: padded [T_max, U, W] (or [U, T_max, W]) -> ragged rows [F, W] * std + mean."""
+    lib = _lib.load()
+    dev = _need_cuda(padded, frame_off, frame_utt, mean, std_dev)
+    assert padded.dim() == 3 and padded.dtype == torch.float32 and frame_off.dtype == torch.int64 and frame_utt.dtype == torch.int32
+    U = frame_off.numel() - 1
+    t_max = padded.shape[1] if batch_first else padded.shape[0]
+    assert (padded.shape[0] if batch_first else padded.shape[1]) == U
+    W = padded.shape[2]
+    F = frame_utt.numel()
+    out = torch.empty((F, W), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.b2w_unpad_denormalise(padded.data_ptr(), W, frame_off.data_ptr(), frame_utt.data_ptr(), F, U, int(t_max), _ptr(mean),
+                                        _ptr(std_dev), 1 if batch_first else 0, out.data_ptr(), W, _stream(dev)),
+              "b2w_unpad_denormalise")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # synthesis
 # ----------------------------------------------------------------------------------------------------------------------
 _randn_tables = {}

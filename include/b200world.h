@@ -213,6 +213,20 @@ B2W_API int b2w_allpass_backward(const float* grad_y, const float* x, const floa
 B2W_API int64_t b2w_mlpg_workspace_doubles(int64_t num_frames, int32_t D);
 B2W_API int b2w_mlpg(const void* feats, int32_t feats_dtype, int64_t feat_stride, const double* var3, const int64_t* frame_off,
                      int32_t num_utts, int32_t D, double* workspace, double* out, int64_t out_stride, void* stream);
+/* ---- trainer-facing batch: for feature rows that are already on the device, replaces
+ * WorldFeatLabelGen.preprocess_sample ((x - mean) / std_dev, W:279-336) + ModularModelHandlerPyTorch.prepare_batch
+ * (idiaptts/src/neural_networks/pytorch/ModularModelHandlerPyTorch.py:389-499: pad_sequence to the longest utterance with
+ * zeros + sequence_mask) and, after inference, the inverse (postprocess_sample de-normalisation, W:338-355, back to ragged rows).
+ * feats [num_frames, width] f32 (row stride feat_stride); out [t_max, num_utts, width] (batch_first 0) or
+ * [num_utts, t_max, width] (1); mask (may be NULL) same leading shape, 1.0 on real frames; mean / std_dev [width] f32 or NULL.
+ * float32 arithmetic with separate operations: bit-identical to numpy. */
+B2W_API int b2w_pad_normalise(const float* feats, int64_t feat_stride, int32_t width, const int64_t* utt_frame_offset,
+                              int32_t num_utts, int32_t t_max, const float* mean, const float* std_dev, int32_t batch_first,
+                              float* out, float* mask, void* stream);
+B2W_API int b2w_unpad_denormalise(const float* padded, int32_t width, const int64_t* utt_frame_offset, const int32_t* frame_utt,
+                                  int64_t num_frames, int32_t num_utts, int32_t t_max, const float* mean, const float* std_dev,
+                                  int32_t batch_first, float* feats, int64_t feat_stride, void* stream);
+
 /* ---- F0 estimation: pyworld.dio (speed = 1) and pyworld.stonemask, the F0 half of pyworld.wav2world
  * (W:792; world/LF0LabelGen.py:263-264).  b->f0 is ignored by b2w_dio and is the initial track for b2w_stonemask; b->t holds
  * i * frame_period / 1000 per utterance (as pyworld.dio returns).  num_samples = utt_sample_offset[num_utts] (the host knows

@@ -303,3 +303,42 @@ def world_metrics(org_sp, org_lf0, org_vuv, org_bap, out_sp, out_lf0, out_vuv, o
     else:
         res["BAP distortion"] = math.sqrt(((org_bap - out_bap) ** 2).mean()) * (10.0 / math.log(10.0) * math.sqrt(2.0))
     return res
+
+
+# --------------------------------------------------------------------------------------------------------------
+# trainer-facing batch
+# --------------------------------------------------------------------------------------------------------------
+def prepare_batch(samples, mean=None, std_dev=None, batch_first=False, min_frames=None):
+    """WorldFeatLabelGen.preprocess_sample (world/WorldFeatLabelGen.py:279-336: np.float32((sample - mean) / std_dev)) on every
+    sample, then ModularModelHandlerPyTorch.prepare_batch (ModularModelHandlerPyTorch.py:389-499): zero-padding to the longest
+    sample (torch pad_sequence; min_frames pads further) and sequence_mask (:463-491).  Returns (padded, mask, lengths)."""
+    lengths = np.array([len(s) for s in samples], np.int64)
+    t_max = int(lengths.max()) if len(samples) else 0
+    if min_frames is not None:
+        t_max = max(t_max, int(min_frames))
+    W = samples[0].shape[1]
+    out = np.zeros((len(samples), t_max, W), np.float32)
+    mask = np.zeros((len(samples), t_max, 1), np.float32)
+    for b, s in enumerate(samples):
+        v = s.astype(np.float32)
+        if mean is not None:
+            v = np.float32((v - np.asarray(mean, np.float32)) / np.asarray(std_dev, np.float32))
+        out[b, :len(s)] = v
+        mask[b, :len(s)] = 1.0
+    if not batch_first:
+        out, mask = out.transpose(1, 0, 2).copy(), mask.transpose(1, 0, 2).copy()
+    return out, mask, lengths
+
+
+def unprepare_batch(padded, lengths, mean=None, std_dev=None, batch_first=False):
+    """Inverse for network outputs: WorldFeatLabelGen.postprocess_sample's de-normalisation (:338-355: sample * std_dev + mean) of the
+    real frames of every batch entry -> list of [T_b, W] float32."""
+    if not batch_first:
+        padded = padded.transpose(1, 0, 2)
+    out = []
+    for b, n in enumerate(lengths):
+        v = padded[b, :n].astype(np.float32)
+        if mean is not None:
+            v = np.float32(v * np.asarray(std_dev, np.float32) + np.asarray(mean, np.float32))
+        out.append(v)
+    return out

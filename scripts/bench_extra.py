@@ -78,3 +78,23 @@ def vtln():
 if __name__ == "__main__":
     synthesis()
     vtln()
+
+# ---- trainer-facing batch: ragged rows -> padded normalised [T_max, B, 64] and back, HBM-bound --------------
+try:
+    rng = np.random.default_rng(9)
+    lens = rng.integers(600, 1302, size=2048)
+    F = int(lens.sum())
+    feats_b = torch.randn((F, 64), device=dev)
+    off_b = torch.from_numpy(np.concatenate(([0], np.cumsum(lens))).astype(np.int64)).to(dev)
+    fu_b = torch.from_numpy(np.repeat(np.arange(len(lens), dtype=np.int32), lens)).to(dev)
+    mean_b, std_b = torch.randn(64, device=dev), torch.rand(64, device=dev) + 0.5
+    ms_p = timed(lambda: ops.pad_normalise(feats_b, off_b, mean_b, std_b, lengths=lens), steps=20)
+    padded_b, _, _ = ops.pad_normalise(feats_b, off_b, mean_b, std_b)
+    ms_u = timed(lambda: ops.unpad_denormalise(padded_b, off_b, fu_b, mean_b, std_b), steps=20)
+    bytes_p = F * 64 * 4 + padded_b.numel() * 4 + padded_b.shape[0] * padded_b.shape[1] * 4
+    bytes_u = 2 * F * 64 * 4
+    print(json.dumps({"config": "trainer batch: 2048 utterances (600-1301 frames) x 64 features, normalise + pad / un-pad + de-normalise",
+                      "pad_ms": ms_p, "unpad_ms": ms_u, "pad_GBs": bytes_p / ms_p / 1e6, "unpad_GBs": bytes_u / ms_u / 1e6,
+                      "pad_frac_of_hbm_peak": bytes_p / ms_p / 1e6 / PEAK, "unpad_frac_of_hbm_peak": bytes_u / ms_u / 1e6 / PEAK}))
+except Exception as e:  # noqa: BLE001
+    print("trainer batch bench failed:", e)
