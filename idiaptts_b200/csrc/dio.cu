@@ -191,7 +191,9 @@ __global__ void __launch_bounds__(kDioThreads) dio_lowcut_kernel(const void* x, 
 __global__ void __launch_bounds__(kDioThreads) dio_band_kernel(const int64_t* soff, int U, DioGeom g, const double* ylc_all,
                                                                double* ev, int64_t ev_plane, int32_t* counts) {
   extern __shared__ double sm[];
-  const int band = blockIdx.x % g.nb, u = blockIdx.x / g.nb;
+  // band-major CTA order: band 0 has the longest filter (8 x the work of the last band), so the heavy CTAs start first and
+  // the tail of the grid is made of short ones
+  const int band = blockIdx.x / U, u = blockIdx.x % U;
   const int H = g.half[band], ntaps = 4 * H, ntaps8 = (ntaps + 7) & ~7;
   double* wr = sm;                                   // [ntaps8] reversed Nuttall
   double* s = wr + ntaps8;                           // staging pad9(kDioTile + ntaps8 + 8)
@@ -241,7 +243,6 @@ __global__ void __launch_bounds__(kDioThreads) dio_band_kernel(const int64_t* so
       const int o = 8 * tid + c;
       v[c] = (o < kDioTile) ? sig[pad9(o)] : 0.0;
     }
-    double fine[4][8];
     unsigned flags[4] = {0, 0, 0, 0};
     unsigned long long cnt = 0;
 #pragma unroll
@@ -251,13 +252,10 @@ __global__ void __launch_bounds__(kDioThreads) dio_band_kernel(const int64_t* so
       const bool in1 = (o < step) && (i + 1 < ylen);
       const bool in2 = (o < step) && (i + 2 < ylen);
       const double a = v[c], b = v[c + 1], d0 = v[c] - v[c + 1], d1 = v[c + 1] - v[c + 2];
-      const double f_sig = (double)(i + 1) - a / (b - a);
-      const double f_dif = (double)(i + 1) - d0 / (d1 - d0);
       const bool e0 = in1 && (0.0 < a) && (b <= 0.0);
       const bool e1 = in1 && (0.0 < -a) && (-b <= 0.0);
       const bool e2 = in2 && (0.0 < d0) && (d1 <= 0.0);
       const bool e3 = in2 && (0.0 < -d0) && (-d1 <= 0.0);
-      fine[0][c] = f_sig; fine[1][c] = f_sig; fine[2][c] = f_dif; fine[3][c] = f_dif;
       flags[0] |= (unsigned)e0 << c; flags[1] |= (unsigned)e1 << c; flags[2] |= (unsigned)e2 << c; flags[3] |= (unsigned)e3 << c;
     }
 #pragma unroll
@@ -278,8 +276,13 @@ __global__ void __launch_bounds__(kDioThreads) dio_band_kernel(const int64_t* so
     for (int k = 0; k < 4; ++k) {
       int pos = run[k] + (int)((excl >> (16 * k)) & 0xffff);
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        if (flags[k] >> c & 1) list[k][pos++] = fine[k][c];
+      for (int c = 0; c < 8; ++c) {
+        if (flags[k] >> c & 1) {  // events are rare: the refinement (an fp64 division) is only done for them
+          const double a = (k < 2) ? v[c] : v[c] - v[c + 1];
+          const double b = (k < 2) ? v[c + 1] : v[c + 1] - v[c + 2];
+          list[k][pos++] = (double)(o0 + 8 * tid + c + 1) - a / (b - a);
+        }
+      }
     }
     __syncthreads();
     const unsigned long long tt = tile_tot;

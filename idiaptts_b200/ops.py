@@ -145,7 +145,7 @@ def raise_for_status(status, what):
 # ----------------------------------------------------------------------------------------------------------------------
 # F0 estimation: DIO + StoneMask
 # ----------------------------------------------------------------------------------------------------------------------
-DIO_MAX_CHUNK_SAMPLES = 48 * 1024 * 1024  # the event lists cost ~120 bytes of workspace per sample: 48 M samples ~ 6 GB
+DIO_MAX_CHUNK_SAMPLES = 96 * 1024 * 1024  # the event lists cost ~120 bytes of workspace per sample: 96 M samples ~ 12 GB (of 180 GB HBM)
 
 
 def _utt_chunks(sample_off_host, max_samples):
