@@ -501,6 +501,7 @@ render_kernel(const void* __restrict__ sp, const void* __restrict__ ap, const in
 }
 
 // ---- overlap-add ---------------------------------------------------------------------------------------------------------------
+constexpr int kOlaTile = 1024;  // output samples per CTA (4 per thread): the two binary searches are amortised over 8 KB of output
 template <typename OT>
 __global__ void __launch_bounds__(256)
 overlap_add_kernel(const double* __restrict__ response, const int64_t* __restrict__ utt_out_offset,
@@ -509,9 +510,8 @@ overlap_add_kernel(const double* __restrict__ response, const int64_t* __restric
   const int u = blockIdx.y;
   const int64_t yoff = utt_out_offset[u];
   const int ylen = (int)(utt_out_offset[u + 1] - yoff);
-  const int n0 = blockIdx.x * 256;
+  const int n0 = blockIdx.x * kOlaTile;
   if (n0 >= ylen) return;
-  const int n = n0 + threadIdx.x;
   const int64_t poff = utt_pulse_offset[u];
   const int P = num_pulses[u];
   const int* idx = pulse_index + poff;
@@ -522,34 +522,46 @@ overlap_add_kernel(const double* __restrict__ response, const int64_t* __restric
     const int mid = (lo + hi) >> 1;
     if (idx[mid] < n0 - H) lo = mid + 1; else hi = mid;
   }
-  // one past the last pulse whose response starts inside this tile: n_p - H + 1 <= n0 + 255
+  // one past the last pulse whose response starts inside this tile: n_p - H + 1 <= n0 + kOlaTile - 1
   int end = lo;
   hi = P;
   while (end < hi) {
     const int mid = (end + hi) >> 1;
-    if (idx[mid] - H + 1 <= n0 + 255) end = mid + 1; else hi = mid;
+    if (idx[mid] - H + 1 <= n0 + kOlaTile - 1) end = mid + 1; else hi = mid;
   }
-  // Four pulses per step: the index loads and the four streaming response loads are independent, so every thread keeps 32
-  // bytes in flight instead of 8 (the kernel is HBM-bound; one dependent 8-byte load per thread left the memory system under-
-  // subscribed).  The sum stays in pulse order: bit-identical to the sequential loop.
+  // Two pulses x four samples per step: eight independent streaming 8-byte loads in flight per thread (the kernel is HBM-bound;
+  // one dependent load per thread and pulse left the memory system under-subscribed).  Every sample still sums its pulses in
+  // pulse order: bit-identical to the sequential loop.
   const double* rbase = response + poff * (int64_t)fft_size;
-  double acc = 0.0;
+  const int n = n0 + threadIdx.x;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
   int p = lo;
-  for (; p + 4 <= end; p += 4) {
-    int j[4];
-    double v[4];
+  for (; p + 2 <= end; p += 2) {
+    const int s0 = idx[p] - H + 1, s1 = idx[p + 1] - H + 1;
+    double v[2][4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) j[k] = n - (idx[p + k] - H + 1);
+    for (int q = 0; q < 4; ++q) {
+      const int j0 = n + 256 * q - s0, j1 = n + 256 * q - s1;
+      v[0][q] = (j0 >= 0 && j0 < fft_size) ? __ldcs(rbase + (int64_t)p * fft_size + j0) : 0.0;
+      v[1][q] = (j1 >= 0 && j1 < fft_size) ? __ldcs(rbase + (int64_t)(p + 1) * fft_size + j1) : 0.0;
+    }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = (j[k] >= 0 && j[k] < fft_size) ? __ldcs(rbase + (int64_t)(p + k) * fft_size + j[k]) : 0.0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) acc += v[k];
+    for (int q = 0; q < 4; ++q) {
+      acc[q] += v[0][q];
+      acc[q] += v[1][q];
+    }
   }
   for (; p < end; ++p) {
-    const int j = n - (idx[p] - H + 1);
-    if (j >= 0 && j < fft_size) acc += __ldcs(rbase + (int64_t)p * fft_size + j);
+    const int s0 = idx[p] - H + 1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = n + 256 * q - s0;
+      if (j >= 0 && j < fft_size) acc[q] += __ldcs(rbase + (int64_t)p * fft_size + j);
+    }
   }
-  if (n < ylen) y[yoff + n] = (OT)acc;
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (n + 256 * q < ylen) y[yoff + n + 256 * q] = (OT)acc[q];
 }
 
 // y[n] = x[n] + p y[n-1] (scipy.signal.lfilter([1], [1, -p])) on the float32-rounded waveform, one thread per utterance
@@ -652,7 +664,7 @@ extern "C" int b2w_synth_overlap_add(const double* response, const int64_t* utt_
   B2W_REQUIRE(num_utts <= 65535, "b2w_synth_overlap_add: at most 65535 utterances per call");
   if (num_utts == 0 || max_out_per_utt == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid((unsigned)((max_out_per_utt + 255) / 256), (unsigned)num_utts);
+  dim3 grid((unsigned)((max_out_per_utt + kOlaTile - 1) / kOlaTile), (unsigned)num_utts);
   if (y_dtype == B2W_F64)
     overlap_add_kernel<double><<<grid, 256, 0, st>>>(response, utt_out_offset, utt_pulse_offset, num_pulses, pulse_index, fft_size, (double*)y);
   else

@@ -75,7 +75,7 @@ def vtln():
                       "hbm_peak_GBs": PEAK}), flush=True)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "batch_only" not in sys.argv:
     synthesis()
     vtln()
 
