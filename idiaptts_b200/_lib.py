@@ -51,8 +51,9 @@ _SIGNATURES = {
     "b2w_stats_accumulate": (c_int32, [c_void_p, c_int64, c_int32, c_int64, c_void_p, c_void_p, c_void_p]),
     "b2w_synth_max_pulses": (c_int64, [c_int64, c_int32]),
     "b2w_synth_randn_table": (c_int32, [c_void_p, c_int64, c_void_p]),
+    "b2w_synth_timebase_chunks": (c_int64, [c_int64]),
     "b2w_synth_timebase": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_double, c_int32,
-                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2w_synth_render": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_int64, c_int32, c_double, c_int32, c_int64, c_void_p, c_void_p]),
     "b2w_synth_overlap_add": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int64,

@@ -200,78 +200,110 @@ __global__ void __launch_bounds__(32) phase_scan_kernel(const int64_t* __restric
   }
 }
 
-// (3) pulse detection and ordered compaction, one CTA per utterance: a pulse sits at sample i when
-// |wrap[i+1] - wrap[i]| > pi, wrap = fmod(total, 2 pi).
+// (3) pulse detection and ordered compaction: a pulse sits at sample i when |wrap[i+1] - wrap[i]| > pi, wrap = fmod(total, 2 pi).
+// Every utterance is cut into chunks of kPulseChunk jumps, one CTA each (a 256-utterance batch used to keep 256 CTAs busy for
+// 1.4 ms with strided loads): pass 1 counts the pulses of every chunk, pass 2 adds up the counts of the chunks before it and
+// writes its pulses in order.  Loads are coalesced, one fmod per jump (the neighbour's value comes by shuffle).
+constexpr int kPulseChunk = 4096;
+
+// fmod(x, 2 pi) for x >= 0, bit-identical to the C library function (whose result is the EXACT remainder) in a handful of
+// instructions instead of the ~450 of the generic fmod: with q = floor(fl(x / y)) in {floor(x / y), floor(x / y) + 1} (rounding is
+// monotonic, so the quotient is never under-estimated), r = x - q y is a multiple of ulp(y) = 2^-50 of magnitude < 8, hence
+// exactly representable, and the fused multiply-add delivers it without rounding; q one too large shows as r < 0.
+__device__ __forceinline__ double fmod_two_pi(double x) {
+  const double y = 2.0 * kPi;
+  if (x < y) return x;
+  const double q = floor(__ddiv_rn(x, y));
+  double r = __fma_rn(-q, y, x);
+  if (r < 0.0) r = __fma_rn(-(q - 1.0), y, x);
+  return r;
+}
+
+template <bool WRITE>
 __global__ void __launch_bounds__(kTbThreads)
-pulse_kernel(const double* __restrict__ f0_all, const int64_t* __restrict__ utt_frame_offset,
-             const int64_t* __restrict__ utt_out_offset, const int64_t* __restrict__ utt_pulse_offset, int fs_i,
-             double frame_period_ms, int fft_size, const double* __restrict__ phase, int* __restrict__ pulse_index,
-             double* __restrict__ pulse_shift, uint8_t* __restrict__ pulse_vuv, int* __restrict__ num_pulses,
-             int* __restrict__ status) {
-  __shared__ int sh_i[kTbThreads / 32 + 1];
-  const int u = blockIdx.x;
+pulse_chunk_kernel(const double* __restrict__ f0_all, const int64_t* __restrict__ utt_frame_offset,
+                   const int64_t* __restrict__ utt_out_offset, const int64_t* __restrict__ utt_pulse_offset, int fs_i,
+                   double frame_period_ms, int fft_size, const double* __restrict__ phase, int* __restrict__ chunk_counts,
+                   int max_chunks, int* __restrict__ pulse_index, double* __restrict__ pulse_shift, uint8_t* __restrict__ pulse_vuv,
+                   int* __restrict__ num_pulses, int* __restrict__ status) {
+  __shared__ int sh_w[kTbThreads / 32];
+  const int u = blockIdx.y, c = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const double* f0 = f0_all + utt_frame_offset[u];
   const int T = (int)(utt_frame_offset[u + 1] - utt_frame_offset[u]);
   const int64_t yoff = utt_out_offset[u];
   const int ylen = (int)(utt_out_offset[u + 1] - yoff);
+  const int njump = (T < 1 || ylen < 2) ? 0 : ylen - 1;
+  const int j0 = c * kPulseChunk;
+  int* my_count = chunk_counts + (int64_t)u * max_chunks + c;
+  if (j0 >= njump) {
+    if (!WRITE && tid == 0) *my_count = 0;
+    if (WRITE && c == 0 && njump == 0 && tid == 0) num_pulses[u] = 0;
+    return;
+  }
+  const int j1 = min(njump, j0 + kPulseChunk);
+  const double two_pi = 2.0 * kPi;
+  const double* tot = phase + yoff;
+  int running = 0;
+  if (WRITE) {
+    for (int k = 0; k < c; ++k) running += chunk_counts[(int64_t)u * max_chunks + k];  // <= a few dozen values, L2 hits
+  }
+  const double* f0 = f0_all + utt_frame_offset[u];
   const int64_t poff = utt_pulse_offset[u];
   const int cap = (int)(utt_pulse_offset[u + 1] - poff);
   const double fs = (double)fs_i;
   const double fp = frame_period_ms / 1000.0;
   const double lowest_f0 = (double)(fs_i / fft_size) + 1.0;
-  const double two_pi = 2.0 * kPi;
-  if (T < 1 || ylen < 2) {
-    if (tid == 0) num_pulses[u] = 0;
-    return;
-  }
-  const double* tot = phase + yoff;
-  // this thread examines the jumps i -> i+1 for i in [beg, end)
-  const int njump = ylen - 1;
-  const int per = (njump + kTbThreads - 1) / kTbThreads;
-  const int beg = min(njump, tid * per), end = min(njump, beg + per);
-  int my_base = 0;
-  for (int sweep = 0; sweep < 2; ++sweep) {
-    int cnt = 0;
-    double w0 = beg < end ? fmod(tot[beg], two_pi) : 0.0;
-    for (int i = beg; i < end; ++i) {
-      const double w1 = fmod(tot[i + 1], two_pi);
-      if (fabs(w1 - w0) > kPi) {
-        if (sweep == 1) {
-          const int slot = my_base + cnt;
-          if (slot < cap) {
-            const double y1 = w0 - two_pi;
-            const double x = -y1 / (w1 - y1);
-            int k = max(1, min(T, (int)((double)i / fs / fp)));
-            while (k > 1 && (double)i / fs < __dmul_rn((double)(k - 1), fp)) --k;
-            double v;
-            sample_f0(f0, T, lowest_f0, fp, fs, i, k, v);
-            pulse_index[poff + slot] = i;
-            pulse_shift[poff + slot] = x / fs;
-            pulse_vuv[poff + slot] = v > 0.5 ? 1 : 0;
-          }
-        }
-        ++cnt;
-      }
-      w0 = w1;
+  int warp_total = 0;  // pass 1: pulses seen by this warp
+  for (int s0 = j0; s0 < j1; s0 += kTbThreads) {
+    const int i = s0 + tid;
+    const bool valid = i < j1;
+    // wrap[i] for this lane's jump; wrap[i+1] from the next lane (the last lane of a warp computes it itself)
+    const double w0 = valid ? fmod_two_pi(tot[i]) : 0.0;
+    double w1 = __shfl_down_sync(0xffffffffu, w0, 1);
+    if (valid && (lane == 31 || i + 1 >= j1)) w1 = fmod_two_pi(tot[i + 1]);
+    const bool is_pulse = valid && fabs(w1 - w0) > kPi;
+    const unsigned ball = __ballot_sync(0xffffffffu, is_pulse);
+    if (!WRITE) {
+      warp_total += __popc(ball);
+      continue;
     }
-    if (sweep == 0) {
-      int inc = cnt;
+    if (lane == 0) sh_w[warp] = __popc(ball);
+    __syncthreads();
+    int before = 0, slab = 0;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += v;
-      }
-      if (lane == 31) sh_i[warp] = inc;
-      __syncthreads();
-      my_base = inc - cnt;
-      for (int w = 0; w < warp; ++w) my_base += sh_i[w];
-      if (tid == kTbThreads - 1) {
-        const int totalp = my_base + cnt;
-        if (totalp > cap) atomicOr(status, B2W_STATUS_F0_TOO_HIGH);
-        num_pulses[u] = min(totalp, cap);
+    for (int w = 0; w < kTbThreads / 32; ++w) {
+      const int v = sh_w[w];
+      before += (w < warp) ? v : 0;
+      slab += v;
+    }
+    if (is_pulse) {
+      const int slot = running + before + __popc(ball & ((1u << lane) - 1u));
+      if (slot < cap) {
+        const double y1 = w0 - two_pi;
+        const double x = -y1 / (w1 - y1);
+        int k = max(1, min(T, (int)((double)i / fs / fp)));
+        while (k > 1 && (double)i / fs < __dmul_rn((double)(k - 1), fp)) --k;
+        double v;
+        sample_f0(f0, T, lowest_f0, fp, fs, i, k, v);
+        pulse_index[poff + slot] = i;
+        pulse_shift[poff + slot] = x / fs;
+        pulse_vuv[poff + slot] = v > 0.5 ? 1 : 0;
       }
     }
+    running += slab;
+    __syncthreads();  // sh_w is rewritten by the next slab
+  }
+  if (!WRITE) {
+    if (lane == 0) sh_w[warp] = warp_total;
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int w = 0; w < kTbThreads / 32; ++w) t += sh_w[w];
+      *my_count = t;
+    }
+  } else if (j1 == njump && tid == 0) {  // the last chunk of the utterance knows the total
+    if (running > cap) atomicOr(status, B2W_STATUS_F0_TOO_HIGH);
+    num_pulses[u] = min(running, cap);
   }
 }
 
@@ -582,6 +614,10 @@ extern "C" int64_t b2w_synth_max_pulses(int64_t y_length, int32_t fs) {
   return (int64_t)((double)y_length * 1200.0 / (double)fs) + 64;
 }
 
+extern "C" int64_t b2w_synth_timebase_chunks(int64_t max_out_per_utt) {
+  return (max_out_per_utt + b2w::kPulseChunk - 1) / b2w::kPulseChunk;
+}
+
 extern "C" int b2w_synth_randn_table(double* table, int64_t n, void* stream) {
   using namespace b2w;
   B2W_REQUIRE(table, "b2w_synth_randn_table: null argument");
@@ -595,10 +631,11 @@ extern "C" int b2w_synth_randn_table(double* table, int64_t n, void* stream) {
 
 extern "C" int b2w_synth_timebase(const double* f0, const int64_t* utt_frame_offset, const int64_t* utt_out_offset,
                                   const int64_t* utt_pulse_offset, int32_t num_utts, int64_t max_out_per_utt, int32_t fs,
-                                  double frame_period_ms, int32_t fft_size, double* phase_ws, int32_t* pulse_index,
-                                  double* pulse_shift, uint8_t* pulse_vuv, int32_t* num_pulses, int32_t* status, void* stream) {
+                                  double frame_period_ms, int32_t fft_size, double* phase_ws, int32_t* chunk_ws,
+                                  int32_t* pulse_index, double* pulse_shift, uint8_t* pulse_vuv, int32_t* num_pulses,
+                                  int32_t* status, void* stream) {
   using namespace b2w;
-  B2W_REQUIRE(f0 && utt_frame_offset && utt_out_offset && utt_pulse_offset && phase_ws && pulse_index && pulse_shift &&
+  B2W_REQUIRE(f0 && utt_frame_offset && utt_out_offset && utt_pulse_offset && phase_ws && chunk_ws && pulse_index && pulse_shift &&
                   pulse_vuv && num_pulses && status,
               "b2w_synth_timebase: null argument");
   B2W_REQUIRE(num_utts <= 65535, "b2w_synth_timebase: at most 65535 utterances per call");
@@ -611,9 +648,18 @@ extern "C" int b2w_synth_timebase(const double* f0, const int64_t* utt_frame_off
   phase_scan_kernel<<<num_utts, 32, 0, st>>>(utt_out_offset, phase_ws);
   rc = check_launch("phase_scan_kernel");
   if (rc) return rc;
-  pulse_kernel<<<num_utts, kTbThreads, 0, st>>>(f0, utt_frame_offset, utt_out_offset, utt_pulse_offset, fs, frame_period_ms,
-                                                fft_size, phase_ws, pulse_index, pulse_shift, pulse_vuv, num_pulses, status);
-  return check_launch("pulse_kernel");
+  const int max_chunks = (int)((max_out_per_utt + kPulseChunk - 1) / kPulseChunk);
+  int* chunk_counts = chunk_ws;
+  dim3 pgrid((unsigned)max_chunks, (unsigned)num_utts);
+  pulse_chunk_kernel<false><<<pgrid, kTbThreads, 0, st>>>(f0, utt_frame_offset, utt_out_offset, utt_pulse_offset, fs, frame_period_ms,
+                                                         fft_size, phase_ws, chunk_counts, max_chunks, pulse_index, pulse_shift,
+                                                         pulse_vuv, num_pulses, status);
+  rc = check_launch("pulse_chunk_kernel<count>");
+  if (rc) return rc;
+  pulse_chunk_kernel<true><<<pgrid, kTbThreads, 0, st>>>(f0, utt_frame_offset, utt_out_offset, utt_pulse_offset, fs, frame_period_ms,
+                                                        fft_size, phase_ws, chunk_counts, max_chunks, pulse_index, pulse_shift,
+                                                        pulse_vuv, num_pulses, status);
+  return check_launch("pulse_chunk_kernel<write>");
 }
 
 extern "C" int b2w_synth_render(const void* sp, const void* ap, int32_t plane_dtype, const int64_t* utt_frame_offset,

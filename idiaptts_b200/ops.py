@@ -605,8 +605,9 @@ def synth_timebase(f0, frame_off, fs, fft_size, frame_period=5.0, status=None):
     p.tab = randn_table(int(ylen.max()) + 1, dev)
     with torch.cuda.device(dev):
         phase_ws = torch.empty(int(out_off[-1]), dtype=torch.float64, device=dev)
+        chunk_ws = torch.empty(U * int(lib.b2w_synth_timebase_chunks(int(ylen.max()))), dtype=torch.int32, device=dev)
         check(lib.b2w_synth_timebase(f0.data_ptr(), frame_off.data_ptr(), p.d_out_off.data_ptr(), p.d_pulse_off.data_ptr(), U,
-                                     int(ylen.max()), int(fs), float(frame_period), fft_size, phase_ws.data_ptr(),
+                                     int(ylen.max()), int(fs), float(frame_period), fft_size, phase_ws.data_ptr(), chunk_ws.data_ptr(),
                                      p.pulse_index.data_ptr(), p.pulse_shift.data_ptr(), p.pulse_vuv.data_ptr(),
                                      p.num_pulses.data_ptr(), p.status.data_ptr(), _stream(dev)), "b2w_synth_timebase")
     return p

@@ -153,19 +153,19 @@ B2W_API int b2w_stats_accumulate(const float* feats, int64_t feat_stride, int32_
 /* ---- synthesis: replaces pyworld.synthesize (W:943) on a ragged batch. ---------------------------------------
  * Inputs are the pyworld arguments per frame: f0 [F], sp [F, K] power, ap [F, K] (sp/ap dtype F64|F32).
  * Stage 1 - time base: per-sample phase increments (parallel), running phase (sequential per utterance, exactly
- *   WORLD's rounding: pulse positions are threshold decisions), pulse detection.  phase_ws: one double per output
- *   sample.  pulse_index/pulse_shift/pulse_vuv: [capacity] per-utterance slabs at utt_pulse_offset[u] (caller sizes
+ *   WORLD's rounding: pulse positions are threshold decisions), pulse detection (chunk-parallel: count pass + ordered write
+ *   pass).  phase_ws: one double per output sample; chunk_ws: num_utts * b2w_synth_timebase_chunks(max_out_per_utt) int32.  pulse_index/pulse_shift/pulse_vuv: [capacity] per-utterance slabs at utt_pulse_offset[u] (caller sizes
  *   them with b2w_synth_max_pulses); num_pulses [num_utts] int32 out.
  * Stage 2 - render: one CTA per pulse builds the periodic + aperiodic minimum-phase responses and writes
  *   response [total pulses, fft_size] f64.
  * Stage 3 - overlap-add: atomic-free gather; every output sample sums, in pulse order, the responses covering it. */
 B2W_API int64_t b2w_synth_max_pulses(int64_t y_length, int32_t fs);
 B2W_API int b2w_synth_randn_table(double* table, int64_t n, void* stream); /* WORLD randn() stream after randn_reseed(): xorshift128 with GF(2) jump-ahead */
+B2W_API int64_t b2w_synth_timebase_chunks(int64_t max_out_per_utt); /* chunk_ws needs num_utts * this many int32 */
 B2W_API int b2w_synth_timebase(const double* f0, const int64_t* utt_frame_offset, const int64_t* utt_out_offset,
                                const int64_t* utt_pulse_offset, int32_t num_utts, int64_t max_out_per_utt, int32_t fs,
-                               double frame_period_ms, int32_t fft_size, double* phase_ws /* [total output samples] */,
-                               int32_t* pulse_index, double* pulse_shift, uint8_t* pulse_vuv, int32_t* num_pulses,
-                               int32_t* status, void* stream);
+                               double frame_period_ms, int32_t fft_size, double* phase_ws, int32_t* chunk_ws, int32_t* pulse_index,
+                               double* pulse_shift, uint8_t* pulse_vuv, int32_t* num_pulses, int32_t* status, void* stream);
 B2W_API int b2w_synth_render(const void* sp, const void* ap, int32_t plane_dtype, const int64_t* utt_frame_offset,
                      const int64_t* utt_pulse_offset, const int32_t* num_pulses, int32_t num_utts,
                      const int32_t* pulse_index, const double* pulse_shift, const uint8_t* pulse_vuv,
