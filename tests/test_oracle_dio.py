@@ -39,3 +39,16 @@ def test_dio_helpers():
     f0, t = dio_np.wav2world_f0(x, fs)
     mid = f0[40:160]
     assert np.all(mid > 0) and np.abs(mid - 150.0).max() < 0.5
+
+
+def test_oracle_dio_is_homogeneous():
+    """DIO only looks at zero crossings: scaling the waveform by a power of two (exact in IEEE arithmetic) changes nothing."""
+    fs = 16000
+    rng = np.random.default_rng(2)
+    n = np.arange(fs)
+    x = 0.3 * np.sin(2 * np.pi * (120.0 + 20.0 * n / fs) * n / fs) + 0.01 * rng.standard_normal(fs)
+    a, t = dio_np.dio(x, fs)
+    b, _ = dio_np.dio(0.25 * x, fs)
+    assert np.array_equal(a, b) and (a > 0).sum() > 50
+    # StoneMask adds 1e-12 to an amplitude sum (FixF0): homogeneous to ~1e-12 only
+    np.testing.assert_allclose(dio_np.stonemask(x, a, t, fs), dio_np.stonemask(0.25 * x, b, t, fs), rtol=1e-9)

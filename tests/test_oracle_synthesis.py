@@ -47,3 +47,31 @@ def test_depreemphasis_inverts_preemphasis():
     rng = np.random.default_rng(0)
     x = rng.standard_normal(1000)
     np.testing.assert_allclose(glue_np.depreemphasis(glue_np.preemphasis(x, 0.97), 0.97), x, atol=1e-9)
+
+
+def test_exact_fmod_two_pi_argument():
+    """The synthesis kernels compute fmod(x, 2 pi) as fma(-q, y, x) with q = floor(fl(x / y)) (q - 1 when the result is negative),
+    csrc/synth.cu fmod_two_pi.  This is the C fmod bit for bit: the quotient is never under-estimated, and the remainder is a
+    multiple of 2^-50 below 8, i.e. exactly representable, so the fused multiply-add does not round.  Checked here with exact
+    rational arithmetic (the fma) against numpy's fmod, including arguments within an ulp of a multiple of 2 pi and the running
+    phase WORLD produces for the 500 Hz unvoiced default at 16 kHz."""
+    from fractions import Fraction
+    rng = np.random.default_rng(0)
+    y = 2.0 * 3.1415926535897932384
+    xs = np.concatenate([rng.uniform(0, 2.5e5, 4000),
+                         y * rng.integers(1, 30000, 4000) * (1 + rng.choice([-1, 0, 1], 4000) * 2.0 ** -52),
+                         np.cumsum(np.full(3000, 2 * np.pi * 500 / 16000))])
+    for x in xs:
+        x = float(x)
+        if x < y:
+            r = x
+        else:
+            q = np.floor(x / y)
+            exact = Fraction(x) - Fraction(q) * Fraction(y)
+            r = float(exact)
+            assert Fraction(r) == exact            # representable: the fma returns it unrounded
+            if r < 0:
+                exact = Fraction(x) - Fraction(q - 1) * Fraction(y)
+                r = float(exact)
+                assert Fraction(r) == exact
+        assert r == float(np.fmod(x, y)) and 0.0 <= r < y
