@@ -75,3 +75,33 @@ def test_exact_fmod_two_pi_argument():
                 r = float(exact)
                 assert Fraction(r) == exact
         assert r == float(np.fmod(x, y)) and 0.0 <= r < y
+
+
+def test_exact_parallel_phase_scan_prototype():
+    """scripts/exact_phase_scan_prototype.py: the running phase total[i] = fl(total[i-1] + inc[i]) evaluated by composing
+    two-state integer maps (associative, hence parallel) is bit-identical to the sequential float64 loop -- also when many
+    increments are exact half-ulp ties (round half to even depends on the parity of the running total) and across binade
+    crossings.  Design aid for the next round's synthesis time-base kernel."""
+    import importlib.util
+    import math
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "exact_phase_scan_prototype", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts",
+                                                   "exact_phase_scan_prototype.py"))
+    proto = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(proto)
+    rng = np.random.default_rng(5)
+    # WORLD-like increments: voiced stretches with varying F0 between 500 Hz unvoiced defaults, three sampling rates
+    for fs in (16000, 22050, 48000):
+        inc = np.full(12000, 2.0 * math.pi * 500.0 / fs)
+        inc[2000:6000] = 2.0 * math.pi * rng.uniform(71, 400, 4000) / fs
+        assert np.array_equal(proto.sequential(inc), proto.exact_scan(inc, block=128))
+    # forced ties: increments of the form (k + 1/2) ulp of the binade the total lives in, mixed with ordinary ones
+    u = 2.0 ** (10 - 52)                      # ulp for totals in [2^10, 2^11)
+    inc = np.concatenate(([1024.0 + 3 * u], (rng.integers(1, 1000, 3000) + 0.5) * u, rng.uniform(0, 1e-3, 3000),
+                          (rng.integers(1, 2 ** 30, 3000) + 0.5) * u, rng.uniform(0.1, 1.0, 4000),
+                          (rng.integers(1, 1000, 2000) + 0.5) * 2 * u))
+    rng.shuffle(inc[1:])
+    a, b = proto.sequential(inc), proto.exact_scan(inc, block=64)
+    assert np.array_equal(a, b)
+    assert a[-1] > 2048.0                     # the run crossed into the next binade (where half of the forced ties tie again)
