@@ -200,6 +200,157 @@ __global__ void __launch_bounds__(32) phase_scan_kernel(const int64_t* __restric
   }
 }
 
+// (2') The same running sum, parallel AND bit-identical (scripts/exact_phase_scan_prototype.py, tests/test_oracle_synthesis.py):
+// while the total stays inside one binade [2^e, 2^(e+1)) it is an integer multiple T of u = 2^(e-52) and
+//     fl(T u + x) = (T + X + d) u,  X = floor(x / u),  rho = x - X u,  d = [rho > u/2], and for an exact tie d = (T + X) & 1,
+// i.e. one addition is the integer map T -> T + X + d(parity of T).  A run of additions is described by two integers (the
+// increment for an even / an odd incoming T) and these pairs compose associatively, so a block scan over them reproduces every
+// sequentially rounded total.  A binade crossing (T reaching 2^53) is found by the scan; the crossing addition itself is one
+// ordinary rounded add, after which the pass restarts with u doubled (~17 crossings per utterance).
+// One CTA per utterance, tiles of 2048 increments (8 per thread).
+constexpr int kScanThreads = 256;
+constexpr int kScanPer = 8;
+constexpr int kScanTile = kScanThreads * kScanPer;
+constexpr long long kScanSat = 1ll << 60;   // increments saturate here: anything >= 2^53 is "crossed", only that matters
+
+struct PMap { long long e, o; };            // increment for an even / odd incoming T
+__device__ __forceinline__ long long psat(long long v) { return v > kScanSat ? kScanSat : v; }
+__device__ __forceinline__ PMap pcompose(PMap a, PMap b) {  // a first, then b
+  PMap r;
+  r.e = psat(a.e + ((a.e & 1) ? b.o : b.e));
+  r.o = psat(a.o + (((1 + a.o) & 1) ? b.o : b.e));
+  return r;
+}
+
+__global__ void __launch_bounds__(kScanThreads) phase_scan_exact_kernel(const int64_t* __restrict__ utt_out_offset,
+                                                                        double* __restrict__ phase) {
+  __shared__ PMap warp_map[kScanThreads / 32];
+  __shared__ double sh_t;
+  __shared__ int sh_cross;
+  const int u_idx = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t yoff = utt_out_offset[u_idx];
+  const int n = (int)(utt_out_offset[u_idx + 1] - yoff);
+  double* ph = phase + yoff;
+  // prologue: the first samples sequentially (0 + x is exact, the total doubles every few samples at the start)
+  const int pro = min(n, 64);
+  if (tid == 0) {
+    double t = 0.0;
+    for (int i = 0; i < pro; ++i) {
+      t = __dadd_rn(t, ph[i]);
+      ph[i] = t;
+    }
+    sh_t = t;
+  }
+  __syncthreads();
+  double t = sh_t;
+  if (!(t >= 1e-200) || !(t < 1e200)) {  // degenerate totals (zero / tiny / huge / NaN): keep the plain sequential chain
+    if (tid == 0) {
+      for (int i = pro; i < n; ++i) {
+        t = __dadd_rn(t, ph[i]);
+        ph[i] = t;
+      }
+    }
+    return;
+  }
+  for (int tile0 = pro; tile0 < n; tile0 += kScanTile) {
+    const int tile1 = min(n, tile0 + kScanTile);
+    const int base = tile0 + tid * kScanPer;      // this thread's elements base .. base + 7
+    double x[kScanPer];
+#pragma unroll
+    for (int k = 0; k < kScanPer; ++k) x[k] = (base + k < tile1) ? ph[base + k] : 0.0;
+    int p = tile0;                                 // elements before p are committed
+    while (p < tile1) {
+      // unit of the current binade
+      const int e = (int)((__double_as_longlong(t) >> 52) & 0x7ff) - 1023;
+      const double u = __longlong_as_double((long long)(e - 52 + 1023) << 52);
+      const double inv_u = __longlong_as_double((long long)(52 - e + 1023) << 52);
+      const long long T0 = (long long)(t * inv_u);
+      const long long limit = 1ll << 53;
+      PMap m[kScanPer];
+      PMap mine = {0, 0};
+#pragma unroll
+      for (int k = 0; k < kScanPer; ++k) {
+        m[k].e = m[k].o = 0;
+        if (base + k >= p && base + k < tile1) {
+          const double xs = x[k] * inv_u;          // exact power-of-two scaling
+          const double Xf = floor(xs);
+          const double rho = xs - Xf;              // exact, in [0, 1)
+          long long X = (Xf >= 1.1529215046068469e18) ? kScanSat : (long long)Xf;
+          const long long b = psat(X + (rho > 0.5 ? 1 : 0));
+          const bool tie = rho == 0.5;
+          m[k].e = b + ((tie && (X & 1)) ? 1 : 0);
+          m[k].o = b + ((tie && !(X & 1)) ? 1 : 0);
+        }
+        mine = pcompose(mine, m[k]);
+      }
+      // block exclusive scan of the per-thread maps under pcompose
+      PMap incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        PMap prev;
+        prev.e = __shfl_up_sync(0xffffffffu, incl.e, o);
+        prev.o = __shfl_up_sync(0xffffffffu, incl.o, o);
+        if (lane >= o) incl = pcompose(prev, incl);
+      }
+      PMap excl;
+      excl.e = __shfl_up_sync(0xffffffffu, incl.e, 1);
+      excl.o = __shfl_up_sync(0xffffffffu, incl.o, 1);
+      if (lane == 0) excl.e = excl.o = 0;
+      __syncthreads();                             // previous pass has read warp_map / sh_cross / sh_t
+      if (lane == 31) warp_map[warp] = incl;
+      if (tid == 0) sh_cross = tile1;
+      __syncthreads();
+      PMap pre = {0, 0};
+      for (int w = 0; w < warp; ++w) pre = pcompose(pre, warp_map[w]);
+      pre = pcompose(pre, excl);
+      // expand this thread's elements from its incoming T
+      long long Tk = T0 + ((T0 & 1) ? pre.o : pre.e);
+      bool alive = Tk < limit;                     // false: a crossing happened before this thread's first element
+      double outv[kScanPer];
+      int my_cross = tile1;
+      long long T_before_cross = Tk;
+#pragma unroll
+      for (int k = 0; k < kScanPer; ++k) {
+        outv[k] = 0.0;
+        if (base + k >= p && base + k < tile1 && alive) {
+          const long long Tn = Tk + ((Tk & 1) ? m[k].o : m[k].e);
+          if (Tn >= limit) {
+            alive = false;
+            my_cross = base + k;
+            T_before_cross = Tk;
+          } else {
+            Tk = Tn;
+            outv[k] = (double)Tk * u;              // exact: Tk < 2^53, u a power of two
+          }
+        }
+      }
+      if (my_cross < tile1) atomicMin(&sh_cross, my_cross);
+      __syncthreads();
+      const int cross = sh_cross;
+#pragma unroll
+      for (int k = 0; k < kScanPer; ++k)
+        if (base + k >= p && base + k < min(cross, tile1)) ph[base + k] = outv[k];
+      if (cross < tile1) {
+        // the crossing addition: an ordinary rounded add from the last committed total
+        if (my_cross == cross) {
+          const double tb = (double)T_before_cross * u;
+          const double tn = __dadd_rn(tb, x[cross - base]);
+          ph[cross] = tn;
+          sh_t = tn;
+        }
+        p = cross + 1;
+      } else {
+        // the owner of the last element publishes the total
+        if (tile1 - 1 >= base && tile1 - 1 < base + kScanPer) sh_t = (double)Tk * u;
+        p = tile1;
+      }
+      __syncthreads();
+      t = sh_t;
+    }
+  }
+}
+
 // (3) pulse detection and ordered compaction: a pulse sits at sample i when |wrap[i+1] - wrap[i]| > pi, wrap = fmod(total, 2 pi).
 // Every utterance is cut into chunks of kPulseChunk jumps, one CTA each (a 256-utterance batch used to keep 256 CTAs busy for
 // 1.4 ms with strided loads): pass 1 counts the pulses of every chunk, pass 2 adds up the counts of the chunks before it and
@@ -645,8 +796,13 @@ extern "C" int b2w_synth_timebase(const double* f0, const int64_t* utt_frame_off
   phase_inc_kernel<<<grid, kTbThreads, 0, st>>>(f0, utt_frame_offset, utt_out_offset, fs, frame_period_ms, fft_size, phase_ws);
   int rc = check_launch("phase_inc_kernel");
   if (rc) return rc;
+#ifdef B2W_SEQUENTIAL_PHASE_SCAN
   phase_scan_kernel<<<num_utts, 32, 0, st>>>(utt_out_offset, phase_ws);
   rc = check_launch("phase_scan_kernel");
+#else
+  phase_scan_exact_kernel<<<num_utts, kScanThreads, 0, st>>>(utt_out_offset, phase_ws);
+  rc = check_launch("phase_scan_exact_kernel");
+#endif
   if (rc) return rc;
   const int max_chunks = (int)((max_out_per_utt + kPulseChunk - 1) / kPulseChunk);
   int* chunk_counts = chunk_ws;
