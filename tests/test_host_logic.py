@@ -183,3 +183,40 @@ def test_f0_stage_host_helpers():
     for n, fs in ((48000, 16000), (143325, 22050), (480000, 48000)):
         h0 = dio_np.mround(fs / bands[0] / 2.0)
         assert dio_np.dio_fft_size(n, fs) >= (n + 1) + 2 * dio_np.mround(fs / 50.0) + 1 + 4 * h0
+
+
+def test_lf0labelgen_reader_protocol(tmp_path):
+    """Host half of LF0LabelGen (world/LF0LabelGen.py:63-210): raw float32 files, normalisation parameters, pre- / post-processing."""
+    from idiaptts_b200.LF0LabelGen import LF0LabelGen
+    from idiaptts_b200.MeanStdDevExtractor import MeanStdDevExtractor
+    rng = np.random.default_rng(0)
+    out = tmp_path / "labels"
+    os.makedirs(str(out / "lf0"))
+    os.makedirs(str(out / "vuv"))
+    lf0 = (5.0 + 0.3 * rng.standard_normal((50, 1))).astype(np.float32)
+    vuv = (rng.random((50, 1)) > 0.4).astype(np.float32)
+    lf0[:, 0].tofile(str(out / "lf0" / "utt1.lf0"))
+    vuv[:, 0].tofile(str(out / "vuv" / "utt1.vuv"))
+    sample = LF0LabelGen.load_sample("utt1", str(out))
+    assert sample.shape == (50, 2) and np.array_equal(sample[:, :1], lf0) and np.array_equal(sample[:, 1:], vuv)
+    assert LF0LabelGen.load_lf0("utt1", str(out)).shape == (50, 1) and LF0LabelGen.load_vuv("utt1", str(out)).shape == (50, 1)
+    ext = MeanStdDevExtractor()
+    ext.add_sample(lf0)
+    ext.save(str(out / "lf0" / "train"))
+    gen = LF0LabelGen(str(out))
+    assert gen.preprocess_sample(sample) is None           # no normalisation parameters yet (the reference logs an error)
+    mean, std = gen.get_normalisation_params(str(out), "train")
+    assert mean.shape == (1, 2) and mean[0, 1] == 0.0 and std[0, 1] == 1.0   # vuv: mean 0, std 1
+    np.testing.assert_allclose(mean[0, 0], lf0.mean(), rtol=1e-6)
+    norm = gen["utt1"]
+    assert norm.dtype == np.float32 and abs(float(norm[:, 0].mean())) < 1e-4
+    np.testing.assert_allclose(gen.postprocess_sample(norm), sample, atol=1e-5)
+    soft = sample.copy()
+    soft[:, 1] = np.clip(soft[:, 1] + 0.3 * rng.standard_normal(50), 0, 1)
+    l, v = LF0LabelGen.convert_to_world_features(soft)
+    assert set(np.unique(v)) <= {0.0, 1.0} and np.array_equal(l, soft[:, 0])
+    assert LF0LabelGen.trim_end_sample(sample, 5).shape == (45, 2) and np.array_equal(LF0LabelGen.trim_end_sample(sample, 5, reverse=True), sample[5:])
+    assert LF0LabelGen.trim_end_sample(sample, 0) is sample
+    if not torch.cuda.is_available():                      # extraction itself needs the GPU: fails loudly without one
+        with pytest.raises(RuntimeError):
+            gen.gen_data(str(tmp_path), None, id_list=[])
