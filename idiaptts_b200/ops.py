@@ -652,32 +652,6 @@ def synthesize(f0, sp, ap, frame_off, fs, frame_period=5.0, deemphasis=0.0, out_
     _need_cuda(f0, sp, ap, frame_off)
     plan = synth_timebase(f0, frame_off, fs, 2 * (sp.shape[1] - 1), frame_period, status)
     return synth_render(plan, sp, ap, deemphasis, out_dtype, debug)
-    tab = randn_table(int(ylen.max()) + 1, dev)
-    st = _stream(dev)
-    with torch.cuda.device(dev):
-        phase_ws = torch.empty(int(out_off[-1]), dtype=torch.float64, device=dev)
-        check(lib.b2w_synth_timebase(f0.data_ptr(), frame_off.data_ptr(), d_out_off.data_ptr(), d_pulse_off.data_ptr(), U,
-                                     int(ylen.max()), int(fs), float(frame_period), fft_size, phase_ws.data_ptr(),
-                                     pulse_index.data_ptr(), pulse_shift.data_ptr(), pulse_vuv.data_ptr(),
-                                     num_pulses.data_ptr(), status.data_ptr(), st), "b2w_synth_timebase")
-        # the response buffer is sized by the ACTUAL pulse counts (one small D2H of U ints)
-        npul = num_pulses.cpu().numpy()[:U].astype(np.int64)
-        max_p = int(npul.max()) if U else 0
-        # responses are addressed by the slab offsets, so allocate slab-sized storage only up to the last used row
-        last_row = int((pulse_off[:-1] + npul).max()) if U else 0
-        response = torch.empty((max(last_row, 1), fft_size), dtype=torch.float64, device=dev)
-        if max_p > 0:
-            check(lib.b2w_synth_render(sp.data_ptr(), ap.data_ptr(), _DT[sp.dtype], frame_off.data_ptr(),
-                                       d_pulse_off.data_ptr(), num_pulses.data_ptr(), U, pulse_index.data_ptr(),
-                                       pulse_shift.data_ptr(), pulse_vuv.data_ptr(), tab.data_ptr(), tab.numel(), int(fs),
-                                       float(frame_period), fft_size, max_p, response.data_ptr(), st), "b2w_synth_render")
-        if debug is not None:  # diagnostics for the parity tests: the pulse table of every utterance
-            debug.update(pulse_off=pulse_off, num_pulses=npul, pulse_index=pulse_index, pulse_shift=pulse_shift,
-                         pulse_vuv=pulse_vuv, response=response)
-        check(lib.b2w_synth_overlap_add(response.data_ptr(), d_out_off.data_ptr(), d_pulse_off.data_ptr(),
-                                        num_pulses.data_ptr(), U, pulse_index.data_ptr(), fft_size, int(ylen.max()),
-                                        float(deemphasis), y.data_ptr(), _DT[y.dtype], st), "b2w_synth_overlap_add")
-    return y, out_off, status
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -253,8 +253,6 @@ B2W_API int b2w_world_metrics(const float* org, const float* out, int64_t stride
 B2W_API int64_t b2w_probe_fp64_fma(int32_t iters, double* scratch, void* stream);
 /* development aid: phase cycle counters of mcep_tc CTA 0 (non-zero only in a -DB2W_MCEP_PROF build) */
 B2W_API int b2w_mcep_prof_read(long long* out16);
-B2W_API int b2w_probe_umma(int32_t n, int32_t count, int32_t nacc, int32_t m, int32_t f16, long long* out4, void* stream);
-B2W_API int b2w_test_umma_gemm(const float* a, const float* bt, int32_t n, int32_t k, float* b_tiled_ws, float* d, void* stream);
 
 /* ---- scalar helpers (host, pure functions): pyworld.get_cheaptrick_fft_size (A:60), get_num_aperiodicities
  * (A:71), and the D4C transform size. */

@@ -1,8 +1,9 @@
 import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from idiaptts_b200 import _lib
-lib = _lib.load()
+import ctypes
+from build_umma_test import build_umma_test
+lib = ctypes.CDLL(build_umma_test())  # development library, NOT part of libb200world.so
 dev = torch.device("cuda", 0)
 out = torch.zeros(4, dtype=torch.int64, device=dev)
 for m, f16 in ((128, 0), (64, 0), (128, 1), (64, 1)):

@@ -2,8 +2,9 @@ import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from idiaptts_b200 import _lib
-lib = _lib.load()
+import ctypes
+from build_umma_test import build_umma_test
+lib = ctypes.CDLL(build_umma_test())  # development library, NOT part of libb200world.so
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)
 for (n, k) in ((16, 8), (32, 8), (16, 16), (32, 64), (128, 32), (128, 64), (64, 16), (256, 16)):
