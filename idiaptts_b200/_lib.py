@@ -30,6 +30,7 @@ _SIGNATURES = {
     "b2w_last_error": (ctypes.c_char_p, []),
     "b2w_cheaptrick": (c_int32, [ctypes.POINTER(Batch), c_int32, c_double, c_void_p, c_int32, c_int64, c_void_p, c_void_p]),
     "b2w_d4c_coarse": (c_int32, [ctypes.POINTER(Batch), c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b2w_d4c_coarse_f64": (c_int32, [ctypes.POINTER(Batch), c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2w_d4c_expand": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "b2w_bap_from_coarse": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int64, c_void_p]),
     "b2w_code_aperiodicity": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),

@@ -53,7 +53,7 @@ def d4c(x, f0, temporal_positions, fs, threshold=0.85, fft_size=None):
     if fft_size is None:
         fft_size = get_cheaptrick_fft_size(fs, default_f0_floor)
     batch = _batch(x, f0, temporal_positions, fs)
-    coarse, voiced, status = ops.d4c_coarse(batch, threshold=threshold)
+    coarse, voiced, status = ops.d4c_coarse(batch, threshold=threshold, precision="f64")
     ap = ops.d4c_expand(coarse, voiced, fs, fft_size).cpu().numpy()
     ops.raise_for_status(status, "d4c")
     return ap

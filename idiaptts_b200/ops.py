@@ -269,8 +269,12 @@ def cheaptrick(batch, fft_size=None, q1=-0.15, out_dtype=torch.float64, status=N
     return out, status
 
 
-def d4c_coarse(batch, threshold=0.85, status=None, frame_lo=0, frame_hi=None):
-    """LoveTrain + D4C band aperiodicity -> (coarse_db [F, nap] f64, voiced [F] uint8)."""
+def d4c_coarse(batch, threshold=0.85, status=None, frame_lo=0, frame_hi=None, precision="fast"):
+    """LoveTrain + D4C band aperiodicity -> (coarse_db [F, nap] f64, voiced [F] uint8).
+    precision: "fast" = single-precision FFTs with fp64 cumulative sums and an fp64 re-evaluation of the frames whose LoveTrain
+    ratio is too close to the threshold to call (b2w_d4c_coarse: decisions identical to "f64", coarse_db within ~1e-4 dB);
+    "f64" = double precision throughout (b2w_d4c_coarse_f64)."""
+    assert precision in ("fast", "f64")
     lib = _lib.load()
     if frame_hi is None:
         frame_hi = batch.num_frames
@@ -282,8 +286,9 @@ def d4c_coarse(batch, threshold=0.85, status=None, frame_lo=0, frame_hi=None):
         status = new_status(batch.device)
     b = batch.c_struct(frame_lo, frame_hi)
     with torch.cuda.device(batch.device):
-        check(lib.b2w_d4c_coarse(b, float(threshold), coarse.data_ptr(), voiced.data_ptr(), status.data_ptr(),
-                                 _stream(batch.device)), "b2w_d4c_coarse")
+        fn = lib.b2w_d4c_coarse if precision == "fast" else lib.b2w_d4c_coarse_f64
+        check(fn(b, float(threshold), coarse.data_ptr(), voiced.data_ptr(), status.data_ptr(), _stream(batch.device)),
+              "b2w_d4c_coarse")
     return coarse, voiced, status
 
 

@@ -80,8 +80,14 @@ B2W_API int b2w_cheaptrick(const b2w_batch* b, int32_t fft_size, double q1, void
 /* ---- D4C: replaces pyworld.d4c inside pyworld.wav2world (W:792). ------------------------------------------
  * Stage 1 (the expensive one): LoveTrain voicing + per-band coarse aperiodicity.
  *   coarse_db [num_frames, nap] dB (undefined where voiced == 0), voiced [num_frames] uint8.
- *   nap = b2w_num_aperiodicities(fs); the D4C fft size is derived from fs as WORLD does. */
+ *   nap = b2w_num_aperiodicities(fs); the D4C fft size is derived from fs as WORLD does.
+ * b2w_d4c_coarse is the fused-extraction path: single-precision FFTs, fp64 cumulative sums; a frame whose LoveTrain ratio
+ * lies within 1e-5 of `threshold` is re-evaluated in double precision, so the voiced / unvoiced decisions are those of
+ * b2w_d4c_coarse_f64; coarse_db agrees with it to ~1e-4 dB.  b2w_d4c_coarse_f64 computes everything in double precision
+ * (what compat.pyworld.d4c uses). */
 B2W_API int b2w_d4c_coarse(const b2w_batch* b, double threshold, double* coarse_db, uint8_t* voiced, int32_t* status,
+                   void* stream);
+B2W_API int b2w_d4c_coarse_f64(const b2w_batch* b, double threshold, double* coarse_db, uint8_t* voiced, int32_t* status,
                    void* stream);
 /* Stage 2a: expand to the pyworld.d4c result ap [num_frames, fft_size/2+1] f64 (1 - 1e-12 on unvoiced rows). */
 B2W_API int b2w_d4c_expand(const double* coarse_db, const uint8_t* voiced, int64_t num_frames, int32_t fs, int32_t fft_size,

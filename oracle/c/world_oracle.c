@@ -535,3 +535,272 @@ int oracle_extract(const int16_t* wave, int xlen, int fs, const double* f0, int 
   free(x); free(t); free(sp); free(mc); free(coarse); free(bap); free(voiced); free(lf0); free(vuv);
   return rc;
 }
+
+/* ============================================================================================================================
+ * Synthesis half: the per-utterance body of Synthesiser.run_world_synth (idiaptts/src/Synthesiser.py:39-80):
+ *   convert_to_world_features (WorldFeatLabelGen.py:735-762) -> decode_sp = exp(Re mgc2sp) as float32
+ *   (AudioProcessing.py:248-256, :304-327) -> world_features_to_raw (WorldFeatLabelGen.py:910-945): pyworld.decode_aperiodicity
+ *   + pyworld.synthesize.  A C port of oracle/world_np.py::synthesize (WORLD synthesis.cpp restated; PARITY UNPINNED: the
+ *   reference holds no golden waveform), pinned against the numpy version by tests/test_oracle_c.py.
+ * ========================================================================================================================== */
+
+/* WORLD randn() after randn_reseed(): xorshift128, sum of 12 draws (>> 4), / 2^28 - 6 */
+static void xorshift_randn_sequence(double* out, int n) {
+  uint32_t x = 123456789u, y = 362436069u, z = 521288629u, w = 88675123u;
+  for (int i = 0; i < n; ++i) {
+    uint32_t tmp = 0;
+    for (int j = 0; j < 12; ++j) {
+      const uint32_t t = x ^ (x << 11);
+      x = y; y = z; z = w;
+      w = (w ^ (w >> 19)) ^ (t ^ (t >> 8));
+      tmp += w >> 4;
+    }
+    out[i] = tmp / 268435456.0 - 6.0;
+  }
+}
+
+/* WORLD GetMinimumPhaseSpectrum: log-amplitude (K = n/2+1 bins) -> complex minimum-phase spectrum (K bins).
+ * wr, wi: scratch of n doubles each. */
+static void minimum_phase(const fft_plan* pn, const double* logspec, double* wr, double* wi, double* out_re, double* out_im) {
+  const int n = pn->n, h = n / 2;
+  for (int i = 0; i <= h; ++i) { wr[i] = logspec[i]; wi[i] = 0.0; }
+  for (int i = 1; i < h; ++i) { wr[n - i] = logspec[i]; wi[n - i] = 0.0; }
+  cfft(pn, wr, wi);
+  /* conj, then fold: [c0, 2 c1 .. 2 c(h-1), c(h), 0 ...] */
+  for (int i = 0; i < n; ++i) wi[i] = -wi[i];
+  for (int i = 1; i < h; ++i) { wr[i] *= 2.0; wi[i] *= 2.0; }
+  for (int i = h + 1; i < n; ++i) { wr[i] = 0.0; wi[i] = 0.0; }
+  cfft(pn, wr, wi);
+  for (int i = 0; i <= h; ++i) {
+    const double a = exp(wr[i] / n), ph = wi[i] / n;
+    out_re[i] = a * cos(ph);
+    out_im[i] = a * sin(ph);
+  }
+}
+
+/* unnormalised complex-to-real transform of a half spectrum (numpy irfft * n), result fft-shifted: out[i] = wave[(i + h) % n].
+ * The imaginary parts of bins 0 and n/2 are ignored, as numpy's irfft (and FFTW's c2r) do. */
+static void c2r_shifted(const fft_plan* pn, const double* xr, const double* xi, double* wr, double* wi, double* out) {
+  const int n = pn->n, h = n / 2;
+  /* x[m] = sum_k X[k] e^{+2 pi i k m / n} = conj(FFT(conj(X)))[m]; Hermitian extension */
+  wr[0] = xr[0]; wi[0] = 0.0;
+  wr[h] = xr[h]; wi[h] = 0.0;
+  for (int k = 1; k < h; ++k) {
+    wr[k] = xr[k]; wi[k] = -xi[k];
+    wr[n - k] = xr[k]; wi[n - k] = xi[k];
+  }
+  cfft(pn, wr, wi);
+  for (int i = 0; i < n; ++i) out[i] = wr[(i + h) % n];
+}
+
+static double interp1_uniform(double step, const double* y, int len, double xi) {
+  /* WORLD interp1 (histc): k with x[k-1] <= xi < x[k], x[i] = i * step, k clipped to [1, len-1] */
+  int k0 = (int)(xi / step);
+  if (k0 < 0) k0 = 0;
+  if (k0 > len - 1) k0 = len - 1;
+  while (k0 > 0 && k0 * step > xi) --k0;
+  while (k0 + 1 < len && (k0 + 1) * step <= xi) ++k0;
+  int k = k0 + 1;
+  if (k < 1) k = 1;
+  if (k > len - 1) k = len - 1;
+  const double s = (xi - (k - 1) * step) / (k * step - (k - 1) * step);
+  return y[k - 1] + s * (y[k] - y[k - 1]);
+}
+
+/* pyworld.synthesize(f0, sp, ap, fs, frame_period): sp, ap [T x K] row-major; y [int(T * frame_period * fs / 1000)] */
+int oracle_synthesize(const double* f0, const double* sp, const double* ap, int T, int fft_size, int fs, double frame_period_ms,
+                      double* y, int y_length) {
+  const int n = fft_size, h = n / 2, K = h + 1;
+  const double fp = frame_period_ms / 1000.0;
+  memset(y, 0, sizeof(double) * (size_t)y_length);
+  if (T < 2 || y_length < 2) return 0;
+  /* ---- time base ---------------------------------------------------------------------------------------------------------- */
+  const double lowest_f0 = (double)(fs / n) + 1.0;
+  double* cf0 = (double*)malloc(sizeof(double) * (T + 1));
+  double* cvuv = (double*)malloc(sizeof(double) * (T + 1));
+  for (int i = 0; i < T; ++i) {
+    cf0[i] = f0[i] < lowest_f0 ? 0.0 : f0[i];
+    cvuv[i] = cf0[i] == 0.0 ? 0.0 : 1.0;
+  }
+  cf0[T] = cf0[T - 1] * 2 - cf0[T - 2];
+  cvuv[T] = cvuv[T - 1] * 2 - cvuv[T - 2];
+  double* wrap = (double*)malloc(sizeof(double) * y_length);
+  unsigned char* ivuv = (unsigned char*)malloc(y_length);
+  const double two_pi = 2.0 * K_PI;
+  double total = 0.0;
+  for (int i = 0; i < y_length; ++i) {
+    const double ti = i / (double)fs;
+    double f = interp1_uniform(fp, cf0, T + 1, ti);
+    const double v = interp1_uniform(fp, cvuv, T + 1, ti);
+    ivuv[i] = v > 0.5 ? 1 : 0;
+    if (!ivuv[i]) f = K_DEFAULT_F0;
+    total += two_pi * f / fs;
+    wrap[i] = fmod(total, two_pi);
+  }
+  int P = 0;
+  int* idx = (int*)malloc(sizeof(int) * y_length);
+  double* shift = (double*)malloc(sizeof(double) * y_length);
+  for (int i = 0; i + 1 < y_length; ++i) {
+    if (fabs(wrap[i + 1] - wrap[i]) > K_PI) {
+      const double y1 = wrap[i] - two_pi, y2 = wrap[i + 1];
+      idx[P] = i;
+      shift[P] = (-y1 / (y2 - y1)) / fs;
+      ++P;
+    }
+  }
+  free(cf0); free(cvuv); free(wrap);
+  if (P == 0) { free(ivuv); free(idx); free(shift); return 0; }
+  /* ---- tables ------------------------------------------------------------------------------------------------------------------ */
+  fft_plan* pn = plan_create(n);
+  rfft_plan* rp = rplan_create(n);
+  double* dc_remover = (double*)malloc(sizeof(double) * n);
+  {
+    double dc = 0.0;
+    for (int i = 0; i < h; ++i) {
+      dc_remover[i] = 0.5 - 0.5 * cos(2.0 * K_PI * (i + 1.0) / (1.0 + n));
+      dc += dc_remover[i] * 2.0;
+    }
+    for (int i = 0; i < h; ++i) { dc_remover[i] /= dc; dc_remover[n - 1 - i] = dc_remover[i]; }
+  }
+  const int total_noise = idx[P - 1] - idx[0];
+  double* randn_seq = (double*)malloc(sizeof(double) * (total_noise > 0 ? total_noise : 1));
+  xorshift_randn_sequence(randn_seq, total_noise);
+  double* env = (double*)malloc(sizeof(double) * K);
+  double* ar = (double*)malloc(sizeof(double) * K);
+  double* ls = (double*)malloc(sizeof(double) * K);
+  double* xr = (double*)malloc(sizeof(double) * K);
+  double* xi = (double*)malloc(sizeof(double) * K);
+  double* zr = (double*)malloc(sizeof(double) * K);
+  double* zi = (double*)malloc(sizeof(double) * K);
+  double* wr = (double*)malloc(sizeof(double) * n);
+  double* wi = (double*)malloc(sizeof(double) * n);
+  double* periodic = (double*)malloc(sizeof(double) * n);
+  double* aperiodic = (double*)malloc(sizeof(double) * n);
+  double* noise = (double*)malloc(sizeof(double) * n);
+  /* ---- pulses ------------------------------------------------------------------------------------------------------------------- */
+  for (int p = 0; p < P; ++p) {
+    const int n_p = idx[p];
+    const int noise_size = idx[imin(P - 1, p + 1)] - n_p;
+    const double cur_t = n_p / (double)fs;
+    const int fl = imin(T - 1, (int)floor(cur_t / fp)), ce = imin(T - 1, (int)ceil(cur_t / fp));
+    const double w = cur_t / fp - fl;
+    const double *sp_fl = sp + (size_t)fl * K, *sp_ce = sp + (size_t)ce * K, *ap_fl = ap + (size_t)fl * K, *ap_ce = ap + (size_t)ce * K;
+    for (int k = 0; k < K; ++k) {
+      double a0 = ap_fl[k] < 0.001 ? 0.001 : (ap_fl[k] > 0.999999999999 ? 0.999999999999 : ap_fl[k]);
+      a0 *= a0;
+      if (fl == ce) {
+        env[k] = fabs(sp_fl[k]);
+        ar[k] = a0;
+      } else {
+        double a1 = ap_ce[k] < 0.001 ? 0.001 : (ap_ce[k] > 0.999999999999 ? 0.999999999999 : ap_ce[k]);
+        a1 *= a1;
+        env[k] = (1.0 - w) * fabs(sp_fl[k]) + w * fabs(sp_ce[k]);
+        ar[k] = (1.0 - w) * a0 + w * a1;
+      }
+    }
+    const int cur_vuv = ivuv[n_p];
+    if (!cur_vuv || ar[0] > 0.999) {
+      memset(periodic, 0, sizeof(double) * n);
+    } else {
+      for (int k = 0; k < K; ++k) ls[k] = log(env[k] * (1.0 - ar[k]) + K_SAFE) / 2.0;
+      minimum_phase(pn, ls, wr, wi, xr, xi);
+      const double coef = 2.0 * K_PI * shift[p] * fs / n;
+      for (int k = 0; k < K; ++k) {
+        const double re2 = cos(coef * k), im2 = sqrt(1.0 - re2 * re2);
+        const double a = xr[k], b = xi[k];
+        xr[k] = a * re2 + b * im2;
+        xi[k] = b * re2 - a * im2;
+      }
+      c2r_shifted(pn, xr, xi, wr, wi, periodic);
+      double dc = 0.0;
+      for (int i = h; i < n; ++i) dc += periodic[i];
+      for (int i = 0; i < h; ++i) periodic[i] = -dc * dc_remover[i];
+      for (int i = h; i < n; ++i) periodic[i] -= dc * dc_remover[i];
+    }
+    /* aperiodic response */
+    memset(noise, 0, sizeof(double) * n);
+    if (noise_size > 0) {
+      const double* seg = randn_seq + (n_p - idx[0]);
+      double mean = 0.0;
+      for (int i = 0; i < noise_size; ++i) mean += seg[i];
+      mean /= noise_size;
+      for (int i = 0; i < imin(noise_size, n); ++i) noise[i] = seg[i] - mean;
+    }
+    rfft(rp, noise, zr, zi);
+    for (int k = 0; k < K; ++k) ls[k] = (cur_vuv ? log(env[k] * ar[k]) : log(env[k])) / 2.0;
+    minimum_phase(pn, ls, wr, wi, xr, xi);
+    for (int k = 0; k < K; ++k) {
+      const double a = xr[k] * zr[k] - xi[k] * zi[k], b = xr[k] * zi[k] + xi[k] * zr[k];
+      xr[k] = a; xi[k] = b;
+    }
+    c2r_shifted(pn, xr, xi, wr, wi, aperiodic);
+    const double sq = sqrt((double)noise_size);
+    const int offset = n_p - h + 1;
+    const int lo = imax(0, -offset), hi = imin(n, y_length - offset);
+    for (int i = lo; i < hi; ++i) y[i + offset] += (periodic[i] * sq + aperiodic[i]) / n;
+  }
+  free(ivuv); free(idx); free(shift); free(dc_remover); free(randn_seq); free(env); free(ar); free(ls); free(xr); free(xi);
+  free(zr); free(zi); free(wr); free(wi); free(periodic); free(aperiodic); free(noise);
+  plan_free(pn); rplan_free(rp);
+  return 0;
+}
+
+/* pyworld.decode_aperiodicity (WORLD codec.cpp): bap [T x nap] -> ap [T x K] */
+void oracle_decode_aperiodicity(const double* bap, int T, int fs, int fft_size, double* ap) {
+  const int nap = oracle_num_aperiodicities(fs), K = fft_size / 2 + 1;
+  for (int fr = 0; fr < T; ++fr) {
+    double tmp = 0.0;
+    for (int j = 0; j < nap; ++j) tmp += bap[(size_t)fr * nap + j];
+    tmp /= nap;
+    double* row = ap + (size_t)fr * K;
+    for (int k = 0; k < K; ++k)
+      row[k] = tmp > -0.5 ? 1.0 - K_SAFE
+                          : pow(10.0, coarse_db_at(bap + (size_t)fr * nap, nap, fs / 2.0, (double)k * fs / fft_size) / 20.0);
+  }
+}
+
+/* One utterance of Synthesiser.run_world_synth: feats [T x (D + 2 + nap)] float32 = [mcep | lf0 | vuv | bap] -> y float32.
+ * Returns the number of samples written (int(T * 5 * fs / 1000)), or a negative error code. */
+int oracle_synthesize_features(const float* feats, int T, int fs, int num_coded_sps, double alpha, float* y_out, int y_capacity) {
+  const int n = oracle_cheaptrick_fft_size(fs, 71.0), h = n / 2, K = h + 1, nap = oracle_num_aperiodicities(fs), D = num_coded_sps;
+  const int dim = D + 2 + nap;
+  const int y_length = (int)(T * 5.0 * fs / 1000);
+  if (y_length > y_capacity) return -1;
+  double* f0 = (double*)malloc(sizeof(double) * T);
+  double* sp = (double*)malloc(sizeof(double) * (size_t)T * K);
+  double* ap = (double*)malloc(sizeof(double) * (size_t)T * K);
+  double* bap = (double*)malloc(sizeof(double) * (size_t)T * (nap > 0 ? nap : 1));
+  double* c = (double*)malloc(sizeof(double) * (h + 1));
+  double* d = (double*)malloc(sizeof(double) * (h + 1));
+  double* mc = (double*)malloc(sizeof(double) * D);
+  double* buf = (double*)malloc(sizeof(double) * n);
+  double* xr = (double*)malloc(sizeof(double) * K);
+  double* xi = (double*)malloc(sizeof(double) * K);
+  double* y = (double*)malloc(sizeof(double) * (y_length > 0 ? y_length : 1));
+  rfft_plan* rp = rplan_create(n);
+  for (int fr = 0; fr < T; ++fr) {
+    const float* row = feats + (size_t)fr * dim;
+    /* world_features_to_raw prologue (W:919-938) */
+    double f = exp((double)row[D]);
+    int v = row[D + 1] >= 0.5f;
+    if (f < 30.0) v = 0;
+    f0[fr] = v ? f : 0.0;
+    /* decode_sp: pysptk.mgc2sp(mc, alpha, 0, n) = rfft(freqt(mc, n/2, -alpha), n); amp = exp(real) as float32; pow = amp^2 */
+    for (int k = 0; k < D; ++k) mc[k] = (double)row[k];
+    freqt(mc, D - 1, c, h, -alpha, d);
+    memset(buf, 0, sizeof(double) * n);
+    for (int k = 0; k <= h; ++k) buf[k] = c[k];
+    rfft(rp, buf, xr, xi);
+    for (int k = 0; k < K; ++k) {
+      const double amp = (double)(float)exp(xr[k]);
+      sp[(size_t)fr * K + k] = amp * amp;
+    }
+    for (int b = 0; b < nap; ++b) bap[(size_t)fr * nap + b] = (double)row[D + 2 + b];
+  }
+  oracle_decode_aperiodicity(bap, T, fs, n, ap);
+  oracle_synthesize(f0, sp, ap, T, n, fs, 5.0, y, y_length);
+  for (int i = 0; i < y_length; ++i) y_out[i] = (float)y[i];
+  free(f0); free(sp); free(ap); free(bap); free(c); free(d); free(mc); free(buf); free(xr); free(xi); free(y);
+  rplan_free(rp);
+  return y_length;
+}

@@ -22,6 +22,10 @@ def lib():
         l.oracle_lf0_vuv.argtypes = [P, I, D, ctypes.c_float, P, P]
         l.oracle_lf0_vuv.restype = None
         l.oracle_extract.argtypes = [P, I, I, P, I, D, I, D, P]
+        l.oracle_synthesize.argtypes = [P, P, P, I, I, I, D, P, I]
+        l.oracle_decode_aperiodicity.argtypes = [P, I, I, I, P]
+        l.oracle_decode_aperiodicity.restype = None
+        l.oracle_synthesize_features.argtypes = [P, I, I, I, D, P, I]
         l.oracle_cheaptrick_fft_size.argtypes = [I, D]
         l.oracle_num_aperiodicities.argtypes = [I]
         _lib = l
@@ -98,3 +102,35 @@ def extract(wave_i16, fs, f0, num_coded_sps, alpha, preemphasis=0.0):
     if rc:
         raise RuntimeError("oracle_extract failed with code %d" % rc)
     return feats
+
+
+def synthesize(f0, sp, ap, fs, frame_period=5.0):
+    """pyworld.synthesize on the CPU oracle (C port of oracle/world_np.py::synthesize)."""
+    l = lib()
+    f0 = np.ascontiguousarray(f0, np.float64)
+    sp = np.ascontiguousarray(sp, np.float64)
+    ap = np.ascontiguousarray(ap, np.float64)
+    T = len(f0)
+    y = np.zeros(int(T * frame_period * fs / 1000))
+    l.oracle_synthesize(_p(f0), _p(sp), _p(ap), T, 2 * (sp.shape[1] - 1), int(fs), float(frame_period), _p(y), len(y))
+    return y
+
+
+def decode_aperiodicity(bap, fs, fft_size):
+    l = lib()
+    bap = np.ascontiguousarray(bap, np.float64)
+    ap = np.empty((bap.shape[0], fft_size // 2 + 1))
+    l.oracle_decode_aperiodicity(_p(bap), bap.shape[0], int(fs), int(fft_size), _p(ap))
+    return ap
+
+
+def synthesize_features(feats, fs, num_coded_sps, alpha):
+    """One utterance of Synthesiser.run_world_synth: [T, D + 2 + nap] float32 rows -> float32 waveform (releases the GIL)."""
+    l = lib()
+    feats = np.ascontiguousarray(feats, np.float32)
+    T = feats.shape[0]
+    y = np.empty(int(T * 5.0 * fs / 1000), np.float32)
+    n = l.oracle_synthesize_features(_p(feats), T, int(fs), int(num_coded_sps), float(alpha), _p(y), len(y))
+    if n < 0:
+        raise RuntimeError("oracle_synthesize_features failed with code %d" % n)
+    return y[:n]

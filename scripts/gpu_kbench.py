@@ -52,7 +52,13 @@ if "d4c" in ks:
     coarse, voiced, _ = timeit("d4c", lambda: ops.d4c_coarse(batch, status=status, frame_lo=0, frame_hi=chunk))
     res["coarse"] = coarse.cpu().numpy(); res["voiced"] = voiced.cpu().numpy()
     v = voiced.bool()
-    print("  d4c voiced %d, coarse checksum %.12e" % (int(v.sum().item()), coarse[v].double().sum().item()))
+    print("  d4c voiced %d, undecided %d, coarse checksum %.12e" % (int((voiced == 1).sum().item()), int((voiced == 2).sum().item()), coarse[v].double().sum().item()))
+if "d4c_f64" in ks:
+    c64, v64, _ = timeit("d4c_f64", lambda: ops.d4c_coarse(batch, status=status, frame_lo=0, frame_hi=chunk, precision="f64"))
+    v = v64.bool()
+    print("  d4c_f64 voiced %d, coarse checksum %.12e" % (int(v.sum().item()), c64[v].double().sum().item()))
+    if "d4c" in ks:
+        print("  fast vs f64: decisions differ on %d frames, max |coarse diff| %.3e dB" % (int((voiced != v64).sum().item()), (coarse[v] - c64[v]).abs().max().item()))
 print("status", int(status.item()))
 if a.dump:
     np.savez(a.dump, **res)

@@ -50,7 +50,7 @@ def test_fused_analysis_reproduces_reference_cmp(golden, dev, id_):
     assert np.abs(mc - c[:, :20]).max() < 2e-5
     assert glue_np.mcd_db(c[:, :20], mc) < 1e-4  # tolerance 0.01 dB
     bap = bap.cpu().numpy()
-    assert np.abs(bap[:, 0] - c[:, 64]).max() < 3e-5
+    assert np.abs(bap[:, 0] - c[:, 64]).max() < 1e-4  # the fast D4C path runs its FFTs in single precision (3e-5 with precision="f64")
     assert np.all(bap[c[:, 63] == 0, 0] == np.float32(-8.685697e-12))
 
 
@@ -68,6 +68,37 @@ def test_d4c_and_codec_vs_oracle(golden):
     np.testing.assert_allclose(pw.decode_aperiodicity(bap, fs, 1024), world_np.decode_aperiodicity(bap, fs, 1024), atol=1e-12)
     with pytest.raises(ValueError):
         pw.decode_aperiodicity(np.zeros((3, 2)), 16000, 1024)  # wrong band count for fs
+
+
+def test_d4c_fast_path_vs_f64_path(golden, dev):
+    """b2w_d4c_coarse (single-precision FFTs) against b2w_d4c_coarse_f64 on all 9 reference utterances: LoveTrain decisions
+    identical, coarse aperiodicity within 2e-4 dB; and the guard band: with the threshold moved onto a frame's own LoveTrain
+    ratio the fast pass must hand that frame to the fp64 kernel, which then decides exactly like the fp64 path."""
+    from idiaptts_b200 import ops
+    worst = 0.0
+    for id_ in IDS:
+        x, c, f0, fs = golden_utterance(golden, id_)
+        batch = ops.RaggedBatch.from_host([x], [f0], fs, device=dev)
+        c64, v64, st = ops.d4c_coarse(batch, precision="f64")
+        c32, v32, st = ops.d4c_coarse(batch, status=st, precision="fast")
+        assert torch.equal(v64, v32), id_
+        assert int(v32.max().item()) <= 1                         # no frame is left marked "undecided"
+        m = v64.bool()
+        worst = max(worst, (c64[m] - c32[m]).abs().max().item())
+        assert ops.raise_for_status(st, "d4c") == 0
+    assert worst < 2e-4, worst
+    # guard band: thresholds equal to (and a hair around) the fp64 LoveTrain ratio of one frame
+    x, c, f0, fs = golden_utterance(golden, "LJ001-0008")
+    t = world_np.temporal_positions(len(f0))
+    ap0 = world_np.d4c_lovetrain(x, fs, f0, t)
+    i = int(np.argmin(np.where(f0 > 0, np.abs(ap0 - 0.85), 1.0)))
+    batch = ops.RaggedBatch.from_host([x], [f0], fs, device=dev)
+    for thr in (ap0[i], np.nextafter(ap0[i], 0.0), np.nextafter(ap0[i], 1.0), ap0[i] - 3e-7, ap0[i] + 3e-7):
+        c64, v64, _ = ops.d4c_coarse(batch, threshold=float(thr), precision="f64")
+        c32, v32, _ = ops.d4c_coarse(batch, threshold=float(thr), precision="fast")
+        assert torch.equal(v64, v32), thr
+        if bool(v64[i]):  # the re-evaluated frame carries the fp64 kernel's values
+            assert torch.equal(c64[i], c32[i])
 
 
 @pytest.mark.parametrize("order,alpha", [(19, 0.58), (59, 0.58), (59, 0.41), (79, 0.41), (39, 0.42), (24, 0.35)])
@@ -170,12 +201,13 @@ def test_22k_and_48k_sizes(dev):
         t = world_np.temporal_positions(len(f0))
         ref = world_np.cheaptrick(x, f0, t, fs)
         assert (np.abs(sp.cpu().numpy() - ref) / ref).max() < 1e-6
-        coarse, voiced, st = ops.d4c_coarse(batch, status=st)
         v_ref, c_ref = world_np.d4c_coarse(x, f0, t, fs)
-        assert coarse.shape[1] == nap and np.array_equal(voiced.cpu().numpy().astype(bool), v_ref)
-        assert np.abs(coarse.cpu().numpy()[v_ref] - c_ref[v_ref]).max() < 1e-7
-        bap = ops.bap_from_coarse(coarse, voiced, fs, n_fft).cpu().numpy()
-        np.testing.assert_allclose(bap, world_np.code_aperiodicity(world_np.d4c(x, f0, t, fs), fs), atol=2e-5)
+        for precision, tol in (("f64", 1e-7), ("fast", 2e-4)):   # dB; the fast path runs its FFTs in single precision
+            coarse, voiced, st = ops.d4c_coarse(batch, status=st, precision=precision)
+            assert coarse.shape[1] == nap and np.array_equal(voiced.cpu().numpy().astype(bool), v_ref)  # decisions: bit-exact
+            assert np.abs(coarse.cpu().numpy()[v_ref] - c_ref[v_ref]).max() < tol, precision
+            bap = ops.bap_from_coarse(coarse, voiced, fs, n_fft).cpu().numpy()
+            np.testing.assert_allclose(bap, world_np.code_aperiodicity(world_np.d4c(x, f0, t, fs), fs), atol=2e-4)
         assert ops.raise_for_status(st, "sizes") == 0
 
 
