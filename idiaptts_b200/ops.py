@@ -126,6 +126,19 @@ class RaggedBatch:
         return b
 
 
+def _timed(events, name, units, fn):
+    """Runs fn(); with an `events` list also brackets it with CUDA events on the current stream and appends
+    (name, units, start, end) -- bench.py's per-kernel timing."""
+    if events is None:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = fn()
+    e1.record()
+    events.append((name, units, e0, e1))
+    return r
+
+
 def new_status(device):
     return torch.zeros(1, dtype=torch.int32, device=device)
 
@@ -581,7 +594,7 @@ class SynthPlan:
     pass
 
 
-def synth_timebase(f0, frame_off, fs, fft_size, frame_period=5.0, status=None):
+def synth_timebase(f0, frame_off, fs, fft_size, frame_period=5.0, status=None, events=None):
     """Launches the pulse-placement kernels (sequential per utterance, a few hundred threads: they overlap well with other
     work on a second stream).  f0 [F] f64, frame_off int64 [U+1] (device).  Returns a SynthPlan; nothing is synchronised."""
     lib = _lib.load()
@@ -611,14 +624,15 @@ def synth_timebase(f0, frame_off, fs, fft_size, frame_period=5.0, status=None):
     with torch.cuda.device(dev):
         phase_ws = torch.empty(int(out_off[-1]), dtype=torch.float64, device=dev)
         chunk_ws = torch.empty(U * int(lib.b2w_synth_timebase_chunks(int(ylen.max()))), dtype=torch.int32, device=dev)
-        check(lib.b2w_synth_timebase(f0.data_ptr(), frame_off.data_ptr(), p.d_out_off.data_ptr(), p.d_pulse_off.data_ptr(), U,
-                                     int(ylen.max()), int(fs), float(frame_period), fft_size, phase_ws.data_ptr(), chunk_ws.data_ptr(),
-                                     p.pulse_index.data_ptr(), p.pulse_shift.data_ptr(), p.pulse_vuv.data_ptr(),
-                                     p.num_pulses.data_ptr(), p.status.data_ptr(), _stream(dev)), "b2w_synth_timebase")
+        _timed(events, "synth_timebase", int(out_off[-1]), lambda: check(lib.b2w_synth_timebase(
+            f0.data_ptr(), frame_off.data_ptr(), p.d_out_off.data_ptr(), p.d_pulse_off.data_ptr(), U,
+            int(ylen.max()), int(fs), float(frame_period), fft_size, phase_ws.data_ptr(), chunk_ws.data_ptr(),
+            p.pulse_index.data_ptr(), p.pulse_shift.data_ptr(), p.pulse_vuv.data_ptr(),
+            p.num_pulses.data_ptr(), p.status.data_ptr(), _stream(dev)), "b2w_synth_timebase"))
     return p
 
 
-def synth_render(p, sp, ap, deemphasis=0.0, out_dtype=torch.float64, debug=None):
+def synth_render(p, sp, ap, deemphasis=0.0, out_dtype=torch.float64, debug=None, events=None):
     """Minimum-phase responses of every pulse of the plan + overlap-add.  sp, ap [F, K] (f64 or f32, same dtype)."""
     lib = _lib.load()
     dev = _need_cuda(sp, ap)
@@ -636,17 +650,20 @@ def synth_render(p, sp, ap, deemphasis=0.0, out_dtype=torch.float64, debug=None)
         # responses are addressed by the slab offsets, so allocate slab-sized storage only up to the last used row
         last_row = int((pulse_off[:-1] + npul).max()) if U else 0
         response = torch.empty((max(last_row, 1), fft_size), dtype=torch.float64, device=dev)
+        total_p = int(npul.sum())
         if max_p > 0:
-            check(lib.b2w_synth_render(sp.data_ptr(), ap.data_ptr(), _DT[sp.dtype], p.frame_off.data_ptr(),
-                                       p.d_pulse_off.data_ptr(), p.num_pulses.data_ptr(), U, p.pulse_index.data_ptr(),
-                                       p.pulse_shift.data_ptr(), p.pulse_vuv.data_ptr(), p.tab.data_ptr(), p.tab.numel(), p.fs,
-                                       p.frame_period, fft_size, max_p, response.data_ptr(), st), "b2w_synth_render")
+            _timed(events, "render", total_p, lambda: check(lib.b2w_synth_render(
+                sp.data_ptr(), ap.data_ptr(), _DT[sp.dtype], p.frame_off.data_ptr(),
+                p.d_pulse_off.data_ptr(), p.num_pulses.data_ptr(), U, p.pulse_index.data_ptr(),
+                p.pulse_shift.data_ptr(), p.pulse_vuv.data_ptr(), p.tab.data_ptr(), p.tab.numel(), p.fs,
+                p.frame_period, fft_size, max_p, response.data_ptr(), st), "b2w_synth_render"))
         if debug is not None:  # diagnostics for the parity tests: the pulse table of every utterance
             debug.update(pulse_off=pulse_off, num_pulses=npul, pulse_index=p.pulse_index, pulse_shift=p.pulse_shift,
                          pulse_vuv=p.pulse_vuv, response=response)
-        check(lib.b2w_synth_overlap_add(response.data_ptr(), p.d_out_off.data_ptr(), p.d_pulse_off.data_ptr(),
-                                        p.num_pulses.data_ptr(), U, p.pulse_index.data_ptr(), fft_size, int(p.ylen.max()),
-                                        float(deemphasis), y.data_ptr(), _DT[y.dtype], st), "b2w_synth_overlap_add")
+        _timed(events, "overlap_add", total_p, lambda: check(lib.b2w_synth_overlap_add(
+            response.data_ptr(), p.d_out_off.data_ptr(), p.d_pulse_off.data_ptr(),
+            p.num_pulses.data_ptr(), U, p.pulse_index.data_ptr(), fft_size, int(p.ylen.max()),
+            float(deemphasis), y.data_ptr(), _DT[y.dtype], st), "b2w_synth_overlap_add"))
     return y, out_off, p.status
 
 

@@ -181,10 +181,12 @@ class WorldSynthesizer:
         self.device = torch.device(device)
         ops.McepTables.get(self.num_coded_sps - 1, self.alpha, self.n_fft, self.device)
 
-    def synthesize(self, feats, frame_off, preemphasis=0.0, out_dtype=torch.float32):
+    def synthesize(self, feats, frame_off, preemphasis=0.0, out_dtype=torch.float32, events=None):
         """feats [F, D + 2 + nap] float32 rows [coded_sp | lf0 | vuv | bap] on the device; frame_off int64 [U+1] on the device.
-        Returns (y packed, out_off numpy int64 [U+1], status)."""
+        Returns (y packed, out_off numpy int64 [U+1], status).  events: optional list that receives (kernel name, units, start
+        event, end event) per launch (bench.py's per-kernel timing)."""
         D = self.num_coded_sps
+        F = feats.shape[0]
         assert feats.shape[1] == D + 2 + self.nap, "WORLD requires all features to be present."
         lf0 = feats[:, D].double()
         vuv = (feats[:, D + 1] >= 0.5)
@@ -192,13 +194,69 @@ class WorldSynthesizer:
         vuv = vuv & ~(f0 < self.f0_silence_threshold)
         f0 = torch.where(vuv, f0, torch.full_like(f0, float(self.lf0_zero)))
         # decode_sp: amp = exp(Re mgc2sp) as float32 (AudioProcessing.py:256), then pow_sp = amp^2 in float64 (W:924)
-        pow_sp = ops.mc2sp(feats, self.alpha, self.n_fft, scale=1.0, do_exp=True, out_dtype=torch.float64, order=D - 1,
-                           mc_stride=feats.shape[1], square=True)
+        pow_sp = ops._timed(events, "mc2sp", F, lambda: ops.mc2sp(feats, self.alpha, self.n_fft, scale=1.0, do_exp=True,
+                                                                 out_dtype=torch.float64, order=D - 1, mc_stride=feats.shape[1],
+                                                                 square=True))
         bap = feats[:, D + 2:].double().contiguous()
-        ap = ops.decode_aperiodicity(bap, self.fs, self.n_fft)
+        ap = ops._timed(events, "decode_ap", F, lambda: ops.decode_aperiodicity(bap, self.fs, self.n_fft))
         # (Measured: decoding the two planes on a side stream while the sequential pulse placement runs on this one is SLOWER,
         # 23.2 ms against 19.8 ms for 256 utterances -- scripts/gpu_synth_phases.py -- so the stages stay in one stream.)
-        plan = ops.synth_timebase(f0.contiguous(), frame_off, self.fs, self.n_fft, self.hop_size_ms)
+        plan = ops.synth_timebase(f0.contiguous(), frame_off, self.fs, self.n_fft, self.hop_size_ms, events=events)
         de = float(preemphasis)
-        y, out_off, status = ops.synth_render(plan, pow_sp, ap, deemphasis=de, out_dtype=torch.float64 if de != 0.0 else out_dtype)
+        y, out_off, status = ops.synth_render(plan, pow_sp, ap, deemphasis=de, out_dtype=torch.float64 if de != 0.0 else out_dtype,
+                                              events=events)
         return y, out_off, status
+
+    def synthesize_corpus(self, feats, frame_off_host, batch_utts=256, out=None, feats_host=None, out_host=None, events=None):
+        """Synthesis of many utterances in batches of `batch_utts` (Synthesiser.run_world_synth over a corpus; the batch bounds
+        the per-pulse response buffer).  feats [F, dim] float32 on the device, or -- end to end -- `feats_host` [F, dim] in
+        pinned host memory, copied batch by batch on a copy stream one batch ahead of the synthesis; frame_off_host: numpy int64
+        [U+1].  Output: `out` (device, float32, packed [sum y_len]) and / or `out_host` (pinned; every batch's samples travel
+        back on a second copy stream while the next batch is synthesised).  Returns (sample offsets numpy int64 [U+1], status).
+        Synchronise the current stream before reading out_host."""
+        dev = self.device
+        fo = np.asarray(frame_off_host, np.int64)
+        U = len(fo) - 1
+        ylen = (np.diff(fo) * self.hop_size_ms * self.fs / 1000).astype(np.int64)
+        out_off = np.concatenate(([0], np.cumsum(ylen)))
+        cur = torch.cuda.current_stream(dev)
+        status = ops.new_status(dev)
+        if not hasattr(self, "_streams"):
+            self._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        s_in, s_out = self._streams
+        s_in.wait_stream(cur)
+        s_out.wait_stream(cur)
+        bounds = [(u0, min(U, u0 + batch_utts)) for u0 in range(0, U, batch_utts)]
+
+        def fetch(b):  # device rows of batch b (staged from the host one batch ahead)
+            u0, u1 = bounds[b]
+            if feats_host is None:
+                return feats[fo[u0]:fo[u1]], None
+            with torch.cuda.stream(s_in):
+                buf = torch.empty((int(fo[u1] - fo[u0]), feats_host.shape[1]), dtype=torch.float32, device=dev)
+                buf.copy_(feats_host[fo[u0]:fo[u1]], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s_in)
+            return buf, ev
+
+        nxt = fetch(0) if bounds else None
+        for b, (u0, u1) in enumerate(bounds):
+            rows, ev = nxt
+            nxt = fetch(b + 1) if b + 1 < len(bounds) else None
+            if ev is not None:
+                cur.wait_event(ev)
+                rows.record_stream(cur)
+            off_b = torch.from_numpy(fo[u0:u1 + 1] - fo[u0]).to(dev)
+            y, _, st = self.synthesize(rows, off_b, events=events)
+            status |= st
+            if out is not None:
+                out[out_off[u0]:out_off[u1]].copy_(y)
+            if out_host is not None:
+                done = torch.cuda.Event()
+                done.record(cur)
+                s_out.wait_event(done)
+                with torch.cuda.stream(s_out):
+                    out_host[out_off[u0]:out_off[u1]].copy_(y, non_blocking=True)
+                y.record_stream(s_out)
+        cur.wait_stream(s_out)
+        return out_off, status

@@ -86,12 +86,33 @@ def waveforms_from_f0(f0, fs, rngs, frame_period_ms=5.0, device="cpu", num_harmo
     return torch.round(y * 32767.0).to(torch.int16)
 
 
+def corpus_durations(utt_ids, seed, mean_dur=6.5, std_dur=0.0, min_dur=1.1, max_dur=10.1, dur_quantum=0.0):
+    """Durations (s) of the utterances with the given global indices, exactly as make_corpus draws them (utterance u's first
+    draw from default_rng(7919 * seed + u)) -- lets every rank of a sharded run know all lengths without synthesising anything."""
+    out = []
+    for u in utt_ids:
+        d = mean_dur
+        if std_dur != 0:
+            d = float(np.clip(np.random.default_rng(7919 * seed + int(u)).normal(mean_dur, std_dur), min_dur, max_dur))
+            if dur_quantum > 0:
+                d = round(d / dur_quantum) * dur_quantum
+        out.append(d)
+    return np.array(out)
+
+
 def make_corpus(num_utts, fs, seed, mean_dur=6.5, std_dur=0.0, min_dur=1.1, max_dur=10.1, frame_period_ms=5.0,
-                device="cpu", batch=64, first_utt=0):
-    """Returns (list of int16 torch tensors on `device`, list of numpy F0 tracks).  Utterance u uses
-    default_rng(7919 * seed + first_utt + u); equal-length utterances are synthesised `batch` at a time."""
-    rngs = [np.random.default_rng(7919 * seed + first_utt + u) for u in range(num_utts)]
+                device="cpu", batch=64, first_utt=0, utt_ids=None, dur_quantum=0.0):
+    """Returns (list of int16 torch tensors on `device`, list of numpy F0 tracks).  Utterance u (global index first_utt + u, or
+    utt_ids[u]) uses default_rng(7919 * seed + index); durations ~ N(mean_dur, std_dur^2) clipped to [min_dur, max_dur] and
+    rounded to multiples of dur_quantum (equal-length utterances are synthesised `batch` at a time, so a quantum keeps the
+    generator fast); std_dur = 0 gives the fixed-length variant."""
+    if utt_ids is None:
+        utt_ids = [first_utt + u for u in range(num_utts)]
+    num_utts = len(utt_ids)
+    rngs = [np.random.default_rng(7919 * seed + int(u)) for u in utt_ids]
     durs = [mean_dur if std_dur == 0 else float(np.clip(r.normal(mean_dur, std_dur), min_dur, max_dur)) for r in rngs]
+    if std_dur != 0 and dur_quantum > 0:
+        durs = [round(d / dur_quantum) * dur_quantum for d in durs]
     Ts = [int(round(d * 1000.0 / frame_period_ms)) + 1 for d in durs]
     f0s = [f0_track(r, T, frame_period_ms) for r, T in zip(rngs, Ts)]
     waves = [None] * num_utts
