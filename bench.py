@@ -1,20 +1,28 @@
 #!/usr/bin/env python
-"""Benchmark of the WORLD feature hot path (BASELINE.json metric: audio-seconds/s).
+"""Benchmark of the WORLD feature hot path (BASELINE.json metric: audio-seconds/s, WORLD analysis + synthesis).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--utts U]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--utts U] [--scaling strong|weak]
 
-Workload (config.workload = "ljspeech_extract"): BASELINE.json configs[1], the LJSpeech-shaped synthetic corpus
-(13,100 utterances x 6.5 s at 22.05 kHz, int16 PCM + cached F0 track) -> WorldFeatLabelGen-style features
-(mcep60, lf0, vuv, bap) + corpus normalisation statistics.  One step = one pass of the extraction over the corpus shard
-of every rank (weak scaling: every rank owns a full-size shard with its own seeds); ranks only exchange the
-statistics (one NCCL all-reduce per step, inside the timed region).
-
-value   : audio-seconds per second with the inputs resident in HBM (CUDA events, max over ranks).
-e2e     : the same pass through host buffers: pinned int16 wave + F0 host->device, extraction, features + statistics
-          device->host, all inside the timed region.
-roofline: the kernel with the largest share of the step, timed live with CUDA events on the launching stream.
-cpu_baseline / --impl reference: the CPU oracle (C restatement of the WORLD/SPTK algorithms; pyworld/pysptk are not installable here)
-          on all host cores over a bounded sample of the same workload.
+Workload (config.workload = "ljspeech_roundtrip"): BASELINE.json configs[1] / configs[2], the LJSpeech-shaped synthetic corpus
+(13,100 utterances, durations ~ N(6.5 s, 1.8 s), 22.05 kHz, int16 PCM + cached F0 track).  One step = one pass of the hot path
+over the corpus shard of this rank:
+    analysis   wav + F0 -> WorldFeatLabelGen features (mcep60, lf0, vuv, bap) + corpus normalisation statistics
+               (the path's ONE exchange step: an NCCL all-reduce of the statistics, inside the timed region), then
+    synthesis  the features just extracted -> waveforms (Synthesiser.run_world_synth, batches of 256 utterances).
+value   : audio-seconds per second with the inputs resident in HBM (CUDA events, max over ranks); `components` gives the
+          analysis and the synthesis halves separately.
+e2e     : the same pass through host buffers: pinned int16 wave + F0 host->device, features + statistics device->host,
+          features host->device, waveforms device->host, all inside the timed region.
+scaling : N > 1 defaults to STRONG scaling (configs[2]: the same 13,100-utterance corpus dealt to the ranks by
+          distributed.shard_utterances); --scaling weak gives every rank a full-size corpus of its own.
+roofline: the kernel with the largest share of the step, timed live with CUDA events on the launching stream; `kernels`
+          lists every kernel of the step with the bound that applies to it.
+parity  : after the timed region the C oracle re-computes k utterances of the bench corpus on the host; the rows / samples the
+          timed region wrote are compared with it (MCD, vuv, bap, lf0, resynthesis SNR) and the run FAILS when out of tolerance.
+workloads: BASELINE.json configs[3] (batched synthesis of 256 utterances from acoustic-model-shaped features) and configs[4]
+          (Neural-VTLN warp forward + backward, 109 speakers), each with value / e2e / roofline / cpu_baseline.
+cpu_baseline / --impl reference: the CPU oracle (C restatement of the WORLD / SPTK algorithms; pyworld / pysptk are not
+          installable here) on all host cores over a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -33,8 +41,12 @@ sys.path.insert(0, ROOT)
 FS = 22050
 UTTS = 13100
 DUR = 6.5
+DUR_STD = 1.8
+DUR_QUANTUM = 0.1   # durations are drawn from N(6.5, 1.8^2) clipped to [1.1, 10.1] s and rounded to 0.1 s
 NUM_CODED_SPS = 60
-METRIC = "audio-seconds/s (WORLD analysis: CheapTrick + D4C + mcep60 + lf0/vuv/bap + stats, cached F0)"
+SYNTH_BATCH = 256
+METRIC = "audio-seconds/s (WORLD analysis+synthesis)"
+TOL = {"mcd_db_max": 0.01, "vuv_mismatch": 0, "bap_abs_max": 1e-3, "lf0_abs_max": 1e-5, "resynthesis_snr_db_min": 60.0}
 
 
 def measured_peaks():
@@ -44,6 +56,16 @@ def measured_peaks():
             d = json.load(f)
         return d, "measured"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def ncu_pipes():
+    """Pipe utilisation of the compute-bound kernels as measured by `ncu --set full` (profiles/ncu_pipes.json, written by
+    scripts/make_profile_summary.py from the capture named in it): these cannot be measured from inside the process."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_pipes.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 class ClockSampler:
@@ -92,33 +114,43 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def corpus_args(fixed):
+    return dict(mean_dur=DUR, std_dur=0.0 if fixed else DUR_STD, dur_quantum=DUR_QUANTUM)
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # CPU oracle arm (cpu_baseline of the default run, and the whole of --impl reference)
 # ----------------------------------------------------------------------------------------------------------------------
-def cpu_oracle_throughput(waves, f0s, fs, alpha, cores, steps=1, warmup=0):
-    """audio-seconds/s of the CPU oracle (oracle/c/world_oracle.c: C restatement of WORLD / SPTK, one utterance per call,
-    the GIL is released inside) over the given sample with a pool of `cores` threads."""
+def cpu_oracle_roundtrip(waves, f0s, fs, alpha, cores, steps=1, warmup=0):
+    """audio-seconds/s of the CPU oracle (oracle/c/world_oracle.c: C restatement of WORLD / SPTK, one utterance per call, the
+    GIL is released inside) over the given sample with a pool of `cores` threads: analysis, then synthesis from the features
+    just extracted -- the same step the GPU arm times.  Returns (rate, seconds per step, audio seconds, analysis share)."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import world_c
     world_c.lib()
 
     def one(job):
         w, f = job
+        t0 = time.perf_counter()
         feats = world_c.extract(w, fs, f, NUM_CODED_SPS, alpha)
-        return feats.sum(0, dtype=np.float64), len(w) / fs
+        t1 = time.perf_counter()
+        y = world_c.synthesize_features(feats, fs, NUM_CODED_SPS, alpha)
+        t2 = time.perf_counter()
+        return float(y[:8].sum()), len(w) / fs, t1 - t0, t2 - t1
 
     jobs = [(np.ascontiguousarray(w), f) for w, f in zip(waves, f0s)]
     with ThreadPoolExecutor(max_workers=cores) as pool:
         for _ in range(warmup):
             list(pool.map(one, jobs[:cores]))
-        times = []
-        audio = 0.0
+        times, audio, ta, ts = [], 0.0, 0.0, 0.0
         for _ in range(steps):
             t0 = time.perf_counter()
             res = list(pool.map(one, jobs))
             times.append(time.perf_counter() - t0)
             audio = sum(r[1] for r in res)
-    return audio / (sum(times) / len(times)), sum(times) / len(times), audio
+            ta, ts = sum(r[2] for r in res), sum(r[3] for r in res)
+    sec = sum(times) / len(times)
+    return audio / sec, sec, audio, ta / max(ta + ts, 1e-9)
 
 
 def run_reference(args):
@@ -130,17 +162,19 @@ def run_reference(args):
     from oracle import sptk_np
     cores = len(os.sched_getaffinity(0))
     alpha = float(sptk_np.mcepalpha(FS))
-    n_utts = max(cores, min(2 * cores, 64))  # bounded sample: about one or two 6.5 s utterances per core and step
-    waves, f0s = synthetic.make_corpus(n_utts, FS, seed=2, mean_dur=DUR, device="cpu")
+    n_utts = max(cores, min(2 * cores, 64))  # bounded sample: about one or two ~6.5 s utterances per core and step
+    waves, f0s = synthetic.make_corpus(n_utts, FS, seed=2, device="cpu", **corpus_args(args.fixed_dur))
     waves = [w.numpy() for w in waves]
-    value, sec, audio = cpu_oracle_throughput(waves, f0s, FS, alpha, cores, steps=args.steps, warmup=min(args.warmup, 1))
+    value, sec, audio, share_a = cpu_oracle_roundtrip(waves, f0s, FS, alpha, cores, steps=args.steps, warmup=min(args.warmup, 1))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "ljspeech_extract", "fs": FS, "utt_seconds": DUR, "num_coded_sps": NUM_CODED_SPS,
-                       "sample_utts": n_utts, "note": "CPU oracle = C restatement of WORLD/SPTK, gcc -O3 -march=native, one thread per utterance (pyworld/pysptk unavailable offline)"},
+            "config": {"workload": "ljspeech_roundtrip", "fs": FS, "utt_seconds_mean": DUR, "num_coded_sps": NUM_CODED_SPS,
+                       "sample_utts": n_utts, "sample_audio_s": audio, "analysis_share_of_cpu_time": round(share_a, 3),
+                       "note": "CPU oracle = C restatement of WORLD/SPTK (analysis + synthesis), gcc -O3 -march=native, one thread per "
+                               "utterance over all host cores (pyworld/pysptk unavailable offline)"},
             "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port",
-                             "sample": "%d utterances x %.1f s per step" % (n_utts, DUR)},
+                             "sample": "%d utterances (%.0f audio-s) per step, analysis + synthesis" % (n_utts, audio)},
             "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -148,10 +182,22 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------------------
+def kernel_table(events, steps):
+    """events: (name, units, start, end) -> {name: {ms_per_step, launches_per_step, units_per_launch, avg_launch_ms}}"""
+    per = {}
+    for name, units, a, b in events:
+        d = per.setdefault(name, [0.0, 0, 0])
+        d[0] += a.elapsed_time(b)
+        d[1] += 1
+        d[2] += units
+    return {k: {"ms_per_step": v[0] / steps, "launches_per_step": v[1] / steps, "units_per_launch": v[2] / max(v[1], 1),
+                "avg_launch_ms": v[0] / max(v[1], 1)} for k, v in per.items()}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from idiaptts_b200 import _lib, ops, pipeline, synthetic
+    from idiaptts_b200 import _lib, distributed, ops, pipeline, synthetic
     from idiaptts_b200.compat.pysptk import mcepalpha
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -164,14 +210,25 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     alpha = float(mcepalpha(FS))
-    utts = args.utts
-    # every rank synthesises its own shard (weak scaling), distinct seeds
+    scaling = args.scaling or "strong"
+    cargs = corpus_args(args.fixed_dur)
     t0 = time.time()
-    waves, f0s = synthetic.make_corpus(utts, FS, seed=2, mean_dur=DUR, device=dev, batch=64, first_utt=rank * utts)
+    if scaling == "strong" and world > 1:
+        # configs[2]: ONE corpus of args.utts utterances, dealt longest-first to the ranks (every rank knows all durations)
+        durs = synthetic.corpus_durations(range(args.utts), 2, **cargs)
+        frames_all = np.round(durs * 200.0).astype(np.int64) + 1
+        ids = distributed.shard_utterances(frames_all, world)[rank]
+        imbalance = float(max(frames_all[s].sum() for s in distributed.shard_utterances(frames_all, world)) * world / frames_all.sum())
+    else:
+        ids = np.arange(args.utts, dtype=np.int64) + (rank * args.utts if world > 1 else 0)
+        imbalance = 1.0
+    waves, f0s = synthetic.make_corpus(0, FS, seed=2, device=dev, batch=64, utt_ids=ids, **cargs)
+    utts = len(waves)
     lens = np.array([w.numel() for w in waves], np.int64)
     flens = np.array([len(f) for f in f0s], np.int64)
     audio_s = float(lens.sum()) / FS
     x_dev = torch.cat(waves)
+    keep_waves = [waves[u].cpu().numpy() for u in range(min(args.parity_utts, utts))] if rank == 0 else []
     del waves
     f0_np = np.concatenate(f0s)
     t_np = np.concatenate([np.arange(n) * 5.0 / 1000.0 for n in flens])
@@ -182,26 +239,33 @@ def run_b200(args):
     host = {"x": x_dev.cpu().pin_memory(), "f0": torch.from_numpy(f0_np).pin_memory(), "t": torch.from_numpy(t_np).pin_memory(),
             "so": torch.from_numpy(sample_off).pin_memory(), "fo": torch.from_numpy(frame_off).pin_memory(),
             "fu": torch.from_numpy(frame_utt).pin_memory()}
-
-    def to_dev():
-        return ops.RaggedBatch(host["x"].to(dev, non_blocking=True), host["so"].to(dev, non_blocking=True),
-                               host["f0"].to(dev, non_blocking=True), host["t"].to(dev, non_blocking=True),
-                               host["fo"].to(dev, non_blocking=True), host["fu"].to(dev, non_blocking=True), FS)
-
-    batch = to_dev()
+    batch = ops.RaggedBatch(x_dev, host["so"].to(dev), host["f0"].to(dev), host["t"].to(dev), host["fo"].to(dev), host["fu"].to(dev), FS)
     F = batch.num_frames
     an = pipeline.WorldAnalyzer(FS, NUM_CODED_SPS, alpha, device=dev, chunk_frames=args.chunk_frames)
+    syn = pipeline.WorldSynthesizer(FS, NUM_CODED_SPS, alpha, device=dev)
     an.iters = torch.zeros(F, dtype=torch.int32, device=dev)
     feats = torch.empty((F, an.dim), dtype=torch.float32, device=dev)
     stat_buf = torch.zeros(2 * an.dim + 1, dtype=torch.float64, device=dev)
+    ylen = (flens * 5.0 * FS / 1000).astype(np.int64)
+    y_off = np.concatenate(([0], np.cumsum(ylen)))
+    y_all = torch.empty(int(y_off[-1]), dtype=torch.float32, device=dev)
+    total_audio = torch.tensor([audio_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_audio)
+    total_audio = float(total_audio.item())
 
-    def step(b, events=None):
+    def step(events=None, marks=None):
         stat_buf.zero_()
-        _, _, status = an.extract(b, feats=feats, sums=stat_buf[:2 * an.dim], events=events)
+        _, _, status = an.extract(batch, feats=feats, sums=stat_buf[:2 * an.dim], events=events)
         stat_buf[2 * an.dim] = float(F)
         if world > 1:
             dist.all_reduce(stat_buf)  # the path's only exchange step: corpus normalisation statistics
-        return status
+        if marks is not None:
+            m = torch.cuda.Event(enable_timing=True)
+            m.record()
+            marks.append(m)
+        _, st2 = syn.synthesize_corpus(feats, frame_off, batch_utts=SYNTH_BATCH, out=y_all, events=events)
+        return status, st2
 
     def barrier():
         if world > 1:
@@ -209,20 +273,24 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        status = step(batch)
+        status, st2 = step()
     barrier()
     ops.raise_for_status(status, "extract")
+    ops.raise_for_status(st2, "synthesize")
 
     # ---- timed region 1: inputs resident in HBM -----------------------------------------------------------------------
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    events = []
+    events, marks, starts = [], [], []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for _ in range(args.steps):
-        step(batch, events)
+        s = torch.cuda.Event(enable_timing=True)
+        s.record()
+        starts.append(s)
+        step(events, marks)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -231,105 +299,88 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_step = float(tmax.item()) / args.steps
-    value = audio_s * world / (ms_step / 1e3)
+    value = total_audio / (ms_step / 1e3)
+    ms_analysis = sum(s.elapsed_time(m) for s, m in zip(starts, marks)) / args.steps
+    ms_synth = ms / args.steps - ms_analysis
     stats_host = stat_buf.cpu().numpy()
+    peaks, peak_src = measured_peaks()
 
-    # per-kernel shares (rank 0's stream)
-    per = {}
-    for name, frames, a, b in events:
-        d = per.setdefault(name, [0.0, 0, 0])
-        d[0] += a.elapsed_time(b)
-        d[1] += 1
-        d[2] += frames
-    total_k = sum(v[0] for v in per.values())
-    top = max(per, key=lambda k: per[k][0])
+    # ---- per-kernel table (rank 0's stream) ---------------------------------------------------------------------------
+    kt = kernel_table(events, args.steps)
+    total_k = sum(v["ms_per_step"] for v in kt.values())
     H = FS * 0.005
     K = an.n_fft // 2 + 1
-    alg_bytes_per_frame = {
-        "cheaptrick": 2 * H + 20 + 4 * K,              # int16 samples of one hop + f0/t/frame_utt in, float32 envelope row out
-        "mcep": 4 * K + 4 * NUM_CODED_SPS,             # float32 envelope row in, 60 float32 coefficients out
-        "d4c": 2 * H + 20 + 8 * an.nap + 1,            # samples + f0/t in, coarse aperiodicity + voiced flag out
-        "bap_from_coarse": 8 * an.nap + 1 + 4 * an.nap,
-        "lf0_vuv": 8 + 8,
-        "stats": 4 * an.dim,
-    }
-    peaks, peak_src = measured_peaks()
-    top_ms = per[top][0] / per[top][1]
-    top_frames = per[top][2] / per[top][1]
-    achieved = alg_bytes_per_frame[top] * top_frames / (top_ms / 1e3) / 1e9
-    # the tensor-core kernel of the step, for the record: algorithmic FLOPs of the warp contractions (initial value +
-    # mean Newton passes x (freqt+FFT and IFFT+frqtr as GEMMs)), not counting the 3x of the TF32 split nor the solves
+    N = an.n_fft
     mean_it = float(an.iters.float().mean().item())
-    m = NUM_CODED_SPS - 1
-    flops_frame = 2.0 * K * (m + 2) + mean_it * 2.0 * K * ((m + 1) + (2 * m + 1))
-    mcep_ms = per["mcep"][0] / per["mcep"][1]
-    mcep_frames = per["mcep"][2] / per["mcep"][1]
-    mcep_tflops = flops_frame * mcep_frames / (mcep_ms / 1e3) / 1e12
-    # measured DRAM traffic of the dominant kernel (ncu --set full capture of this command, bytes per frame -> per launch)
+    m_ord = NUM_CODED_SPS - 1
+    # algorithmic bytes per unit (frames for the analysis and plane kernels, pulses for render / overlap-add, samples for the
+    # time base): what the kernel must read and write given the layouts of DESIGN.md 3
+    alg_bytes = {
+        "lf0_vuv": 8 + 8, "cheaptrick": 2 * H + 20 + 4 * K, "mcep": 4 * K + 4 * NUM_CODED_SPS, "d4c": 2 * H + 20 + 8 * an.nap + 1,
+        "bap_from_coarse": 8 * an.nap + 1 + 4 * an.nap, "stats": 4 * an.dim,
+        "mc2sp": 4 * NUM_CODED_SPS + 8 * K, "decode_ap": 8 * an.nap + 8 * K, "synth_timebase": 3 * 8,
+        "render": 2 * 2 * 8 * K + 8 * N, "overlap_add": 8 * N + 4 * H_pulse(FS),
+    }
+    bound = {"lf0_vuv": "latency", "cheaptrick": "l1_shared_pipe+fp64", "mcep": "tensor", "d4c": "issue+l1_shared_pipe",
+             "bap_from_coarse": "latency", "stats": "hbm", "mc2sp": "fp32_fma+hbm", "decode_ap": "hbm", "synth_timebase": "latency",
+             "render": "l1_shared_pipe+fp64", "overlap_add": "hbm"}
+    pipes = ncu_pipes()
+    kernels = {}
+    for k, v in kt.items():
+        gbs = alg_bytes.get(k, 0) * v["units_per_launch"] / (v["avg_launch_ms"] / 1e3) / 1e9 if v["avg_launch_ms"] > 0 else 0.0
+        kernels[k] = {"share_of_step": round(v["ms_per_step"] / total_k, 4), "avg_launch_ms": round(v["avg_launch_ms"], 4),
+                      "launches_per_step": v["launches_per_step"], "units_per_launch": round(v["units_per_launch"], 1),
+                      "bound": bound.get(k, "?"), "algorithmic_GBps": round(gbs, 2), "hbm_frac": round(gbs / peaks["hbm_gbs"], 5)}
+        if k in pipes:
+            kernels[k]["ncu"] = pipes[k]
+    # tensor-core kernel: algorithmic FLOPs of the warp contractions (initial value + mean Newton passes x (freqt+FFT and
+    # IFFT+frqtr as GEMMs)); the 3xTF32 split issues three TF32 MMAs per algorithmic one
+    flops_frame = 2.0 * K * (m_ord + 2) + mean_it * 2.0 * K * ((m_ord + 1) + (2 * m_ord + 1))
+    mcep_tflops = flops_frame * kt["mcep"]["units_per_launch"] / (kt["mcep"]["avg_launch_ms"] / 1e3) / 1e12
+    tf32_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) / 2.0
+    kernels["mcep"].update({"tensor_tflops_algorithmic": round(mcep_tflops, 2), "tensor_tflops_issued_tf32": round(3 * mcep_tflops, 2),
+                            "tensor_frac_of_tf32_peak": round(3 * mcep_tflops / tf32_peak, 4), "mean_newton_passes": round(mean_it, 3)})
+    top = max(kt, key=lambda k: kt[k]["ms_per_step"])
     traffic = None
     try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as f:
-            traffic = float(json.load(f)[top]["dram_bytes_per_frame"]) * top_frames
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            tj = json.load(f)[top]
+            traffic = float(tj.get("dram_bytes_per_unit", tj.get("dram_bytes_per_frame"))) * kt[top]["units_per_launch"]
     except Exception:
         pass
-    # compute side of the dominant kernels: algorithmic fp64 FFT flops (5 N log2 N per complex FFT, nothing else counted)
-    # against the fp64 FMA rate measured right here with a pure-FMA probe kernel
-    probe = torch.zeros(8, dtype=torch.float64, device=dev)
-    lib = _lib.load()
-    lib.b2w_probe_fp64_fma(1 << 12, probe.data_ptr(), torch.cuda.current_stream().cuda_stream)
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record()
-    nfma = lib.b2w_probe_fp64_fma(1 << 15, probe.data_ptr(), torch.cuda.current_stream().cuda_stream)
-    p1.record()
-    torch.cuda.synchronize()
-    fp64_peak = 2.0 * nfma / (p0.elapsed_time(p1) / 1e3) / 1e12
-    n4 = 2048 if FS <= 24000 else 4096
-    lo_f, hi_f = 0, min(F, an.chunk_frames)
-    _, vflag, _ = ops.d4c_coarse(batch, frame_lo=lo_f, frame_hi=hi_f)
-    f0_pos = float((batch.f0[lo_f:hi_f] > 0).float().mean().item())     # frames that enter D4C (1 FFT: LoveTrain)
-    full = float(vflag.float().mean().item())                            # frames that run the whole of D4C
-    fft_flop = lambda n: 5.0 * n * math.log2(n)
-    d4c_flop_frame = f0_pos * fft_flop(n4) + full * (2 + (an.nap + 1) // 2) * fft_flop(n4)
-    ct_flop_frame = 3 * fft_flop(an.n_fft // 2)
-    def tfl(name, flop_frame):
-        return flop_frame * (per[name][2] / per[name][1]) / (per[name][0] / per[name][1] / 1e3) / 1e12
-    compute = {"fp64_fma_peak_tflops_measured": round(fp64_peak, 2),
-               "d4c": {"fft_tflops": round(tfl("d4c", d4c_flop_frame), 3), "frac_of_fp64_peak": round(tfl("d4c", d4c_flop_frame) / fp64_peak, 4),
-                       "frames_with_f0": round(f0_pos, 4), "frames_full_d4c": round(full, 4)},
-               "cheaptrick": {"fft_tflops": round(tfl("cheaptrick", ct_flop_frame), 3),
-                              "frac_of_fp64_peak": round(tfl("cheaptrick", ct_flop_frame) / fp64_peak, 4)},
-               "note": "FFT flops only (5 N log2 N per complex FFT); windows, smoothing, order statistics, log/exp are not counted. "
-                       "ncu (profiles/): these kernels are bound by the L1/shared-memory data pipe and the fp64 pipe together"}
-    roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src, "compute": compute,
-                "share_of_step": per[top][0] / total_k,
-                "shares": {k: round(v[0] / total_k, 4) for k, v in per.items()},
-                "avg_launch_ms": {k: round(v[0] / v[1], 3) for k, v in per.items()},
-                "mcep_tensor": {"bound": "tensor", "achieved": mcep_tflops, "unit": "TFLOP/s (algorithmic, fp32-equivalent)",
-                                "peak": peaks.get("bf16_tflops_sustained"), "peak_unit": "TFLOP/s bf16 dense (measured)",
-                                "mean_newton_passes": mean_it,
-                                "note": "tcgen05 kind::tf32 with the 3xTF32 split; the kernel is bound by issue slots / latency of the exp "
-                                        "epilogue and the per-frame 60x60 register-resident solves, not by the tensor pipe"},
-                "note": "compute-bound kernel (fp64 FFTs / fp32 contractions): the HBM fraction is reported because the "
-                        "metric asks for it, see DESIGN.md for the per-kernel bounds"}
+    if top == "mcep":
+        roofline = {"kernel": top, "bound": "tensor", "achieved": 3 * mcep_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
+                    "frac": 3 * mcep_tflops / tf32_peak, "traffic": traffic, "peak_source": peak_src,
+                    "note": "TF32 MMAs issued (3xTF32 split = 3 per algorithmic MMA) against the dense TF32 peak = half the measured bf16 "
+                            "rate; the kernel is bound by its per-frame 60x60 solves and the exp epilogue (kernels.mcep.ncu), not by the "
+                            "tensor pipe"}
+    else:
+        a = kernels[top]["algorithmic_GBps"]
+        roofline = {"kernel": top, "bound": "hbm", "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": a / peaks["hbm_gbs"],
+                    "traffic": traffic, "peak_source": peak_src, "binding": bound.get(top),
+                    "note": "the HBM fraction is what the metric asks for; this kernel is bound on chip (see `binding` and kernels.%s.ncu: "
+                            "pipe utilisation from the ncu capture under profiles/)" % top}
+    roofline["share_of_step"] = kernels[top]["share_of_step"]
 
     # ---- timed region 2: end to end through host buffers ---------------------------------------------------------------
     feats_host = torch.empty((F, an.dim), dtype=torch.float32).pin_memory()
+    y_host = torch.empty(int(y_off[-1]), dtype=torch.float32).pin_memory()
     stats_pinned = torch.empty(2 * an.dim + 1, dtype=torch.float64).pin_memory()
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
-    d2h = feats_host.numel() * 4 + stats_pinned.numel() * 8
-
+    h2d = sum(v.numel() * v.element_size() for v in host.values()) + feats_host.numel() * 4
+    d2h = feats_host.numel() * 4 + stats_pinned.numel() * 8 + y_host.numel() * 4
     e2e_state = {"buf": None}
 
     def e2e_step():
-        # the public end-to-end call: pinned host corpus in, pinned host features + statistics out, copies overlapped with
-        # the analysis of neighbouring frame chunks (pipeline.WorldAnalyzer.extract_from_host)
+        # the public end-to-end calls: pinned host corpus in, pinned host features + statistics out (WorldAnalyzer.extract_from_host),
+        # then pinned host features in, pinned host waveforms out (WorldSynthesizer.synthesize_corpus); copies overlap the kernels
         stat_buf.zero_()
         _, _, _, e2e_state["buf"] = an.extract_from_host(host, feats_host, dev_buffers=e2e_state["buf"], sums=stat_buf[:2 * an.dim])
         stat_buf[2 * an.dim] = float(F)
         if world > 1:
             dist.all_reduce(stat_buf)
         stats_pinned.copy_(stat_buf, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the features must have landed in host memory before they are read back
+        syn.synthesize_corpus(None, frame_off, batch_utts=SYNTH_BATCH, feats_host=feats_host, out_host=y_host)
 
     e2e_step()
     barrier()
@@ -342,92 +393,238 @@ def run_b200(args):
     t2 = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_value = audio_s * world / (float(t2.item()) / args.steps / 1e3)
+    e2e_value = total_audio / (float(t2.item()) / args.steps / 1e3)
+    del e2e_state
 
-    # ---- secondary measurements (rank 0): BASELINE.json configs[3] (batched synthesis of 256 utterances from the features just
-    # extracted) and configs[4] (Neural-VTLN warp forward + backward, VCTK-shaped) -- reported next to the headline, not part of it
-    secondary = None
-    if rank == 0 and not args.no_secondary:
-        def t_ms(fn, reps=3):
-            fn()
-            torch.cuda.synchronize()
-            best = 1e30
-            for _ in range(reps):
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                fn()
-                b.record()
-                torch.cuda.synchronize()
-                best = min(best, a.elapsed_time(b))
-            return best
-        nu = min(256, utts)
-        f_end = int(frame_off[nu])
-        syn = pipeline.WorldSynthesizer(FS, NUM_CODED_SPS, alpha, device=dev)
-        sub_feats, sub_off = feats[:f_end].contiguous(), batch.frame_off[:nu + 1].contiguous()
-        ms_syn = t_ms(lambda: syn.synthesize(sub_feats, sub_off))
-        syn_audio = f_end * 0.005
-        n_v, spk, utt_v, T_v = 60, 109, 4, 1301
-        rows_v = spk * utt_v * T_v
-        gen_v = torch.Generator(device=dev).manual_seed(5)
-        xv = torch.randn((rows_v, n_v), generator=gen_v, device=dev)
-        gv = torch.randn((rows_v, n_v), generator=gen_v, device=dev)
-        av = (torch.rand(spk, generator=gen_v, device=dev) * 0.4 - 0.2).repeat_interleave(utt_v * T_v).contiguous()
-        ms_vf = t_ms(lambda: ops.allpass_forward(xv, av, n_v), 5)
-        ms_vb = t_ms(lambda: ops.allpass_backward(gv, xv, av, n_v), 5)
-        secondary = {"synthesis": {"workload": "batched WORLD synthesis of %d utterances from mgc60+lf0+vuv+bap" % nu, "ms": round(ms_syn, 3),
-                                   "audio_s_per_s": syn_audio / (ms_syn / 1e3)},
-                     "analysis_plus_synthesis_audio_s_per_s": 1.0 / (1.0 / (audio_s / (ms_step / 1e3)) + 1.0 / (syn_audio / (ms_syn / 1e3))),
-                     "vtln": {"workload": "all-pass warp, 109 speakers x 4 utts x 1301 frames, n = 60, one alpha per speaker",
-                              "fwd_ms": round(ms_vf, 4), "bwd_ms": round(ms_vb, 4),
-                              "fwd_frac_of_hbm_peak": rows_v * (8 * n_v + 4) / (ms_vf / 1e3) / 1e9 / peaks["hbm_gbs"],
-                              "bwd_frac_of_hbm_peak": rows_v * (12 * n_v + 8) / (ms_vb / 1e3) / 1e9 / peaks["hbm_gbs"]}}
-        # F0 stage (not part of the headline, which is quoted with cached F0): DIO + StoneMask over the first 512
-        # utterances, and what the un-cached pyworld.wav2world path would run at
-        nf0 = min(512, utts)
-        sub = ops.RaggedBatch(batch.x[:int(sample_off[nf0])], batch.sample_off[:nf0 + 1].contiguous(), batch.f0[:int(frame_off[nf0])],
-                              batch.t[:int(frame_off[nf0])], batch.frame_off[:nf0 + 1].contiguous(),
-                              batch.frame_utt[:int(frame_off[nf0])], FS)
-        ms_dio = t_ms(lambda: ops.dio(sub), 2)
-        f0_dio = ops.dio(sub)
-        ms_sm = t_ms(lambda: ops.stonemask(sub, f0_dio), 2)
-        f0_audio = int(sample_off[nf0]) / FS
-        f0_rate = f0_audio / ((ms_dio + ms_sm) / 1e3)
-        dio_dfma = 2.0 * int(sample_off[nf0]) * ops.dio_fir_taps(FS)   # flop of the two FIR stages
-        secondary["f0_stage"] = {"workload": "DIO + StoneMask (pyworld.wav2world's F0 half), %d utterances" % nf0,
-                                 "dio_ms": round(ms_dio, 3), "stonemask_ms": round(ms_sm, 3), "audio_s_per_s": f0_rate,
-                                 "dio_fir_tflops_fp64": dio_dfma / (ms_dio / 1e3) / 1e12,
-                                 "analysis_with_f0_estimation_audio_s_per_s": 1.0 / (1.0 / (audio_s / (ms_step / 1e3)) + 1.0 / f0_rate)}
-        del xv, gv, av, sub_feats, sub, f0_dio
-
+    line = None
     if rank == 0:
-        # ---- CPU baseline on a bounded sample of the same workload (N = 1 only) -------------------------------------
+        # ---- parity of what the timed region wrote, against the CPU oracle (bounded: args.parity_utts utterances) -------------
+        parity = check_parity(keep_waves, f0s, feats, frame_off, y_all, y_off, alpha, an.nap) if keep_waves else None
+        # ---- configs[3] / configs[4] as workloads of their own -----------------------------------------------------------------
+        workloads = None
+        if not args.no_workloads:
+            workloads = {"synth256": bench_synth256(args, dev, syn, feats, frame_off, stats_host, an, peaks, alpha),
+                         "vtln109": bench_vtln109(args, dev, peaks)}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             # separate process: no fork of a CUDA-initialised interpreter
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                               capture_output=True, text=True)
+            cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0"]
+            r = subprocess.run(cmd + (["--fixed-dur"] if args.fixed_dur else []), capture_output=True, text=True)
             try:
                 cpu = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
             except Exception:
                 cpu = {"value": None, "unit": "audio-s/s", "cores": 0, "kind": "port", "sample": "failed: " + r.stderr[-300:]}
         n = float(stats_host[2 * an.dim])
         mean, std = pipeline.mean_std_from_sums(stats_host, n, an.dim)
+        launches = an.kernel_launches(F) + syn.kernel_launches(utts, SYNTH_BATCH)
         line = {"metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+f32",
-                "data": "synthetic",
-                "config": {"workload": "ljspeech_extract", "utts_per_gpu": utts, "fs": FS, "utt_seconds": DUR,
-                           "frames_per_gpu": int(F), "audio_seconds_per_gpu": audio_s, "num_coded_sps": NUM_CODED_SPS,
-                           "mgc_alpha": alpha, "fft_size": an.n_fft, "num_bap": an.nap, "chunk_frames": an.chunk_frames,
-                           "l2": "inputs (%.2f GB int16) and outputs (%.2f GB) exceed the 126 MB L2" % (
-                               host["x"].numel() * 2 / 1e9, feats.numel() * 4 / 1e9),
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling if world > 1 else "weak", "vs_baseline": None,
+                "dtype": "f32 FFTs + f64 scans (analysis), 3xTF32 (mel-cepstrum), f64 (synthesis)", "data": "synthetic",
+                "config": {"workload": "ljspeech_roundtrip", "utts_total": int(args.utts * (world if scaling == "weak" and world > 1 else 1)),
+                           "utts_this_rank": utts, "fs": FS, "utt_seconds": "N(%.1f, %.1f^2) clipped [1.1, 10.1]" % (DUR, DUR_STD)
+                           if not args.fixed_dur else DUR, "audio_seconds_total": total_audio, "frames_this_rank": int(F),
+                           "num_coded_sps": NUM_CODED_SPS, "mgc_alpha": alpha, "fft_size": an.n_fft, "num_bap": an.nap,
+                           "chunk_frames": an.chunk_frames, "synth_batch_utts": SYNTH_BATCH, "shard_imbalance": round(imbalance, 4),
+                           "l2": "inputs (%.2f GB int16), features (%.2f GB) and waveforms (%.2f GB) exceed the 126 MB L2" % (
+                               host["x"].numel() * 2 / 1e9, feats.numel() * 4 / 1e9, y_all.numel() * 4 / 1e9),
                            "corpus_gen_s": round(gen_s, 1), "mean_c0": float(mean[0]), "std_c0": float(std[0])},
+                "components": {"analysis": {"audio_s_per_s": audio_s / (ms_analysis / 1e3), "ms_per_step": ms_analysis,
+                                            "what": "wav + cached F0 -> mcep60/lf0/vuv/bap + statistics all-reduce (rank 0)"},
+                               "synthesis": {"audio_s_per_s": audio_s / (ms_synth / 1e3), "ms_per_step": ms_synth,
+                                             "what": "features -> waveforms, batches of %d utterances (rank 0)" % SYNTH_BATCH}},
                 "clocks": clocks, "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(h2d),
                                           "d2h_bytes_per_step": int(d2h)},
-                "gpu_launches": int(args.steps * an.kernel_launches(F)), "roofline": roofline, "cpu_baseline": cpu,
-                "secondary": secondary}
+                "gpu_launches": int(args.steps * launches), "roofline": roofline, "kernels": kernels, "parity": parity,
+                "cpu_baseline": cpu, "workloads": workloads}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if line is not None and line["parity"] is not None and not line["parity"]["ok"]:
+        raise SystemExit("parity check failed: %s" % json.dumps(line["parity"]))
+
+
+def H_pulse(fs):
+    """mean output samples per pulse of the synthetic corpus (~ fs / mean pulse rate, ~ 310 pulses per audio-second)"""
+    return fs / 310.0
+
+
+def check_parity(waves, f0s, feats, frame_off, y_all, y_off, alpha, nap):
+    """C oracle on the first len(waves) utterances of rank 0's shard vs the feature rows / waveforms of the timed region."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import glue_np, world_c
+    world_c.lib()
+    D = NUM_CODED_SPS
+    k = len(waves)
+    cores = len(os.sched_getaffinity(0))
+    gpu_rows = [feats[int(frame_off[u]):int(frame_off[u + 1])].cpu().numpy() for u in range(k)]
+    gpu_y = [y_all[int(y_off[u]):int(y_off[u + 1])].cpu().numpy().astype(np.float64) for u in range(k)]
+
+    def one(u):
+        ref = world_c.extract(waves[u], FS, f0s[u], D, alpha)
+        y_ref = world_c.synthesize_features(gpu_rows[u], FS, D, alpha).astype(np.float64)   # from the GPU's own features
+        return ref, y_ref
+
+    with ThreadPoolExecutor(max_workers=min(cores, k)) as pool:
+        res = list(pool.map(one, range(k)))
+    out = {"utterances": k, "mcd_db_max": 0.0, "vuv_mismatch": 0, "bap_abs_max": 0.0, "lf0_abs_max": 0.0, "resynthesis_snr_db_min": 1e9,
+           "frames": int(sum(len(r) for r in gpu_rows))}
+    for u, (ref, y_ref) in enumerate(res):
+        g = gpu_rows[u]
+        out["mcd_db_max"] = max(out["mcd_db_max"], float(glue_np.mcd_db(ref[:, :D], g[:, :D])))
+        out["vuv_mismatch"] += int((ref[:, D + 1] != g[:, D + 1]).sum())
+        out["bap_abs_max"] = max(out["bap_abs_max"], float(np.abs(ref[:, D + 2:] - g[:, D + 2:]).max()))
+        out["lf0_abs_max"] = max(out["lf0_abs_max"], float(np.abs(ref[:, D] - g[:, D]).max()))
+        err = ((gpu_y[u] - y_ref) ** 2).sum()
+        out["resynthesis_snr_db_min"] = min(out["resynthesis_snr_db_min"], float(10 * np.log10((y_ref ** 2).sum() / max(err, 1e-300))))
+    out["tolerances"] = TOL
+    out["ok"] = bool(out["mcd_db_max"] < TOL["mcd_db_max"] and out["vuv_mismatch"] == 0 and out["bap_abs_max"] < TOL["bap_abs_max"]
+                     and out["lf0_abs_max"] < TOL["lf0_abs_max"] and out["resynthesis_snr_db_min"] > TOL["resynthesis_snr_db_min"])
+    out["oracle"] = "oracle/c/world_oracle.c (analysis half pinned to the reference's fixtures; synthesis half = restatement, unpinned)"
+    return out
+
+
+class L2Flusher:
+    """Between timed iterations of the small workloads: write a buffer larger than the 126 MB L2."""
+
+    def __init__(self, dev):
+        import torch
+        self.buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def __call__(self):
+        self.buf.zero_()
+
+
+def timed_steps(fn, steps, warmup, flush):
+    """W warm-up calls, then K calls timed one by one with CUDA events (an L2 flush between them, outside the timed spans)."""
+    import torch
+    for _ in range(max(warmup, 1)):
+        fn()
+    torch.cuda.synchronize()
+    total = 0.0
+    for _ in range(steps):
+        flush()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        total += a.elapsed_time(b)
+    return total / steps
+
+
+def bench_synth256(args, dev, syn, feats, frame_off, stats_host, an, peaks, alpha):
+    """BASELINE.json configs[3]: batched WORLD synthesis of 256 utterances from acoustic-model-shaped outputs = the features of the
+    first 256 corpus utterances + N(0, (0.05 sigma_d)^2) per dimension, vuv = clip(vuv + N(0, 0.1^2), 0, 1), seed 4."""
+    import torch
+    from idiaptts_b200 import pipeline
+    D = NUM_CODED_SPS
+    nu = min(256, len(frame_off) - 1)
+    f_end = int(frame_off[nu])
+    n = float(stats_host[2 * an.dim])
+    _, std = pipeline.mean_std_from_sums(stats_host, n, an.dim)
+    gen = torch.Generator(device=dev).manual_seed(4)
+    sub = feats[:f_end].clone()
+    sub += torch.randn(sub.shape, generator=gen, device=dev) * torch.from_numpy((0.05 * std).astype(np.float32)).to(dev)
+    sub[:, D + 1] = torch.clamp(feats[:f_end, D + 1] + 0.1 * torch.randn(f_end, generator=gen, device=dev), 0.0, 1.0)
+    fo = np.asarray(frame_off[:nu + 1], np.int64)
+    audio = f_end * 0.005
+    flush = L2Flusher(dev)
+    events = []
+    ms = timed_steps(lambda: syn.synthesize_corpus(sub, fo, batch_utts=256), args.steps, args.warmup, flush)
+    syn.synthesize_corpus(sub, fo, batch_utts=256, events=events)
+    torch.cuda.synchronize()
+    kt = kernel_table(events, 1)
+    sub_host = sub.cpu().pin_memory()
+    ylen = (np.diff(fo) * 5.0 * FS / 1000).astype(np.int64)
+    y_host = torch.empty(int(ylen.sum()), dtype=torch.float32).pin_memory()
+    ms_e2e = timed_steps(lambda: syn.synthesize_corpus(None, fo, batch_utts=256, feats_host=sub_host, out_host=y_host),
+                         args.steps, args.warmup, flush)
+    K, N = an.n_fft // 2 + 1, an.n_fft
+    oa = kt.get("overlap_add")
+    pulses = oa["units_per_launch"] if oa else 0
+    oa_gbs = (pulses * 8 * N + int(ylen.sum()) * 4) / (oa["avg_launch_ms"] / 1e3) / 1e9 if oa else 0.0
+    top = max(kt, key=lambda k: kt[k]["ms_per_step"])
+    # CPU oracle on a bounded sample of the same rows
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import world_c
+    world_c.lib()
+    cores = len(os.sched_getaffinity(0))
+    ns = min(nu, max(cores, 16))
+    rows = [sub_host[int(fo[u]):int(fo[u + 1])].numpy() for u in range(ns)]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=cores) as pool:
+        list(pool.map(lambda r: world_c.synthesize_features(r, FS, D, alpha)[:1], rows))
+    cpu_rate = float(fo[ns]) * 0.005 / (time.perf_counter() - t0)
+    return {"workload": "batched WORLD synthesis of %d utterances from acoustic-model-shaped features (mgc60+lf0+vuv+bap, seed 4)" % nu,
+            "metric": "audio-seconds/s (WORLD synthesis)", "value": audio / (ms / 1e3), "unit": "audio-s/s", "ms_per_step": ms,
+            "steps": args.steps, "warmup": args.warmup, "l2": "flushed between timed iterations (256 MB write)",
+            "e2e": {"value": audio / (ms_e2e / 1e3), "unit": "audio-s/s", "h2d_bytes_per_step": int(sub_host.numel() * 4),
+                    "d2h_bytes_per_step": int(y_host.numel() * 4)},
+            "kernels": {k: {"ms": round(v["ms_per_step"], 4), "share": round(v["ms_per_step"] / sum(x["ms_per_step"] for x in kt.values()), 4)}
+                        for k, v in kt.items()},
+            "roofline": {"kernel": "overlap_add", "bound": "hbm", "achieved": oa_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": oa_gbs / peaks["hbm_gbs"], "traffic": None,
+                         "note": "the HBM-bound kernel of the workload (one 8 KB response read per pulse, float32 samples written); the "
+                                 "dominant kernel is `%s` (on-chip bound, see kernels.render.ncu of the main line)" % top},
+            "cpu_baseline": {"value": cpu_rate, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                             "sample": "%d utterances of the same rows" % ns}}
+
+
+def bench_vtln109(args, dev, peaks):
+    """BASELINE.json configs[4]: Neural-VTLN all-pass warp forward + backward on VCTK-shaped mgc batches: 109 speakers x 4
+    utterances x 1301 frames x 60 coefficients, one alpha ~ U[-0.2, 0.2] per speaker, grad_out ~ N(0, 1), seed 5."""
+    import torch
+    from idiaptts_b200 import ops
+    n_v, spk, utt_v, T_v = 60, 109, 4, 1301
+    rows = spk * utt_v * T_v
+    gen = torch.Generator(device=dev).manual_seed(5)
+    x = torch.randn((rows, n_v), generator=gen, device=dev)
+    g = torch.randn((rows, n_v), generator=gen, device=dev)
+    a = (torch.rand(spk, generator=gen, device=dev) * 0.4 - 0.2).repeat_interleave(utt_v * T_v).contiguous()
+    flush = L2Flusher(dev)
+    ms_f = timed_steps(lambda: ops.allpass_forward(x, a, n_v), args.steps, args.warmup, flush)
+    ms_b = timed_steps(lambda: ops.allpass_backward(g, x, a, n_v), args.steps, args.warmup, flush)
+    # end to end: pinned host x / grad_out / alpha in, y / grad_x / grad_alpha back
+    xh, gh, ah = x.cpu().pin_memory(), g.cpu().pin_memory(), a.cpu().pin_memory()
+    yh, gxh, gah = torch.empty_like(xh).pin_memory(), torch.empty_like(xh).pin_memory(), torch.empty_like(ah).pin_memory()
+
+    def e2e():
+        xd, gd, ad = xh.to(dev, non_blocking=True), gh.to(dev, non_blocking=True), ah.to(dev, non_blocking=True)
+        y = ops.allpass_forward(xd, ad, n_v)
+        gx, ga = ops.allpass_backward(gd, xd, ad, n_v)
+        yh.copy_(y, non_blocking=True)
+        gxh.copy_(gx, non_blocking=True)
+        gah.copy_(ga, non_blocking=True)
+
+    ms_e = timed_steps(e2e, args.steps, args.warmup, flush)
+    bytes_f, bytes_b = rows * (8 * n_v + 4), rows * (12 * n_v + 8)
+    gbs = (bytes_f + bytes_b) / ((ms_f + ms_b) / 1e3) / 1e9
+    # CPU: the reference layer's own formulation (AllPassWarp.py:148-205: per-frame warp matrix W = einsum(w3, alpha^k), then bmm)
+    # restated with CPU torch on a bounded sample of rows, forward + autograd backward, all host cores (values do not matter for
+    # the timing: at n = 60 the reference's float32 polynomial tensor overflows anyway, SURVEY 0.5)
+    ns = 8192
+    w3 = torch.randn(n_v, n_v, 2 * n_v) * 1e-3
+    xs = xh[:ns].clone().requires_grad_(True)
+    as_ = ah[:ns].clone().requires_grad_(True)
+    t0 = time.perf_counter()
+    pw = as_[:, None] ** torch.arange(2 * n_v, dtype=torch.float32)[None, :]
+    Wm = torch.einsum("bk,rck->brc", pw, w3)
+    ys = torch.bmm(xs[:, None, :], Wm)[:, 0, :]
+    ys.backward(gh[:ns])
+    cpu_rows = ns / (time.perf_counter() - t0)
+    cores = torch.get_num_threads()
+    return {"workload": "Neural-VTLN all-pass warp fwd + bwd, %d speakers x %d utts x %d frames, n = %d, one alpha per speaker (seed 5)" % (
+                spk, utt_v, T_v, n_v),
+            "metric": "frames/s (VTLN warp forward + backward)", "value": rows / ((ms_f + ms_b) / 1e3), "unit": "frames/s",
+            "fwd_ms": round(ms_f, 4), "bwd_ms": round(ms_b, 4), "steps": args.steps, "warmup": args.warmup,
+            "l2": "flushed between timed iterations (256 MB write)",
+            "e2e": {"value": rows / (ms_e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": int(rows * (8 * n_v + 4)),
+                    "d2h_bytes_per_step": int(rows * (8 * n_v + 4))},
+            "roofline": {"kernel": "allpass_tc_forward + allpass_tc_backward", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
+                         "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None,
+                         "fwd_frac": bytes_f / (ms_f / 1e3) / 1e9 / peaks["hbm_gbs"], "bwd_frac": bytes_b / (ms_b / 1e3) / 1e9 / peaks["hbm_gbs"]},
+            "cpu_baseline": {"value": cpu_rows, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": "%d rows, CPU torch restatement of AllPassWarp.forward (einsum + bmm) + autograd backward" % ns}}
 
 
 def main():
@@ -436,10 +633,13 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--utts", type=int, default=UTTS, help="utterances per GPU (default: the full LJSpeech-shaped corpus)")
+    ap.add_argument("--utts", type=int, default=UTTS, help="utterances of the corpus (strong scaling: in total; weak: per GPU)")
+    ap.add_argument("--scaling", default=None, choices=["strong", "weak"], help="N > 1: strong (default, configs[2]) or weak")
+    ap.add_argument("--fixed-dur", action="store_true", help="the fixed 6.5 s variant of the corpus")
     ap.add_argument("--chunk-frames", type=int, default=1 << 18)
+    ap.add_argument("--parity-utts", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the synthesis / VTLN side measurements")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the synth256 / vtln109 workloads")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -153,7 +153,7 @@ class WorldAnalyzer:
     def kernel_launches(self, num_frames):
         """Number of libb200world kernels one extract() call launches (for bench.py's gpu_launches)."""
         chunks = max(1, math.ceil(num_frames / self.chunk_frames))
-        return 1 + 4 * chunks + 1
+        return 1 + 5 * chunks + 1   # lf0_vuv; per chunk cheaptrick, mcep, d4c (single-precision pass + fp64 re-evaluation), bap; stats
 
 
 def mean_std_from_sums(sums, n, dim):
@@ -206,6 +206,11 @@ class WorldSynthesizer:
         y, out_off, status = ops.synth_render(plan, pow_sp, ap, deemphasis=de, out_dtype=torch.float64 if de != 0.0 else out_dtype,
                                               events=events)
         return y, out_off, status
+
+    def kernel_launches(self, num_utts, batch_utts=256):
+        """Number of libb200world kernels synthesize_corpus launches (for bench.py's gpu_launches): per batch mc2sp, decode_ap,
+        the four time-base kernels, render, overlap-add."""
+        return 8 * max(1, math.ceil(num_utts / batch_utts))
 
     def synthesize_corpus(self, feats, frame_off_host, batch_utts=256, out=None, feats_host=None, out_host=None, events=None):
         """Synthesis of many utterances in batches of `batch_utts` (Synthesiser.run_world_synth over a corpus; the batch bounds
