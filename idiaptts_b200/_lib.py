@@ -59,6 +59,10 @@ _SIGNATURES = {
                                    c_void_p, c_void_p, c_int64, c_int32, c_double, c_int32, c_int64, c_void_p, c_void_p]),
     "b2w_synth_overlap_add": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int64,
                                         c_double, c_void_p, c_int32, c_void_p]),
+    "b2w_synth_render_f32": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_int64, c_int32, c_double, c_int32, c_int64, c_void_p, c_void_p]),
+    "b2w_synth_overlap_add_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int64,
+                                            c_double, c_void_p, c_int32, c_void_p]),
     "b2w_allpass_forward": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                       c_void_p]),
     "b2w_allpass_forward_tc": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p,

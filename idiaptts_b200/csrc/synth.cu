@@ -685,9 +685,9 @@ render_kernel(const void* __restrict__ sp, const void* __restrict__ ap, const in
 
 // ---- overlap-add ---------------------------------------------------------------------------------------------------------------
 constexpr int kOlaTile = 1024;  // output samples per CTA (4 per thread): the two binary searches are amortised over 8 KB of output
-template <typename OT>
+template <typename OT, typename RT>
 __global__ void __launch_bounds__(256)
-overlap_add_kernel(const double* __restrict__ response, const int64_t* __restrict__ utt_out_offset,
+overlap_add_kernel(const RT* __restrict__ response, const int64_t* __restrict__ utt_out_offset,
                    const int64_t* __restrict__ utt_pulse_offset, const int* __restrict__ num_pulses,
                    const int* __restrict__ pulse_index, int fft_size, OT* __restrict__ y) {
   const int u = blockIdx.y;
@@ -715,7 +715,7 @@ overlap_add_kernel(const double* __restrict__ response, const int64_t* __restric
   // Two pulses x four samples per step: eight independent streaming 8-byte loads in flight per thread (the kernel is HBM-bound;
   // one dependent load per thread and pulse left the memory system under-subscribed).  Every sample still sums its pulses in
   // pulse order: bit-identical to the sequential loop.
-  const double* rbase = response + poff * (int64_t)fft_size;
+  const RT* rbase = response + poff * (int64_t)fft_size;
   const int n = n0 + threadIdx.x;
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   int p = lo;
@@ -725,8 +725,8 @@ overlap_add_kernel(const double* __restrict__ response, const int64_t* __restric
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int j0 = n + 256 * q - s0, j1 = n + 256 * q - s1;
-      v[0][q] = (j0 >= 0 && j0 < fft_size) ? __ldcs(rbase + (int64_t)p * fft_size + j0) : 0.0;
-      v[1][q] = (j1 >= 0 && j1 < fft_size) ? __ldcs(rbase + (int64_t)(p + 1) * fft_size + j1) : 0.0;
+      v[0][q] = (j0 >= 0 && j0 < fft_size) ? (double)__ldcs(rbase + (int64_t)p * fft_size + j0) : 0.0;
+      v[1][q] = (j1 >= 0 && j1 < fft_size) ? (double)__ldcs(rbase + (int64_t)(p + 1) * fft_size + j1) : 0.0;
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -739,7 +739,7 @@ overlap_add_kernel(const double* __restrict__ response, const int64_t* __restric
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int j = n + 256 * q - s0;
-      if (j >= 0 && j < fft_size) acc[q] += __ldcs(rbase + (int64_t)p * fft_size + j);
+      if (j >= 0 && j < fft_size) acc[q] += (double)__ldcs(rbase + (int64_t)p * fft_size + j);
     }
   }
 #pragma unroll
@@ -855,9 +855,9 @@ extern "C" int b2w_synth_render(const void* sp, const void* ap, int32_t plane_dt
   return check_launch("render_kernel");
 }
 
-extern "C" int b2w_synth_overlap_add(const double* response, const int64_t* utt_out_offset, const int64_t* utt_pulse_offset,
-                                     const int32_t* num_pulses, int32_t num_utts, const int32_t* pulse_index, int32_t fft_size,
-                                     int64_t max_out_per_utt, double deemphasis, void* y, int32_t y_dtype, void* stream) {
+static int overlap_add_launch(const void* response, int response_is_f32, const int64_t* utt_out_offset,
+                              const int64_t* utt_pulse_offset, const int32_t* num_pulses, int32_t num_utts, const int32_t* pulse_index,
+                              int32_t fft_size, int64_t max_out_per_utt, double deemphasis, void* y, int32_t y_dtype, void* stream) {
   using namespace b2w;
   B2W_REQUIRE(response && utt_out_offset && utt_pulse_offset && num_pulses && pulse_index && y,
               "b2w_synth_overlap_add: null argument");
@@ -867,10 +867,14 @@ extern "C" int b2w_synth_overlap_add(const double* response, const int64_t* utt_
   if (num_utts == 0 || max_out_per_utt == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((unsigned)((max_out_per_utt + kOlaTile - 1) / kOlaTile), (unsigned)num_utts);
-  if (y_dtype == B2W_F64)
-    overlap_add_kernel<double><<<grid, 256, 0, st>>>(response, utt_out_offset, utt_pulse_offset, num_pulses, pulse_index, fft_size, (double*)y);
-  else
-    overlap_add_kernel<float><<<grid, 256, 0, st>>>(response, utt_out_offset, utt_pulse_offset, num_pulses, pulse_index, fft_size, (float*)y);
+#define B2W_OLA(OT, RT) \
+  overlap_add_kernel<OT, RT><<<grid, 256, 0, st>>>((const RT*)response, utt_out_offset, utt_pulse_offset, num_pulses, pulse_index, fft_size, (OT*)y)
+  if (response_is_f32) {
+    if (y_dtype == B2W_F64) B2W_OLA(double, float); else B2W_OLA(float, float);
+  } else {
+    if (y_dtype == B2W_F64) B2W_OLA(double, double); else B2W_OLA(float, double);
+  }
+#undef B2W_OLA
   int rc = check_launch("overlap_add_kernel");
   if (rc) return rc;
   if (deemphasis != 0.0) {
@@ -878,4 +882,43 @@ extern "C" int b2w_synth_overlap_add(const double* response, const int64_t* utt_
     return check_launch("deemphasis_kernel");
   }
   return 0;
+}
+
+extern "C" int b2w_synth_overlap_add(const double* response, const int64_t* utt_out_offset, const int64_t* utt_pulse_offset,
+                                     const int32_t* num_pulses, int32_t num_utts, const int32_t* pulse_index, int32_t fft_size,
+                                     int64_t max_out_per_utt, double deemphasis, void* y, int32_t y_dtype, void* stream) {
+  return overlap_add_launch(response, 0, utt_out_offset, utt_pulse_offset, num_pulses, num_utts, pulse_index, fft_size,
+                            max_out_per_utt, deemphasis, y, y_dtype, stream);
+}
+
+extern "C" int b2w_synth_overlap_add_f32(const float* response, const int64_t* utt_out_offset, const int64_t* utt_pulse_offset,
+                                         const int32_t* num_pulses, int32_t num_utts, const int32_t* pulse_index, int32_t fft_size,
+                                         int64_t max_out_per_utt, double deemphasis, void* y, int32_t y_dtype, void* stream) {
+  return overlap_add_launch(response, 1, utt_out_offset, utt_pulse_offset, num_pulses, num_utts, pulse_index, fft_size,
+                            max_out_per_utt, deemphasis, y, y_dtype, stream);
+}
+
+namespace b2w {
+int render_fast_launch(const void* sp, const void* ap, int plane_dtype, const int64_t* utt_frame_offset,
+                       const int64_t* utt_pulse_offset, const int* num_pulses, int num_utts, const int* pulse_index,
+                       const double* pulse_shift, const uint8_t* pulse_vuv, const double* randn_table, int64_t randn_len, int fs,
+                       double frame_period_ms, int64_t total_rows, float* response, cudaStream_t st);  // synth_fast.cu
+}
+
+// The batched fast path's response kernel: one warp per pulse, single-precision transforms, float32 responses [total_rows, 1024]
+// (total_rows = utt_pulse_offset[num_utts] on the host).  fft_size must be 1024 (fs <= 32 kHz); other sizes: b2w_synth_render.
+extern "C" int b2w_synth_render_f32(const void* sp, const void* ap, int32_t plane_dtype, const int64_t* utt_frame_offset,
+                                    const int64_t* utt_pulse_offset, const int32_t* num_pulses, int32_t num_utts,
+                                    const int32_t* pulse_index, const double* pulse_shift, const uint8_t* pulse_vuv,
+                                    const double* randn_table, int64_t randn_table_len, int32_t fs, double frame_period_ms,
+                                    int32_t fft_size, int64_t total_rows, float* response, void* stream) {
+  using namespace b2w;
+  B2W_REQUIRE(sp && ap && utt_frame_offset && utt_pulse_offset && num_pulses && pulse_index && pulse_shift && pulse_vuv &&
+                  randn_table && response,
+              "b2w_synth_render_f32: null argument");
+  B2W_REQUIRE(plane_dtype == B2W_F64 || plane_dtype == B2W_F32, "b2w_synth_render_f32: bad plane dtype %d", plane_dtype);
+  B2W_REQUIRE(fft_size == 1024, "b2w_synth_render_f32: fft_size %d (only 1024; use b2w_synth_render)", fft_size);
+  if (num_utts == 0 || total_rows == 0) return 0;
+  return render_fast_launch(sp, ap, plane_dtype, utt_frame_offset, utt_pulse_offset, num_pulses, num_utts, pulse_index, pulse_shift,
+                            pulse_vuv, randn_table, randn_table_len, fs, frame_period_ms, total_rows, response, (cudaStream_t)stream);
 }

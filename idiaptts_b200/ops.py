@@ -632,8 +632,14 @@ def synth_timebase(f0, frame_off, fs, fft_size, frame_period=5.0, status=None, e
     return p
 
 
-def synth_render(p, sp, ap, deemphasis=0.0, out_dtype=torch.float64, debug=None, events=None):
-    """Minimum-phase responses of every pulse of the plan + overlap-add.  sp, ap [F, K] (f64 or f32, same dtype)."""
+def synth_render(p, sp, ap, deemphasis=0.0, out_dtype=torch.float64, debug=None, events=None, precision="f64"):
+    """Minimum-phase responses of every pulse of the plan + overlap-add.  sp, ap [F, K] (f64 or f32, same dtype).
+    precision: "f64" = double precision throughout (pyworld-compatible calls); "fast" = one warp per pulse, single-precision
+    transforms, float32 responses (the batched Synthesiser path; fft size 1024 only, other sizes fall back to "f64"): same pulse
+    decisions, waveform SNR against "f64" ~ 110 dB."""
+    assert precision in ("f64", "fast")
+    if p.fft_size != 1024:
+        precision = "f64"
     lib = _lib.load()
     dev = _need_cuda(sp, ap)
     assert sp.dtype == ap.dtype and sp.dtype in (torch.float32, torch.float64)
@@ -649,9 +655,16 @@ def synth_render(p, sp, ap, deemphasis=0.0, out_dtype=torch.float64, debug=None,
         max_p = int(npul.max()) if U else 0
         # responses are addressed by the slab offsets, so allocate slab-sized storage only up to the last used row
         last_row = int((pulse_off[:-1] + npul).max()) if U else 0
-        response = torch.empty((max(last_row, 1), fft_size), dtype=torch.float64, device=dev)
+        fast = precision == "fast"
+        response = torch.empty((max(last_row, 1), fft_size), dtype=torch.float32 if fast else torch.float64, device=dev)
         total_p = int(npul.sum())
-        if max_p > 0:
+        if max_p > 0 and fast:
+            _timed(events, "render", total_p, lambda: check(lib.b2w_synth_render_f32(
+                sp.data_ptr(), ap.data_ptr(), _DT[sp.dtype], p.frame_off.data_ptr(),
+                p.d_pulse_off.data_ptr(), p.num_pulses.data_ptr(), U, p.pulse_index.data_ptr(),
+                p.pulse_shift.data_ptr(), p.pulse_vuv.data_ptr(), p.tab.data_ptr(), p.tab.numel(), p.fs,
+                p.frame_period, fft_size, last_row, response.data_ptr(), st), "b2w_synth_render_f32"))
+        elif max_p > 0:
             _timed(events, "render", total_p, lambda: check(lib.b2w_synth_render(
                 sp.data_ptr(), ap.data_ptr(), _DT[sp.dtype], p.frame_off.data_ptr(),
                 p.d_pulse_off.data_ptr(), p.num_pulses.data_ptr(), U, p.pulse_index.data_ptr(),
@@ -660,7 +673,7 @@ def synth_render(p, sp, ap, deemphasis=0.0, out_dtype=torch.float64, debug=None,
         if debug is not None:  # diagnostics for the parity tests: the pulse table of every utterance
             debug.update(pulse_off=pulse_off, num_pulses=npul, pulse_index=p.pulse_index, pulse_shift=p.pulse_shift,
                          pulse_vuv=p.pulse_vuv, response=response)
-        _timed(events, "overlap_add", total_p, lambda: check(lib.b2w_synth_overlap_add(
+        _timed(events, "overlap_add", total_p, lambda: check((lib.b2w_synth_overlap_add_f32 if fast else lib.b2w_synth_overlap_add)(
             response.data_ptr(), p.d_out_off.data_ptr(), p.d_pulse_off.data_ptr(),
             p.num_pulses.data_ptr(), U, p.pulse_index.data_ptr(), fft_size, int(p.ylen.max()),
             float(deemphasis), y.data_ptr(), _DT[y.dtype], st), "b2w_synth_overlap_add"))

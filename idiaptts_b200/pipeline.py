@@ -168,7 +168,8 @@ def mean_std_from_sums(sums, n, dim):
 
 class WorldSynthesizer:
     def __init__(self, fs, num_coded_sps=60, mgc_alpha=None, hop_size_ms=5.0, n_fft=None, f0_silence_threshold=30, lf0_zero=0,
-                 device="cuda"):
+                 device="cuda", precision="fast"):
+        """precision: "fast" (default) = single-precision per-pulse transforms (ops.synth_render), "f64" = double precision."""
         from .compat.pysptk import mcepalpha
         self.fs = int(fs)
         self.num_coded_sps = int(num_coded_sps)
@@ -179,6 +180,7 @@ class WorldSynthesizer:
         self.f0_silence_threshold = f0_silence_threshold
         self.lf0_zero = lf0_zero
         self.device = torch.device(device)
+        self.precision = precision
         ops.McepTables.get(self.num_coded_sps - 1, self.alpha, self.n_fft, self.device)
 
     def synthesize(self, feats, frame_off, preemphasis=0.0, out_dtype=torch.float32, events=None):
@@ -204,7 +206,7 @@ class WorldSynthesizer:
         plan = ops.synth_timebase(f0.contiguous(), frame_off, self.fs, self.n_fft, self.hop_size_ms, events=events)
         de = float(preemphasis)
         y, out_off, status = ops.synth_render(plan, pow_sp, ap, deemphasis=de, out_dtype=torch.float64 if de != 0.0 else out_dtype,
-                                              events=events)
+                                              events=events, precision=self.precision)
         return y, out_off, status
 
     def kernel_launches(self, num_utts, batch_utts=256):

@@ -177,6 +177,17 @@ B2W_API int b2w_synth_render(const void* sp, const void* ap, int32_t plane_dtype
                      const int32_t* pulse_index, const double* pulse_shift, const uint8_t* pulse_vuv,
                      const double* randn_table, int64_t randn_table_len, int32_t fs, double frame_period_ms,
                      int32_t fft_size, int64_t max_pulses_per_utt, double* response, void* stream);
+/* Fast path of the batched synthesis (Synthesiser.run_world_synth): one warp per pulse, single-precision transforms, float32
+ * responses [total_rows, fft_size] with total_rows = utt_pulse_offset[num_utts]; fft_size must be 1024 (fs <= 32 kHz).  Pulse
+ * decisions (frame indices, voiced test) are those of b2w_synth_render; waveform SNR against it ~ 110 dB. */
+B2W_API int b2w_synth_render_f32(const void* sp, const void* ap, int32_t plane_dtype, const int64_t* utt_frame_offset,
+                     const int64_t* utt_pulse_offset, const int32_t* num_pulses, int32_t num_utts,
+                     const int32_t* pulse_index, const double* pulse_shift, const uint8_t* pulse_vuv,
+                     const double* randn_table, int64_t randn_table_len, int32_t fs, double frame_period_ms,
+                     int32_t fft_size, int64_t total_rows, float* response, void* stream);
+B2W_API int b2w_synth_overlap_add_f32(const float* response, const int64_t* utt_out_offset, const int64_t* utt_pulse_offset,
+                          const int32_t* num_pulses, int32_t num_utts, const int32_t* pulse_index, int32_t fft_size,
+                          int64_t max_out_per_utt, double deemphasis, void* y, int32_t y_dtype, void* stream);
 B2W_API int b2w_synth_overlap_add(const double* response, const int64_t* utt_out_offset, const int64_t* utt_pulse_offset,
                           const int32_t* num_pulses, int32_t num_utts, const int32_t* pulse_index, int32_t fft_size,
                           int64_t max_out_per_utt, double deemphasis, void* y, int32_t y_dtype, void* stream);
