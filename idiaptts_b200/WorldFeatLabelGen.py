@@ -53,28 +53,198 @@ class WorldFeatLabelGen(object):
 
     logger = logging.getLogger(__name__)
 
-    def __init__(self, dir_labels=None, add_deltas=False, preemphasis=0.0, n_fft=None, win_length_ms=None, num_coded_sps=60,
-                 num_bap=1, sp_type="mcep", hop_size_ms=5, load_sp=True, load_lf0=True, load_vuv=True, load_bap=True,
-                 f0_cache=None, mgc_alpha=None):
-        self.dir_labels = dir_labels
-        self.add_deltas = add_deltas
-        self.preemphasis = preemphasis
-        self.n_fft = n_fft
-        self.win_length_ms = win_length_ms
-        self.num_coded_sps = num_coded_sps
-        self.num_bap = num_bap
-        self.sp_type = sp_type
-        self.hop_size_ms = hop_size_ms
-        self.load_sp, self.load_lf0, self.load_vuv, self.load_bap = load_sp, load_lf0, load_vuv, load_bap
-        self.f0_cache = f0_cache
-        self.mgc_alpha = mgc_alpha
+    class Config(object):
+        """WorldFeatLabelGen.Config (world/WorldFeatLabelGen.py:62-138): the reader configuration trainers hand to the data
+        pipeline.  Same fields and defaults; the NpzDataReader machinery behind it in the reference is out of scope, so this
+        object just carries the fields and builds a reader whose normalisation parameters are loaded (create_reader, :133-138)."""
+
+        class NormType(object):
+            NONE = "NONE"
+            MEAN_VARIANCE = "MEAN_VARIANCE"
+            MEAN_STDDEV = "MEAN_STDDEV"
+            MIN_MAX = "MIN_MAX"
+
+        def __init__(self, name, directory=None, indices=None, norm_params_path=None, norm_params=None,
+                     norm_type=NormType.MEAN_VARIANCE, output_names=None, preprocessing_fn=None, preprocess_before_norm=False,
+                     postprocessing_fn=None, postprocess_before_norm=False, add_deltas=False, preemphasis=0.0, n_fft=None,
+                     win_length_ms=None, num_coded_sps=60, num_bap=1, sp_type="mcep", load_sp=True, load_lf0=True, load_vuv=True,
+                     load_bap=True, apply_mlpg=True, **kwargs):
+            if norm_type is None:
+                norm_type = self.NormType.MEAN_VARIANCE if add_deltas else self.NormType.MEAN_STDDEV
+            self.name = name
+            self.directory = list(directory) if isinstance(directory, (tuple, list)) else [directory]
+            self.dir_labels = self.directory[0]
+            self.indices = indices
+            self.norm_params_path = norm_params_path
+            self.norm_params = norm_params
+            self.norm_type = norm_type
+            self.output_names = output_names if output_names is not None else [name]
+            self.preprocessing_fn = preprocessing_fn
+            self.preprocess_before_norm = preprocess_before_norm
+            self.postprocessing_fn = postprocessing_fn
+            self.postprocess_before_norm = postprocess_before_norm
+            self.add_deltas = add_deltas
+            self.apply_mlpg = apply_mlpg
+            self.preemphasis = preemphasis
+            self.n_fft = n_fft
+            self.win_length_ms = win_length_ms
+            self.num_coded_sps = num_coded_sps
+            self.num_bap = num_bap
+            self.sp_type = sp_type
+            self.load_sp, self.load_lf0, self.load_vuv, self.load_bap = load_sp, load_lf0, load_vuv, load_bap
+            self.extra = kwargs
+
+        def create_reader(self):
+            reader = WorldFeatLabelGen(self)
+            if self.norm_params is not None:
+                reader.norm_params = self.norm_params
+            else:
+                reader.get_normalisation_params(self.norm_params_path)
+            return reader
+
+    _LEGACY_DEFAULTS = {"add_deltas": False, "preprocessing_fn": None, "preemphasis": 0.0, "n_fft": None, "win_length_ms": None,
+                        "num_coded_sps": 60, "num_bap": 1, "sp_type": "mcep", "hop_size_ms": 5, "load_sp": True, "load_lf0": True,
+                        "load_vuv": True, "load_bap": True}
+
+    def __init__(self, *args, **kwargs):
+        """Two forms, as in the reference (:140-228): WorldFeatLabelGen(config) with a WorldFeatLabelGen.Config, or the legacy
+        WorldFeatLabelGen(dir_labels, add_deltas=..., num_coded_sps=..., ...) keyword form.  Extensions of this package (keyword
+        only): f0_cache (cached F0 tracks: dict / directory, north_star), mgc_alpha (override of fs_to_mgc_alpha)."""
+        self.f0_cache = kwargs.pop("f0_cache", None)
+        self.mgc_alpha = kwargs.pop("mgc_alpha", None)
+        if len(args) == 1 and isinstance(args[0], WorldFeatLabelGen.Config):
+            config = args[0]
+            fields = {k: getattr(config, k) for k in ("add_deltas", "preprocessing_fn", "preemphasis", "n_fft", "win_length_ms",
+                                                      "num_coded_sps", "num_bap", "sp_type", "load_sp", "load_lf0", "load_vuv", "load_bap")}
+            fields["hop_size_ms"] = 5  # the reference's Config form never sets it (SURVEY 7.3-7); 5 ms is what every recipe uses
+            self.dir_labels = config.dir_labels
+            self.output_names = config.output_names
+            self.apply_mlpg = config.apply_mlpg
+            self.legacy_getitem = False
+        else:
+            if "dir_labels" in kwargs:
+                self.dir_labels = kwargs.pop("dir_labels")
+            else:
+                self.dir_labels = args[0] if args else None
+            unknown = set(kwargs) - set(self._LEGACY_DEFAULTS)
+            if unknown:
+                raise TypeError("unexpected keyword arguments: {}".format(sorted(unknown)))
+            fields = dict(self._LEGACY_DEFAULTS)
+            fields.update(kwargs)
+            self.output_names = ["acoustic_features"]
+            self.apply_mlpg = False
+            self.legacy_getitem = True
+        self.add_deltas = fields["add_deltas"]
+        self.preprocessing_fn = fields["preprocessing_fn"]
+        self.preemphasis = fields["preemphasis"]
+        self.n_fft = fields["n_fft"]
+        self.win_length_ms = fields["win_length_ms"]
+        self.num_coded_sps = fields["num_coded_sps"]
+        self.num_bap = fields["num_bap"]
+        self.sp_type = fields["sp_type"]
+        self.hop_size_ms = fields["hop_size_ms"]
+        self.load_sp, self.load_lf0, self.load_vuv, self.load_bap = (fields["load_sp"], fields["load_lf0"], fields["load_vuv"],
+                                                                     fields["load_bap"])
+        self.load_flags = (self.load_sp, self.load_lf0, self.load_vuv, self.load_bap)
         self.norm_params = None
+        self.covs = [None] * 4  # coded_sp, lf0, (vuv: never used), bap
         self.dir_coded_sps = self.sp_type
         if self.num_coded_sps != -1:
             self.dir_coded_sps += str(self.num_coded_sps)
         self.dir_deltas = WorldFeatLabelGen.dir_deltas + "_" + self.dir_coded_sps
-        if sp_type != "mcep":
+        if self.sp_type != "mcep":
             raise NotImplementedError("only sp_type='mcep' is on the accelerated path (SURVEY.md 8f N3)")
+
+    # ---- normalisation parameters -----------------------------------------------------------------------------------------------
+    def get_normalisation_params(self, dir_out=None, file_name=None):
+        """WorldFeatLabelGen.get_normalisation_params (:575-732): read the per-feature normalisation files gen_data wrote and set
+        self.norm_params = (mean [1, W], std_dev [1, W]) over the loaded features in the order coded_sp, lf0, vuv, bap (vuv: mean 0,
+        std_dev 1); with add_deltas also self.covs[idx] (what MLPG needs).  Files per feature sub-directory:
+            <file_name->mean-std_dev.npz                     (add_deltas False)
+            <file_name->deltas-mean-covariance.npz           (add_deltas True)
+        (.bin variants are read when the .npz is missing); then the legacy single-directory layout
+        cmp_<sp><D>/<file_name-><feature>-mean-covariance.bin (:661-732).
+        Reference quirk not mirrored: with add_deltas AND a file_name the reference raises UnboundLocalError (`full_file_name +=`
+        before assignment, :609); here the documented name "<file_name>-deltas" is used."""
+        if dir_out is None:
+            dir_out = self.dir_labels
+        sub_dirs = (self.dir_coded_sps, self.dir_lf0, self.dir_vuv, self.dir_bap)
+        has_name = file_name is not None and os.path.basename(file_name) != ""
+
+        def load_any(ext_cls, base):
+            try:
+                return ext_cls.load(base + ".npz")
+            except FileNotFoundError:
+                return ext_cls.load(base + ".bin")
+
+        try:
+            means, std_devs = [], []
+            for idx, (load, subdir) in enumerate(zip(self.load_flags, sub_dirs)):
+                if not load:
+                    continue
+                if subdir == self.dir_vuv:
+                    means.append(np.atleast_2d(0.0))
+                    std_devs.append(np.atleast_2d(1.0))
+                    continue
+                prefix = os.path.join(dir_out, subdir, (file_name + "-") if has_name else "")
+                if self.add_deltas:
+                    mean, cov, std_dev = load_any(MeanCovarianceExtractor, prefix + "deltas-" + MeanCovarianceExtractor.file_name_appendix)
+                    self.covs[idx] = cov
+                else:
+                    mean, std_dev = load_any(MeanStdDevExtractor, prefix + MeanStdDevExtractor.file_name_appendix)
+                means.append(np.atleast_2d(mean))
+                std_devs.append(np.atleast_2d(std_dev))
+            self.norm_params = (np.concatenate(means, axis=1), np.concatenate(std_devs, axis=1))
+            return self.norm_params
+        except FileNotFoundError as e0:
+            # LEGACY layout: one directory cmp_<sp><D> with a mean-covariance .bin per feature (always with deltas)
+            prefix = (file_name + "-") if has_name else ""
+            means, std_devs = [], []
+            for idx, (load, subdir) in enumerate(zip(self.load_flags, sub_dirs)):
+                if not load:
+                    continue
+                if subdir == self.dir_vuv:
+                    means.append(np.atleast_2d(0.0))
+                    std_devs.append(np.atleast_2d(1.0))
+                    continue
+                new_style = os.path.join(dir_out, self.dir_deltas, "{}{}-{}.bin".format(prefix, subdir, MeanCovarianceExtractor.file_name_appendix))
+                old_style = os.path.join(dir_out, self.dir_deltas, "{}{}_{}.bin".format(prefix, MeanCovarianceExtractor.file_name_appendix, subdir))
+                try:
+                    mean, cov, std_dev = MeanCovarianceExtractor.load(new_style)
+                except FileNotFoundError as e1:
+                    try:
+                        mean, cov, std_dev = MeanCovarianceExtractor.load(old_style)
+                        self.logger.warning("Found legacy style normalisation parameters at %s. Consider recreating features or "
+                                            "renaming to %s", old_style, new_style)
+                    except FileNotFoundError as e2:
+                        raise FileNotFoundError([e0, e1, e2])
+                if not self.add_deltas:
+                    d = len(cov) // 3
+                    assert len(cov) == 3 * d, "Feature size {} is not dividable by 3. Are deltas features contained?".format(len(cov))
+                    cov, mean, std_dev = cov[:d, :d], mean[:d], std_dev[:d]
+                self.covs[idx] = cov
+                means.append(np.atleast_2d(mean))
+                std_devs.append(np.atleast_2d(std_dev))
+            self.norm_params = (np.concatenate(means, axis=1), np.concatenate(std_devs, axis=1))
+            if self.add_deltas:
+                self.norm_params = (self.norm_params[0][0], self.norm_params[1][0])
+            return self.norm_params
+
+    def _get_norm_params_subset(self, norm_params):
+        """:296-330 is a no-op slicing in the reference whenever all four features are loaded; kept for callers that pass
+        parameters of ALL features to a reader that loads a subset: returns the columns of the loaded features."""
+        mean, std_dev = norm_params
+        f3 = 3 if self.add_deltas else 1
+        widths = (self.num_coded_sps * f3, f3, 1, self.num_bap * f3)
+        keep, pos = [], 0
+        for load, w in zip(self.load_flags, widths):
+            if load:
+                keep.extend(range(pos, pos + w))
+            pos += w
+        mean, std_dev = np.atleast_2d(mean), np.atleast_2d(std_dev)
+        if mean.shape[1] != pos:
+            return norm_params
+        return mean[:, keep], std_dev[:, keep]
 
     # ---- layout conversion -------------------------------------------------------------------------------------------
     @staticmethod
@@ -350,7 +520,7 @@ class WorldFeatLabelGen(object):
                 ext = MeanCovarianceExtractor()
                 gram = stat_np[1 + 6 * dim:].reshape(3 * dim, 3 * dim)
                 ext.add_sums(n_total, stat_np[1:1 + 3 * dim][c][None, :], gram[np.ix_(c, c)])
-                mean, cov, std = ext.get_params()
+                mean, cov = ext.get_params()
                 output_means.append(mean)
                 output_std_dev.append(cov)
             else:
@@ -374,8 +544,11 @@ class WorldFeatLabelGen(object):
             else:
                 output_means, output_std_dev = None, None
         self.norm_params = (output_means, output_std_dev)
-        if self.add_deltas:  # covariance matrices per feature in the reference's indexing (coded_sp, lf0, vuv, bap)
-            self.covs = list(output_std_dev)
+        if self.add_deltas:  # covariance matrices per LOADED feature -> the reference's indexing (coded_sp, lf0, vuv, bap)
+            loaded = [i for i, l in enumerate(self.load_flags) if l]
+            self.covs = [None] * 4
+            for i, c in zip(loaded, output_std_dev):
+                self.covs[i] = None if i == 2 else np.asarray(c, np.float32)
         if return_dict:
             return label_dict, output_means, output_std_dev
         return output_means, output_std_dev
@@ -436,8 +609,17 @@ class WorldFeatLabelGen(object):
         return np.concatenate(out, axis=1)
 
     def __getitem__(self, id_name):
-        """Load and normalise one sample (the reference's LabelGen protocol, legacy single-array form)."""
-        return self.preprocess_sample(self.load(os.path.splitext(os.path.basename(id_name))[0]))
+        """Load and normalise one sample (the reference's reader protocol, :290-300): the legacy constructor form returns the
+        array, the Config form a dict {output_name: array}.  Normalisation parameters must have been set
+        (get_normalisation_params / gen_data / Config.norm_params): a reader without them raises instead of silently
+        returning un-normalised features."""
+        if self.norm_params is None:
+            raise RuntimeError("normalisation parameters are not loaded: call get_normalisation_params(dir_out, file_name) first")
+        sample = self.load(os.path.splitext(os.path.basename(id_name))[0])
+        if self.preprocessing_fn is not None:
+            sample = self.preprocessing_fn(sample)
+        sample = self.preprocess_sample(sample)
+        return sample if self.legacy_getitem else {self.output_names[0]: sample}
 
     def _flat_norm_params(self, norm_params=None):
         mean, std = norm_params if norm_params is not None else (self.norm_params if self.norm_params is not None else (None, None))

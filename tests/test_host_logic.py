@@ -70,16 +70,16 @@ def test_mean_std_extractor_matches_reference_bins(golden, tmp_path):
     assert sorted(np.load(str(tmp_path / "a-mean-std_dev.npz")).files) == ["mean", "std_dev", "sum_length"]
     mean_c, std_c = MeanStdDevExtractor.combine_mean_std([str(tmp_path / "a-stats.npz"), str(tmp_path / "b-stats.npz")],
                                                          dir_out=str(tmp_path), save_txt=False)
-    np.testing.assert_allclose(mean_c[0], m2, rtol=1e-12)
-    np.testing.assert_allclose(std_c[0], s2, rtol=1e-10)
+    np.testing.assert_allclose(np.squeeze(mean_c), m2, rtol=1e-12)
+    np.testing.assert_allclose(np.squeeze(std_c), s2, rtol=1e-10)
     lm, ls = MeanStdDevExtractor.load(str(tmp_path / "mean-std_dev.npz"))
-    np.testing.assert_allclose(lm[0], m2, rtol=1e-6)
+    np.testing.assert_allclose(np.squeeze(lm), m2, rtol=1e-6)
     # legacy .bin reader
     with open(tmp_path / "legacy.bin", "wb") as f:
         f.write(np.int32(11579).tobytes())
         f.write(ref.astype(np.float64).tobytes())
     bm, bs = MeanStdDevExtractor.load(str(tmp_path / "legacy.bin"))
-    np.testing.assert_allclose(bm[0], ref[0], rtol=1e-6)
+    np.testing.assert_allclose(np.squeeze(bm), ref[0], rtol=1e-6)
 
 
 def test_mean_covariance_extractor(tmp_path):
@@ -88,12 +88,34 @@ def test_mean_covariance_extractor(tmp_path):
     e = MeanCovarianceExtractor()
     e.add_sample(x[:200])
     e.add_sample(x[200:])
-    mean, cov, std = e.get_params()
+    mean, cov = e.get_params()                                   # two values, like the reference
     np.testing.assert_allclose(mean[0], x.mean(0), atol=1e-12)
     np.testing.assert_allclose(cov, np.cov(x.T, bias=True), atol=1e-12)
+    np.testing.assert_allclose(e.get_std_dev(), x.std(0), atol=1e-12)
     e.save(str(tmp_path / "set"))
+    assert sorted(np.load(str(tmp_path / "set-stats.npz")).files) == ["sum_frames", "sum_length", "sum_product_frames"]
+    assert sorted(np.load(str(tmp_path / "set-mean-covariance.npz")).files) == ["covariance", "mean", "sum_length"]
     m, c, s = MeanCovarianceExtractor.load(str(tmp_path / "set-mean-covariance.npz"))
+    assert m.shape == (6,) and c.shape == (6, 6) and s.shape == (6,) and m.dtype == np.float32   # squeezed like the reference
     np.testing.assert_allclose(c, cov, atol=1e-6)
+    np.testing.assert_allclose(s, x.std(0), atol=1e-6)
+    # legacy .bin: int32 N, int32 rows, then [rows, d] float64 = mean row + covariance
+    with open(tmp_path / "legacy-mean-covariance.bin", "wb") as f:
+        f.write(np.array([500, 7], np.int32).tobytes())
+        f.write(np.concatenate((mean, cov), axis=0).astype(np.float64).tobytes())
+    bm, bc, bs = MeanCovarianceExtractor.load(str(tmp_path / "legacy-mean-covariance.bin"))
+    np.testing.assert_allclose(bm, x.mean(0), atol=1e-6)
+    np.testing.assert_allclose(bc, cov, atol=1e-6)
+    # merging two subsets through their stats files, with a file-name prefix
+    a, b = MeanCovarianceExtractor(), MeanCovarianceExtractor()
+    a.add_sample(x[:123])
+    b.add_sample(x[123:])
+    a.save(str(tmp_path / "a"))
+    b.save(str(tmp_path / "b"))
+    mc, cc = MeanCovarianceExtractor.combine_mean_covariance([str(tmp_path / "a-stats.npz"), str(tmp_path / "b-stats.npz")],
+                                                             dir_out=str(tmp_path), file_name="all", save_txt=False)
+    np.testing.assert_allclose(cc, cov, atol=1e-12)
+    assert (tmp_path / "all-mean-covariance.npz").exists() and (tmp_path / "all-stats.npz").exists()
 
 
 def test_shard_utterances_balances_and_covers():
@@ -220,3 +242,87 @@ def test_lf0labelgen_reader_protocol(tmp_path):
     if not torch.cuda.is_available():                      # extraction itself needs the GPU: fails loudly without one
         with pytest.raises(RuntimeError):
             gen.gen_data(str(tmp_path), None, id_list=[])
+
+
+def _write_world_label_dir(root, rng, ids, D=6, nap=1, add_deltas=False, list_name="train"):
+    """What WorldFeatLabelGen.gen_data leaves on disk (save_output :1121-1172 + the per-feature normalisation files), written
+    with numpy only so the reader protocol can be tested without a GPU."""
+    from idiaptts_b200.MeanCovarianceExtractor import MeanCovarianceExtractor as MC
+    feats = {"mcep": ("mcep%d" % D, D), "lf0": ("lf0", 1), "vuv": ("vuv", 1), "bap": ("bap", nap)}
+    data = {}
+    for key, (sub, d) in feats.items():
+        os.makedirs(os.path.join(root, sub), exist_ok=True)
+        ext = MC() if add_deltas else MeanStdDevExtractor()
+        for i in ids:
+            T = 30 + 3 * len(i)
+            x = (rng.standard_normal((T, d)) * (1.0 + np.arange(d)) + 0.5 * np.arange(d)).astype(np.float32)
+            if key == "vuv":
+                x = (x > 0).astype(np.float32)
+                np.savez(os.path.join(root, sub, i), vuv=x)
+                data[(key, i)] = x
+                continue
+            if add_deltas:
+                dl, ddl = np.gradient(x, axis=0).astype(np.float32), np.gradient(np.gradient(x, axis=0), axis=0).astype(np.float32)
+                np.savez(os.path.join(root, sub, i), **{key: x, key + "_deltas": dl, key + "_double_deltas": ddl})
+                full = np.concatenate((x, dl, ddl), axis=1)
+            else:
+                np.savez(os.path.join(root, sub, i), **{key: x})
+                full = x
+            data[(key, i)] = full
+            ext.add_sample(full)
+        if key != "vuv":
+            ext.save(os.path.join(root, sub, list_name + ("-deltas" if add_deltas else "")))
+    return data
+
+
+@pytest.mark.parametrize("add_deltas", [False, True])
+def test_trainer_call_sequence_on_a_fresh_reader(tmp_path, add_deltas):
+    """The sequence every reference trainer runs (AcousticModelTrainer.py:413-423, :439, :492): construct a reader on a label
+    directory, get_normalisation_params(dir_out, file_name), __getitem__, postprocess_sample -- on a FRESH WorldFeatLabelGen (one
+    that never ran gen_data), in the legacy keyword form and through WorldFeatLabelGen.Config.create_reader()."""
+    rng = np.random.default_rng(3)
+    ids = ["a", "bb", "ccc"]
+    D, nap = 6, 1
+    root = str(tmp_path / "labels")
+    data = _write_world_label_dir(root, rng, ids, D, nap, add_deltas)
+    reader = WorldFeatLabelGen(root, add_deltas=add_deltas, num_coded_sps=D, num_bap=nap)
+    with pytest.raises(RuntimeError, match="get_normalisation_params"):
+        reader["a"]                                           # no silent un-normalised data
+    mean, std = reader.get_normalisation_params(root, "train")
+    f3 = 3 if add_deltas else 1
+    W = (D + 1 + nap) * f3 + 1
+    assert np.asarray(mean).reshape(1, -1).shape == (1, W) and np.asarray(std).reshape(1, -1).shape == (1, W)
+    mean, std = np.asarray(mean).reshape(-1), np.asarray(std).reshape(-1)
+    vuv_col = (D + 1) * f3
+    assert mean[vuv_col] == 0.0 and std[vuv_col] == 1.0      # vuv is never normalised (:616-618)
+    raw = np.concatenate([data[(k, "bb")] for k in ("mcep", "lf0", "vuv", "bap")], axis=1)
+    assert np.array_equal(reader.load("bb"), raw)
+    x = reader["bb"]
+    np.testing.assert_allclose(x, (raw - mean) / std, rtol=1e-5, atol=1e-6)
+    # means really are the corpus means
+    allrows = np.concatenate([np.concatenate([data[(k, i)] for k in ("mcep", "lf0", "vuv", "bap")], axis=1) for i in ids])
+    keep = np.arange(W) != vuv_col
+    np.testing.assert_allclose(mean[keep], allrows.mean(0)[keep], rtol=1e-4, atol=1e-5)
+    if add_deltas:
+        assert reader.covs[0].shape == (3 * D, 3 * D) and reader.covs[1].shape == (3, 3) and reader.covs[3].shape == (3 * nap, 3 * nap)
+        assert reader.covs[2] is None
+        back = reader.postprocess_sample(x.copy(), apply_mlpg=False)          # MLPG itself needs the GPU (tests/test_mlpg.py)
+        assert back.shape == (len(raw), D + 2 + nap)
+        np.testing.assert_allclose(back[:, :D], raw[:, :D], rtol=1e-4, atol=1e-4)
+    else:
+        back = reader.postprocess_sample(x.copy())
+        np.testing.assert_allclose(back, raw, rtol=1e-4, atol=1e-4)
+    # the Config form: fields, create_reader() loads the parameters, __getitem__ returns a dict keyed by the output name
+    cfg = WorldFeatLabelGen.Config(name="acoustic_features", directory=root, norm_params_path=root, add_deltas=add_deltas,
+                                   num_coded_sps=D, num_bap=nap)
+    assert cfg.dir_labels == root and cfg.sp_type == "mcep" and cfg.load_bap
+    r2 = WorldFeatLabelGen(cfg)
+    assert r2.legacy_getitem is False and r2.norm_params is None
+    r2.get_normalisation_params(root, "train")
+    out = r2["bb"]
+    assert set(out) == {"acoustic_features"}
+    np.testing.assert_allclose(out["acoustic_features"], x, rtol=1e-6)
+    # unknown keyword arguments are an error, the package's extensions are accepted
+    with pytest.raises(TypeError):
+        WorldFeatLabelGen(root, not_an_option=1)
+    WorldFeatLabelGen(root, f0_cache={}, mgc_alpha=0.5)
