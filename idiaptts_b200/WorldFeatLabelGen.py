@@ -418,58 +418,67 @@ class WorldFeatLabelGen(object):
         else:
             mine = np.arange(len(id_list))
         my_ids = [id_list[i] for i in mine]
-        waves, f0s, fs = [], [], None
-        for name in my_ids:
-            x, cur_fs = AudioProcessing.read_wav(os.path.join(dir_in, name + "." + file_ext))
-            if fs is None:
-                fs = cur_fs
-            elif fs != cur_fs:
-                raise ValueError("mixed sampling rates in one gen_data call ({} vs {})".format(fs, cur_fs))
-            f0 = self._lookup_f0(f0_cache, name)
-            T = ops.num_frames(len(x), cur_fs, self.hop_size_ms)
-            if f0 is None:
-                f0 = np.zeros(T)
-            if len(f0) != T:
-                raise ValueError("{}: cached F0 has {} frames, the waveform gives {}".format(name, len(f0), T))
-            waves.append(x)
-            f0s.append(f0)
-        if fs is None:
-            fs = headers[0][1] if headers else 16000
+        # every rank sizes the statistics buffer from the wav HEADERS (all ranks read all headers), so a rank whose shard fails
+        # still takes part in the all-reduce: the failure travels in the last element and every rank raises after the collective
+        fs = headers[0][1] if headers else 16000
         nap = ops.get_num_aperiodicities(fs)
         D = self.num_coded_sps
         dim = D + 2 + nap
         alpha = self.mgc_alpha if self.mgc_alpha is not None else AudioProcessing.fs_to_mgc_alpha(fs)
-        stat = torch.zeros(1 + 2 * dim * (3 if self.add_deltas else 1) + (3 * dim) ** 2 * (1 if self.add_deltas else 0),
+        stat = torch.zeros(1 + 2 * dim * (3 if self.add_deltas else 1) + (3 * dim) ** 2 * (1 if self.add_deltas else 0) + 1,
                            dtype=torch.float64, device=dev)
-        feats_np, offs = None, None
-        if waves:
-            same = all(w.dtype == waves[0].dtype for w in waves)
-            if not same:
-                waves = [w.astype(np.float64) / 32768.0 if w.dtype == np.int16 else w.astype(np.float64) for w in waves]
-            batch = ops.RaggedBatch.from_host(waves, f0s, fs, frame_period=self.hop_size_ms, preemphasis=self.preemphasis, device=dev)
-            if f0_cache is None:
-                ops.estimate_f0(batch, frame_period=self.hop_size_ms)
-            an = pipeline.WorldAnalyzer(fs, D, alpha, self.hop_size_ms, self.n_fft, WorldFeatLabelGen.f0_silence_threshold,
-                                        WorldFeatLabelGen.lf0_zero, device=dev)
-            feats, sums, status = an.extract(batch)
-            F = batch.num_frames
-            if self.add_deltas:
-                d, dd = ops.deltas(feats, batch.frame_off)
-                full = torch.cat((feats, d, dd), dim=1).contiguous()  # [F, 3*dim] = [static | delta | delta-delta]
-                sums3 = torch.zeros(2 * 3 * dim, dtype=torch.float64, device=dev)
-                gram = torch.zeros((3 * dim) ** 2, dtype=torch.float64, device=dev)
-                ops.stats_accumulate(full, sums3, gram)
-                stat[1:1 + 6 * dim] = sums3
-                stat[1 + 6 * dim:] = gram
-                feats_np = full.cpu().numpy()
-            else:
-                stat[1:1 + 2 * dim] = sums
-                feats_np = feats.cpu().numpy()
-            stat[0] = float(F)
-            offs = batch.frame_off.cpu().numpy()
-            ops.raise_for_status(status, "gen_data")
+        feats_np, offs, failure = None, None, None
+        try:
+            waves, f0s = [], []
+            for name in my_ids:
+                x, cur_fs = AudioProcessing.read_wav(os.path.join(dir_in, name + "." + file_ext))
+                if fs != cur_fs:
+                    raise ValueError("mixed sampling rates in one gen_data call ({} vs {})".format(fs, cur_fs))
+                f0 = self._lookup_f0(f0_cache, name)
+                T = ops.num_frames(len(x), cur_fs, self.hop_size_ms)
+                if f0 is None:
+                    f0 = np.zeros(T)
+                if len(f0) != T:
+                    raise ValueError("{}: cached F0 has {} frames, the waveform gives {}".format(name, len(f0), T))
+                waves.append(x)
+                f0s.append(f0)
+            if waves:
+                same = all(w.dtype == waves[0].dtype for w in waves)
+                if not same:
+                    waves = [w.astype(np.float64) / 32768.0 if w.dtype == np.int16 else w.astype(np.float64) for w in waves]
+                batch = ops.RaggedBatch.from_host(waves, f0s, fs, frame_period=self.hop_size_ms, preemphasis=self.preemphasis, device=dev)
+                if f0_cache is None:
+                    ops.estimate_f0(batch, frame_period=self.hop_size_ms)
+                an = pipeline.WorldAnalyzer(fs, D, alpha, self.hop_size_ms, self.n_fft, WorldFeatLabelGen.f0_silence_threshold,
+                                            WorldFeatLabelGen.lf0_zero, device=dev)
+                feats, sums, status = an.extract(batch)
+                F = batch.num_frames
+                if self.add_deltas:
+                    d, dd = ops.deltas(feats, batch.frame_off)
+                    full = torch.cat((feats, d, dd), dim=1).contiguous()  # [F, 3*dim] = [static | delta | delta-delta]
+                    sums3 = torch.zeros(2 * 3 * dim, dtype=torch.float64, device=dev)
+                    gram = torch.zeros((3 * dim) ** 2, dtype=torch.float64, device=dev)
+                    ops.stats_accumulate(full, sums3, gram)
+                    stat[1:1 + 6 * dim] = sums3
+                    stat[1 + 6 * dim:-1] = gram
+                    feats_np = full.cpu().numpy()
+                else:
+                    stat[1:1 + 2 * dim] = sums
+                    feats_np = feats.cpu().numpy()
+                stat[0] = float(F)
+                offs = batch.frame_off.cpu().numpy()
+                ops.raise_for_status(status, "gen_data")
+        except Exception as e:  # noqa: BLE001 -- re-raised below, after the collective
+            failure = e
+            stat.zero_()
+            stat[-1] = 1.0
         distributed.allreduce_stats(stat)
         stat_np = stat.cpu().numpy()
+        if failure is not None:
+            raise failure
+        if stat_np[-1] > 0:
+            raise RuntimeError("gen_data failed on {} other rank(s); see their error".format(int(round(stat_np[-1]))))
+        stat_np = stat_np[:-1]
         n_total = int(round(stat_np[0]))
 
         # per-feature column groups of the static block

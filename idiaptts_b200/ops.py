@@ -692,6 +692,14 @@ def synthesize(f0, sp, ap, frame_off, fs, frame_period=5.0, deemphasis=0.0, out_
 # ----------------------------------------------------------------------------------------------------------------------
 # Neural-VTLN all-pass warp
 # ----------------------------------------------------------------------------------------------------------------------
+def _check_allpass_blocks(blocks):
+    """The reference halves / doubles c0 only in the first three n-blocks (static, delta, delta-delta: AllPassWarp.py:162, :171,
+    `0:3n:n`); the kernels apply it to every block, which is the same thing up to three blocks -- all the layer is used with."""
+    if blocks > 3:
+        raise ValueError("all-pass warp of {} n-blocks: the reference's single-sided c0 adaptation covers blocks 0-2 only "
+                         "(AllPassWarp.py:162); more than 3 blocks are not supported".format(blocks))
+
+
 def allpass_forward(x, alpha, n, mean=None, std_dev=None, impl=None):
     """x [rows, blocks*n] f32, alpha [rows] f32 -> y [rows, blocks*n].
     impl: "tc" = tensor-core GEMM for runs of rows that share alpha + recursion for the rest (default when n % 4 == 0, n <= 64),
@@ -701,6 +709,7 @@ def allpass_forward(x, alpha, n, mean=None, std_dev=None, impl=None):
     assert x.dtype == torch.float32 and alpha.dtype == torch.float32 and x.dim() == 2
     rows, width = x.shape
     assert width % n == 0 and alpha.numel() == rows
+    _check_allpass_blocks(width // n)
     y = torch.empty_like(x)
     if impl is None:
         impl = "tc" if (n % 4 == 0 and n <= 64 and x.data_ptr() % 16 == 0) else "cc"
@@ -722,6 +731,7 @@ def allpass_backward(grad_y, x, alpha, n, mean=None, std_dev=None, impl=None):
     dev = _need_cuda(grad_y, x, alpha, mean, std_dev)
     rows, width = x.shape
     blocks = width // n
+    _check_allpass_blocks(blocks)
     gx = torch.empty_like(x)
     ga = torch.empty_like(alpha)
     ws = torch.empty(rows * blocks, dtype=torch.float32, device=dev)

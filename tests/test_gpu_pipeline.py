@@ -122,6 +122,11 @@ def test_gen_data_files_and_statistics(tmp_path, add_deltas):
         assert os.path.exists(str(tmp_path / "out" / "mcep60" / "train-deltas-mean-covariance.npz"))
     else:
         np.testing.assert_allclose(back, static, rtol=1e-4, atol=1e-4)
+    # a FRESH reader (never ran gen_data) finds the same parameters on disk: the trainer call sequence
+    fresh = WorldFeatLabelGen(str(tmp_path / "out"), add_deltas=add_deltas, num_coded_sps=60, num_bap=2)
+    fresh.get_normalisation_params(str(tmp_path / "out"), "train")
+    np.testing.assert_allclose(fresh[ids[2]], norm, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(fresh.postprocess_sample(fresh[ids[2]], apply_mlpg=True), back, rtol=1e-4, atol=1e-4)
     # without an F0 cache the F0 stage of pyworld.wav2world (DIO + StoneMask) runs on the device
     ld2, _, _ = WorldFeatLabelGen(str(tmp_path / "o2"), num_coded_sps=60, num_bap=2).gen_data(str(tmp_path / "wav"), None, id_list=ids,
                                                                                             return_dict=True)
