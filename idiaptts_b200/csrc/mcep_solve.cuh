@@ -16,11 +16,15 @@ __host__ __device__ inline int ldl_workspace_floats(int NBk, int KB) { return (N
 template <int KB>
 __device__ __forceinline__ int blk_index(int I, int Kb) { return (I * (I + 1) / 2 + Kb) * KB; }
 
-// returns false (warp-uniform) when a pivot is not positive
+// returns false (warp-uniform) when a pivot is not positive.
+// General form (mgcep.cu): M[i][k] = rt[|i-k|] + hk[i+k] with a separate Hankel sequence hk (nullptr: hk = rt, the mcep case) and
+// right-hand side rhs (nullptr: rt[i] - al[i], the mcep case).
 template <int KB>
 __device__ __forceinline__ bool warp_ldl_solve(const float* __restrict__ rt, const float* __restrict__ al, int n, int NBk,
                                               const uint16_t* __restrict__ tri, float* __restrict__ ws,
-                                              float* __restrict__ x_out) {
+                                              float* __restrict__ x_out, const float* __restrict__ hk = nullptr,
+                                              const float* __restrict__ rhs = nullptr) {
+  if (hk == nullptr) hk = rt;
   const int lane = threadIdx.x & 31;
   const int np = 4 * NBk;
   float* A = ws;                                     // NBk (NBk+1) / 2 blocks
@@ -34,20 +38,20 @@ __device__ __forceinline__ bool warp_ldl_solve(const float* __restrict__ rt, con
       const int i = 4 * I + r, k = 4 * Kb;
       float4 v;
       if (i < n && k + 3 < n) {
-        v.x = rt[abs(i - k)] + rt[i + k];
-        v.y = rt[abs(i - k - 1)] + rt[i + k + 1];
-        v.z = rt[abs(i - k - 2)] + rt[i + k + 2];
-        v.w = rt[abs(i - k - 3)] + rt[i + k + 3];
+        v.x = rt[abs(i - k)] + hk[i + k];
+        v.y = rt[abs(i - k - 1)] + hk[i + k + 1];
+        v.z = rt[abs(i - k - 2)] + hk[i + k + 2];
+        v.w = rt[abs(i - k - 3)] + hk[i + k + 3];
       } else {
         float t[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) t[c] = (i < n && k + c < n) ? rt[abs(i - k - c)] + rt[i + k + c] : (i == k + c ? 1.f : 0.f);
+        for (int c = 0; c < 4; ++c) t[c] = (i < n && k + c < n) ? rt[abs(i - k - c)] + hk[i + k + c] : (i == k + c ? 1.f : 0.f);
         v = make_float4(t[0], t[1], t[2], t[3]);
       }
       *reinterpret_cast<float4*>(A + blk_index<KB>(I, Kb) + 4 * r) = v;
     }
   }
-  for (int i = lane; i < np; i += 32) bv[i] = (i < n) ? rt[i] - al[i] : 0.f;
+  for (int i = lane; i < np; i += 32) bv[i] = (i < n) ? (rhs ? rhs[i] : rt[i] - al[i]) : 0.f;
   __syncwarp();
   bool ok = true;
   for (int J = 0; J < NBk; ++J) {
