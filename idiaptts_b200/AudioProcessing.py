@@ -7,6 +7,8 @@ and Merlin post-filtering; they raise NotImplementedError instead of silently do
 import os
 import wave
 
+import logging
+
 import numpy as np
 import torch
 
@@ -63,8 +65,15 @@ class AudioProcessing:
         return mcep.astype(np.float32, copy=False)
 
     @staticmethod
-    def extract_mgc(*args, **kwargs):
-        raise NotImplementedError("sp_type='mgc' (gamma = -1/3) is outside the accelerated path (SURVEY.md 8f N3)")
+    def extract_mgc(amp_sp, fs=None, num_coded_sps=60, mgc_alpha=None):
+        """pysptk.mgcep(amp_sp, order, alpha, gamma = -1/3, eps=1e-8, etype=1, itype=3) on the GPU -> float32 [T, num_coded_sps]
+        (reference :123-140; SURVEY 8f N3, parity unpinned)."""
+        if mgc_alpha is None:
+            assert fs is not None, "Either sampling rate or mgc alpha has to be given."
+            mgc_alpha = AudioProcessing.fs_to_mgc_alpha(fs)
+        mgc = _sptk.mgcep(amp_sp, order=num_coded_sps - 1, alpha=mgc_alpha, gamma=AudioProcessing.mgc_gamma, eps=1.0e-8, min_det=0.0,
+                          etype=1, itype=3)
+        return mgc.astype(np.float32, copy=False)
 
     @staticmethod
     def mcep_to_amp_sp(mcep, fs, alpha=None):
@@ -77,11 +86,38 @@ class AudioProcessing:
         return amp.cpu().numpy()
 
     @staticmethod
+    def mgc_to_amp_sp(mgc, fs, alpha=None, gamma=None, n_fft=None):
+        """exp(Re pysptk.mgc2sp(mgc, alpha, gamma, n_fft)) as float32 (reference :259-275)."""
+        if alpha is None:
+            alpha = AudioProcessing.fs_to_mgc_alpha(fs)
+        if gamma is None:
+            gamma = AudioProcessing.mgc_gamma
+        if n_fft is None:
+            n_fft = AudioProcessing.fs_to_frame_length(fs)
+        if not torch.cuda.is_available():
+            raise RuntimeError("idiaptts_b200 needs a CUDA device; there is no CPU fallback")
+        c = torch.from_numpy(np.ascontiguousarray(mgc, dtype=np.float64)).cuda()
+        return ops.mgc2sp(c, alpha, gamma, n_fft, out_dtype=torch.float32).cpu().numpy()
+
+    @staticmethod
+    def merlin_post_filter(coded_sp, alpha, fft_size=1024):
+        """nnmnkwii.postfilters.merlin_post_filter (reference :308-311) on the GPU."""
+        if not torch.cuda.is_available():
+            raise RuntimeError("idiaptts_b200 needs a CUDA device; there is no CPU fallback")
+        c = torch.from_numpy(np.ascontiguousarray(coded_sp, dtype=np.float64)).cuda()
+        return ops.merlin_post_filter(c, alpha, fft_size).cpu().numpy()
+
+    @staticmethod
     def decode_sp(coded_sp, sp_type="mcep", fs=None, alpha=None, mgc_gamma=None, n_fft=None, post_filtering=False):
         if post_filtering:
-            raise NotImplementedError("merlin_post_filter is outside the accelerated path (SURVEY.md 8f N3)")
+            if sp_type in ["mcep", "mgc"]:
+                coded_sp = AudioProcessing.merlin_post_filter(coded_sp, AudioProcessing.fs_to_mgc_alpha(fs))
+            else:
+                logging.warning("Post-filtering only implemented for cepstrum features.")
         if sp_type == "mcep":
             return AudioProcessing.mcep_to_amp_sp(coded_sp, fs, alpha)
+        if sp_type == "mgc":
+            return AudioProcessing.mgc_to_amp_sp(coded_sp, fs, alpha, mgc_gamma, n_fft)
         if sp_type == "amp_sp":
             return coded_sp
         raise NotImplementedError("Unknown or unsupported feature type {}. No decoding method available.".format(sp_type))

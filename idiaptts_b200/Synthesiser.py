@@ -21,8 +21,9 @@ class Synthesiser(object):
         """{id: [T, D]} -> {id: waveform float32}; the compute half of run_world_synth."""
         if not torch.cuda.is_available():
             raise RuntimeError("idiaptts_b200 needs a CUDA device; there is no CPU fallback")
-        if getattr(hparams, "sp_type", "mcep") != "mcep" or getattr(hparams, "do_post_filtering", False):
-            raise NotImplementedError("only sp_type='mcep' without post-filtering is on the accelerated path")
+        sp_type = getattr(hparams, "sp_type", "mcep")
+        if sp_type not in ("mcep", "mgc"):
+            raise NotImplementedError("sp_type '{}': only 'mcep' and 'mgc' are on the accelerated path".format(sp_type))
         dev = torch.device("cuda", torch.cuda.current_device())
         D, nb, fs = hparams.num_coded_sps, hparams.num_bap, hparams.synth_fs
         rows, lens, ids = [], [], []
@@ -36,7 +37,9 @@ class Synthesiser(object):
             return {}
         syn = pipeline.WorldSynthesizer(fs, D, getattr(hparams, "mgc_alpha", None),
                                         f0_silence_threshold=getattr(hparams, "f0_silence_threshold", WorldFeatLabelGen.f0_silence_threshold),
-                                        lf0_zero=getattr(hparams, "lf0_zero", WorldFeatLabelGen.lf0_zero), device=dev)
+                                        lf0_zero=getattr(hparams, "lf0_zero", WorldFeatLabelGen.lf0_zero), device=dev,
+                                        sp_type=sp_type, mgc_gamma=getattr(hparams, "mgc_gamma", None) or -1.0 / 3.0,
+                                        post_filtering=getattr(hparams, "do_post_filtering", False))
         feats = torch.from_numpy(np.concatenate(rows)).to(dev)
         frame_off = torch.from_numpy(np.concatenate(([0], np.cumsum(lens))).astype(np.int64)).to(dev)
         y, out_off, status = syn.synthesize(feats, frame_off, preemphasis=getattr(hparams, "preemphasis", 0.0))

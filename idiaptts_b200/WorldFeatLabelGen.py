@@ -152,8 +152,8 @@ class WorldFeatLabelGen(object):
         if self.num_coded_sps != -1:
             self.dir_coded_sps += str(self.num_coded_sps)
         self.dir_deltas = WorldFeatLabelGen.dir_deltas + "_" + self.dir_coded_sps
-        if self.sp_type != "mcep":
-            raise NotImplementedError("only sp_type='mcep' is on the accelerated path (SURVEY.md 8f N3)")
+        if self.sp_type not in ("mcep", "mgc"):
+            raise NotImplementedError("sp_type '{}': only 'mcep' and 'mgc' are on the accelerated path".format(self.sp_type))
 
     # ---- normalisation parameters -----------------------------------------------------------------------------------------------
     def get_normalisation_params(self, dir_out=None, file_name=None):
@@ -330,8 +330,8 @@ class WorldFeatLabelGen(object):
                          sp_type="mcep", num_coded_sps=40, load_sp=True, load_lf0=True, load_vuv=True, load_bap=True,
                          f0_silence_threshold=None, lf0_zero=None, f0=None, f0_cache=None, mgc_alpha=None):
         """Acoustic features of one audio file: (coded_sp, lf0, vuv, bap)."""
-        if sp_type != "mcep":
-            raise NotImplementedError("only sp_type='mcep' is on the accelerated path (SURVEY.md 8f N3)")
+        if sp_type not in ("mcep", "mgc"):
+            raise NotImplementedError("sp_type '{}': only 'mcep' and 'mgc' are on the accelerated path".format(sp_type))
         audio_name = os.path.join(dir_in, file_name + "." + file_ext)
         raw, fs = AudioProcessing.get_raw(audio_name, preemphasis)
         if f0 is None:
@@ -345,8 +345,11 @@ class WorldFeatLabelGen(object):
                                                                                               len(vuv), file_name))
         coded_sp = None
         if load_sp:
-            coded_sp = AudioProcessing.extract_mcep(amp_sp, num_coded_sps=num_coded_sps,
-                                                    mgc_alpha=AudioProcessing.fs_to_mgc_alpha(fs) if mgc_alpha is None else mgc_alpha)
+            a = AudioProcessing.fs_to_mgc_alpha(fs) if mgc_alpha is None else mgc_alpha
+            if sp_type == "mcep":
+                coded_sp = AudioProcessing.extract_mcep(amp_sp, num_coded_sps=num_coded_sps, mgc_alpha=a)
+            else:
+                coded_sp = AudioProcessing.extract_mgc(amp_sp, fs=fs, num_coded_sps=num_coded_sps, mgc_alpha=a)
             assert len(coded_sp) == len(lf0), "Requires testing. Possibly trimming is a solution."
         logging.info("Extracted features from {} at {} Hz with {} ms frame hop.".format(os.path.basename(file_name), fs, hop_size_ms))
         coded_sp, lf0, vuv, bap = WorldFeatLabelGen.trim_to_shortest([coded_sp, lf0, vuv, bap])
@@ -450,7 +453,8 @@ class WorldFeatLabelGen(object):
                 if f0_cache is None:
                     ops.estimate_f0(batch, frame_period=self.hop_size_ms)
                 an = pipeline.WorldAnalyzer(fs, D, alpha, self.hop_size_ms, self.n_fft, WorldFeatLabelGen.f0_silence_threshold,
-                                            WorldFeatLabelGen.lf0_zero, device=dev)
+                                            WorldFeatLabelGen.lf0_zero, device=dev, sp_type=self.sp_type,
+                                            mgc_gamma=AudioProcessing.mgc_gamma)
                 feats, sums, status = an.extract(batch)
                 F = batch.num_frames
                 if self.add_deltas:

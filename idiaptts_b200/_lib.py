@@ -87,6 +87,11 @@ _SIGNATURES = {
     "b2w_dio": (c_int32, [ctypes.POINTER(Batch), c_int64, c_void_p, c_double, c_double, c_double, c_double, c_double, c_int32,
                           c_void_p, c_void_p, c_void_p]),
     "b2w_stonemask": (c_int32, [ctypes.POINTER(Batch), c_void_p, c_void_p]),
+    "b2w_mgcep": (c_int32, [c_void_p, c_int32, c_int32, c_int64, c_int32, c_int32, c_double, c_int32, c_int32, c_double, c_double,
+                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p,
+                            c_void_p]),
+    "b2w_mgc2sp": (c_int32, [c_void_p, c_int32, c_int64, c_int64, c_int32, c_int32, c_double, c_void_p, c_void_p, c_void_p, c_int32,
+                             c_void_p]),
     "b2w_probe_fp64_fma": (c_int64, [c_int32, c_void_p, c_void_p]),
     "b2w_mcep_prof_read": (c_int32, [c_void_p]),
     "b2w_cheaptrick_fft_size": (c_int32, [c_int32, c_double]),

@@ -44,14 +44,38 @@ def mcep(x, order=25, alpha=0.35, miniter=2, maxiter=30, threshold=0.001, etype=
     return out[0] if single else out
 
 
+def mgcep(x, order=25, alpha=0.35, gamma=0.0, num_recursions=None, miniter=2, maxiter=30, threshold=0.001, etype=0, eps=0.0,
+          min_det=1.0e-6, itype=0, otype=0):
+    """pysptk.mgcep for spectral input (itype 3 amplitude / 4 periodogram, etype 0/1, otype 0): mel-generalised cepstral analysis
+    (SURVEY 8f N3).  PARITY UNPINNED: restated from the published criterion (csrc/mgcep.cu), not from SPTK's source."""
+    if itype not in (3, 4):
+        raise NotImplementedError("only itype=3 (amplitude) and itype=4 (periodogram) inputs are accelerated "
+                                  "(IdiapTTS uses itype=3, AudioProcessing.py:138)")
+    if otype != 0:
+        raise NotImplementedError("only otype=0 (cepstral coefficients) is implemented")
+    if etype not in (0, 1):
+        raise ValueError("etype must be 0 or 1 on this path")
+    if not (-1.0 <= gamma <= 0.0):
+        raise ValueError("gamma must be in [-1, 0]")
+    x2, single = _as2d(x)
+    plane = torch.from_numpy(x2).to(_device())
+    mgc, status = ops.mgcep(plane, order, alpha, gamma, is_power=(itype == 4), miniter=miniter, maxiter=maxiter, threshold=threshold,
+                            eps=eps if etype == 1 else 0.0, out_dtype=torch.float64)
+    out = mgc.cpu().numpy()
+    ops.raise_for_status(status, "mgcep")
+    return out[0] if single else out
+
+
 def mgc2sp(ceps, alpha=0.0, gamma=0.0, fftlen=256):
-    """pysptk.mgc2sp for gamma == 0.  Returns a complex array like pysptk; only the real part (log amplitude) is computed on
-    this path because that is all the reference reads (AudioProcessing.py:256 `amp_sp.real`); the imaginary part is 0."""
-    if gamma != 0.0:
-        raise NotImplementedError("gamma != 0 (generalised cepstrum) is outside the accelerated path (SURVEY 8f N3)")
+    """pysptk.mgc2sp.  Returns a complex array like pysptk; only the real part (log amplitude) is computed on this path because
+    that is all the reference reads (AudioProcessing.py:256, :275 `amp_sp.real`); the imaginary part is 0.  gamma != 0 evaluates
+    log |1 + gamma C|^(1/gamma) directly (pysptk goes through a 512-term cepstrum: 3e-8 relative apart, oracle/mgc_np.py)."""
     c2, single = _as2d(ceps)
     mc = torch.from_numpy(c2).to(_device())
-    sp = ops.mc2sp(mc, alpha, fftlen, scale=1.0, do_exp=False, out_dtype=torch.float64).cpu().numpy()
+    if gamma != 0.0:
+        sp = torch.log(ops.mgc2sp(mc, alpha, gamma, fftlen, out_dtype=torch.float64)).cpu().numpy()
+    else:
+        sp = ops.mc2sp(mc, alpha, fftlen, scale=1.0, do_exp=False, out_dtype=torch.float64).cpu().numpy()
     out = sp.astype(np.complex128)
     return out[0] if single else out
 

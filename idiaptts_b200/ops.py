@@ -448,6 +448,116 @@ def mcep(plane, order, alpha, is_power=False, miniter=2, maxiter=30, threshold=0
     return out, status
 
 
+class MgcTables:
+    """cos / sin tables of the all-pass warped frequency for the generalised mel-cepstrum kernels (b2w_mgcep, b2w_mgc2sp):
+    forward [pad4(order + 1), K] (coefficients -> spectrum) and reduction [K, pad4(2 order + 1)] with the bin weights of the
+    mean over the circle folded in (per-bin weights -> gradient / Toeplitz / Hankel sequences); float64 on the host, float32
+    on the device.  (order, alpha, fft_size) -> cached per device."""
+    _cache = {}
+    _lock = threading.Lock()
+
+    def __init__(self, order, alpha, fft_size, device):
+        lib = _lib.load()
+        K = fft_size // 2 + 1
+        mp, np2 = lib.b2w_mcep_pad(order + 1), lib.b2w_mcep_pad(2 * order + 1)
+        w = 2.0 * np.pi * np.arange(K) / fft_size
+        wt = w + 2.0 * np.arctan2(alpha * np.sin(w), 1.0 - alpha * np.cos(w))   # warped frequency of the first-order all-pass
+        fwd_cos, fwd_sin = np.zeros((mp, K)), np.zeros((mp, K))
+        k = np.arange(order + 1)[:, None]
+        fwd_cos[:order + 1], fwd_sin[:order + 1] = np.cos(k * wt[None, :]), np.sin(k * wt[None, :])
+        W = np.full(K, 2.0 / fft_size)
+        W[0] = W[-1] = 1.0 / fft_size
+        red_cos, red_sin = np.zeros((K, np2)), np.zeros((K, np2))
+        n = np.arange(2 * order + 1)[None, :]
+        red_cos[:, :2 * order + 1] = W[:, None] * np.cos(wt[:, None] * n)
+        red_sin[:, :2 * order + 1] = W[:, None] * np.sin(wt[:, None] * n)
+        self.host64 = (fwd_cos, fwd_sin, red_cos, red_sin)
+        to = lambda a: torch.from_numpy(a.astype(np.float32)).to(device)
+        self.fwd_cos, self.fwd_sin, self.red_cos, self.red_sin = to(fwd_cos), to(fwd_sin), to(red_cos), to(red_sin)
+
+    @classmethod
+    def get(cls, order, alpha, fft_size, device):
+        key = (int(order), float(alpha), int(fft_size), str(torch.device(device)))
+        with cls._lock:
+            tab = cls._cache.get(key)
+            if tab is None:
+                tab = cls(order, alpha, fft_size, device)
+                cls._cache[key] = tab
+            return tab
+
+
+def mgcep(plane, order, alpha, gamma, is_power=False, miniter=2, maxiter=30, threshold=0.001, eps=1.0e-8, out=None,
+          out_stride=None, out_dtype=torch.float32, iters=None, status=None):
+    """pysptk.mgcep(itype=3 (amplitude) or 4 (power), etype=1, otype=0) on a [F, K] plane -> mgc [F, order+1] (SURVEY 8f N3;
+    parity unpinned, see csrc/mgcep.cu).  gamma in [-1, 0); gamma = 0 is `mcep`."""
+    if gamma == 0.0:
+        return mcep(plane, order, alpha, is_power, miniter, maxiter, threshold, eps, out, out_stride, out_dtype, iters, status)
+    lib = _lib.load()
+    assert plane.dim() == 2 and plane.dtype in (torch.float32, torch.float64)
+    if not plane.is_cuda:
+        raise ValueError("idiaptts_b200 operators need CUDA tensors (there is no CPU fallback)")
+    plane = plane.contiguous()
+    F, K = plane.shape
+    dev = plane.device
+    fft_size = 2 * (K - 1)
+    tab0 = McepTables.get(order, alpha, fft_size, dev)
+    tab = MgcTables.get(order, alpha, fft_size, dev)
+    if out is None:
+        out = torch.empty((F, order + 1), dtype=out_dtype, device=dev)
+        out_stride = order + 1
+    if status is None:
+        status = new_status(dev)
+    with torch.cuda.device(dev):
+        check(lib.b2w_mgcep(plane.data_ptr(), _DT[plane.dtype], 1 if is_power else 0, F, fft_size, int(order), float(gamma),
+                            int(miniter), int(maxiter), float(threshold), float(eps), tab0.m0t.data_ptr(), tab.fwd_cos.data_ptr(),
+                            tab.fwd_sin.data_ptr(), tab.red_cos.data_ptr(), tab.red_sin.data_ptr(), out.data_ptr(), _DT[out.dtype],
+                            int(out_stride), _ptr(iters), status.data_ptr(), _stream(dev)), "b2w_mgcep")
+    return out, status
+
+
+def mgc2sp(mgc, alpha, gamma, fft_size, out_dtype=torch.float32, order=None, mgc_stride=None):
+    """Amplitude spectrum |H| [F, K] of generalised mel-cepstra (AudioProcessing.mgc_to_amp_sp = exp(Re pysptk.mgc2sp));
+    gamma = 0 is mc2sp."""
+    if gamma == 0.0:
+        return mc2sp(mgc, alpha, fft_size, out_dtype=out_dtype, order=order, mc_stride=mgc_stride)
+    lib = _lib.load()
+    dev = _need_cuda(mgc)
+    assert mgc.dim() == 2 and mgc.dtype in (torch.float32, torch.float64)
+    F = mgc.shape[0]
+    if order is None:
+        order = mgc.shape[1] - 1
+    if mgc_stride is None:
+        mgc_stride = mgc.shape[1]
+    tab = MgcTables.get(order, alpha, fft_size, dev)
+    out = torch.empty((F, fft_size // 2 + 1), dtype=out_dtype, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.b2w_mgc2sp(mgc.data_ptr(), _DT[mgc.dtype], int(mgc_stride), F, int(fft_size), int(order), float(gamma),
+                             tab.fwd_cos.data_ptr(), tab.fwd_sin.data_ptr(), out.data_ptr(), _DT[out.dtype], _stream(dev)),
+              "b2w_mgc2sp")
+    return out
+
+
+def merlin_post_filter(mgc, alpha, fft_size=1024, coef=1.4):
+    """nnmnkwii.postfilters.merlin_post_filter on [F, D] mel-cepstra (device): coefficients from c(2) on are scaled by `coef`
+    and c(0) is shifted so that the energy r(0) = mean |H|^2 of the minimum-phase response is unchanged (mc2b / b2mc only
+    move c(0) here).  The two energies come from the mel-cepstrum -> power-spectrum kernel (b2w_mc2sp) and a weighted row sum."""
+    dev = _need_cuda(mgc)
+    assert mgc.dim() == 2
+    x = mgc.to(torch.float32).contiguous()
+    F, D = x.shape
+    weight = torch.full((D,), float(coef), dtype=torch.float32, device=dev)
+    weight[:2] = 1.0
+    scaled = (x * weight).contiguous()
+    K = fft_size // 2 + 1
+    W = torch.full((K,), 2.0 / fft_size, dtype=torch.float64, device=dev)
+    W[0] = W[-1] = 1.0 / fft_size
+    r0 = mc2sp(x, alpha, fft_size, scale=2.0, do_exp=True, out_dtype=torch.float64) @ W
+    p_r0 = mc2sp(scaled, alpha, fft_size, scale=2.0, do_exp=True, out_dtype=torch.float64) @ W
+    out = scaled.double()
+    out[:, 0] += 0.5 * torch.log(r0 / p_r0)
+    return out
+
+
 def mc2sp(mc, alpha, fft_size, scale=1.0, do_exp=True, out_dtype=torch.float32, order=None, mc_stride=None, square=False, out=None):
     """(exp of) scale * Re FFT(freqt(mc, fft_size/2, -alpha)): log-amplitude / amplitude / power spectrum from mel-cepstra.
     square=True (with do_exp, float64 output): the float32 amplitude squared in float64, i.e. world_features_to_raw's pow_sp."""

@@ -18,8 +18,12 @@ from . import ops
 
 class WorldAnalyzer:
     def __init__(self, fs, num_coded_sps=60, mgc_alpha=None, hop_size_ms=5.0, n_fft=None, f0_silence_threshold=30,
-                 lf0_zero=0, chunk_frames=1 << 18, device="cuda"):
+                 lf0_zero=0, chunk_frames=1 << 18, device="cuda", sp_type="mcep", mgc_gamma=-1.0 / 3.0):
+        """sp_type: "mcep" (pysptk.mcep, the default recipe) or "mgc" (pysptk.mgcep with mgc_gamma)."""
         from .compat.pysptk import mcepalpha
+        assert sp_type in ("mcep", "mgc")
+        self.sp_type = sp_type
+        self.gamma = float(mgc_gamma) if sp_type == "mgc" else 0.0
         self.fs = int(fs)
         self.num_coded_sps = int(num_coded_sps)
         self.alpha = float(mcepalpha(fs) if mgc_alpha is None else mgc_alpha)
@@ -84,8 +88,12 @@ class WorldAnalyzer:
             timed("cheaptrick", nf, lambda: ops.cheaptrick(batch, fft_size=self.n_fft, status=status, frame_lo=lo, frame_hi=hi,
                                                            out=spc))
             it = None if self.iters is None else self.iters[lo:hi]
-            timed("mcep", nf, lambda: ops.mcep(spc, D - 1, self.alpha, is_power=True, out=flat[lo * self.dim:],
-                                               out_stride=self.dim, status=status, iters=it))
+            if self.gamma == 0.0:
+                timed("mcep", nf, lambda: ops.mcep(spc, D - 1, self.alpha, is_power=True, out=flat[lo * self.dim:],
+                                                   out_stride=self.dim, status=status, iters=it))
+            else:
+                timed("mgcep", nf, lambda: ops.mgcep(spc, D - 1, self.alpha, self.gamma, is_power=True, out=flat[lo * self.dim:],
+                                                     out_stride=self.dim, status=status, iters=it))
             coarse, voiced, _ = timed("d4c", nf, lambda: ops.d4c_coarse(batch, status=status, frame_lo=lo, frame_hi=hi))
             timed("bap_from_coarse", nf, lambda: ops.bap_from_coarse(coarse, voiced, self.fs, self.n_fft,
                                                                      out=flat[lo * self.dim + D + 2:], out_stride=self.dim))
@@ -168,9 +176,14 @@ def mean_std_from_sums(sums, n, dim):
 
 class WorldSynthesizer:
     def __init__(self, fs, num_coded_sps=60, mgc_alpha=None, hop_size_ms=5.0, n_fft=None, f0_silence_threshold=30, lf0_zero=0,
-                 device="cuda", precision="fast"):
-        """precision: "fast" (default) = single-precision per-pulse transforms (ops.synth_render), "f64" = double precision."""
+                 device="cuda", precision="fast", sp_type="mcep", mgc_gamma=-1.0 / 3.0, post_filtering=False):
+        """precision: "fast" (default) = single-precision per-pulse transforms (ops.synth_render), "f64" = double precision.
+        sp_type "mgc": the coded spectrum is a generalised mel-cepstrum with mgc_gamma (AudioProcessing.mgc_to_amp_sp);
+        post_filtering: nnmnkwii's merlin_post_filter on the coded spectrum before decoding (AudioProcessing.decode_sp)."""
         from .compat.pysptk import mcepalpha
+        assert sp_type in ("mcep", "mgc")
+        self.gamma = float(mgc_gamma) if sp_type == "mgc" else 0.0
+        self.post_filtering = bool(post_filtering)
         self.fs = int(fs)
         self.num_coded_sps = int(num_coded_sps)
         self.alpha = float(mcepalpha(fs) if mgc_alpha is None else mgc_alpha)
@@ -196,9 +209,19 @@ class WorldSynthesizer:
         vuv = vuv & ~(f0 < self.f0_silence_threshold)
         f0 = torch.where(vuv, f0, torch.full_like(f0, float(self.lf0_zero)))
         # decode_sp: amp = exp(Re mgc2sp) as float32 (AudioProcessing.py:256), then pow_sp = amp^2 in float64 (W:924)
-        pow_sp = ops._timed(events, "mc2sp", F, lambda: ops.mc2sp(feats, self.alpha, self.n_fft, scale=1.0, do_exp=True,
-                                                                 out_dtype=torch.float64, order=D - 1, mc_stride=feats.shape[1],
-                                                                 square=True))
+        coded, cstride = feats, feats.shape[1]
+        if self.post_filtering:  # decode_sp filters with fs_to_mgc_alpha(fs), whatever alpha the features were coded with (A:310)
+            from .compat.pysptk import mcepalpha
+            coded = ops.merlin_post_filter(feats[:, :D], float(mcepalpha(self.fs)), self.n_fft).float().contiguous()
+            cstride = D
+        if self.gamma == 0.0:
+            pow_sp = ops._timed(events, "mc2sp", F, lambda: ops.mc2sp(coded, self.alpha, self.n_fft, scale=1.0, do_exp=True,
+                                                                     out_dtype=torch.float64, order=D - 1, mc_stride=cstride,
+                                                                     square=True))
+        else:
+            amp = ops._timed(events, "mgc2sp", F, lambda: ops.mgc2sp(coded, self.alpha, self.gamma, self.n_fft, out_dtype=torch.float32,
+                                                                    order=D - 1, mgc_stride=cstride))
+            pow_sp = amp.double() ** 2
         bap = feats[:, D + 2:].double().contiguous()
         ap = ops._timed(events, "decode_ap", F, lambda: ops.decode_aperiodicity(bap, self.fs, self.n_fft))
         # (Measured: decoding the two planes on a side stream while the sequential pulse placement runs on this one is SLOWER,

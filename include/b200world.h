@@ -271,6 +271,18 @@ B2W_API int64_t b2w_probe_fp64_fma(int32_t iters, double* scratch, void* stream)
 /* development aid: phase cycle counters of mcep_tc CTA 0 (non-zero only in a -DB2W_MCEP_PROF build) */
 B2W_API int b2w_mcep_prof_read(long long* out16);
 
+/* ---- generalised mel-cepstrum (sp_type = "mgc"): replaces pysptk.mgcep(amp_sp, order, alpha, gamma, eps = 1e-8,
+ * etype = 1, itype = 3) in AudioProcessing.extract_mgc (A:123-140) and exp(Re pysptk.mgc2sp(mgc, alpha, gamma, fftlen)) in
+ * AudioProcessing.mgc_to_amp_sp (A:259-275).  PARITY UNPINNED (csrc/mgcep.cu, oracle/mgc_np.py).  gamma in [-1, 0).
+ * Tables (float32, device; layouts in csrc/mgcep.cu, built by ops.MgcTables): m0t [K, pad4(order + 2)] of b2w_mcep_tables_host,
+ * fwd_cos / fwd_sin [pad4(order + 1), K], red_cos / red_sin [K, pad4(2 order + 1)]. */
+B2W_API int b2w_mgcep(const void* in, int32_t in_dtype, int32_t in_is_power, int64_t num_frames, int32_t fft_size, int32_t order,
+                      double gamma, int32_t miniter, int32_t maxiter, double threshold, double eps, const float* m0t,
+                      const float* fwd_cos, const float* fwd_sin, const float* red_cos, const float* red_sin, void* mgc,
+                      int32_t mgc_dtype, int64_t mgc_stride, int32_t* iters, int32_t* status, void* stream);
+B2W_API int b2w_mgc2sp(const void* mgc, int32_t mgc_dtype, int64_t mgc_stride, int64_t num_frames, int32_t fft_size, int32_t order,
+                       double gamma, const float* fwd_cos, const float* fwd_sin, void* amp, int32_t amp_dtype, void* stream);
+
 /* ---- scalar helpers (host, pure functions): pyworld.get_cheaptrick_fft_size (A:60), get_num_aperiodicities
  * (A:71), and the D4C transform size. */
 B2W_API int32_t b2w_cheaptrick_fft_size(int32_t fs, double f0_floor);

@@ -161,15 +161,20 @@ def test_scalar_mappings_and_out_of_scope_errors():
     assert AudioProcessing.fs_to_frame_length(16000) == 1024 and AudioProcessing.fs_to_frame_length(48000) == 2048
     assert AudioProcessing.fs_to_num_bap(16000) == 1 and AudioProcessing.fs_to_num_bap(22050) == 2
     assert abs(AudioProcessing.fs_to_mgc_alpha(16000) - 0.41) < 1e-9 and abs(AudioProcessing.fs_to_mgc_alpha(22050) - 0.455) < 1e-9
+    assert abs(AudioProcessing.mgc_gamma + 1.0 / 3.0) < 1e-15
     with pytest.raises(NotImplementedError):
-        AudioProcessing.extract_mgc(None)
-    with pytest.raises(NotImplementedError):
-        AudioProcessing.decode_sp(np.zeros((2, 60)), "mgc", 16000)
+        AudioProcessing.decode_sp(np.zeros((2, 60)), "mfbanks", 16000)     # other vocoder paths stay out of scope
+    if not torch.cuda.is_available():  # the mgc branch is built and, like everything else, needs the GPU
+        with pytest.raises(RuntimeError, match="CUDA"):
+            AudioProcessing.extract_mgc(np.ones((3, 513)), fs=16000)
+        with pytest.raises(RuntimeError, match="CUDA"):
+            AudioProcessing.decode_sp(np.zeros((2, 60)), "mgc", 16000)
     if not torch.cuda.is_available():  # no cached F0 -> DIO + StoneMask on the device: without a GPU this fails loudly
         with pytest.raises(RuntimeError):
             WorldFeatLabelGen.world_extract_features(np.zeros(1600), 16000, 5)
+    assert WorldFeatLabelGen(sp_type="mgc").dir_coded_sps == "mgc60"
     with pytest.raises(NotImplementedError):
-        WorldFeatLabelGen(sp_type="mgc")
+        WorldFeatLabelGen(sp_type="mfbanks")
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the behaviour WITHOUT a GPU")
