@@ -16,21 +16,13 @@
 //     weight, the voiced test ar[0] > 0.999, the aperiodic ratio itself (1 - ar loses all accuracy in single precision).
 // Responses are float32 [pulse][N]; overlap_add sums them in double, in pulse order (bit-reproducible).
 // Accuracy against the fp64 path: resynthesis SNR ~ 110 dB (tolerance 60 dB).
-#include "fft32.cuh"
+#include "wfft512.cuh"
 
 namespace b2w {
 namespace {
 
-using f32::ZQ;
-using f32::cadd;
-using f32::cmul;
-using f32::cmul_mi;
-using f32::cscale;
-using f32::csub;
-
-constexpr int kN = 1024;        // fft size this kernel is built for (fs <= 32 kHz); other sizes take the fp64 kernel
-constexpr int kM = kN / 2;      // complex transform length
-constexpr int kK = kM + 1;      // bins
+using namespace w512;           // kN = 1024 (the fft size this kernel is built for: fs <= 32 kHz; other sizes take the fp64 kernel),
+                                // kM = 512 complex points, kK = 513 bins, wfft512, for_real_bins
 constexpr int kWarps = 4;       // pulses per CTA
 
 struct Smem {
@@ -44,61 +36,6 @@ struct Smem {
   static constexpr int dcr_off = twn_off + 512 * 8;                     // DC remover weights, i < 512
   static constexpr int total_bytes = dcr_off + 512 * 4;
 };
-
-// Forward complex FFT of 512 points by one warp.  v[q] = x[lane + 32 q] on entry; the spectrum ends up in z (natural order,
-// padded layout ZQ).  The caller guarantees that no lane still reads z.
-__device__ __forceinline__ void wfft512(float2* z, float2* v, const float2* tw16, const float2* tw512, int lane) {
-  f32::dft16(v);
-  {
-    float2* zo = z + 17 * lane;  // ZQ(16 lane + q)
-#pragma unroll
-    for (int q = 0; q < 16; ++q) zo[q] = v[q];
-  }
-  __syncwarp();
-  float2* zi = z + lane + (lane >> 4);  // ZQ(lane)
-#pragma unroll
-  for (int q = 0; q < 16; ++q) v[q] = zi[34 * q];  // ZQ(lane + 32 q)
-  __syncwarp();
-  {
-    const int k = lane & 15;
-    f32::apply_twiddles<16>(v, tw16[k]);
-    f32::dft16(v);
-    float2* zo = z + 17 * (lane - k) + k;  // ZQ(16 (lane - k) + k + 16 q) = ... + 17 q
-#pragma unroll
-    for (int q = 0; q < 16; ++q) zo[17 * q] = v[q];
-  }
-  __syncwarp();
-#pragma unroll
-  for (int b = 0; b < 8; ++b) {  // radix 2, sub-length 256: (j, j + 256), in place
-    float2* pa = zi + 34 * b;
-    const float2 a = pa[0];
-    const float2 t = cmul(pa[272], tw512[lane + 32 * b]);
-    pa[0] = cadd(a, t);
-    pa[272] = csub(a, t);
-  }
-  __syncwarp();
-}
-
-// Walks the bins k = lane + 32 j <= 512 of the length-1024 REAL transform whose packed half-size transform sits in z:
-// f(k, X[k]).  X[k] = E + w^k O with E = (Z[k] + conj Z[M - k]) / 2, O = (Z[k] - conj Z[M - k]) / (2 i).
-template <typename F>
-__device__ __forceinline__ void for_real_bins(const float2* z, const float2* twn, int lane, F f) {
-  const float2* za = z + lane + (lane >> 4);
-  const int mir = (kM - lane) & (kM - 1);
-  const float2* zb = z + mir + (mir >> 4);
-#pragma unroll
-  for (int j = 0; j <= 16; ++j) {
-    if (j == 16 && lane != 0) break;  // bin M belongs to lane 0
-    const int k = lane + 32 * j;
-    const float2 a = (j == 16) ? z[0] : za[34 * j];
-    const float2 bq = (lane == 0) ? z[(j == 0 || j == 16) ? 0 : (kM - 32 * j) / 16 * 17] : zb[-34 * j];
-    const float2 b = float2{bq.x, -bq.y};
-    const float2 e = cscale(cadd(a, b), 0.5f);
-    const float2 o = cmul_mi(cscale(csub(a, b), 0.5f));
-    const float2 w = (j == 16) ? float2{-1.0f, 0.0f} : twn[k];
-    f(k, cadd(e, cmul(w, o)));
-  }
-}
 
 // WORLD GetMinimumPhaseSpectrum: log-amplitude L[0 .. 512] (floats, may alias X) -> complex spectrum X[0 .. 512].
 __device__ __forceinline__ void minimum_phase(const float* L, float2* z, float2* X, const float2* tw16, const float2* tw512,
@@ -243,7 +180,7 @@ render_fast_kernel(const void* __restrict__ sp, const void* __restrict__ ap, con
     double env0, ar0;
     env_ar(0, env0, ar0);
     const bool has_periodic = cur_vuv && !(ar0 > 0.999);
-#pragma unroll 1
+#pragma unroll 4   // four bins = sixteen independent plane loads in flight per lane (the loop was latency bound: long scoreboard)
     for (int k = lane; k < kK; k += 32) {
       double env, ar;
       env_ar(k, env, ar);

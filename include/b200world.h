@@ -73,7 +73,10 @@ typedef struct {
 /* ---- CheapTrick: replaces pyworld.cheaptrick inside pyworld.wav2world (W:792). ------------------------------
  * sp [num_frames, fft_size/2+1] power spectral envelope, sp_dtype B2W_F64 (pyworld-compatible) or B2W_F32
  * (fused extract path), row stride sp_stride elements (>= fft_size/2+1; the fused path pads rows to a multiple of 8 floats so
- * that b2w_mcep_tc can read them with aligned 16-byte loads). fft_size in {512, 1024, 2048, 4096}. status: 1 int32. */
+ * that b2w_mcep_tc can read them with aligned 16-byte loads). fft_size in {512, 1024, 2048, 4096}. status: 1 int32.
+ * B2W_F64 planes are computed in double precision throughout (1e-9 relative against WORLD); a B2W_F32 plane at fft_size 1024
+ * takes the mixed-precision kernel of the fused path (double-precision waveform transform and cumulative sums, single-precision
+ * cepstral transforms: <= 5e-5 relative, tolerance 1e-4). */
 B2W_API int b2w_cheaptrick(const b2w_batch* b, int32_t fft_size, double q1, void* sp, int32_t sp_dtype, int64_t sp_stride,
                    int32_t* status, void* stream);
 
