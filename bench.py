@@ -321,9 +321,9 @@ def run_b200(args):
         "mc2sp": 4 * NUM_CODED_SPS + 8 * K, "decode_ap": 8 * an.nap + 8 * K, "synth_timebase": 3 * 8,
         "render": 2 * 2 * 8 * K + 8 * N, "overlap_add": 8 * N + 4 * H_pulse(FS),
     }
-    bound = {"lf0_vuv": "latency", "cheaptrick": "l1_shared_pipe+fp64", "mcep": "tensor", "d4c": "issue+l1_shared_pipe",
+    bound = {"lf0_vuv": "latency", "cheaptrick": "l1_shared_pipe", "mcep": "tensor", "d4c": "issue+l1_shared_pipe",
              "bap_from_coarse": "latency", "stats": "hbm", "mc2sp": "fp32_fma+hbm", "decode_ap": "hbm", "synth_timebase": "latency",
-             "render": "l1_shared_pipe+fp64", "overlap_add": "hbm"}
+             "render": "l1_shared_pipe+latency", "overlap_add": "hbm"}
     pipes = ncu_pipes()
     kernels = {}
     for k, v in kt.items():

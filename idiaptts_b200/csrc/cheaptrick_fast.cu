@@ -40,8 +40,15 @@ struct Smem {
 };
 
 template <int DT>
-__device__ __forceinline__ double sample_d(const void* x, int64_t base, int idx, int xlen, double p) {
-  return emph_sample<DT>(x, base, max(0, min(xlen - 1, idx)), p);
+__device__ __forceinline__ float sample_f(const void* x, int64_t base, int idx, int xlen, double p, float pf) {
+  idx = max(0, min(xlen - 1, idx));
+  if (DT == B2W_I16) {  // value / 32768 is exact in single precision; one rounding in the pre-emphasis
+    const int16_t* xs = reinterpret_cast<const int16_t*>(x) + base;
+    float v = (float)xs[idx];
+    if (pf != 0.0f && idx > 0) v = fmaf(-pf, (float)xs[idx - 1], v);
+    return v * (1.0f / 32768.0f);
+  }
+  return (float)emph_sample<DT>(x, base, idx, p);
 }
 
 template <int XDT>
@@ -75,7 +82,9 @@ cheaptrick_fast_kernel(b2w_batch b, double q1, float* __restrict__ sp, int64_t s
   float2* zf = reinterpret_cast<float2*>(mine);
   double* C = reinterpret_cast<double*>(mine);
   float* P = reinterpret_cast<float*>(mine + Smem::z_bytes);
+  float* seg = reinterpret_cast<float*>(mine);  // the frame's waveform segment, staged in the (still idle) FFT buffer
   const double fs = (double)b.fs;
+  const float pf = (float)b.preemphasis;
   const double f0_floor = 3.0 * fs / (kN - 3.0);
 
   for (int64_t frame = (int64_t)blockIdx.x * kWarps + warp; frame < b.num_frames; frame += (int64_t)gridDim.x * kWarps) {
@@ -87,6 +96,11 @@ cheaptrick_fast_kernel(b2w_batch b, double q1, float* __restrict__ sp, int64_t s
     const int half = mround_pos(1.5 * fs / f0);
     const int wlen = 2 * half + 1;  // <= 1021 for f0 > f0_floor
     const int origin = mround_pos(__dadd_rn(__dmul_rn(b.t[frame], fs), 0.001));
+
+    // the samples under the window, read once, coalesced (the two window passes below would otherwise wait on strided global
+    // loads: the first version of this kernel spent most of its time there)
+    for (int i = lane; i < wlen; i += 32) seg[i] = sample_f<XDT>(b.x, s0, origin + i - half, xlen, b.preemphasis, pf);
+    __syncwarp();
 
     // ---- A: Hann window by rotation recurrence (samples 2 n and 2 n + 1, n = lane + 32 q), the three sums -------------------
     const double theta = kPi * f0 / 1.5 / fs;  // angle per sample
@@ -104,13 +118,13 @@ cheaptrick_fast_kernel(b2w_batch b, double q1, float* __restrict__ sp, int64_t s
         const int i = 2 * (lane + 32 * q);
         if (i < wlen) {
           const double w0 = 0.5 * c + 0.5;
-          const double x0 = sample_d<XDT>(b.x, s0, origin + i - half, xlen, b.preemphasis);
+          const double x0 = (double)seg[i];
           sum_w2 += w0 * w0;
           sum_xw += x0 * w0;
           sum_w += w0;
           if (i + 1 < wlen) {
             const double w1 = 0.5 * (c * c1 - s * s1) + 0.5;
-            const double x1 = sample_d<XDT>(b.x, s0, origin + i + 1 - half, xlen, b.preemphasis);
+            const double x1 = (double)seg[i + 1];
             sum_w2 += w1 * w1;
             sum_xw += x1 * w1;
             sum_w += w1;
@@ -140,10 +154,10 @@ cheaptrick_fast_kernel(b2w_batch b, double q1, float* __restrict__ sp, int64_t s
           const int i = 2 * (lane + 32 * q);
           if (i < wlen) {
             const double w0 = (0.5 * c + 0.5) * inv_avg;
-            v[q].x = (sample_d<XDT>(b.x, s0, origin + i - half, xlen, b.preemphasis) - coef) * w0;
+            v[q].x = ((double)seg[i] - coef) * w0;
             if (i + 1 < wlen) {
               const double w1 = (0.5 * (c * c1 - s * s1) + 0.5) * inv_avg;
-              v[q].y = (sample_d<XDT>(b.x, s0, origin + i + 1 - half, xlen, b.preemphasis) - coef) * w1;
+              v[q].y = ((double)seg[i + 1] - coef) * w1;
             }
           }
           const double cn = c * cd - s * sd;
@@ -151,6 +165,7 @@ cheaptrick_fast_kernel(b2w_batch b, double q1, float* __restrict__ sp, int64_t s
           c = cn;
         }
       }
+      __syncwarp();  // every lane has read its samples: the transform may overwrite the staging area
       wfft512_f64(zd, v, tw256d, tw512d, lane);
     }
     for_real_bins_f64(zd, twnd, lane, [&](int k, double2 X) { P[k] = (float)(X.x * X.x + X.y * X.y); });
@@ -159,14 +174,14 @@ cheaptrick_fast_kernel(b2w_batch b, double q1, float* __restrict__ sp, int64_t s
     // ---- D: DC correction (fold the spectrum below f0 back around f0) ----------------------------------------------------------
     {
       int upper = 2 + (int)(f0 * kN / fs);
-      if (upper + 1 > kK || upper - 1 > 64) {  // f0 far above WORLD's domain: keep memory safe and flag it
+      if (upper + 1 > kK || upper - 1 > 96) {  // f0 far above WORLD's domain: keep memory safe and flag it
         if (lane == 0) atomicOr(status, B2W_STATUS_F0_TOO_HIGH);
-        upper = min(kK - 1, 65);
+        upper = min(kK - 1, 97);
       }
       const double inv_dx = -(double)kN / fs;
-      float add[2];
+      float add[3];
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
+      for (int e = 0; e < 3; ++e) {
         const int i = lane + 32 * e;
         add[e] = 0.0f;
         if (i < upper - 1) {
@@ -180,7 +195,7 @@ cheaptrick_fast_kernel(b2w_batch b, double q1, float* __restrict__ sp, int64_t s
       }
       __syncwarp();
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
+      for (int e = 0; e < 3; ++e) {
         const int i = lane + 32 * e;
         if (i < upper - 1) P[i] += add[e];
       }
