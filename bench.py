@@ -318,8 +318,8 @@ def run_b200(args):
     alg_bytes = {
         "lf0_vuv": 8 + 8, "cheaptrick": 2 * H + 20 + 4 * K, "mcep": 4 * K + 4 * NUM_CODED_SPS, "d4c": 2 * H + 20 + 8 * an.nap + 1,
         "bap_from_coarse": 8 * an.nap + 1 + 4 * an.nap, "stats": 4 * an.dim,
-        "mc2sp": 4 * NUM_CODED_SPS + 8 * K, "decode_ap": 8 * an.nap + 8 * K, "synth_timebase": 3 * 8,
-        "render": 2 * 2 * 8 * K + 8 * N, "overlap_add": 8 * N + 4 * H_pulse(FS),
+        "mc2sp": 4 * NUM_CODED_SPS + 4 * K, "decode_ap": 8 * an.nap + 4 * K, "synth_timebase": 3 * 8,   # float32 planes (fast path)
+        "render": 2 * 2 * 4 * K + 4 * N, "overlap_add": 4 * N + 4 * H_pulse(FS),                      # float32 responses
     }
     bound = {"lf0_vuv": "latency", "cheaptrick": "l1_shared_pipe", "mcep": "tensor", "d4c": "issue+l1_shared_pipe",
              "bap_from_coarse": "latency", "stats": "hbm", "mc2sp": "fp32_fma+hbm", "decode_ap": "hbm", "synth_timebase": "latency",
@@ -542,7 +542,7 @@ def bench_synth256(args, dev, syn, feats, frame_off, stats_host, an, peaks, alph
     K, N = an.n_fft // 2 + 1, an.n_fft
     oa = kt.get("overlap_add")
     pulses = oa["units_per_launch"] if oa else 0
-    oa_gbs = (pulses * 8 * N + int(ylen.sum()) * 4) / (oa["avg_launch_ms"] / 1e3) / 1e9 if oa else 0.0
+    oa_gbs = (pulses * 4 * N + int(ylen.sum()) * 4) / (oa["avg_launch_ms"] / 1e3) / 1e9 if oa else 0.0   # float32 responses
     top = max(kt, key=lambda k: kt[k]["ms_per_step"])
     # CPU oracle on a bounded sample of the same rows
     from concurrent.futures import ThreadPoolExecutor
@@ -564,7 +564,7 @@ def bench_synth256(args, dev, syn, feats, frame_off, stats_host, an, peaks, alph
                         for k, v in kt.items()},
             "roofline": {"kernel": "overlap_add", "bound": "hbm", "achieved": oa_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": oa_gbs / peaks["hbm_gbs"], "traffic": None,
-                         "note": "the HBM-bound kernel of the workload (one 8 KB response read per pulse, float32 samples written); the "
+                         "note": "the HBM-bound kernel of the workload (one 4 KB float32 response read per pulse, float32 samples written); the "
                                  "dominant kernel is `%s` (on-chip bound, see kernels.render.ncu of the main line)" % top},
             "cpu_baseline": {"value": cpu_rate, "unit": "audio-s/s", "cores": cores, "kind": "port",
                              "sample": "%d utterances of the same rows" % ns}}

@@ -35,6 +35,7 @@ _SIGNATURES = {
     "b2w_bap_from_coarse": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int64, c_void_p]),
     "b2w_code_aperiodicity": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "b2w_decode_aperiodicity": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
+    "b2w_decode_aperiodicity_f32": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "b2w_mcep_pad": (c_int32, [c_int32]),
     "b2w_mcep_tables_host": (c_int32, [c_int32, c_double, c_int32, c_void_p, c_void_p, c_void_p]),
     "b2w_mcep": (c_int32, [c_void_p, c_int32, c_int32, c_int64, c_int32, c_int32, c_double, c_int32, c_int32, c_double,

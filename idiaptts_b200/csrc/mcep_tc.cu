@@ -25,11 +25,13 @@ constexpr int kTcF = 128;        // frames per CTA = UMMA M
 #ifdef B2W_TC_ISSUER_WARP            // experiment: a 17th warp issues, all 16 others are epilogue warps (120 registers / thread)
 constexpr int kTcThreads = 544;
 constexpr int kTcIssuer = 512;
+constexpr int kTcProducer = 513;
 constexpr int kTcEpiWarp0 = 0;
 constexpr int kTcEpiThreads = 512;
 #else
 constexpr int kTcThreads = 512;  // 16 warps: TMEM lane quarter q = warp & 3, column group g = warp >> 2
-constexpr int kTcIssuer = 0;     // the thread that streams the matrices and issues the MMAs
+constexpr int kTcIssuer = 0;     // the thread that issues the MMAs
+constexpr int kTcProducer = 32;  // the thread that streams the constant matrices (bulk async copies)
 constexpr int kTcEpiWarp0 = 4;   // epilogue warps 4 .. 11 (two per TMEM lane quarter)
 constexpr int kTcEpiThreads = 256;
 #endif
@@ -43,6 +45,7 @@ constexpr uint32_t kB2Bytes = kTcN2 * kTcBK * 4;   // one of hi / lo of the M2^T
 constexpr uint32_t kStageBytes = 2 * kB1Bytes + 2 * kB2Bytes;  // 48 KB per chunk: [B1 hi | B1 lo | B2 hi | B2 lo]
 constexpr uint32_t kA1Bytes = kTcF * kTcMP * 4;    // 32 KB, one of hi / lo
 constexpr uint32_t kA2Bytes = kTcF * kTcBK * 4;    // 16 KB, one of hi / lo
+constexpr int kTcBars = 12;
 constexpr int kTmemCols = 256;                     // D1[0] at columns 0..31, D2 at columns 32..159, D1[1] at columns 160..191
 
 // Phase timing of CTA 0 (build with -DB2W_MCEP_PROF via scripts/build_variant.py; read with b2w_mcep_prof_read): slots 0-7 are
@@ -164,8 +167,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
   int* act = reinterpret_cast<int*>(sv + kTcF);                   // [128]
   int* itc = act + kTcF;                                          // [128]
   int* qcnt = itc + kTcF;                                         // [4] work counters of the lane quarters
-  uint64_t* bars = reinterpret_cast<uint64_t*>(qcnt + 4);         // full[2], g1[2], d1_free[2], a2_full, g2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(qcnt + 4);         // full_b1[2], g1[2], d1_free[2], a2_full, -, g2[2], full_b2[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kTcBars);
   int* colbase = reinterpret_cast<int*>(tmem_slot + 2);            // [64] packed-column offsets of the register-resident solver
   uint16_t* tri = reinterpret_cast<uint16_t*>(colbase + 64);
 
@@ -175,21 +178,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
   const int K = p.K, m = p.m;
   const int64_t frame0 = (int64_t)blockIdx.x * kTcF;
   const int nvalid = (int)min((int64_t)kTcF, p.num_frames - frame0);
-  uint64_t* bar_full = bars;        // [2] stage loaded (bytes)
-  uint64_t* bar_g1 = bars + 2;      // [2] GEMM1 into D1[slot] complete
+  uint64_t* bar_full1 = bars;       // [2] Cmat half of stage [slot] loaded (bytes)
+  uint64_t* bar_g1 = bars + 2;      // [2] GEMM1 into D1[slot] complete: the Cmat half of the stage is free
   uint64_t* bar_d1free = bars + 4;  // [2] every epilogue thread has read D1[slot]
   uint64_t* bar_a2 = bars + 6;      //     every epilogue thread has written its part of A2
-  uint64_t* bar_g2 = bars + 7;      //     GEMM2 complete: A2 and the stage are free, D2 accumulated
+  uint64_t* bar_g2 = bars + 8;      // [2] GEMM2 of a chunk in stage [slot] complete: A2 and the M2^T half are free, D2 accumulated
+  uint64_t* bar_full2 = bars + 10;  // [2] M2^T half of stage [slot] loaded (bytes)
 
   if (tid == 0) {
-    umma::mbar_init(&bar_full[0], 1);
-    umma::mbar_init(&bar_full[1], 1);
+    umma::mbar_init(&bar_full1[0], 1);
+    umma::mbar_init(&bar_full1[1], 1);
+    umma::mbar_init(&bar_full2[0], 1);
+    umma::mbar_init(&bar_full2[1], 1);
     umma::mbar_init(&bar_g1[0], 1);
     umma::mbar_init(&bar_g1[1], 1);
     umma::mbar_init(&bar_d1free[0], kTcEpiThreads);
     umma::mbar_init(&bar_d1free[1], kTcEpiThreads);
     umma::mbar_init(bar_a2, kTcEpiThreads);
-    umma::mbar_init(bar_g2, 1);
+    umma::mbar_init(&bar_g2[0], 1);
+    umma::mbar_init(&bar_g2[1], 1);
     umma::mbar_fence_init();
   }
   if (warp == 0) umma::tmem_alloc(tmem_slot, kTmemCols);
@@ -215,7 +222,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
   const uint32_t idesc1 = umma::idesc_tf32(kTcF, kTcBK);
   const uint32_t idesc2 = umma::idesc_tf32(kTcF, kTcN2);
   // barrier parities: every completion of a barrier is consumed by exactly one wait of each role that uses it
-  uint32_t ph_full[2] = {0, 0}, ph_g1[2] = {0, 0}, ph_d1free[2] = {0, 0}, ph_a2 = 0, ph_g2 = 0;
+  uint32_t ph_full1[2] = {0, 0}, ph_full2[2] = {0, 0}, ph_g1[2] = {0, 0}, ph_d1free[2] = {0, 0}, ph_a2 = 0, ph_g2[2] = {0, 0};
   const bool is_epi = warp >= kTcEpiWarp0 && warp < kTcEpiWarp0 + kTcEpiThreads / 32;
   const int eh = (warp - kTcEpiWarp0) >> 2;  // epilogue column group: bins CPT eh .. CPT eh + CPT - 1 of the chunk
   bool zero_per = false;

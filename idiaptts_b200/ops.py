@@ -344,7 +344,8 @@ def code_aperiodicity(ap, fs):
     return out
 
 
-def decode_aperiodicity(bap, fs, fft_size, out=None):
+def decode_aperiodicity(bap, fs, fft_size, out=None, out_dtype=torch.float64):
+    """pyworld.decode_aperiodicity on [F, nap] float64 -> [F, K] float64 (or float32 for the fast synthesis path)."""
     lib = _lib.load()
     dev = _need_cuda(bap)
     assert bap.dtype == torch.float64 and bap.dim() == 2
@@ -353,11 +354,11 @@ def decode_aperiodicity(bap, fs, fft_size, out=None):
         raise ValueError("coded aperiodicity has %d bands, fs=%d needs %d" % (bap.shape[1], fs, nap))
     F = bap.shape[0]
     if out is None:
-        out = torch.empty((F, fft_size // 2 + 1), dtype=torch.float64, device=dev)
-    assert out.dtype == torch.float64 and out.shape == (F, fft_size // 2 + 1) and out.is_contiguous()
+        out = torch.empty((F, fft_size // 2 + 1), dtype=out_dtype, device=dev)
+    assert out.dtype in (torch.float64, torch.float32) and out.shape == (F, fft_size // 2 + 1) and out.is_contiguous()
+    fn = lib.b2w_decode_aperiodicity if out.dtype == torch.float64 else lib.b2w_decode_aperiodicity_f32
     with torch.cuda.device(dev):
-        check(lib.b2w_decode_aperiodicity(bap.data_ptr(), F, int(fs), int(fft_size), out.data_ptr(), _stream(dev)),
-              "b2w_decode_aperiodicity")
+        check(fn(bap.data_ptr(), F, int(fs), int(fft_size), out.data_ptr(), _stream(dev)), "b2w_decode_aperiodicity")
     return out
 
 

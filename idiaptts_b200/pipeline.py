@@ -214,16 +214,19 @@ class WorldSynthesizer:
             from .compat.pysptk import mcepalpha
             coded = ops.merlin_post_filter(feats[:, :D], float(mcepalpha(self.fs)), self.n_fft).float().contiguous()
             cstride = D
+        # the fast path keeps both spectral planes in float32 (half the HBM traffic of the three kernels that touch them; the
+        # per-pulse kernel interpolates and clamps them in double either way)
+        plane_dtype = torch.float32 if (self.precision == "fast" and self.n_fft == 1024) else torch.float64
         if self.gamma == 0.0:
             pow_sp = ops._timed(events, "mc2sp", F, lambda: ops.mc2sp(coded, self.alpha, self.n_fft, scale=1.0, do_exp=True,
-                                                                     out_dtype=torch.float64, order=D - 1, mc_stride=cstride,
+                                                                     out_dtype=plane_dtype, order=D - 1, mc_stride=cstride,
                                                                      square=True))
         else:
             amp = ops._timed(events, "mgc2sp", F, lambda: ops.mgc2sp(coded, self.alpha, self.gamma, self.n_fft, out_dtype=torch.float32,
                                                                     order=D - 1, mgc_stride=cstride))
-            pow_sp = amp.double() ** 2
+            pow_sp = (amp.double() ** 2).to(plane_dtype)
         bap = feats[:, D + 2:].double().contiguous()
-        ap = ops._timed(events, "decode_ap", F, lambda: ops.decode_aperiodicity(bap, self.fs, self.n_fft))
+        ap = ops._timed(events, "decode_ap", F, lambda: ops.decode_aperiodicity(bap, self.fs, self.n_fft, out_dtype=plane_dtype))
         # (Measured: decoding the two planes on a side stream while the sequential pulse placement runs on this one is SLOWER,
         # 23.2 ms against 19.8 ms for 256 utterances -- scripts/gpu_synth_phases.py -- so the stages stay in one stream.)
         plan = ops.synth_timebase(f0.contiguous(), frame_off, self.fs, self.n_fft, self.hop_size_ms, events=events)

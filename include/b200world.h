@@ -105,6 +105,8 @@ B2W_API int b2w_code_aperiodicity(const double* ap, int64_t num_frames, int32_t 
                           void* stream);
 B2W_API int b2w_decode_aperiodicity(const double* bap, int64_t num_frames, int32_t fs, int32_t fft_size, double* ap,
                             void* stream);
+/* float32 plane for the batched fast synthesis path (b2w_synth_render_f32 reads either type) */
+B2W_API int b2w_decode_aperiodicity_f32(const double* bap, int64_t num_frames, int32_t fs, int32_t fft_size, float* ap, void* stream);
 
 /* ---- mel-cepstral analysis: replaces pysptk.mcep(itype=3|4, etype=1) (A:146). --------------------------------
  * Host helper (runs on the CPU inside the call, fp64): builds the three precomputed all-pass warping matrices

@@ -267,3 +267,71 @@ def test_padded_planes_give_identical_results(golden, dev):
     assert torch.equal(mc_a, mc_b) and torch.equal(it_a, it_b)
     mc_c, _ = ops.mcep(tight.double(), 59, 0.58, is_power=True)                                 # float64 plane: scalar-load path
     assert (mc_c - mc_a).abs().max().item() < 1e-5
+
+
+def test_digital_silence_frames(dev):
+    """WORLD adds two safeguard noises (randn() * 1e-12 to every windowed sample, eps * |randn()| to the smoothed spectrum); the
+    oracle and the kernels use 0 and + eps instead.  On digital silence those terms are the ONLY signal: check
+    that the kernels and the oracle agree there (they must: same substitution), that the envelope is the floor the substitution
+    implies, that nothing is NaN, and that a frame half in silence is still within tolerance."""
+    from idiaptts_b200 import ops
+    fs = 16000
+    x = np.zeros(8000)
+    rng = np.random.default_rng(5)
+    n = np.arange(4000)                             # the second half: a 150 Hz harmonic signal in a little noise
+    x[4000:] = 0.01 * rng.standard_normal(4000) + sum(0.1 / h * np.sin(2 * np.pi * 150 * h * n / fs) for h in range(1, 20))
+    f0 = np.zeros(101)
+    f0[20:40] = 120.0                               # a "voiced" stretch inside the silence (what a bad F0 cache would give)
+    f0[60:90] = 150.0
+    t = world_np.temporal_positions(len(f0))
+    ref = world_np.cheaptrick(x, f0, t, fs)
+    batch = ops.RaggedBatch.from_host([x], [f0], fs, device=dev)
+    for dt, tol in ((torch.float64, 1e-6), (torch.float32, 1e-4)):
+        sp, st = ops.cheaptrick(batch, out_dtype=dt)
+        out = sp.cpu().numpy().astype(np.float64)
+        assert np.isfinite(out).all() and (out > 0).all()
+        assert (np.abs(out - ref) / ref).max() < tol, dt
+    silent = ref[:30]
+    assert silent.max() < 1e-12                      # eps-floor envelope: exp(lifter(log(0 + eps))) ~ 2.2e-16
+    mc, st = ops.mcep(torch.from_numpy(ref).to(dev), 59, 0.41, is_power=True)
+    assert torch.isfinite(mc).all()
+    # D4C: LoveTrain divides two zero band powers on silent "voiced" frames (NaN in WORLD too); decisions equal the oracle's
+    v_ref, c_ref = world_np.d4c_coarse(x, f0, t, fs)
+    for precision in ("f64", "fast"):
+        coarse, voiced, _ = ops.d4c_coarse(batch, precision=precision)
+        v = voiced.cpu().numpy().astype(bool)
+        assert np.array_equal(v[60:90], v_ref[60:90])          # frames with signal: identical decisions
+        m = v_ref & v
+        m[:50] = False
+        assert m.sum() >= 25                                    # LoveTrain keeps the harmonic stretch voiced
+        assert np.abs(coarse.cpu().numpy()[m] - c_ref[m]).max() < (1e-7 if precision == "f64" else 5e-4)
+
+
+def test_config2_shaped_utterances_vs_c_oracle(dev):
+    """BASELINE.json configs[1] shape (6.5 s utterances at 22.05 kHz, alpha = mcepalpha(22050), nap = 2): the fused extraction and
+    the batched synthesis against the C oracle on the SAME corpus generator bench.py uses -- the test-suite twin of the bench's
+    parity block."""
+    from idiaptts_b200 import ops, pipeline, synthetic
+    from oracle import world_c
+    fs = 22050
+    waves, f0s = synthetic.make_corpus(3, fs, seed=2, mean_dur=6.5, std_dur=1.8, dur_quantum=0.1)
+    an = pipeline.WorldAnalyzer(fs, 60, device=dev)
+    batch = ops.RaggedBatch.from_host([w.numpy() for w in waves], f0s, fs, device=dev)
+    feats, _, st = an.extract(batch)
+    assert ops.raise_for_status(st, "extract") & ~8 == 0
+    syn = pipeline.WorldSynthesizer(fs, 60, device=dev)
+    y, out_off, st = syn.synthesize(feats, batch.frame_off)
+    assert ops.raise_for_status(st, "synth") == 0
+    fh, yh = feats.cpu().numpy(), y.cpu().numpy().astype(np.float64)
+    fo = batch.frame_off.cpu().numpy()
+    for u in range(3):
+        ref = world_c.extract(waves[u].numpy(), fs, f0s[u], 60, an.alpha)
+        g = fh[fo[u]:fo[u + 1]]
+        assert g.shape == ref.shape == (world_np.num_frames(len(waves[u]), fs), 64)      # frame count: bit-exact
+        assert glue_np.mcd_db(ref[:, :60], g[:, :60]) < 0.01
+        assert np.array_equal(ref[:, 61], g[:, 61])                                      # vuv: bit-exact
+        assert np.abs(ref[:, 60] - g[:, 60]).max() < 1e-5 and np.abs(ref[:, 62:] - g[:, 62:]).max() < 1e-3
+        y_ref = world_c.synthesize_features(g, fs, 60, an.alpha).astype(np.float64)
+        got = yh[out_off[u]:out_off[u + 1]]
+        assert len(got) == len(y_ref)
+        assert 10 * np.log10((y_ref ** 2).sum() / ((got - y_ref) ** 2).sum()) > 60
