@@ -7,11 +7,14 @@
 //
 //   per Newton iteration, for each chunk of 32 frequency bins j0 .. j0+31 (17 chunks at K = 513):
 //     GEMM1   D1[128 x 32]   = mc[128 x 64] . Cmat[64 x 32 chunk]          24 MMAs (8 K-steps x 3 split products)
-//     epilogue (all threads)  P = per * exp(-2 D1)  -> hi/lo TF32 tiles in shared memory (A operand of GEMM2)
+//     epilogue (8 warps)      P = per * exp(-2 D1)  -> hi/lo TF32 in TENSOR MEMORY (tcgen05.st; GEMM2 takes its A operand from
+//                             there, double buffered: no shared-memory round trip, no proxy fence)
 //     GEMM2   D2[128 x 128] += P[128 x 32] . M2^T[32 chunk x 128]          12 MMAs
-//   The GEMM phase is warp specialised: thread 0 only streams the matrices and issues MMAs (GEMM1 of chunk c + 1 is in the tensor
-//   pipe while chunk c's epilogue runs: D1 is double buffered in tensor memory), warps 4-11 are the epilogue (one TMEM lane =
-//   one frame per thread, 16 bins each), everything is handed over through mbarriers -- no CTA barrier inside the chunk loop.
+//   The GEMM phase is warp specialised: thread 32 only streams the matrices (the Cmat and M2^T halves of a stage are refilled
+//   independently, each as soon as its own GEMM has completed), thread 0 only issues MMAs and never waits for one to complete
+//   (GEMM1 of chunk c + 1 is in the tensor pipe while chunk c's epilogue runs: D1 is double buffered in tensor memory), warps
+//   4-11 are the epilogue (one TMEM lane = one frame per thread, 16 bins each), everything is handed over through mbarriers
+//   -- no CTA barrier inside the chunk loop.
 //   then D2 row f = r~ of frame f: stopping rule on r~[0], and for the frames still iterating one warp each builds and
 //   solves the (m+1) x (m+1) Toeplitz-plus-Hankel system (mcep_solve.cuh) and updates mc (fp32, shared memory).
 //   Pass 0 (initial value) uses the same machinery: P = log(per), the stream holds M0^T instead of M2^T, GEMM1 is skipped.
@@ -22,31 +25,31 @@
 namespace b2w {
 
 constexpr int kTcF = 128;        // frames per CTA = UMMA M
-#ifdef B2W_TC_ISSUER_WARP            // experiment: a 17th warp issues, all 16 others are epilogue warps (120 registers / thread)
-constexpr int kTcThreads = 544;
-constexpr int kTcIssuer = 512;
-constexpr int kTcProducer = 513;
-constexpr int kTcEpiWarp0 = 0;
-constexpr int kTcEpiThreads = 512;
-#else
 constexpr int kTcThreads = 512;  // 16 warps: TMEM lane quarter q = warp & 3, column group g = warp >> 2
 constexpr int kTcIssuer = 0;     // the thread that issues the MMAs
 constexpr int kTcProducer = 32;  // the thread that streams the constant matrices (bulk async copies)
-constexpr int kTcEpiWarp0 = 4;   // epilogue warps 4 .. 11 (two per TMEM lane quarter)
-constexpr int kTcEpiThreads = 256;
-#endif
+constexpr int kTcEpiWarp0 = 4;   // epilogue warps 4 .. 15: three sets of four (one warp per TMEM lane quarter)
+constexpr int kTcEpiSets = 3;
 constexpr int kTcSolveWarps = 16;
 constexpr int kTcBK = 32;        // bins per chunk
 constexpr int kTcMP = 64;        // padded cepstral dimension (K of GEMM1)
+constexpr int kTcMS = 68;        // row stride of the fp32 mel-cepstra in shared memory (16-byte aligned rows, 8 rows span all banks)
+constexpr int kTcNST = 3;        // stages of the constant-matrix ring
 constexpr int kTcN2 = 128;       // padded r~ length (N of GEMM2)
 constexpr int kTcKB = 20;        // padded block stride of the solve workspace (bank-conflict free float4 accesses)
 constexpr uint32_t kB1Bytes = kTcBK * kTcMP * 4;   // one of hi / lo of the Cmat chunk   [N = 16 rows (bins)] x [K = 64]
 constexpr uint32_t kB2Bytes = kTcN2 * kTcBK * 4;   // one of hi / lo of the M2^T chunk   [N = 128 rows]       x [K = 16]
 constexpr uint32_t kStageBytes = 2 * kB1Bytes + 2 * kB2Bytes;  // 48 KB per chunk: [B1 hi | B1 lo | B2 hi | B2 lo]
-constexpr uint32_t kA1Bytes = kTcF * kTcMP * 4;    // 32 KB, one of hi / lo
-constexpr uint32_t kA2Bytes = kTcF * kTcBK * 4;    // 16 KB, one of hi / lo
-constexpr int kTcBars = 12;
-constexpr int kTmemCols = 256;                     // D1[0] at columns 0..31, D2 at columns 32..159, D1[1] at columns 160..191
+constexpr int kTcBars = 4 * kTcNST + 4;
+#ifndef B2W_TC_COPIES
+#define B2W_TC_COPIES 4
+#endif
+constexpr int kTcCopies = B2W_TC_COPIES;  // replicas of the pre-tiled streams: CTA b reads replica b % kTcCopies (all CTAs stream the same 816 KB
+                                          // per pass at about the same time; replicas spread that over more L2 lines / slices)
+// tensor memory map (columns): D1[0] 0..31 | D2 32..159 | D1[1] 160..191 | A2[b] hi / lo at 192 + 64 b / 224 + 64 b | A1 hi 320..383 | A1 lo 384..447
+constexpr int kTmemCols = 512;
+constexpr int kTmA2 = 192;
+constexpr int kTmA1 = 320;
 
 // Phase timing of CTA 0 (build with -DB2W_MCEP_PROF via scripts/build_variant.py; read with b2w_mcep_prof_read): slots 0-7 are
 // the issuer thread, 8-13 one epilogue thread, 14-15 the pass as seen by thread 32.
@@ -116,8 +119,10 @@ __global__ void mcep_tc_pretile_kernel(const float* __restrict__ m0t, int np0, c
     float h0, l0, h1, l1;
     umma::split_tf32(v0, h0, l0);
     umma::split_tf32(v1, h1, l1);
-    stream0[e] = lo ? l0 : h0;
-    stream1[e] = lo ? l1 : h1;
+    for (int r = 0; r < kTcCopies; ++r) {
+      stream0[(size_t)r * total + e] = lo ? l0 : h0;
+      stream1[(size_t)r * total + e] = lo ? l1 : h1;
+    }
   }
 }
 
@@ -150,24 +155,20 @@ template <typename IT, int NS>
 __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   // ---- shared memory map ----------------------------------------------------------------------------------------------
-  // GEMM phase:  [A1 hi 32K | A1 lo 32K | stage 0 48K | stage 1 48K | A2 hi 16K | A2 lo 16K]  = 192 KB
+  // GEMM phase:  [stage 0 48K | stage 1 48K | stage 2 48K]  (both A operands live in tensor memory)
   // solve phase: the same region holds the 16 per-warp workspaces
   uint8_t* region = smem_raw;
-  float* a1_hi = reinterpret_cast<float*>(region);
-  float* a1_lo = reinterpret_cast<float*>(region + kA1Bytes);
-  uint8_t* stage_base = region + 2 * kA1Bytes;
-  float* a2_hi = reinterpret_cast<float*>(stage_base + 2 * kStageBytes);
-  float* a2_lo = reinterpret_cast<float*>(stage_base + 2 * kStageBytes + kA2Bytes);
-  const uint32_t gemm_bytes = 2 * kA1Bytes + 2 * kStageBytes + 2 * kA2Bytes;
+  uint8_t* stage_base = region;
+  const uint32_t gemm_bytes = kTcNST * kStageBytes;
   const uint32_t ws_bytes = (uint32_t)kTcSolveWarps * (uint32_t)p.ws_floats * 4u;
   const uint32_t region_bytes = gemm_bytes > ws_bytes ? gemm_bytes : ws_bytes;
-  float* mc = reinterpret_cast<float*>(region + region_bytes);  // [128][64] fp32
-  float* al = mc + kTcF * kTcMP;                                  // [64]
+  float* mc = reinterpret_cast<float*>(region + region_bytes);  // [128][kTcMS] fp32
+  float* al = mc + kTcF * kTcMS;                                  // [64]
   float* sv = al + kTcMP;                                         // [128]
   int* act = reinterpret_cast<int*>(sv + kTcF);                   // [128]
   int* itc = act + kTcF;                                          // [128]
   int* qcnt = itc + kTcF;                                         // [4] work counters of the lane quarters
-  uint64_t* bars = reinterpret_cast<uint64_t*>(qcnt + 4);         // full_b1[2], g1[2], d1_free[2], a2_full, -, g2[2], full_b2[2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(qcnt + 4);         // see below
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kTcBars);
   int* colbase = reinterpret_cast<int*>(tmem_slot + 2);            // [64] packed-column offsets of the register-resident solver
   uint16_t* tri = reinterpret_cast<uint16_t*>(colbase + 64);
@@ -178,25 +179,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
   const int K = p.K, m = p.m;
   const int64_t frame0 = (int64_t)blockIdx.x * kTcF;
   const int nvalid = (int)min((int64_t)kTcF, p.num_frames - frame0);
-  uint64_t* bar_full1 = bars;       // [2] Cmat half of stage [slot] loaded (bytes)
-  uint64_t* bar_g1 = bars + 2;      // [2] GEMM1 into D1[slot] complete: the Cmat half of the stage is free
-  uint64_t* bar_d1free = bars + 4;  // [2] every epilogue thread has read D1[slot]
-  uint64_t* bar_a2 = bars + 6;      //     every epilogue thread has written its part of A2
-  uint64_t* bar_g2 = bars + 8;      // [2] GEMM2 of a chunk in stage [slot] complete: A2 and the M2^T half are free, D2 accumulated
-  uint64_t* bar_full2 = bars + 10;  // [2] M2^T half of stage [slot] loaded (bytes)
+  uint64_t* bar_d1free = bars;                  // [2] every epilogue warp has read D1[c & 1]
+  uint64_t* bar_a2 = bars + 2;                  // [2] every epilogue warp has written its part of A2[c & 1] (tensor memory)
+  uint64_t* bar_full1 = bars + 4;               // [NST] Cmat half of stage [c % NST] loaded (bytes)
+  uint64_t* bar_full2 = bars + 4 + kTcNST;      // [NST] M2^T half of the stage loaded (bytes)
+  uint64_t* bar_g1 = bars + 4 + 2 * kTcNST;     // [NST] GEMM1 of the chunk in this stage complete: D1 ready, the Cmat half is free
+  uint64_t* bar_g2 = bars + 4 + 3 * kTcNST;     // [NST] GEMM2 of the chunk in this stage complete: A2[c & 1] and the M2^T half are free
 
   if (tid == 0) {
-    umma::mbar_init(&bar_full1[0], 1);
-    umma::mbar_init(&bar_full1[1], 1);
-    umma::mbar_init(&bar_full2[0], 1);
-    umma::mbar_init(&bar_full2[1], 1);
-    umma::mbar_init(&bar_g1[0], 1);
-    umma::mbar_init(&bar_g1[1], 1);
-    umma::mbar_init(&bar_d1free[0], kTcEpiThreads);
-    umma::mbar_init(&bar_d1free[1], kTcEpiThreads);
-    umma::mbar_init(bar_a2, kTcEpiThreads);
-    umma::mbar_init(&bar_g2[0], 1);
-    umma::mbar_init(&bar_g2[1], 1);
+    for (int i = 0; i < 4; ++i) umma::mbar_init(&bars[i], 8);  // two half-chunk items x four warps, one elected arrival each
+    for (int i = 4; i < kTcBars; ++i) umma::mbar_init(&bars[i], 1);
     umma::mbar_fence_init();
   }
   if (warp == 0) umma::tmem_alloc(tmem_slot, kTmemCols);
@@ -213,7 +205,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
     itc[tid] = 0;
     sv[tid] = 0.f;
   }
-  for (int i = tid; i < kTcF * kTcMP; i += kTcThreads) mc[i] = 0.f;
+  for (int i = tid; i < kTcF * kTcMS; i += kTcThreads) mc[i] = 0.f;
   umma::tc_fence_before_sync();
   __syncthreads();
   umma::tc_fence_after_sync();
@@ -221,135 +213,152 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
   const uint32_t t_d2 = tmem + ((uint32_t)(32 * q) << 16) + 32;   // D2: columns 32..159
   const uint32_t idesc1 = umma::idesc_tf32(kTcF, kTcBK);
   const uint32_t idesc2 = umma::idesc_tf32(kTcF, kTcN2);
-  // barrier parities: every completion of a barrier is consumed by exactly one wait of each role that uses it
-  uint32_t ph_full1[2] = {0, 0}, ph_full2[2] = {0, 0}, ph_g1[2] = {0, 0}, ph_d1free[2] = {0, 0}, ph_a2 = 0, ph_g2[2] = {0, 0};
-  const bool is_epi = warp >= kTcEpiWarp0 && warp < kTcEpiWarp0 + kTcEpiThreads / 32;
-  const int eh = (warp - kTcEpiWarp0) >> 2;  // epilogue column group: bins CPT eh .. CPT eh + CPT - 1 of the chunk
+  // Barrier parities are STATELESS: the barrier of slot c % n completes once per chunk with that residue, so the completion a role
+  // waits for has the index (earlier passes) * (chunks per pass on that slot) + c / n, and its parity is the low bit.  No role has
+  // to see every completion, and no phase word is carried through the solve phase.  (A wait is only ever issued when the previous
+  // completion of the same barrier is known to have happened -- the tensor pipe completes in order and every role touches each
+  // slot at most n chunks apart -- so the parity test cannot be fooled by a barrier two phases behind.)
+  const int nch = p.nchunks;
+  auto wait_slot = [&](uint64_t* arr, int n, int c, int passes_before) {
+    const int slot = c % n;
+    const int per_pass = (nch - slot + n - 1) / n;
+    umma::mbar_wait(&arr[slot], (uint32_t)(passes_before * per_pass + c / n) & 1u);
+  };
   bool zero_per = false;
   PROF_DECL;
   PROF_START();
 
   for (int pass = 0; pass <= p.maxiter; ++pass) {
-    const float* stream = pass == 0 ? p.stream0 : p.stream1;
+    const float* stream = (pass == 0 ? p.stream0 : p.stream1) + (size_t)(blockIdx.x % kTcCopies) * ((size_t)p.nchunks * (kStageBytes / 4));
     // ---- A1 = hi/lo split of mc (Newton passes) ----------------------------------------------------------------------
-    if (pass > 0) {
-      for (int e = tid; e < kTcF * (kTcMP / 4); e += kTcThreads) {
-        const int r = e & (kTcF - 1), kc = e >> 7;  // consecutive threads -> consecutive rows: conflict-free 16 B stores
-        const float4 v = *reinterpret_cast<const float4*>(mc + r * kTcMP + 4 * kc);
-        float4 h, l;
-        umma::split_tf32(v.x, h.x, l.x);
-        umma::split_tf32(v.y, h.y, l.y);
-        umma::split_tf32(v.z, h.z, l.z);
-        umma::split_tf32(v.w, h.w, l.w);
-        const uint32_t off = umma::tile_off(kTcF, r, 4 * kc) / 4;
-        *reinterpret_cast<float4*>(a1_hi + off) = h;
-        *reinterpret_cast<float4*>(a1_lo + off) = l;
+    if (pass > 0) {  // thread (q, g, lane): row 32 q + lane, coefficients 16 g .. 16 g + 15 -> tensor memory columns of A1 hi / lo
+      float hi[16], lo[16];
+#pragma unroll
+      for (int i4 = 0; i4 < 4; ++i4) {
+        const float4 v = *reinterpret_cast<const float4*>(mc + row * kTcMS + 16 * g + 4 * i4);
+        umma::split_tf32(v.x, hi[4 * i4], lo[4 * i4]);
+        umma::split_tf32(v.y, hi[4 * i4 + 1], lo[4 * i4 + 1]);
+        umma::split_tf32(v.z, hi[4 * i4 + 2], lo[4 * i4 + 2]);
+        umma::split_tf32(v.w, hi[4 * i4 + 3], lo[4 * i4 + 3]);
       }
-      umma::fence_proxy_async();
+      const uint32_t t_a1 = tmem + ((uint32_t)(32 * q) << 16) + kTmA1 + 16 * g;
+      umma::tmem_st16(t_a1, hi);
+      umma::tmem_st16(t_a1 + kTcMP, lo);
+      umma::tmem_st_wait();
     }
+    umma::fence_proxy_async();  // the solve phase wrote the stage region through the generic proxy; the bulk copies come next
+    umma::tc_fence_before_sync();
     __syncthreads();
-    const int nch = p.nchunks;
-    if (tid == kTcIssuer) {
-      // ---- issuer: stream the matrices, keep the tensor pipe fed ------------------------------------------------------------
-      auto load = [&](int c) {
-        const int s = c & 1;
-        umma::mbar_expect_tx(&bar_full[s], kStageBytes);
-        umma::bulk_g2s(stage_base + s * kStageBytes, reinterpret_cast<const uint8_t*>(stream) + (size_t)c * kStageBytes, kStageBytes,
-                       &bar_full[s]);
+    umma::tc_fence_after_sync();
+    if (tid == kTcProducer) {
+      // ---- producer: streams the constant matrices.  The two halves of a stage have their own barriers: the Cmat half is free as
+      // soon as GEMM1 of the chunk NST back has completed (a whole chunk earlier than its GEMM2), the M2^T half when that GEMM2 has.
+      for (int c = 0, s = 0; c < nch; ++c, s = (s + 1 == kTcNST ? 0 : s + 1)) {
+        uint8_t* dst = stage_base + s * kStageBytes;
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(stream) + (size_t)c * kStageBytes;
+        if (pass > 0) {
+          if (c >= kTcNST) wait_slot(bar_g1, kTcNST, c - kTcNST, pass - 1);
+          umma::mbar_expect_tx(&bar_full1[s], 2 * kB1Bytes);
+          umma::bulk_g2s(dst, src, 2 * kB1Bytes, &bar_full1[s]);
+        }
+        if (c >= kTcNST) wait_slot(bar_g2, kTcNST, c - kTcNST, pass);
+        umma::mbar_expect_tx(&bar_full2[s], 2 * kB2Bytes);
+        umma::bulk_g2s(dst + 2 * kB1Bytes, src + 2 * kB1Bytes, 2 * kB2Bytes, &bar_full2[s]);
+      }
+    } else if (warp == kTcIssuer / 32) {
+      // ---- issuer warp: keeps the tensor pipe fed; it never waits for an MMA to complete.  The WHOLE warp runs this branch and the
+      // MMAs are issued under elect.sync: ptxas then keeps the descriptors in uniform registers and emits the tcgen05.mma back to
+      // back; under a plain `if (tid == 0)` it wraps EVERY tcgen05.mma into an elect / R2UR / branch loop (~60 cycles per MMA).
+      const uint32_t tm_u = __shfl_sync(0xffffffffu, tmem, 0);
+      const uint32_t st_u = __shfl_sync(0xffffffffu, umma::smem_u32(stage_base), 0);
+      const uint32_t bar_u = __shfl_sync(0xffffffffu, umma::smem_u32(bars), 0);
+      auto commit = [&](uint64_t* bar) {
+        const uint32_t addr = bar_u + 8u * (uint32_t)(bar - bars);
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(addr) : "memory");
       };
-      const uint32_t a_lbo = kTcF * 16;
-      auto gemm1 = [&](int c) {  // D1[c & 1] = mc . Cmat chunk
-        const int s = c & 1;
-        const uint32_t b1h = umma::smem_u32(stage_base + s * kStageBytes), b1l = b1h + kB1Bytes, b_lbo = kTcBK * 16;
-        umma::mma_3xtf32<kTcMP / 8>(tmem + (s ? 160 : 0), umma::smem_desc(umma::smem_u32(a1_hi), a_lbo, 128),
-                                    umma::smem_desc(umma::smem_u32(a1_lo), a_lbo, 128), umma::smem_desc(b1h, b_lbo, 128),
-                                    umma::smem_desc(b1l, b_lbo, 128), 2 * a_lbo, 2 * b_lbo, idesc1, false);
-        umma::mma_commit(&bar_g1[s]);
+      auto gemm1 = [&](int c, int s) {  // D1[c & 1] = mc . Cmat chunk (stage s)
+        const uint32_t b1h = st_u + s * kStageBytes, b1l = b1h + kB1Bytes, b_lbo = kTcBK * 16;
+        if (umma::elect_one()) {
+          umma::mma_3xtf32_ts<kTcMP / 8>(tm_u + ((c & 1) ? 160 : 0), tm_u + kTmA1, tm_u + kTmA1 + kTcMP, umma::smem_desc(b1h, b_lbo, 128),
+                                         umma::smem_desc(b1l, b_lbo, 128), 2 * b_lbo, idesc1, false);
+          commit(&bar_g1[s]);
+        }
+        __syncwarp();
       };
       PROF_LAP(0);  // outside the GEMM phase (A1 split, solves, barriers)
-      for (int c = 0; c < 2 && c < nch; ++c) load(c);
       if (pass > 0) {
-        umma::mbar_wait(&bar_full[0], ph_full[0]);
-        ph_full[0] ^= 1;
+        wait_slot(bar_full1, kTcNST, 0, pass - 1);
         umma::tc_fence_after_sync();
-        gemm1(0);
+        gemm1(0, 0);
       }
-      for (int c = 0; c < nch; ++c) {
-        const int s = c & 1;
-        if (pass > 0) {
-          if (c + 1 < nch) {  // GEMM1 of the next chunk goes ahead of this chunk's GEMM2
-            const int sn = (c + 1) & 1;
-            PROF_LAP(1);
-            umma::mbar_wait(&bar_full[sn], ph_full[sn]);
-            ph_full[sn] ^= 1;
-            PROF_LAP(2);  // wait stage
-            if (c + 1 >= 2) {  // D1[sn] was last read by the epilogue of chunk c - 1
-              umma::mbar_wait(&bar_d1free[sn], ph_d1free[sn]);
-              ph_d1free[sn] ^= 1;
-            }
-            PROF_LAP(3);  // wait D1 free
-            umma::tc_fence_after_sync();
-            gemm1(c + 1);
-            PROF_LAP(4);  // GEMM1 issue
-          }
-        } else {
-          umma::mbar_wait(&bar_full[s], ph_full[s]);
-          ph_full[s] ^= 1;
+      for (int c = 0, s = 0; c < nch; ++c) {
+        const int sn = (s + 1 == kTcNST ? 0 : s + 1);
+        if (pass > 0 && c + 1 < nch) {  // GEMM1 of the next chunk goes ahead of this chunk's GEMM2
+          PROF_LAP(1);
+          wait_slot(bar_full1, kTcNST, c + 1, pass - 1);
+          PROF_LAP(2);  // wait Cmat half
+          if (c + 1 >= 2) wait_slot(bar_d1free, 2, c - 1, pass - 1);  // D1[(c + 1) & 1] was last read by the epilogue of chunk c - 1
+          PROF_LAP(3);  // wait D1 free
+          umma::tc_fence_after_sync();
+          gemm1(c + 1, sn);
+          PROF_LAP(4);  // GEMM1 issue
         }
-        umma::mbar_wait(bar_a2, ph_a2);  // the epilogue has written P of chunk c
-        ph_a2 ^= 1;
+        wait_slot(bar_full2, kTcNST, c, pass);
+        PROF_LAP(7);  // wait M2^T half
+        wait_slot(bar_a2, 2, c, pass);  // the epilogue has written P of chunk c
         PROF_LAP(5);  // wait A2
         umma::tc_fence_after_sync();
         {
-          const uint32_t b2h = umma::smem_u32(stage_base + s * kStageBytes) + 2 * kB1Bytes, b2l = b2h + kB2Bytes, b_lbo = kTcN2 * 16;
-          umma::mma_3xtf32<kTcBK / 8>(tmem + 32, umma::smem_desc(umma::smem_u32(a2_hi), a_lbo, 128),
-                                      umma::smem_desc(umma::smem_u32(a2_lo), a_lbo, 128), umma::smem_desc(b2h, b_lbo, 128),
-                                      umma::smem_desc(b2l, b_lbo, 128), 2 * a_lbo, 2 * b_lbo, idesc2, c > 0);
-          umma::mma_commit(bar_g2);
+          const uint32_t b2h = st_u + s * kStageBytes + 2 * kB1Bytes, b2l = b2h + kB2Bytes, b_lbo = kTcN2 * 16;
+          const uint32_t a2h = tm_u + kTmA2 + 64 * (c & 1), a2l = a2h + 32;
+          if (umma::elect_one()) {
+            umma::mma_3xtf32_ts<kTcBK / 8>(tm_u + 32, a2h, a2l, umma::smem_desc(b2h, b_lbo, 128), umma::smem_desc(b2l, b_lbo, 128), 2 * b_lbo,
+                                           idesc2, c > 0);
+            commit(&bar_g2[s]);
+          }
+          __syncwarp();
         }
         PROF_LAP(6);  // GEMM2 issue
-        umma::mbar_wait(bar_g2, ph_g2);  // GEMM2(c) complete: stage s is free
-        ph_g2 ^= 1;
-        PROF_LAP(7);  // wait GEMM2
-        if (c + 2 < nch) load(c + 2);
+        s = sn;
       }
-      if (pass > 0) {  // consume the D1 releases of the last two chunks (keeps the parities in step)
-        for (int c = (nch >= 2 ? nch - 2 : 0); c < nch; ++c) {
-          umma::mbar_wait(&bar_d1free[c & 1], ph_d1free[c & 1]);
-          ph_d1free[c & 1] ^= 1;
-        }
-      }
-    } else if (is_epi) {
-      // ---- epilogue warps: P = per * exp(-2 D1) (pass 0: log per) -> hi / lo TF32 tiles of A2 ------------------------------------
-      constexpr int CPT = kTcBK / (kTcEpiThreads / 128);  // bins per thread (16 with 8 epilogue warps)
-      float pern[CPT];                // raw periodogram values, prefetched one chunk ahead
+    } else if (warp >= kTcEpiWarp0) {
+      // ---- epilogue: P = per * exp(-2 D1) (pass 0: log per) -> hi / lo TF32 columns of A2 in tensor memory ---------------------
+      // Twelve warps = three sets of four (one warp per TMEM lane quarter).  A work item is half a chunk (128 rows x 16 bins); the
+      // sets take the items round robin, so consecutive items of a set are 1.5 chunks apart.
+      constexpr int CPT = kTcBK / 2;  // bins per thread and item
+      static_assert(CPT == 16, "the tensor-memory load / store below move 16 columns per thread");
+      const int nitems = 2 * nch;
+      float pern[CPT];                // raw periodogram values, prefetched one item ahead
+      int item = (warp >> 2) - 1;
 #pragma unroll
       for (int h = 0; h < CPT / 8; ++h)
-        tc_load_raw8<IT>(p, frame0 + row, CPT * eh + 8 * h, row < nvalid, *reinterpret_cast<float(*)[8]>(pern + 8 * h));
-      for (int c = 0; c < nch; ++c) {
-        const int s = c & 1;
+        tc_load_raw8<IT>(p, frame0 + row, (item >> 1) * kTcBK + CPT * (item & 1) + 8 * h, row < nvalid && item < nitems,
+                         *reinterpret_cast<float(*)[8]>(pern + 8 * h));
+      for (; item < nitems; item += kTcEpiSets) {
+        const int c = item >> 1, eh = item & 1;
+        const int s = c & 1;  // D1 / A2 slot
         const int j0 = c * kTcBK + CPT * eh;
         float perv[CPT];
 #pragma unroll
         for (int i = 0; i < CPT; ++i) perv[i] = (j0 + i < K) ? (p.in_is_power ? pern[i] + p.eps : fmaf(pern[i], pern[i], p.eps)) : 1.f;
-        if (c + 1 < nch) {
+        if (item + kTcEpiSets < nitems) {
+          const int nx = item + kTcEpiSets;
 #pragma unroll
           for (int h = 0; h < CPT / 8; ++h)
-            tc_load_raw8<IT>(p, frame0 + row, j0 + kTcBK + 8 * h, row < nvalid, *reinterpret_cast<float(*)[8]>(pern + 8 * h));
+            tc_load_raw8<IT>(p, frame0 + row, (nx >> 1) * kTcBK + CPT * (nx & 1) + 8 * h, row < nvalid, *reinterpret_cast<float(*)[8]>(pern + 8 * h));
         }
         float cv[CPT];
 #pragma unroll
         for (int i = 0; i < CPT; ++i) cv[i] = 0.f;
         PROF_LAP(8);  // epilogue: loads / prefetch issue (+ everything outside the GEMM phase)
         if (pass > 0) {
-          umma::mbar_wait(&bar_g1[s], ph_g1[s]);
-          ph_g1[s] ^= 1;
+          wait_slot(bar_g1, kTcNST, c, pass - 1);
           PROF_LAP(9);  // epilogue: wait GEMM1
           umma::tc_fence_after_sync();
-          if constexpr (CPT == 16) umma::tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + (s ? 160 : 0) + CPT * eh, cv);
-          else umma::tmem_ld8(tmem + ((uint32_t)(32 * q) << 16) + (s ? 160 : 0) + CPT * eh, cv);
+          umma::tmem_ld16(tmem + ((uint32_t)(32 * q) << 16) + (s ? 160 : 0) + CPT * eh, cv);
           umma::tc_fence_before_sync();
-          umma::mbar_arrive(&bar_d1free[s]);
+          __syncwarp();
+          if (lane == 0) umma::mbar_arrive(&bar_d1free[s]);
         }
         float ph[CPT], pl[CPT];
 #pragma unroll
@@ -359,23 +368,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
           umma::split_tf32((j0 + i < K) ? val : 0.f, ph[i], pl[i]);
         }
         PROF_LAP(10);  // epilogue: tmem ld + exp + split
-        if (c > 0) {  // A2 is single-buffered: GEMM2 of the previous chunk must have consumed it
-          umma::mbar_wait(bar_g2, ph_g2);
-          ph_g2 ^= 1;
+        if (c >= 2) wait_slot(bar_g2, kTcNST, c - 2, pass);  // A2[s] (double buffered) was last read by GEMM2 of chunk c - 2
+        PROF_LAP(11);  // epilogue: wait A2 free
+        {
+          const uint32_t t_a2 = tmem + ((uint32_t)(32 * q) << 16) + kTmA2 + 64 * s + CPT * eh;
+          umma::tmem_st16(t_a2, ph);
+          umma::tmem_st16(t_a2 + 32, pl);
+          umma::tmem_st_wait();
         }
-        PROF_LAP(11);  // epilogue: wait A2 free (GEMM2 of the previous chunk)
-#pragma unroll
-        for (int h4 = 0; h4 < CPT / 4; ++h4) {
-          const uint32_t off = umma::tile_off(kTcF, row, CPT * eh + 4 * h4) / 4;
-          *reinterpret_cast<float4*>(a2_hi + off) = make_float4(ph[4 * h4], ph[4 * h4 + 1], ph[4 * h4 + 2], ph[4 * h4 + 3]);
-          *reinterpret_cast<float4*>(a2_lo + off) = make_float4(pl[4 * h4], pl[4 * h4 + 1], pl[4 * h4 + 2], pl[4 * h4 + 3]);
-        }
-        umma::fence_proxy_async();
-        umma::mbar_arrive(bar_a2);
+        umma::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(&bar_a2[s]);
         PROF_LAP(12);  // epilogue: A2 stores + fence + arrive
       }
-      umma::mbar_wait(bar_g2, ph_g2);  // the last chunk's GEMM2 completes D2
-      ph_g2 ^= 1;
+      wait_slot(bar_g2, kTcNST, nch - 1, pass);  // the last chunk's GEMM2 completes D2
     }
     umma::tc_fence_before_sync();
     __syncthreads();  // D2 is complete (the epilogue warps and the issuer have waited for the last GEMM2)
@@ -388,7 +394,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int k = 16 * g + i;
-        if (k <= m) mc[row * kTcMP + k] = v[i];
+        if (k <= m) mc[row * kTcMS + k] = v[i];
         if (k == m + 1) sv[row] = v[i];
       }
       umma::tc_fence_before_sync();
@@ -445,13 +451,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
           float x0, x1;
           ok = warp_rr_solve<NS>(rtrow, al, ws, colbase, x0, x1);
           if (ok) {
-            if (lane < NS) mc[f * kTcMP + lane] += x0;
-            if (lane + 32 < NS) mc[f * kTcMP + lane + 32] += x1;
+            if (lane < NS) mc[f * kTcMS + lane] += x0;
+            if (lane + 32 < NS) mc[f * kTcMS + lane + 32] += x1;
           }
         } else {
           ok = warp_ldl_solve<kTcKB>(rtrow, al, m + 1, p.NBk, tri, ws, xo);
           if (ok) {
-            for (int k = lane; k <= m; k += 32) mc[f * kTcMP + k] += xo[k];
+            for (int k = lane; k <= m; k += 32) mc[f * kTcMS + k] += xo[k];
           }
         }
         if (!ok && lane == 0) {
@@ -477,7 +483,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
   __syncthreads();
   for (int i = tid; i < nvalid * (m + 1); i += kTcThreads) {
     const int f = i / (m + 1), k = i - f * (m + 1);
-    const float v = mc[f * kTcMP + k];
+    const float v = mc[f * kTcMS + k];
     if (p.mc_dtype == B2W_F64) reinterpret_cast<double*>(p.mc_out)[(frame0 + f) * p.mc_stride + k] = (double)v;
     else reinterpret_cast<float*>(p.mc_out)[(frame0 + f) * p.mc_stride + k] = v;
   }
@@ -496,7 +502,7 @@ extern "C" int b2w_mcep_prof_read(long long* out16) {
 extern "C" int64_t b2w_mcep_tc_stream_floats(int32_t fft_size) {
   const int K = fft_size / 2 + 1;
   const int nchunks = (K + b2w::kTcBK - 1) / b2w::kTcBK;
-  return (int64_t)nchunks * (b2w::kStageBytes / 4);
+  return (int64_t)nchunks * (b2w::kStageBytes / 4) * b2w::kTcCopies;
 }
 
 extern "C" int b2w_mcep_tc_pretile(int32_t order, int32_t fft_size, const float* m0t, const float* cmat, const float* m2t,
@@ -520,7 +526,7 @@ extern "C" int b2w_mcep_tc(const void* in, int32_t in_dtype, int32_t in_is_power
   B2W_REQUIRE(in && stream0 && stream1 && mc && status, "b2w_mcep_tc: null argument");
   B2W_REQUIRE(in_dtype == B2W_F64 || in_dtype == B2W_F32, "b2w_mcep_tc: bad in_dtype %d", in_dtype);
   B2W_REQUIRE(mc_dtype == B2W_F64 || mc_dtype == B2W_F32, "b2w_mcep_tc: bad mc_dtype %d", mc_dtype);
-  B2W_REQUIRE(order >= 1 && order <= 62, "b2w_mcep_tc: order %d out of range [1, 62] (use b2w_mcep)", order);
+  B2W_REQUIRE(order >= 1 && order <= 59, "b2w_mcep_tc: order %d out of range [1, 59] (use b2w_mcep)", order);
   B2W_REQUIRE(fft_size >= 64 && (fft_size & (fft_size - 1)) == 0, "b2w_mcep_tc: bad fft_size %d", fft_size);
   B2W_REQUIRE(mc_stride >= order + 1 && maxiter >= 1 && miniter >= 1, "b2w_mcep_tc: bad stride / iteration limits");
   B2W_REQUIRE(in_stride >= fft_size / 2 + 1, "b2w_mcep_tc: in_stride %lld < fft_size/2+1", (long long)in_stride);
@@ -532,14 +538,14 @@ extern "C" int b2w_mcep_tc(const void* in, int32_t in_dtype, int32_t in_is_power
   p.K = fft_size / 2 + 1; p.m = order; p.NBk = (order + 1 + 3) / 4;
   p.nchunks = (p.K + kTcBK - 1) / kTcBK;
   p.ws_floats = ldl_workspace_floats(p.NBk, kTcKB) + kTcN2 + kTcMP;
-  if (order + 1 == 20 || order + 1 == 40 || order + 1 == 60) p.ws_floats = max(p.ws_floats, rr_workspace_floats(order + 1));
+  if (order + 1 == 20 || order + 1 == 40 || order + 1 == 60) p.ws_floats = rr_workspace_floats(order + 1);  // register-resident solver
   p.miniter = miniter; p.maxiter = maxiter; p.threshold = (float)threshold; p.eps = (float)eps; p.alpha = (float)alpha;
   p.stream0 = stream0; p.stream1 = stream1; p.mc_out = mc; p.mc_dtype = mc_dtype; p.mc_stride = mc_stride;
   p.iters = iters; p.status = status;
-  const uint32_t gemm_bytes = 2 * kA1Bytes + 2 * kStageBytes + 2 * kA2Bytes;
+  const uint32_t gemm_bytes = kTcNST * kStageBytes;
   const uint32_t ws_bytes = (uint32_t)kTcSolveWarps * (uint32_t)p.ws_floats * 4u;
   const uint32_t region_bytes = gemm_bytes > ws_bytes ? gemm_bytes : ws_bytes;
-  const size_t smem = region_bytes + sizeof(float) * (kTcF * kTcMP + kTcMP + kTcF) + sizeof(int) * (2 * kTcF + 4) + 8 * 8 + 8 + 64 * sizeof(int) +
+  const size_t smem = region_bytes + sizeof(float) * (kTcF * kTcMS + kTcMP + kTcF) + sizeof(int) * (2 * kTcF + 4) + 8 * kTcBars + 8 + 64 * sizeof(int) +
                       sizeof(uint16_t) * (size_t)(p.NBk * (p.NBk - 1) / 2 + 2) + 16;
   B2W_REQUIRE(smem <= 227 * 1024, "b2w_mcep_tc: %zu bytes of shared memory needed", smem);
   const int64_t grid = (num_frames + kTcF - 1) / kTcF;

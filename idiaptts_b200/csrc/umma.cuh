@@ -57,6 +57,20 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 // generic-proxy writes to shared memory -> visible to the async proxy (tensor core operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// true in exactly one (the lowest active) lane of a converged warp; ptxas recognises the elected region as single-threaded and
+// feeds the uniform-register operands of tcgen05.mma without a per-lane loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- tensor memory ---------------------------------------------------------------------------------------------------------
 // one full warp; ncols power of two >= 32; the allocated base address is written to *slot (shared memory)
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
@@ -104,6 +118,19 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 lanes x 32-bit, 16 consecutive columns, registers -> tensor memory (thread i of warp w writes TMEM lane 32 (w % 4) + i);
+// the caller orders the stores with tmem_st_wait() before it signals the consumer
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ---- descriptors -------------------------------------------------------------------------------------------------------------
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, leading (K) and stride (M/N) byte offsets
 // in 16-byte units, version 1 (Blackwell), no swizzle
@@ -143,6 +170,28 @@ __device__ __forceinline__ void mma_3xtf32(uint32_t d_tmem, uint64_t a_hi, uint6
     mma_tf32(d_tmem, a_lo + ks * da, b_hi + ks * db, idesc, accumulate || ks > 0);
     mma_tf32(d_tmem, a_hi + ks * da, b_lo + ks * db, idesc, true);
     mma_tf32(d_tmem, a_hi + ks * da, b_hi + ks * db, idesc, true);
+  }
+}
+// A operand in tensor memory (lane = row, one 32-bit column per K element: a K-step of 8 is 8 columns), B in shared memory
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+template <int KS>
+__device__ __forceinline__ void mma_3xtf32_ts(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                              uint32_t b_step_bytes, uint32_t idesc, bool accumulate) {
+  const uint64_t db = b_step_bytes >> 4;
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    mma_tf32_ts(d_tmem, a_lo + 8 * ks, b_hi + ks * db, idesc, accumulate || ks > 0);
+    mma_tf32_ts(d_tmem, a_hi + 8 * ks, b_lo + ks * db, idesc, true);
+    mma_tf32_ts(d_tmem, a_hi + 8 * ks, b_hi + ks * db, idesc, true);
   }
 }
 // all previously issued MMAs of this thread arrive on the mbarrier when they have completed (implies fence::before_thread_sync)

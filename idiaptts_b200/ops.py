@@ -384,9 +384,9 @@ class McepTables:
         self.m0t = torch.from_numpy(m0t.astype(np.float32)).to(device)
         self.cmat = torch.from_numpy(cmat.astype(np.float32)).to(device)
         self.m2t = torch.from_numpy(m2t.astype(np.float32)).to(device)
-        # pre-tiled hi/lo TF32 streams of the tensor-core kernel (order <= 62)
+        # pre-tiled hi/lo TF32 streams of the tensor-core kernel (order <= 59: the solver workspaces of larger orders do not fit)
         self.stream0 = self.stream1 = None
-        if self.order <= 62:
+        if self.order <= 59:
             n = int(lib.b2w_mcep_tc_stream_floats(self.fft_size))
             self.stream0 = torch.empty(n, dtype=torch.float32, device=device)
             self.stream1 = torch.empty(n, dtype=torch.float32, device=device)
@@ -410,7 +410,7 @@ class McepTables:
 def mcep(plane, order, alpha, is_power=False, miniter=2, maxiter=30, threshold=0.001, eps=1.0e-8, out=None,
          out_stride=None, out_dtype=torch.float32, iters=None, status=None, impl=None):
     """pysptk.mcep(itype=3 (amplitude) or 4 (power), etype=1) on a [F, K] plane -> mc [F, order+1].
-    impl: "tc" = tcgen05 tensor-core kernel (default for order <= 62), "cc" = CUDA-core kernel (any order <= 127)."""
+    impl: "tc" = tcgen05 tensor-core kernel (default for order <= 59), "cc" = CUDA-core kernel (any order <= 127)."""
     lib = _lib.load()
     assert plane.dim() == 2 and plane.dtype in (torch.float32, torch.float64)
     F, K = plane.shape
@@ -431,7 +431,7 @@ def mcep(plane, order, alpha, is_power=False, miniter=2, maxiter=30, threshold=0
         impl = "tc" if tab.stream0 is not None else "cc"
     if impl == "tc":
         if tab.stream0 is None:
-            raise ValueError("the tensor-core mcep kernel supports order <= 62")
+            raise ValueError("the tensor-core mcep kernel supports order <= 59")
         with torch.cuda.device(dev):
             check(lib.b2w_mcep_tc(plane.data_ptr(), _DT[plane.dtype], 1 if is_power else 0, in_stride, F, fft_size,
                                   int(order), float(alpha),

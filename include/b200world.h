@@ -126,7 +126,7 @@ B2W_API int b2w_mcep(const void* in, int32_t in_dtype, int32_t in_is_power, int6
              int32_t order, double alpha, int32_t miniter, int32_t maxiter, double threshold, double eps,
              const float* m0t, const float* cmat, const float* m2t, void* mc, int32_t mc_dtype, int64_t mc_stride,
              int32_t* iters, int32_t* status, void* stream);
-/* Tensor-core version of b2w_mcep for order <= 62 (the production path): the contractions run as tcgen05.mma kind::tf32
+/* Tensor-core version of b2w_mcep for order <= 59 (the production path): the contractions run as tcgen05.mma kind::tf32
  * with the 3xTF32 split, 128 frames per CTA, accumulators in tensor memory, the matrices streamed by bulk async copies
  * from two pre-tiled device buffers of b2w_mcep_tc_stream_floats(fft_size) floats each, which b2w_mcep_tc_pretile builds
  * from the fp32 device copies of the b2w_mcep_tables_host matrices. */

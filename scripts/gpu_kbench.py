@@ -23,7 +23,8 @@ status = ops.new_status(dev)
 n_fft = ops.get_cheaptrick_fft_size(FS)
 alpha = 0.455
 ops.McepTables.get(59, alpha, n_fft, dev)
-sp = torch.empty((chunk, n_fft // 2 + 1), dtype=torch.float32, device=dev)
+K = n_fft // 2 + 1
+sp = torch.empty((chunk, (K + 7) // 8 * 8), dtype=torch.float32, device=dev)[:, :K]   # rows padded as in pipeline.WorldAnalyzer (aligned 16-byte loads)
 mc = torch.empty((chunk, 60), dtype=torch.float32, device=dev)
 print("lib %s, %d utts, %d frames, chunk %d" % (_lib.LIB_PATH, a.utts, F, chunk), flush=True)
 
