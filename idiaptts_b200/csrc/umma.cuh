@@ -25,6 +25,17 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#ifdef B2W_MBAR_HINT_NS   // experiment: explicit suspend-time hint (the thread sleeps in hardware until the phase completes or the time is up)
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)B2W_MBAR_HINT_NS)
+      : "memory");
+#else
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -34,11 +45,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
 }
 // Bounded wait: a barrier that never completes (a programming error in the producer) traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+#ifdef B2W_MBAR_BACKOFF   // experiment: long waits stop polling the barrier unit every few cycles
+    if (spins > 8) __nanosleep(B2W_MBAR_BACKOFF);
+#endif
     if (spins > (1u << 26)) __trap();
   }
 }

@@ -29,10 +29,20 @@ __global__ void __launch_bounds__(kVtThreads)
 allpass_forward_kernel(const float* __restrict__ x, const float* __restrict__ alpha, int64_t rows, int n, int blocks,
                        const float* __restrict__ mean, const float* __restrict__ std_dev, float* __restrict__ y,
                        const uint8_t* __restrict__ tile_mask) {
-  if (tile_mask && !tile_mask[blockIdx.x]) return;  // tile already done by the tensor-core kernel (vtln_tc.cu)
   extern __shared__ float sh[];  // [kVtThreads][n+1]
   const int64_t units = rows * blocks;
-  const int64_t u0 = (int64_t)blockIdx.x * kVtThreads;
+  // With a tile mask (second launch behind the tensor-core kernel of vtln_tc.cu, which has done every tile whose byte is zero) a
+  // small grid walks the mask; without one every CTA owns the tile of its index.
+  const int64_t num_tiles = (units + kVtThreads - 1) / kVtThreads;
+  if (tile_mask) {  // one parallel look at this CTA's share of the mask: usually nothing is flagged and the CTA is done
+    bool any = false;
+    for (int64_t tile = blockIdx.x + (int64_t)threadIdx.x * gridDim.x; tile < num_tiles; tile += (int64_t)kVtThreads * gridDim.x)
+      any = any || tile_mask[tile] != 0;
+    if (!__syncthreads_or(any)) return;
+  }
+  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+  if (tile_mask && !tile_mask[tile]) continue;
+  const int64_t u0 = tile * kVtThreads;
   const int nun = (int)min((int64_t)kVtThreads, units - u0);
   stage<true>(sh, const_cast<float*>(x), u0 * n, nun * n, n);
   __syncthreads();
@@ -78,6 +88,8 @@ allpass_forward_kernel(const float* __restrict__ x, const float* __restrict__ al
   }
   __syncthreads();
   stage<false>(sh, y, u0 * n, nun * n, n);
+  __syncthreads();
+  }
 }
 
 template <int NMAX>
@@ -85,12 +97,20 @@ __global__ void __launch_bounds__(kVtThreads)
 allpass_backward_kernel(const float* __restrict__ gy, const float* __restrict__ x, const float* __restrict__ alpha,
                         int64_t rows, int n, int blocks, const float* __restrict__ mean, const float* __restrict__ std_dev,
                         float* __restrict__ gx, float* __restrict__ galpha_unit, const uint8_t* __restrict__ tile_mask) {
-  if (tile_mask && !tile_mask[blockIdx.x]) return;  // tile already done by the tensor-core kernel (vtln_tc.cu)
   extern __shared__ float sh[];  // [2][kVtThreads][n+1]
   float* shx = sh;
   float* shg = sh + kVtThreads * (n + 1);
   const int64_t units = rows * blocks;
-  const int64_t u0 = (int64_t)blockIdx.x * kVtThreads;
+  const int64_t num_tiles = (units + kVtThreads - 1) / kVtThreads;
+  if (tile_mask) {  // (see allpass_forward_kernel)
+    bool any = false;
+    for (int64_t tile = blockIdx.x + (int64_t)threadIdx.x * gridDim.x; tile < num_tiles; tile += (int64_t)kVtThreads * gridDim.x)
+      any = any || tile_mask[tile] != 0;
+    if (!__syncthreads_or(any)) return;
+  }
+  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+  if (tile_mask && !tile_mask[tile]) continue;
+  const int64_t u0 = tile * kVtThreads;
   const int nun = (int)min((int64_t)kVtThreads, units - u0);
   stage<true>(shx, const_cast<float*>(x), u0 * n, nun * n, n);
   stage<true>(shg, const_cast<float*>(gy), u0 * n, nun * n, n);
@@ -178,6 +198,8 @@ allpass_backward_kernel(const float* __restrict__ gy, const float* __restrict__ 
   }
   __syncthreads();
   stage<false>(shx, gx, u0 * n, nun * n, n);
+  __syncthreads();
+  }
 }
 
 // galpha[row] = sum over the row's blocks of the per-unit contributions
@@ -205,8 +227,9 @@ extern "C" int b2w_allpass_forward_masked(const float* x, const float* alpha, in
   B2W_REQUIRE(n >= 2 && n <= 128 && blocks >= 1, "b2w_allpass_forward: n %d (2..128) / blocks %d out of range", n, blocks);
   if (rows == 0) return 0;
   const int64_t units = rows * blocks;
-  const int64_t grid = (units + kVtThreads - 1) / kVtThreads;
+  int64_t grid = (units + kVtThreads - 1) / kVtThreads;
   B2W_REQUIRE(grid < ((int64_t)1 << 31), "b2w_allpass_forward: too many rows");
+  if (tile_mask && grid > 2 * 148) grid = 2 * 148;  // flagged tiles are rare: a resident grid that scans the mask
   const size_t smem = sizeof(float) * kVtThreads * (n + 1);
   cudaStream_t st = (cudaStream_t)stream;
 #define B2W_VT_FWD(NMAX)                                                                                   \
@@ -235,8 +258,9 @@ extern "C" int b2w_allpass_backward_masked(const float* grad_y, const float* x, 
   B2W_REQUIRE(n >= 2 && n <= 128 && blocks >= 1, "b2w_allpass_backward: n %d (2..128) / blocks %d out of range", n, blocks);
   if (rows == 0) return 0;
   const int64_t units = rows * blocks;
-  const int64_t grid = (units + kVtThreads - 1) / kVtThreads;
+  int64_t grid = (units + kVtThreads - 1) / kVtThreads;
   B2W_REQUIRE(grid < ((int64_t)1 << 31), "b2w_allpass_backward: too many rows");
+  if (tile_mask && grid > 2 * 148) grid = 2 * 148;  // flagged tiles are rare: a resident grid that scans the mask
   const size_t smem = sizeof(float) * 2 * kVtThreads * (n + 1);
   cudaStream_t st = (cudaStream_t)stream;
 #define B2W_VT_BWD(NMAX)                                                                                    \

@@ -275,6 +275,7 @@ B2W_API int b2w_world_metrics(const float* org, const float* out, int64_t stride
 B2W_API int64_t b2w_probe_fp64_fma(int32_t iters, double* scratch, void* stream);
 /* development aid: phase cycle counters of mcep_tc CTA 0 (non-zero only in a -DB2W_MCEP_PROF build) */
 B2W_API int b2w_mcep_prof_read(long long* out16);
+B2W_API int b2w_vtf_prof_read(long long* out16);   /* same for allpass_tc_forward_kernel (-DB2W_VTF_PROF builds) */
 
 /* ---- generalised mel-cepstrum (sp_type = "mgc"): replaces pysptk.mgcep(amp_sp, order, alpha, gamma, eps = 1e-8,
  * etype = 1, itype = 3) in AudioProcessing.extract_mgc (A:123-140) and exp(Re pysptk.mgc2sp(mgc, alpha, gamma, fftlen)) in

@@ -29,3 +29,15 @@ if "bwd" in sys.argv:
             print("bwd %s: %.4f ms  %.1f GB/s  %.3f of HBM peak" % (impl, ms, rows * (12 * n + 8) / ms / 1e6, rows * (12 * n + 8) / ms / 1e6 / PEAK))
         except TypeError as e:
             print("bwd", impl, "n/a", e)
+
+if os.environ.get("B2W_LIB", "").find("vtfprof") >= 0:
+    import ctypes
+    from idiaptts_b200 import _lib
+    _lib.load().b2w_vtf_prof_reset() if hasattr(_lib.load(), 'b2w_vtf_prof_reset') else None
+    ops.allpass_forward(x, alpha, n, impl="tc"); torch.cuda.synchronize()
+    buf = (ctypes.c_longlong * 16)()
+    _lib.load().b2w_vtf_prof_read(ctypes.cast(buf, ctypes.c_void_p))
+    names = ["issuer: alpha runs", "issuer: wait matrix", "issuer: wait A", "issuer: MMA issue", "builder: build cycles (sum)", "builder: builds", "builder: start of first build", "builder: fence + arrive (sum)", "group: wait raw tile", "group: read+convert+st",
+             "group: wait MMA", "group: wait out stage", "group: epilogue", "-", "-", "-"]
+    for n_, v in zip(names, buf):
+        print("  %-28s %10d cycles" % (n_, v))
