@@ -17,9 +17,6 @@ namespace b2w {
 
 constexpr int kVtcF = 128;       // units per tile = UMMA M
 constexpr int kVtcNP = 64;       // padded n (K and N of the GEMM)
-constexpr int kVtcThreads = 256;
-constexpr int kVtcStageStride = kVtcNP + 1;  // output staging row stride (floats): conflict-free scalar stores
-constexpr uint32_t kVtcABytes = kVtcF * kVtcNP * 4;   // 32 KB, one of hi / lo
 constexpr uint32_t kVtcBBytes = kVtcNP * kVtcNP * 4;  // 16 KB, one of hi / lo
 
 
@@ -114,7 +111,6 @@ struct VtfSmem {
 };
 constexpr int kVtfTmA = 0;     // A[b] hi at 128 b, lo at 128 b + 64
 constexpr int kVtfTmD = 256;   // D[b] at 256 + 64 b
-constexpr int kVtfTmD2 = 384;  // second accumulator of a two-run tile at 384 + 64 b
 
 __device__ long long g_vtf_prof[16];
 #ifdef B2W_VTF_PROF
@@ -242,30 +238,30 @@ allpass_tc_forward_kernel(const float* __restrict__ x, const float* __restrict__
 
   if (warp == 1) {
     // ---- producer -----------------------------------------------------------------------------------------------------------
-    for (int i = 0; i < kVtfNST && i < cnt; ++i) {  // the first tiles are on their way before anything else happens
-      if (lane == 0) {
-        umma::mbar_expect_tx(&bar_full[i], (uint32_t)tile_units(i) * row_bytes);
-        umma::bulk_g2s(smem + VtfSmem::in + i * kVtfStageBytes, x + (t_begin + i) * kVtcF * n, (uint32_t)tile_units(i) * row_bytes, &bar_full[i]);
-      }
-    }
+    // A tile with two alpha runs (a speaker boundary) is emitted as two partial segments, so everybody downstream only ever sees
+    // segments with ONE alpha (rows beyond the segment's length are zero / ignored, like in the last tile).  (ok, last, units,
+    // first unit relative to the CTA's range) and the alpha travel with the stage.
     load_runs(0);
     load_runs(1);
+    int sidx = 0;
     for (int i = 0; i < cnt; ++i) {
-      const int s = i % kVtfNST;
       const int nun = tile_units(i);
-      if (lane == 0 && i >= kVtfNST) {
-        wait_slot(bar_empty, kVtfNST, i - kVtfNST);
-        umma::mbar_expect_tx(&bar_full[s], (uint32_t)nun * row_bytes);
-        umma::bulk_g2s(smem + VtfSmem::in + s * kVtfStageBytes, x + (t_begin + i) * kVtcF * n, (uint32_t)nun * row_bytes, &bar_full[s]);
-      }
-      __syncwarp();
       const VtfRuns r = runs_of(i);
-      if (lane == 0) {
-        tinfo[i & 7] = make_int4(r.ok ? 1 : 0, r.n0, nun, 0);  // (slot i & 7 was last read for tile i - 8: long retired)
-        tinfo[8 + (i & 7)] = make_int4(__float_as_int(r.a0), __float_as_int(r.a1), 0, 0);
-        tile_mixed[t_begin + i] = r.ok ? 0 : 1;
-        umma::mbar_arrive(&bar_full[s]);
+      const int nseg = (r.ok && r.n0 < nun) ? 2 : 1;
+      for (int sg = 0; sg < nseg; ++sg, ++sidx) {
+        if (lane == 0) {
+          const int s = sidx % kVtfNST;
+          const int off = sg ? r.n0 : 0, cu = nseg == 2 ? (sg ? nun - r.n0 : r.n0) : nun;
+          const int ustart = i * kVtcF + off;
+          if (sidx >= kVtfNST) wait_slot(bar_empty, kVtfNST, sidx - kVtfNST);
+          umma::mbar_expect_tx(&bar_full[s], (uint32_t)cu * row_bytes);
+          umma::bulk_g2s(smem + VtfSmem::in + s * kVtfStageBytes, x + (t_begin * kVtcF + ustart) * n, (uint32_t)cu * row_bytes, &bar_full[s]);
+          tinfo[sidx & 7] = make_int4(r.ok ? 1 : 0, (i == cnt - 1 && sg == nseg - 1) ? 1 : 0, cu, ustart);  // (slot last read 8 segments ago)
+          tinfo[8 + (sidx & 7)] = make_int4(__float_as_int(sg ? r.a1 : r.a0), 0, 0, 0);
+          umma::mbar_arrive(&bar_full[s]);
+        }
       }
+      if (lane == 0) tile_mixed[t_begin + i] = r.ok ? 0 : 1;
       __syncwarp();
     }
   } else if (warp == 2) {
@@ -336,39 +332,36 @@ allpass_tc_forward_kernel(const float* __restrict__ x, const float* __restrict__
       __syncwarp();
     };
     next_matrix(alpha_of(t_begin * kVtcF));
-    for (int i = 0; i < cnt; ++i) {
+    for (int i = 0;; ++i) {
       const int b = i & 1;
-      wait_slot(bar_afull, 2, i);  // (the converters arrive after the producer's classification of tile i has become visible to them)
+      wait_slot(bar_afull, 2, i);  // (the converters arrive after the producer's description of segment i has become visible to them)
       VPROF_LAP(2);  // issuer: wait A
-      const int4 ti = tinfo[i & 7], ta = tinfo[8 + (i & 7)];
-      const bool ok = ti.x != 0;
-      const float a0 = __int_as_float(ta.x), a1 = __int_as_float(ta.y);
-      if (ok && a0 != cached) next_matrix(a0);
+      const int4 ti = tinfo[i & 7];
+      const float a0 = __int_as_float(tinfo[8 + (i & 7)].x);
+      if (ti.x && a0 != cached) next_matrix(a0);
       VPROF_LAP(1);  // issuer: wait matrix
       umma::tc_fence_after_sync();
-      if (ok) mma(b, kVtfTmD + 64 * b);
-      if (ok && ti.y < ti.z) {  // rows of the second run: same A operand, the next speaker's matrix, second accumulator
-        next_matrix(a1);
-        mma(b, kVtfTmD2 + 64 * b);
-      }
+      if (ti.x) mma(b, kVtfTmD + 64 * b);
       commit_to(&bar_dfull[b]);
       VPROF_LAP(3);  // issuer: MMA issue
+      if (ti.y) break;
     }
     VPROF_FLUSH(0, 4);
   } else if (warp == 3) {
     // ---- store thread: one bulk store per tile ------------------------------------------------------------------------------------
     if (lane == 0) {
-      for (int j = 0; j < cnt; ++j) {
+      for (int j = 0;; ++j) {
         wait_slot(bar_ofull, 2, j);
         const int4 ti = tinfo[j & 7];
         if (ti.x) {
-          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(y + (t_begin + j) * kVtcF * n),
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(y + (t_begin * kVtcF + ti.w) * n),
                        "r"(umma::smem_u32(smem + VtfSmem::out + (j & 1) * kVtfStageBytes)), "r"((uint32_t)ti.z * row_bytes)
                        : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
         umma::mbar_arrive(&bar_ofree[j & 1]);
+        if (ti.y) break;
       }
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
@@ -379,12 +372,14 @@ allpass_tc_forward_kernel(const float* __restrict__ x, const float* __restrict__
     const int qc = gw >> 2;                    // columns 16 qc .. 16 qc + 15 of the row
     const int row = 32 * q + lane;
     const uint32_t t_row = tmem + ((uint32_t)(32 * q) << 16);
-    for (int i = 0; i <= cnt; ++i) {
-      if (i < cnt) {
+    int total = 0x7fffffff;  // number of segments, known when the one flagged `last` arrives
+    for (int i = 0; i <= total; ++i) {
+      if (i < total) {
         const int s = i % kVtfNST, b = i & 1;
         wait_slot(bar_full, kVtfNST, i);
         VPROF_LAP(8);  // group: wait raw tile
         const int4 ti = tinfo[i & 7];
+        if (ti.y) total = i + 1;
         float hi[16], lo[16];
         if (ti.x) {
           const float4* src = reinterpret_cast<const float4*>(smem + VtfSmem::in + s * kVtfStageBytes + (size_t)row * row_bytes) + 4 * qc;
@@ -431,12 +426,6 @@ allpass_tc_forward_kernel(const float* __restrict__ x, const float* __restrict__
           float* orow = reinterpret_cast<float*>(smem + VtfSmem::out + b * kVtfStageBytes) + (size_t)row * n;
           float d[16];
           umma::tmem_ld16(t_row + kVtfTmD + 64 * b + 16 * qc, d);
-          if (tj.y < tj.z) {  // two runs: rows of the second run take the second accumulator (warp-wide load, per-row choice)
-            float d2[16];
-            umma::tmem_ld16(t_row + kVtfTmD2 + 64 * b + 16 * qc, d2);
-#pragma unroll
-            for (int e = 0; e < 16; ++e) d[e] = row < tj.y ? d[e] : d2[e];
-          }
 #pragma unroll
           for (int e = 0; e < 16; e += 4) {
             const int c = 16 * qc + e;
@@ -466,257 +455,452 @@ allpass_tc_forward_kernel(const float* __restrict__ x, const float* __restrict__
 
 // ---- backward -------------------------------------------------------------------------------------------------------------------
 // gx = (gy / std) . Bb^T . std,  Bb[r][j] = S1_r A[j][r] S2_j   (the transposed forward matrix)
-// galpha(unit) = < gy / std , X' . Bt^T >,  Bt[j][r] = S2_j dA/dalpha[j][r] S1_r   (tangent of the same wavefront recursion)
+// galpha(unit) = < gy / std , X' . Bt^T >,  Bt[j][r] = S2_j dA/dalpha[j][r] S1_r   (tangent of the same recursion)
 // Two GEMMs per tile into two accumulators; tiles whose units do not share ONE alpha go to the recursion kernel.
-struct VtcBwdSmem {
-  static constexpr uint32_t g_hi = 0, g_lo = kVtcABytes, x_hi = 2 * kVtcABytes, x_lo = 3 * kVtcABytes;
-  static constexpr uint32_t bb_hi = 4 * kVtcABytes, bb_lo = bb_hi + kVtcBBytes, bt_hi = bb_lo + kVtcBBytes, bt_lo = bt_hi + kVtcBBytes;
-  static constexpr uint32_t vec = bt_lo + kVtcBBytes;
-  static constexpr uint32_t misc = vec + 3 * kVtcNP * 4;
-  static constexpr uint32_t total = misc + 64;
-};
+//
+// Same pipeline as the forward kernel, at OPERAND granularity: the stage ring, the converters and the tensor pipe work on the items
+// G(0), X(0), G(1), X(1), ...  Tensor memory: A_G | A_X (hi / lo, 128 columns each, single buffered: A_G is free again when the
+// first GEMM of the tile has completed, A_X when the second has), D1[2], D2[2] (64 columns each, by tile parity).  The sixteen
+// converter warps run  G(i) -> X(i) -> epilogue(i - 1);  the epilogue writes its quarter rows of gx straight to global memory
+// (64 contiguous bytes per thread) and leaves the partial dot products of d alpha in shared memory for the reduce warp.
 
+// Row-wise construction of both matrices (see vtc_build_matrix): with E = A(alpha) and T = dA / dalpha,
+//     E[j][r] = a E[j][r-1] + gE_r,   T[j][r] = a T[j][r-1] + gT_r          (first-order recurrences over r, resolved by warp scans)
+//     row 0:   gE = [r == 0],                              gT = E[0][r-1]
+//     row 1:   gE = (1 - a^2) E[0][r-1],                   gT = -2 a E[0][r-1] + (1 - a^2) T[0][r-1] + E[1][r-1]
+//     row j:   gE = E[j-1][r-1] - a E[j-1][r],             gT = T[j-1][r-1] - a T[j-1][r] + E[j][r-1] - E[j-1][r]
+// and column 0 of every row below the first is zero.
 __device__ __forceinline__ void vtc_build_matrices_bwd(float* bb_hi, float* bb_lo, float* bt_hi, float* bt_lo, float a, int n) {
   const int lane = threadIdx.x & 31;
-  const float bcoef = 1.f - a * a;
-  float ce[2] = {0.f, 0.f}, ct[2] = {0.f, 0.f}, ne[2] = {0.f, 0.f}, nt[2] = {0.f, 0.f};
-  for (int d = 0; d <= 2 * n - 2; ++d) {
-    const float ue0 = __shfl_up_sync(0xffffffffu, ce[0], 1), ut0 = __shfl_up_sync(0xffffffffu, ct[0], 1);
-    float ue1 = __shfl_up_sync(0xffffffffu, ce[1], 1), ut1 = __shfl_up_sync(0xffffffffu, ct[1], 1);
-    const float we = __shfl_sync(0xffffffffu, ce[0], 31), wt = __shfl_sync(0xffffffffu, ct[0], 31);
-    if (lane == 0) { ue1 = we; ut1 = wt; }
+  const int r0 = 2 * lane;
+  float pw[5];  // a^2, a^4, a^8, a^16, a^32
+  pw[0] = a * a;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int j = lane + 32 * h, r = d - j;
-      const float ue = h ? ue1 : ue0, ut = h ? ut1 : ut0;
-      if (j < n && r >= 0 && r < n) {
-        float e, t;
-        if (r == 0) { e = (j == 0) ? 1.f : 0.f; t = 0.f; }
-        else if (j == 0) { e = a * ce[h]; t = fmaf(a, ct[h], ce[h]); }
-        else if (j == 1) { e = fmaf(bcoef, ne[h], a * ce[h]); t = fmaf(-2.f * a, ne[h], fmaf(bcoef, nt[h], fmaf(a, ct[h], ce[h]))); }
-        else { const float diff = ce[h] - ue; e = fmaf(a, diff, ne[h]); t = nt[h] + diff + a * (ct[h] - ut); }
-        ce[h] = e;
-        ct[h] = t;
-        float sc = 1.f;
-        if (j == 0) sc *= 2.f;
-        if (r == 0) sc *= 0.5f;
-        float hi, lo;
-        umma::split_tf32(e * sc, hi, lo);
-        uint32_t off = umma::tile_off(kVtcNP, r, j) / 4;   // Bb[n = r][k = j]
-        bb_hi[off] = hi;
-        bb_lo[off] = lo;
-        umma::split_tf32(t * sc, hi, lo);
-        off = umma::tile_off(kVtcNP, j, r) / 4;            // Bt[n = j][k = r]
-        bt_hi[off] = hi;
-        bt_lo[off] = lo;
+  for (int i = 1; i < 5; ++i) pw[i] = pw[i - 1] * pw[i - 1];
+  const float bcoef = 1.f - a * a;
+  // v[r] = a v[r-1] + g[r] for this lane's two columns (v[-1] = 0): affine maps of the incoming carry, Kogge-Stone over the lanes
+  auto scan_row = [&](float g0, float g1, float& v0, float& v1) {
+    float x = fmaf(a, g0, g1);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const float t = __shfl_up_sync(0xffffffffu, x, 1 << i);
+      if (lane >= (1 << i)) x = fmaf(pw[i], t, x);
+    }
+    float carry = __shfl_up_sync(0xffffffffu, x, 1);
+    if (lane == 0) carry = 0.f;
+    v0 = fmaf(a, carry, g0);
+    v1 = x;
+  };
+  auto left_of = [&](float v1) {  // value of column r0 - 1 (0 for column -1)
+    const float l = __shfl_up_sync(0xffffffffu, v1, 1);
+    return lane == 0 ? 0.f : l;
+  };
+  float e0 = 0.f, e1 = 0.f, t0 = 0.f, t1 = 0.f;  // previous row
+  const bool in = r0 < n;
+  const uint32_t cbt = (uint32_t)(r0 >> 2) * (kVtcNP * 4) + (r0 & 3);  // Bt[n = j][k = r]: float offset of column r0 inside row j
+  for (int j = 0; j < n; ++j) {
+    float ne0, ne1, nt0, nt1;
+    if (j == 0) {
+      scan_row(lane == 0 ? 1.f : 0.f, 0.f, ne0, ne1);
+      scan_row(left_of(ne1), ne0, nt0, nt1);
+    } else {
+      const float el = left_of(e1), tl = left_of(t1);
+      const float cn = j == 1 ? bcoef : 1.f, cu = j == 1 ? 0.f : a;
+      scan_row(lane == 0 ? 0.f : fmaf(cn, el, -cu * e0), fmaf(cn, e0, -cu * e1), ne0, ne1);
+      const float nel = left_of(ne1);  // E[j][r0 - 1]
+      float gt0, gt1;
+      if (j == 1) {
+        gt0 = fmaf(-2.f * a, el, fmaf(bcoef, tl, nel));
+        gt1 = fmaf(-2.f * a, e0, fmaf(bcoef, t0, ne0));
+      } else {
+        gt0 = (tl - a * t0) + (nel - e0);
+        gt1 = (t0 - a * t1) + (ne0 - e1);
       }
-      ne[h] = ue;
-      nt[h] = ut;
+      scan_row(lane == 0 ? 0.f : gt0, gt1, nt0, nt1);
+    }
+    e0 = ne0; e1 = ne1; t0 = nt0; t1 = nt1;
+    if (in) {
+      const float s2 = j == 0 ? 2.f : 1.f, s1 = lane == 0 ? 0.5f : 1.f;
+      // Bb[n = r][k = j]
+      const uint32_t kb = (uint32_t)(j >> 2) * (kVtcNP * 4) + (j & 3);
+      bb_hi[umma::tile_off(kVtcNP, r0, 0) / 4 + kb] = e0 * s2 * s1;
+      bb_hi[umma::tile_off(kVtcNP, r0 + 1, 0) / 4 + kb] = e1 * s2;
+      *reinterpret_cast<float2*>(bt_hi + umma::tile_off(kVtcNP, j, 0) / 4 + cbt) = make_float2(t0 * s2 * s1, t1 * s2);
+    }
+  }
+  __syncwarp();
+  for (int e = lane; e < kVtcNP * kVtcNP / 4; e += 32) {  // (entries outside n x n stay zero: the buffers are cleared once)
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      float* ph = m ? bt_hi : bb_hi;
+      float* pl = m ? bt_lo : bb_lo;
+      const float4 v = reinterpret_cast<const float4*>(ph)[e];
+      float4 hi, lo;
+      umma::split_tf32(v.x, hi.x, lo.x);
+      umma::split_tf32(v.y, hi.y, lo.y);
+      umma::split_tf32(v.z, hi.z, lo.z);
+      umma::split_tf32(v.w, hi.w, lo.w);
+      reinterpret_cast<float4*>(ph)[e] = hi;
+      reinterpret_cast<float4*>(pl)[e] = lo;
     }
   }
 }
 
-__global__ void __launch_bounds__(kVtcThreads, 1)
+constexpr int kVtbThreads = 640;          // warp 0 issuer, 1 producer, 2 builder, 3 reduce, 4-19 converter / epilogue
+struct VtbSmem {                          // offsets that do not depend on the stage size
+  static constexpr uint32_t bmat = 0;                                 // [2][bb_hi | bb_lo | bt_hi | bt_lo] 2 x 64 KB
+  static constexpr uint32_t vec = 8 * kVtcBBytes;                     // mean[64], std[64], 1/std[64]
+  static constexpr uint32_t gpart = vec + 3 * kVtcNP * 4;             // [2][4][128] partial dot products
+  static constexpr uint32_t bars = gpart + 2 * 4 * kVtcF * 4;
+  static constexpr uint32_t nbars = 2 * 4 + 14;                       // full[4], empty[4], then see the kernel
+  static constexpr uint32_t misc = bars + nbars * 8;                  // tmem slot, tile info ring
+  static constexpr uint32_t stages = (misc + 16 + 8 * 32 + 127) & ~127u;  // [nst][stage_bytes]
+  static_assert(misc % 16 == 0 && stages % 128 == 0, "alignment of the tile info ring / the bulk copy destinations");
+};
+constexpr int kVtbTmAG = 0, kVtbTmAX = 128, kVtbTmD1 = 256, kVtbTmD2 = 384;
+
+__global__ void __launch_bounds__(kVtbThreads, 1)
 allpass_tc_backward_kernel(const float* __restrict__ gy, const float* __restrict__ x, const float* __restrict__ alpha, int64_t units, int n,
                            int blocks, const float* __restrict__ mean, const float* __restrict__ std_dev, float* __restrict__ gx,
-                           float* __restrict__ galpha_unit, uint8_t* __restrict__ tile_mixed, int64_t num_tiles) {
+                           float* __restrict__ galpha_unit, uint8_t* __restrict__ tile_mixed, int64_t num_tiles, int nst,
+                           uint32_t stage_bytes) {
   extern __shared__ __align__(128) uint8_t smem[];
-  float* g_hi = reinterpret_cast<float*>(smem + VtcBwdSmem::g_hi);
-  float* g_lo = reinterpret_cast<float*>(smem + VtcBwdSmem::g_lo);
-  float* x_hi = reinterpret_cast<float*>(smem + VtcBwdSmem::x_hi);
-  float* x_lo = reinterpret_cast<float*>(smem + VtcBwdSmem::x_lo);
-  float* bb_hi = reinterpret_cast<float*>(smem + VtcBwdSmem::bb_hi);
-  float* bb_lo = reinterpret_cast<float*>(smem + VtcBwdSmem::bb_lo);
-  float* bt_hi = reinterpret_cast<float*>(smem + VtcBwdSmem::bt_hi);
-  float* bt_lo = reinterpret_cast<float*>(smem + VtcBwdSmem::bt_lo);
-  float* stage = x_hi;  // gx staging aliases the X tiles once both GEMMs have completed (the G tiles stay intact for the dot)
-  float* vmean = reinterpret_cast<float*>(smem + VtcBwdSmem::vec);
+  float* vmean = reinterpret_cast<float*>(smem + VtbSmem::vec);
   float* vstd = vmean + kVtcNP;
   float* vrstd = vstd + kVtcNP;
-  __shared__ float ga_half[kVtcF];
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + VtcBwdSmem::misc);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  float* gpart = reinterpret_cast<float*>(smem + VtbSmem::gpart);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + VtbSmem::bars);
+  uint64_t* bar_full = bars;              // [nst <= 4] operand tile (+ the tile's classification with the G item) has landed
+  uint64_t* bar_empty = bars + 4;         // [nst <= 4] every converter warp has read the operand tile
+  uint64_t* bar_ag = bars + 8;            // A_G written (16 warps), once per tile
+  uint64_t* bar_ax = bars + 9;            // A_X written
+  uint64_t* bar_d1 = bars + 10;           // [2] first GEMM of the tile complete: D1[b] ready, A_G free
+  uint64_t* bar_d2 = bars + 12;           // [2] second GEMM complete: D2[b] ready, A_X free
+  uint64_t* bar_ofull = bars + 14;        // [2] partial dot products of the tile written (16 warps)
+  uint64_t* bar_ofree = bars + 16;        // [2] the reduce warp has consumed them
+  uint64_t* bar_bfull = bars + 18;        // [2] matrix set [k & 1] holds build k
+  uint64_t* bar_bfree = bars + 20;        // [2] every MMA that read matrix set [k & 1] has completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + VtbSmem::misc);
+  int4* tinfo = reinterpret_cast<int4*>(smem + VtbSmem::misc + 16);  // [8] (ok, -, nun, -) of tile i at i & 7, then [8] (alpha)
+  uint8_t* stages = smem + VtbSmem::stages;
+
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t per = (num_tiles + gridDim.x - 1) / gridDim.x;
   const int64_t t_begin = (int64_t)blockIdx.x * per;
   const int64_t t_end = min(num_tiles, t_begin + per);
   if (t_begin >= t_end) return;
+  const int cnt = (int)(t_end - t_begin);
+
   if (tid == 0) {
-    umma::mbar_init(bar, 1);
+    for (int i = 0; i < 4; ++i) {
+      umma::mbar_init(&bar_full[i], 2);
+      umma::mbar_init(&bar_empty[i], kVtfGW);
+    }
+    umma::mbar_init(bar_ag, kVtfGW);
+    umma::mbar_init(bar_ax, kVtfGW);
+    for (int i = 0; i < 2; ++i) {
+      umma::mbar_init(&bar_d1[i], 1);
+      umma::mbar_init(&bar_d2[i], 1);
+      umma::mbar_init(&bar_ofull[i], kVtfGW);
+      umma::mbar_init(&bar_ofree[i], 1);
+      umma::mbar_init(&bar_bfull[i], 1);
+      umma::mbar_init(&bar_bfree[i], 1);
+    }
     umma::mbar_fence_init();
   }
-  if (warp == 0) umma::tmem_alloc(tmem_slot, 128);
-  for (int i = tid; i < (int)(VtcBwdSmem::vec / 4); i += kVtcThreads) reinterpret_cast<float*>(smem)[i] = 0.f;
+  if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
+  const bool norm_ok = blocks == 1 || (mean == nullptr && std_dev == nullptr);
+  const bool has_norm = mean != nullptr || std_dev != nullptr;
+  if (tid < kVtcNP) {
+    const bool in = tid < n && blocks == 1;
+    vmean[tid] = (in && mean) ? mean[tid] : 0.f;
+    const float sd = (in && std_dev) ? std_dev[tid] : 1.f;
+    vstd[tid] = sd;
+    vrstd[tid] = 1.f / sd;
+  }
+  for (int i = tid; i < (int)(8 * kVtcBBytes / 4); i += kVtbThreads) reinterpret_cast<float*>(smem + VtbSmem::bmat)[i] = 0.f;
   umma::tc_fence_before_sync();
   __syncthreads();
   umma::tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t idesc = umma::idesc_tf32(kVtcF, kVtcNP);
   const int nq = n / 4;
-  constexpr int kPre = 8;
-  const int my_r = lane & 7, my_kq = lane >> 3;
-  uint32_t phase = 0;
-  float cached_alpha = 0.f;
-  bool have_matrix = false;
-  int cached_blk = -1;
-  float4 pg[kPre], px[kPre];
-  float pre_alpha = 0.f;
-  auto prefetch = [&](int64_t t) {
-    const int64_t u0 = t * kVtcF;
-    const int nun = (int)min((int64_t)kVtcF, units - u0);
-    const float4* sg = reinterpret_cast<const float4*>(gy + u0 * n);
-    const float4* sx = reinterpret_cast<const float4*>(x + u0 * n);
+  const uint32_t row_bytes = (uint32_t)n * 4u;
+  auto wait_idx = [&](uint64_t* bar, int index) { umma::mbar_wait(bar, (uint32_t)index & 1u); };
+  auto wait_item = [&](uint64_t* arr, int k) { umma::mbar_wait(&arr[k % nst], (uint32_t)(k / nst) & 1u); };  // stage barriers, by item
+  auto alpha_of = [&](int64_t u) { return blocks == 1 ? alpha[u] : alpha[u / blocks]; };
+  auto tile_units = [&](int i) { return (int)min((int64_t)kVtcF, units - (t_begin + i) * kVtcF); };
+  float run_ar0[4], run_ar1[4], run_a00 = 0.f, run_a01 = 0.f, run_a10 = 0.f, run_a11 = 0.f;
+  auto load_into = [&](int i, float (&ar)[4], float& a0, float& a1) {
+    const int64_t u0 = (t_begin + i) * kVtcF;
+    const int nun = tile_units(i);
+    a0 = alpha_of(u0);
+    a1 = alpha_of(u0 + nun - 1);
 #pragma unroll
-    for (int i = 0; i < kPre; ++i) {
-      const int item = warp + 8 * i;
-      const int r = 8 * (item >> 2) + my_r, kq = 4 * (item & 3) + my_kq;
-      pg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      px[i] = pg[i];
-      if (r < nun && kq < nq) {
-        pg[i] = __ldg(sg + r * nq + kq);
-        px[i] = __ldg(sx + r * nq + kq);
-      }
-    }
-    pre_alpha = (tid < nun) ? alpha[(u0 + tid) / blocks] : 0.f;
+    for (int h = 0; h < 4; ++h) ar[h] = lane + 32 * h < nun ? alpha_of(u0 + lane + 32 * h) : 0.f;
   };
-  auto put = [&](float* hi_t, float* lo_t, int r, int k, float4 v) {
-    float4 h, l;
-    umma::split_tf32(v.x, h.x, l.x);
-    umma::split_tf32(v.y, h.y, l.y);
-    umma::split_tf32(v.z, h.z, l.z);
-    umma::split_tf32(v.w, h.w, l.w);
-    const uint32_t off = umma::tile_off(kVtcF, r, k) / 4;
-    *reinterpret_cast<float4*>(hi_t + off) = h;
-    *reinterpret_cast<float4*>(lo_t + off) = l;
+  auto load_runs = [&](int i) {
+    if (i >= cnt) return;
+    if (i & 1) load_into(i, run_ar1, run_a01, run_a11);
+    else load_into(i, run_ar0, run_a00, run_a10);
+  };
+  auto runs_of = [&](int i) {  // classification of tile i (refills the slot with tile i + 2)
+    VtfRuns r;
+    if (i & 1) r = vtf_runs(run_ar1, run_a01, run_a11, tile_units(i), lane);
+    else r = vtf_runs(run_ar0, run_a00, run_a10, tile_units(i), lane);
+    load_runs(i + 2);
+    r.ok = r.ok && norm_ok;
+    return r;
   };
 
-  prefetch(t_begin);
-  for (int64_t t = t_begin; t < t_end; ++t) {
-    const int64_t u0 = t * kVtcF;
-    const int nun = (int)min((int64_t)kVtcF, units - u0);
-    const int64_t row0 = u0 / blocks;
-    const float a0 = alpha[row0];
-    const int blk0 = (int)(u0 - row0 * blocks);
-    const bool norm_ok = blocks == 1 || (mean == nullptr && std_dev == nullptr);
-    const bool ok = __syncthreads_and(tid >= nun || pre_alpha == a0) && norm_ok;
-    if (tid == 0) tile_mixed[t] = ok ? 0 : 1;
-    if (!ok) {
-      if (t + 1 < t_end) prefetch(t + 1);
-      continue;
-    }
-    bool rewritten = false;
-    if (cached_blk != blk0) {
-      if (tid < kVtcNP) {
-        const bool in = tid < n;
-        vmean[tid] = (in && mean) ? mean[blk0 * n + tid] : 0.f;
-        const float sd = (in && std_dev) ? std_dev[blk0 * n + tid] : 1.f;
-        vstd[tid] = sd;
-        vrstd[tid] = 1.f / sd;
-      }
-      rewritten = true;
-    }
-    cached_blk = blk0;
-    if (!have_matrix || a0 != cached_alpha) {
-      if (warp == 0) vtc_build_matrices_bwd(bb_hi, bb_lo, bt_hi, bt_lo, a0, n);
-      cached_alpha = a0;
-      have_matrix = true;
-      rewritten = true;
-    }
-    if (rewritten) __syncthreads();  // block-uniform condition
+  if (warp == 1) {
+    // ---- producer: items 2 i (gy tile) and 2 i + 1 (x tile) ---------------------------------------------------------------------
+    // Segments with ONE alpha, as in the forward kernel; a segment is two items: its gy rows (with the description) and its x rows.
+    load_runs(0);
+    load_runs(1);
+    int sidx = 0;
+    for (int i = 0; i < cnt; ++i) {
+      const int nun = tile_units(i);
+      const VtfRuns r = runs_of(i);
+      const int nseg = (r.ok && r.n0 < nun) ? 2 : 1;
+      for (int sg = 0; sg < nseg; ++sg, ++sidx) {
+        if (lane == 0) {
+          const int off = sg ? r.n0 : 0, cu = nseg == 2 ? (sg ? nun - r.n0 : r.n0) : nun;
+          const int ustart = i * kVtcF + off;
+          const uint32_t bytes = (uint32_t)cu * row_bytes;
 #pragma unroll
-    for (int i = 0; i < kPre; ++i) {
-      const int item = warp + 8 * i;
-      const int r = 8 * (item >> 2) + my_r, kq = 4 * (item & 3) + my_kq;
-      if (kq < nq) {
-        const int k = 4 * kq;
-        float4 g = pg[i], v = px[i];
-        if (r < nun) {
-          g.x *= vrstd[k]; g.y *= vrstd[k + 1]; g.z *= vrstd[k + 2]; g.w *= vrstd[k + 3];
-          v.x = fmaf(v.x, vstd[k], vmean[k]);
-          v.y = fmaf(v.y, vstd[k + 1], vmean[k + 1]);
-          v.z = fmaf(v.z, vstd[k + 2], vmean[k + 2]);
-          v.w = fmaf(v.w, vstd[k + 3], vmean[k + 3]);
+          for (int h = 0; h < 2; ++h) {
+            const int k = 2 * sidx + h, s = k % nst;
+            if (k >= nst) wait_item(bar_empty, k - nst);
+            umma::mbar_expect_tx(&bar_full[s], bytes);
+            umma::bulk_g2s(stages + (size_t)s * stage_bytes, (h ? x : gy) + (t_begin * kVtcF + ustart) * n, bytes, &bar_full[s]);
+            if (h == 0) {
+              tinfo[sidx & 7] = make_int4(r.ok ? 1 : 0, (i == cnt - 1 && sg == nseg - 1) ? 1 : 0, cu, ustart);
+              tinfo[8 + (sidx & 7)] = make_int4(__float_as_int(sg ? r.a1 : r.a0), 0, 0, 0);
+            }
+            umma::mbar_arrive(&bar_full[s]);
+          }
         }
-        put(g_hi, g_lo, r, k, g);
-        put(x_hi, x_lo, r, k, v);
       }
-    }
-    // K padding of the X tiles (the gx staging of the previous tile aliases them); the G tiles' padding is never written
-    for (int e = tid; e < kVtcF * (kVtcNP / 4 - nq); e += kVtcThreads) {
-      const int r = e % kVtcF, k = n + 4 * (e / kVtcF);
-      const uint32_t off = umma::tile_off(kVtcF, r, k) / 4;
-      *reinterpret_cast<float4*>(x_hi + off) = make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(x_lo + off) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    umma::fence_proxy_async();
-    umma::tc_fence_before_sync();
-    __syncthreads();
-    if (warp == 0) {  // converged warp, warp-uniform operands, MMAs under elect.sync (see the forward kernel)
-      umma::tc_fence_after_sync();
-      const uint32_t a_lbo = kVtcF * 16, b_lbo = kVtcNP * 16;
-      const uint32_t tm_u = __shfl_sync(0xffffffffu, tmem, 0);
-      const uint32_t sm_u = __shfl_sync(0xffffffffu, umma::smem_u32(smem), 0);
-      if (umma::elect_one()) {
-        umma::mma_3xtf32<kVtcNP / 8>(tm_u, umma::smem_desc(sm_u + VtcBwdSmem::g_hi, a_lbo, 128), umma::smem_desc(sm_u + VtcBwdSmem::g_lo, a_lbo, 128),
-                                     umma::smem_desc(sm_u + VtcBwdSmem::bb_hi, b_lbo, 128), umma::smem_desc(sm_u + VtcBwdSmem::bb_lo, b_lbo, 128),
-                                     2 * a_lbo, 2 * b_lbo, idesc, false);
-        umma::mma_3xtf32<kVtcNP / 8>(tm_u + 64, umma::smem_desc(sm_u + VtcBwdSmem::x_hi, a_lbo, 128), umma::smem_desc(sm_u + VtcBwdSmem::x_lo, a_lbo, 128),
-                                     umma::smem_desc(sm_u + VtcBwdSmem::bt_hi, b_lbo, 128), umma::smem_desc(sm_u + VtcBwdSmem::bt_lo, b_lbo, 128),
-                                     2 * a_lbo, 2 * b_lbo, idesc, false);
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(sm_u + (uint32_t)VtcBwdSmem::misc) : "memory");
-      }
+      if (lane == 0) tile_mixed[t_begin + i] = r.ok ? 0 : 1;
       __syncwarp();
     }
-    if (t + 1 < t_end) prefetch(t + 1);
-    umma::mbar_wait(bar, phase);
-    phase ^= 1;
-    umma::tc_fence_after_sync();
-    {
-      // all eight warps: warp w owns TMEM lane quarter w & 3 (its rows) and column half w >> 2; the two halves of a row's
-      // d alpha dot product meet in shared memory
-      const int row = 32 * (warp & 3) + lane;
-      const int c0 = 32 * (warp >> 2);
-      const uint32_t taddr = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + c0;
-      float v[16];
-      float ga = 0.f;
+  } else if (warp == 2) {
+    // ---- builder ----------------------------------------------------------------------------------------------------------------
+    float cached = 0.f;
+    int k = 0;
+    auto build = [&](float a) {
+      if (k >= 2) umma::mbar_wait(&bar_bfree[k & 1], (uint32_t)((k >> 1) - 1) & 1u);
+      float* bh = reinterpret_cast<float*>(smem + VtbSmem::bmat + (k & 1) * 4 * kVtcBBytes);
+      vtc_build_matrices_bwd(bh, bh + kVtcBBytes / 4, bh + 2 * (kVtcBBytes / 4), bh + 3 * (kVtcBBytes / 4), a, n);
+      umma::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&bar_bfull[k & 1]);
+      ++k;
+      cached = a;
+    };
+    build(alpha_of(t_begin * kVtcF));
+    load_runs(0);
+    load_runs(1);
+    for (int i = 0; i < cnt; ++i) {
+      const VtfRuns r = runs_of(i);
+      if (!r.ok) continue;
+      if (r.a0 != cached) build(r.a0);
+      if (r.n0 < tile_units(i)) build(r.a1);
+    }
+  } else if (warp == 0) {
+    // ---- issuer ---------------------------------------------------------------------------------------------------------------------
+    const uint32_t tm_u = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t sm_u = __shfl_sync(0xffffffffu, umma::smem_u32(smem), 0);
+    const uint32_t idesc = umma::idesc_tf32(kVtcF, kVtcNP);
+    float cached = 0.f;
+    int k = 0;
+    auto commit_to = [&](uint64_t* bar) {
+      if (umma::elect_one())
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                         sm_u + (uint32_t)VtbSmem::bars + 8u * (uint32_t)(bar - bars))
+                     : "memory");
+      __syncwarp();
+    };
+    auto next_matrix = [&](float a) {
+      umma::mbar_wait(&bar_bfull[k & 1], (uint32_t)(k >> 1) & 1u);
+      if (k >= 1) commit_to(&bar_bfree[(k - 1) & 1]);
+      ++k;
+      cached = a;
+    };
+    auto mma = [&](uint32_t a_col, uint32_t mat, uint32_t d_col) {  // mat: 0 = Bb, 1 = Bt of the current set
+      if (umma::elect_one()) {
+        const uint32_t b_lbo = kVtcNP * 16;
+        const uint32_t bh = sm_u + VtbSmem::bmat + ((k - 1) & 1) * 4 * kVtcBBytes + mat * 2 * kVtcBBytes;
+        umma::mma_3xtf32_ts<kVtcNP / 8>(tm_u + d_col, tm_u + a_col, tm_u + a_col + 64, umma::smem_desc(bh, b_lbo, 128),
+                                        umma::smem_desc(bh + kVtcBBytes, b_lbo, 128), 2 * b_lbo, idesc, false);
+      }
+      __syncwarp();
+    };
+    next_matrix(alpha_of(t_begin * kVtcF));
+    for (int i = 0;; ++i) {
+      const int b = i & 1;
+      wait_idx(bar_ag, i);
+      const int4 ti = tinfo[i & 7];
+      const float a0 = __int_as_float(tinfo[8 + (i & 7)].x);
+      if (ti.x && a0 != cached) next_matrix(a0);
+      umma::tc_fence_after_sync();
+      if (ti.x) mma(kVtbTmAG, 0, kVtbTmD1 + 64 * b);
+      commit_to(&bar_d1[b]);
+      wait_idx(bar_ax, i);
+      umma::tc_fence_after_sync();
+      if (ti.x) mma(kVtbTmAX, 1, kVtbTmD2 + 64 * b);
+      commit_to(&bar_d2[b]);
+      if (ti.y) break;
+    }
+  } else if (warp == 3) {
+    // ---- reduce warp: d alpha of every unit = sum of the four quarter-row partial dot products --------------------------------------
+    for (int j = 0;; ++j) {
+      const int b = j & 1;
+      wait_idx(&bar_ofull[b], j >> 1);
+      const int4 tj = tinfo[j & 7];
+      if (tj.x) {
+        const float* gp = gpart + b * 4 * kVtcF;
+        const int64_t u0 = t_begin * kVtcF + tj.w;
 #pragma unroll
-      for (int cb = 0; cb < 2; ++cb) {
-        umma::tmem_ld16(taddr + 16 * cb, v);  // D1: gradient w.r.t. the de-normalised input
-#pragma unroll
-        for (int i = 0; i < 16; ++i) stage[row * kVtcStageStride + c0 + 16 * cb + i] = v[i] * vstd[c0 + 16 * cb + i];
-        umma::tmem_ld16(taddr + 64 + 16 * cb, v);  // D2: d y / d alpha
-#pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          const uint32_t off = umma::tile_off(kVtcF, row, c0 + 16 * cb + i) / 4;
-          const float4 gh = *reinterpret_cast<const float4*>(g_hi + off), gl = *reinterpret_cast<const float4*>(g_lo + off);
-          ga = fmaf(gh.x + gl.x, v[i], ga);
-          ga = fmaf(gh.y + gl.y, v[i + 1], ga);
-          ga = fmaf(gh.z + gl.z, v[i + 2], ga);
-          ga = fmaf(gh.w + gl.w, v[i + 3], ga);
+        for (int h = 0; h < 4; ++h) {
+          const int row = lane + 32 * h;
+          if (row < tj.z) galpha_unit[u0 + row] = (gp[row] + gp[kVtcF + row]) + (gp[2 * kVtcF + row] + gp[3 * kVtcF + row]);
         }
       }
-      if (warp >= 4) ga_half[row] = ga;
-      umma::tc_fence_before_sync();
-      __syncthreads();
-      if (warp < 4 && row < nun) galpha_unit[u0 + row] = ga + ga_half[row];
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&bar_ofree[b]);
+      if (tj.y) break;
     }
-    {
-      float4* dst = reinterpret_cast<float4*>(gx + u0 * n);
+  } else {
+    // ---- converter / epilogue -----------------------------------------------------------------------------------------------------
+    const int gw = warp - 4;
+    const int q = warp & 3;                    // TMEM lane quarter of this warp
+    const int qc = gw >> 2;                    // columns 16 qc .. 16 qc + 15 of the row
+    const int row = 32 * q + lane;
+    const uint32_t t_row = tmem + ((uint32_t)(32 * q) << 16);
+    float gprev[16];                           // this thread's part of gy / std of the previous tile (for the dot product)
 #pragma unroll
-      for (int i = 0; i < kPre; ++i) {
-        const int item = warp + 8 * i;
-        const int r = 8 * (item >> 2) + my_r, kq = 4 * (item & 3) + my_kq;
-        if (r < nun && kq < nq) {
-          const float* sp = stage + r * kVtcStageStride + 4 * kq;
-          dst[r * nq + kq] = make_float4(sp[0], sp[1], sp[2], sp[3]);
+    for (int e = 0; e < 16; ++e) gprev[e] = 0.f;
+    int total = 0x7fffffff;  // number of segments, known when the one flagged `last` arrives
+    for (int i = 0; i <= total; ++i) {
+      float gcur[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) gcur[e] = 0.f;
+      if (i < total) {
+        const int kg = 2 * i, kx = 2 * i + 1;
+        // ---- G(i) -> A_G ----
+        wait_item(bar_full, kg);
+        const int4 ti = tinfo[i & 7];
+        if (ti.y) total = i + 1;
+        if (i >= 1) wait_idx(&bar_d1[(i - 1) & 1], (i - 1) >> 1);  // the first GEMM of the previous tile has read A_G
+        float hi[16], lo[16];
+        if (ti.x) {
+          const float4* src = reinterpret_cast<const float4*>(stages + (size_t)(kg % nst) * stage_bytes + (size_t)row * row_bytes) + 4 * qc;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (4 * qc + c < nq && row < ti.z) {
+              w = src[c];
+              if (has_norm) {
+                const float4 rs = reinterpret_cast<const float4*>(vrstd)[4 * qc + c];
+                w.x *= rs.x; w.y *= rs.y; w.z *= rs.z; w.w *= rs.w;
+              }
+            }
+            gcur[4 * c] = w.x; gcur[4 * c + 1] = w.y; gcur[4 * c + 2] = w.z; gcur[4 * c + 3] = w.w;
+            umma::split_tf32(w.x, hi[4 * c], lo[4 * c]);
+            umma::split_tf32(w.y, hi[4 * c + 1], lo[4 * c + 1]);
+            umma::split_tf32(w.z, hi[4 * c + 2], lo[4 * c + 2]);
+            umma::split_tf32(w.w, hi[4 * c + 3], lo[4 * c + 3]);
+          }
         }
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(&bar_empty[kg % nst]);
+        if (ti.x) {
+          umma::tmem_st16(t_row + kVtbTmAG + 16 * qc, hi);
+          umma::tmem_st16(t_row + kVtbTmAG + 64 + 16 * qc, lo);
+          umma::tmem_st_wait();
+        }
+        umma::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(bar_ag);
+        // ---- X(i) -> A_X ----
+        wait_item(bar_full, kx);
+        if (i >= 1) wait_idx(&bar_d2[(i - 1) & 1], (i - 1) >> 1);  // the second GEMM of the previous tile has read A_X
+        if (ti.x) {
+          const float4* src = reinterpret_cast<const float4*>(stages + (size_t)(kx % nst) * stage_bytes + (size_t)row * row_bytes) + 4 * qc;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (4 * qc + c < nq && row < ti.z) {
+              w = src[c];
+              if (has_norm) {
+                const float4 sd = reinterpret_cast<const float4*>(vstd)[4 * qc + c], mu = reinterpret_cast<const float4*>(vmean)[4 * qc + c];
+                w.x = fmaf(w.x, sd.x, mu.x);
+                w.y = fmaf(w.y, sd.y, mu.y);
+                w.z = fmaf(w.z, sd.z, mu.z);
+                w.w = fmaf(w.w, sd.w, mu.w);
+              }
+            }
+            umma::split_tf32(w.x, hi[4 * c], lo[4 * c]);
+            umma::split_tf32(w.y, hi[4 * c + 1], lo[4 * c + 1]);
+            umma::split_tf32(w.z, hi[4 * c + 2], lo[4 * c + 2]);
+            umma::split_tf32(w.w, hi[4 * c + 3], lo[4 * c + 3]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(&bar_empty[kx % nst]);
+        if (ti.x) {
+          umma::tmem_st16(t_row + kVtbTmAX + 16 * qc, hi);
+          umma::tmem_st16(t_row + kVtbTmAX + 64 + 16 * qc, lo);
+          umma::tmem_st_wait();
+        }
+        umma::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(bar_ax);
       }
+      if (i >= 1) {
+        // ---- epilogue of tile i - 1 ----
+        const int j = i - 1, b = j & 1;
+        const int4 tj = tinfo[j & 7];
+        if (i == total) {  // (before that both GEMMs of segment i - 1 have been waited for above)
+          wait_idx(&bar_d1[b], j >> 1);
+          wait_idx(&bar_d2[b], j >> 1);
+        }
+        umma::tc_fence_after_sync();
+        if (j >= 2) wait_idx(&bar_ofree[b], (j >> 1) - 1);
+        if (tj.x) {
+          float d[16];
+          umma::tmem_ld16(t_row + kVtbTmD1 + 64 * b + 16 * qc, d);  // gradient w.r.t. the de-normalised input
+          float* orow = gx + (t_begin * kVtcF + tj.w + row) * n;
+#pragma unroll
+          for (int e = 0; e < 16; e += 4) {
+            const int c = 16 * qc + e;
+            if (c < n && row < tj.z) {
+              float4 o = make_float4(d[e], d[e + 1], d[e + 2], d[e + 3]);
+              if (has_norm) {
+                const float4 sd = *reinterpret_cast<const float4*>(vstd + c);
+                o.x *= sd.x; o.y *= sd.y; o.z *= sd.z; o.w *= sd.w;
+              }
+              *reinterpret_cast<float4*>(orow + c) = o;
+            }
+          }
+          umma::tmem_ld16(t_row + kVtbTmD2 + 64 * b + 16 * qc, d);  // d y / d alpha
+          float ga = 0.f;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) ga = fmaf(gprev[e], d[e], ga);
+          gpart[(b * 4 + qc) * kVtcF + row] = ga;
+        }
+        umma::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(&bar_ofull[b]);
+      }
+#pragma unroll
+      for (int e = 0; e < 16; ++e) gprev[e] = gcur[e];
     }
-    __syncthreads();
   }
   umma::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(tmem, 128);
+  if (warp == 0) umma::tmem_dealloc(tmem, 512);
 }
 
 }  // namespace b2w
@@ -765,9 +949,12 @@ extern "C" int b2w_allpass_backward_tc(const float* grad_y, const float* x, cons
   const int64_t num_tiles = (units + kVtcF - 1) / kVtcF;
   const int grid = (int)(num_tiles < 148 ? num_tiles : 148);
   cudaStream_t st = (cudaStream_t)stream;
-  cudaFuncSetAttribute(allpass_tc_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VtcBwdSmem::total);
-  allpass_tc_backward_kernel<<<grid, kVtcThreads, VtcBwdSmem::total, st>>>(grad_y, x, alpha, units, n, blocks, mean, std_dev, grad_x,
-                                                                           unit_workspace, tile_flags, num_tiles);
+  const uint32_t stage_bytes = ((uint32_t)kVtcF * (uint32_t)n * 4u + 127u) & ~127u;
+  const int nst = (VtbSmem::stages + 3 * stage_bytes <= 227 * 1024) ? 3 : 2;   // three operand stages when they fit (n <= 60)
+  const uint32_t smem = VtbSmem::stages + (uint32_t)nst * stage_bytes;
+  cudaFuncSetAttribute(allpass_tc_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  allpass_tc_backward_kernel<<<grid, kVtbThreads, smem, st>>>(grad_y, x, alpha, units, n, blocks, mean, std_dev, grad_x, unit_workspace,
+                                                              tile_flags, num_tiles, nst, stage_bytes);
   int rc = check_launch("allpass_tc_backward_kernel");
   if (rc) return rc;
   return b2w_allpass_backward_masked(grad_y, x, alpha, rows, n, blocks, mean, std_dev, grad_x, grad_alpha, unit_workspace, tile_flags, stream);

@@ -1,9 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_vtln.py -m gpu -q -x > gpurun_out/r02n_pytest.txt 2>&1; tail -3 gpurun_out/r02n_pytest.txt
-timeout 300 python scripts/gpu_vtln_bench.py > gpurun_out/r02n_vtln.txt 2>&1; cat gpurun_out/r02n_vtln.txt
-B2W_LIB=variants/libb200world_vtfprof.so timeout 300 python scripts/gpu_vtln_bench.py > gpurun_out/r02n_vtln_prof.txt 2>&1; cat gpurun_out/r02n_vtln_prof.txt
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02n_vtln_launches.csv python scripts/gpu_vtln_bench.py > /dev/null 2>&1
+timeout 900 python -m pytest tests/test_gpu_vtln.py -m gpu -q -x > gpurun_out/r02n_pytest.txt 2>&1; tail -4 gpurun_out/r02n_pytest.txt
+timeout 300 python scripts/gpu_vtln_bench.py bwd > gpurun_out/r02n_vtln.txt 2>&1; cat gpurun_out/r02n_vtln.txt
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02n_vtln_launches.csv python scripts/gpu_vtln_bench.py bwd > /dev/null 2>&1
 python - <<'PY'
 import csv, collections
 rows=[r for r in csv.reader(open('gpurun_out/r02n_vtln_launches.csv')) if len(r)>10]
