@@ -267,12 +267,13 @@ extern "C" int b2w_allpass_backward_masked(const float* grad_y, const float* x, 
   do {                                                                                                      \
     cudaFuncSetAttribute(allpass_backward_kernel<NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     allpass_backward_kernel<NMAX><<<(unsigned)grid, kVtThreads, smem, st>>>(grad_y, x, alpha, rows, n, blocks, mean, std_dev, \
-                                                                            grad_x, unit_workspace, tile_mask); \
+                                                                            grad_x, blocks == 1 ? grad_alpha : unit_workspace, tile_mask); \
   } while (0)
   if (n <= 32) B2W_VT_BWD(32); else if (n <= 64) B2W_VT_BWD(64); else B2W_VT_BWD(128);
 #undef B2W_VT_BWD
   int rc = check_launch("allpass_backward_kernel");
   if (rc) return rc;
+  if (blocks == 1) return 0;  // a unit is a row: the per-unit values went straight to grad_alpha
   reduce_blocks_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(unit_workspace, rows, blocks, grad_alpha);
   return check_launch("reduce_blocks_kernel");
 }

@@ -626,6 +626,7 @@ allpass_tc_backward_kernel(const float* __restrict__ gy, const float* __restrict
   const int nq = n / 4;
   const uint32_t row_bytes = (uint32_t)n * 4u;
   auto wait_idx = [&](uint64_t* bar, int index) { umma::mbar_wait(bar, (uint32_t)index & 1u); };
+  VPROF_DECL;
   auto wait_item = [&](uint64_t* arr, int k) { umma::mbar_wait(&arr[k % nst], (uint32_t)(k / nst) & 1u); };  // stage barriers, by item
   auto alpha_of = [&](int64_t u) { return blocks == 1 ? alpha[u] : alpha[u / blocks]; };
   auto tile_units = [&](int i) { return (int)min((int64_t)kVtcF, units - (t_begin + i) * kVtcF); };
@@ -740,25 +741,40 @@ allpass_tc_backward_kernel(const float* __restrict__ gy, const float* __restrict
     for (int i = 0;; ++i) {
       const int b = i & 1;
       wait_idx(bar_ag, i);
+      VPROF_LAP(0);  // issuer: wait A_G
       const int4 ti = tinfo[i & 7];
       const float a0 = __int_as_float(tinfo[8 + (i & 7)].x);
       if (ti.x && a0 != cached) next_matrix(a0);
+      VPROF_LAP(1);  // issuer: wait matrix
       umma::tc_fence_after_sync();
       if (ti.x) mma(kVtbTmAG, 0, kVtbTmD1 + 64 * b);
       commit_to(&bar_d1[b]);
+      VPROF_LAP(2);  // issuer: GEMM 1 issue
       wait_idx(bar_ax, i);
+      VPROF_LAP(3);  // issuer: wait A_X
       umma::tc_fence_after_sync();
       if (ti.x) mma(kVtbTmAX, 1, kVtbTmD2 + 64 * b);
       commit_to(&bar_d2[b]);
+      VPROF_LAP(4);  // issuer: GEMM 2 issue
       if (ti.y) break;
     }
+    VPROF_FLUSH(0, 5);
   } else if (warp == 3) {
-    // ---- reduce warp: d alpha of every unit = sum of the four quarter-row partial dot products --------------------------------------
+    // ---- store / reduce warp: gx of a segment leaves with one bulk store from the stage its rows were staged in (the stage that held
+    // the x rows of the NEXT segment), which is then handed back to the producer; d alpha of every unit = sum of the four quarter-row
+    // partial dot products
     for (int j = 0;; ++j) {
       const int b = j & 1;
       wait_idx(&bar_ofull[b], j >> 1);
       const int4 tj = tinfo[j & 7];
+      const int s = (2 * (j + 1) + 1) % nst;  // staging = stage of item X(j + 1) (for the last segment: a stage nobody uses any more)
       if (tj.x) {
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gx + (t_begin * kVtcF + tj.w) * n),
+                       "r"(umma::smem_u32(stages + (size_t)s * stage_bytes)), "r"((uint32_t)tj.z * row_bytes)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
         const float* gp = gpart + b * 4 * kVtcF;
         const int64_t u0 = t_begin * kVtcF + tj.w;
 #pragma unroll
@@ -766,11 +782,16 @@ allpass_tc_backward_kernel(const float* __restrict__ gy, const float* __restrict
           const int row = lane + 32 * h;
           if (row < tj.z) galpha_unit[u0 + row] = (gp[row] + gp[kVtcF + row]) + (gp[2 * kVtcF + row] + gp[3 * kVtcF + row]);
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       }
       __syncwarp();
-      if (lane == 0) umma::mbar_arrive(&bar_ofree[b]);
+      if (lane == 0) {
+        umma::mbar_arrive(&bar_ofree[b]);
+        if (!tj.y) umma::mbar_arrive_n(&bar_empty[s], kVtfGW);  // on behalf of the sixteen converter warps that read the x rows
+      }
       if (tj.y) break;
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else {
     // ---- converter / epilogue -----------------------------------------------------------------------------------------------------
     const int gw = warp - 4;
@@ -790,9 +811,11 @@ allpass_tc_backward_kernel(const float* __restrict__ gy, const float* __restrict
         const int kg = 2 * i, kx = 2 * i + 1;
         // ---- G(i) -> A_G ----
         wait_item(bar_full, kg);
+        VPROF_LAP(8);  // group: wait gy rows
         const int4 ti = tinfo[i & 7];
         if (ti.y) total = i + 1;
         if (i >= 1) wait_idx(&bar_d1[(i - 1) & 1], (i - 1) >> 1);  // the first GEMM of the previous tile has read A_G
+        VPROF_LAP(9);  // group: wait A_G free
         float hi[16], lo[16];
         if (ti.x) {
           const float4* src = reinterpret_cast<const float4*>(stages + (size_t)(kg % nst) * stage_bytes + (size_t)row * row_bytes) + 4 * qc;
@@ -823,9 +846,11 @@ allpass_tc_backward_kernel(const float* __restrict__ gy, const float* __restrict
         umma::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) umma::mbar_arrive(bar_ag);
+        VPROF_LAP(10);  // group: convert G
         // ---- X(i) -> A_X ----
         wait_item(bar_full, kx);
         if (i >= 1) wait_idx(&bar_d2[(i - 1) & 1], (i - 1) >> 1);  // the second GEMM of the previous tile has read A_X
+        VPROF_LAP(11);  // group: wait x rows + A_X free
         if (ti.x) {
           const float4* src = reinterpret_cast<const float4*>(stages + (size_t)(kx % nst) * stage_bytes + (size_t)row * row_bytes) + 4 * qc;
 #pragma unroll
@@ -847,8 +872,12 @@ allpass_tc_backward_kernel(const float* __restrict__ gy, const float* __restrict
             umma::split_tf32(w.w, hi[4 * c + 3], lo[4 * c + 3]);
           }
         }
-        __syncwarp();
-        if (lane == 0) umma::mbar_arrive(&bar_empty[kx % nst]);
+        // (the stage of the x rows is NOT released here: it becomes the staging buffer of the previous segment's gx rows and is
+        // handed back to the producer by the store warp once the bulk store has read it; segment 0 has no predecessor)
+        if (i == 0) {
+          __syncwarp();
+          if (lane == 0) umma::mbar_arrive(&bar_empty[kx % nst]);
+        }
         if (ti.x) {
           umma::tmem_st16(t_row + kVtbTmAX + 16 * qc, hi);
           umma::tmem_st16(t_row + kVtbTmAX + 64 + 16 * qc, lo);
@@ -857,6 +886,7 @@ allpass_tc_backward_kernel(const float* __restrict__ gy, const float* __restrict
         umma::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) umma::mbar_arrive(bar_ax);
+        VPROF_LAP(12);  // group: convert X
       }
       if (i >= 1) {
         // ---- epilogue of tile i - 1 ----
@@ -871,7 +901,7 @@ allpass_tc_backward_kernel(const float* __restrict__ gy, const float* __restrict
         if (tj.x) {
           float d[16];
           umma::tmem_ld16(t_row + kVtbTmD1 + 64 * b + 16 * qc, d);  // gradient w.r.t. the de-normalised input
-          float* orow = gx + (t_begin * kVtcF + tj.w + row) * n;
+          float* orow = reinterpret_cast<float*>(stages + (size_t)((2 * i + 1) % nst) * stage_bytes) + (size_t)row * n;
 #pragma unroll
           for (int e = 0; e < 16; e += 4) {
             const int c = 16 * qc + e;
@@ -889,14 +919,17 @@ allpass_tc_backward_kernel(const float* __restrict__ gy, const float* __restrict
 #pragma unroll
           for (int e = 0; e < 16; ++e) ga = fmaf(gprev[e], d[e], ga);
           gpart[(b * 4 + qc) * kVtcF + row] = ga;
+          umma::fence_proxy_async();  // the staged gx rows are read by a bulk store
         }
         umma::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) umma::mbar_arrive(&bar_ofull[b]);
+        VPROF_LAP(13);  // group: epilogue
       }
 #pragma unroll
       for (int e = 0; e < 16; ++e) gprev[e] = gcur[e];
     }
+    VPROF_FLUSH(8, 14);
   }
   umma::tc_fence_before_sync();
   __syncthreads();
@@ -953,7 +986,8 @@ extern "C" int b2w_allpass_backward_tc(const float* grad_y, const float* x, cons
   const int nst = (VtbSmem::stages + 3 * stage_bytes <= 227 * 1024) ? 3 : 2;   // three operand stages when they fit (n <= 60)
   const uint32_t smem = VtbSmem::stages + (uint32_t)nst * stage_bytes;
   cudaFuncSetAttribute(allpass_tc_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  allpass_tc_backward_kernel<<<grid, kVtbThreads, smem, st>>>(grad_y, x, alpha, units, n, blocks, mean, std_dev, grad_x, unit_workspace,
+  allpass_tc_backward_kernel<<<grid, kVtbThreads, smem, st>>>(grad_y, x, alpha, units, n, blocks, mean, std_dev, grad_x,
+                                                              blocks == 1 ? grad_alpha : unit_workspace,
                                                               tile_flags, num_tiles, nst, stage_bytes);
   int rc = check_launch("allpass_tc_backward_kernel");
   if (rc) return rc;

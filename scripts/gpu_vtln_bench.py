@@ -33,11 +33,19 @@ if "bwd" in sys.argv:
 if os.environ.get("B2W_LIB", "").find("vtfprof") >= 0:
     import ctypes
     from idiaptts_b200 import _lib
-    _lib.load().b2w_vtf_prof_reset() if hasattr(_lib.load(), 'b2w_vtf_prof_reset') else None
-    ops.allpass_forward(x, alpha, n, impl="tc"); torch.cuda.synchronize()
+    bwd = os.environ.get("B2W_PROF_BWD") == "1"
+    if bwd:
+        ops.allpass_backward(gy, x, alpha, n, impl="tc")
+        names = ["issuer: wait A_G", "issuer: wait matrix", "issuer: GEMM 1 issue", "issuer: wait A_X", "issuer: GEMM 2 issue", "-", "-", "-",
+                 "group: wait gy rows", "group: wait A_G free", "group: convert G", "group: wait x rows + A_X free", "group: convert X",
+                 "group: epilogue", "-", "-"]
+    else:
+        ops.allpass_forward(x, alpha, n, impl="tc")
+        names = ["issuer: alpha runs", "issuer: wait matrix", "issuer: wait A", "issuer: MMA issue", "builder: build cycles (sum)", "builder: builds",
+                 "builder: start of first build", "builder: fence + arrive (sum)", "group: wait raw tile", "group: read+convert+st",
+                 "group: wait MMA", "group: wait out stage", "group: epilogue", "-", "-", "-"]
+    torch.cuda.synchronize()
     buf = (ctypes.c_longlong * 16)()
     _lib.load().b2w_vtf_prof_read(ctypes.cast(buf, ctypes.c_void_p))
-    names = ["issuer: alpha runs", "issuer: wait matrix", "issuer: wait A", "issuer: MMA issue", "builder: build cycles (sum)", "builder: builds", "builder: start of first build", "builder: fence + arrive (sum)", "group: wait raw tile", "group: read+convert+st",
-             "group: wait MMA", "group: wait out stage", "group: epilogue", "-", "-", "-"]
     for n_, v in zip(names, buf):
-        print("  %-28s %10d cycles" % (n_, v))
+        print("  %-30s %10d cycles" % (n_, v))
