@@ -264,7 +264,7 @@ def run_b200(args):
             m = torch.cuda.Event(enable_timing=True)
             m.record()
             marks.append(m)
-        _, st2 = syn.synthesize_corpus(feats, frame_off, batch_utts=SYNTH_BATCH, out=y_all, events=events)
+        _, st2 = syn.synthesize_corpus(feats, frame_off, batch_utts=args.synth_batch, out=y_all, events=events)
         return status, st2
 
     def barrier():
@@ -380,7 +380,7 @@ def run_b200(args):
             dist.all_reduce(stat_buf)
         stats_pinned.copy_(stat_buf, non_blocking=True)
         torch.cuda.current_stream().synchronize()   # the features must have landed in host memory before they are read back
-        syn.synthesize_corpus(None, frame_off, batch_utts=SYNTH_BATCH, feats_host=feats_host, out_host=y_host)
+        syn.synthesize_corpus(None, frame_off, batch_utts=args.synth_batch, feats_host=feats_host, out_host=y_host)
 
     e2e_step()
     barrier()
@@ -416,7 +416,7 @@ def run_b200(args):
                 cpu = {"value": None, "unit": "audio-s/s", "cores": 0, "kind": "port", "sample": "failed: " + r.stderr[-300:]}
         n = float(stats_host[2 * an.dim])
         mean, std = pipeline.mean_std_from_sums(stats_host, n, an.dim)
-        launches = an.kernel_launches(F) + syn.kernel_launches(utts, SYNTH_BATCH)
+        launches = an.kernel_launches(F) + syn.kernel_launches(utts, args.synth_batch)
         line = {"metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling if world > 1 else "weak", "vs_baseline": None,
                 "dtype": "f32 FFTs + f64 scans (analysis), 3xTF32 (mel-cepstrum), f64 (synthesis)", "data": "synthetic",
@@ -424,14 +424,14 @@ def run_b200(args):
                            "utts_this_rank": utts, "fs": FS, "utt_seconds": "N(%.1f, %.1f^2) clipped [1.1, 10.1]" % (DUR, DUR_STD)
                            if not args.fixed_dur else DUR, "audio_seconds_total": total_audio, "frames_this_rank": int(F),
                            "num_coded_sps": NUM_CODED_SPS, "mgc_alpha": alpha, "fft_size": an.n_fft, "num_bap": an.nap,
-                           "chunk_frames": an.chunk_frames, "synth_batch_utts": SYNTH_BATCH, "shard_imbalance": round(imbalance, 4),
+                           "chunk_frames": an.chunk_frames, "synth_batch_utts": args.synth_batch, "shard_imbalance": round(imbalance, 4),
                            "l2": "inputs (%.2f GB int16), features (%.2f GB) and waveforms (%.2f GB) exceed the 126 MB L2" % (
                                host["x"].numel() * 2 / 1e9, feats.numel() * 4 / 1e9, y_all.numel() * 4 / 1e9),
                            "corpus_gen_s": round(gen_s, 1), "mean_c0": float(mean[0]), "std_c0": float(std[0])},
                 "components": {"analysis": {"audio_s_per_s": audio_s / (ms_analysis / 1e3), "ms_per_step": ms_analysis,
                                             "what": "wav + cached F0 -> mcep60/lf0/vuv/bap + statistics all-reduce (rank 0)"},
                                "synthesis": {"audio_s_per_s": audio_s / (ms_synth / 1e3), "ms_per_step": ms_synth,
-                                             "what": "features -> waveforms, batches of %d utterances (rank 0)" % SYNTH_BATCH}},
+                                             "what": "features -> waveforms, batches of %d utterances (rank 0)" % args.synth_batch}},
                 "clocks": clocks, "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(h2d),
                                           "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(args.steps * launches), "roofline": roofline, "kernels": kernels, "parity": parity,
@@ -638,6 +638,7 @@ def main():
     ap.add_argument("--fixed-dur", action="store_true", help="the fixed 6.5 s variant of the corpus")
     ap.add_argument("--chunk-frames", type=int, default=1 << 18)
     ap.add_argument("--parity-utts", type=int, default=16)
+    ap.add_argument("--synth-batch", type=int, default=SYNTH_BATCH, help="utterances per batched synthesis call of the corpus pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-workloads", action="store_true", help="skip the synth256 / vtln109 workloads")
     args = ap.parse_args()

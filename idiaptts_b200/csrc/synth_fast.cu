@@ -38,7 +38,8 @@ struct Smem {
 };
 
 // WORLD GetMinimumPhaseSpectrum: log-amplitude L[0 .. 512] (floats, may alias X) -> complex spectrum X[0 .. 512].
-__device__ __forceinline__ void minimum_phase(const float* L, float2* z, float2* X, const float2* tw16, const float2* tw512,
+// (Out of line, like the transform tail: called twice per pulse.)
+__device__ __noinline__ void minimum_phase(const float* L, float2* z, float2* X, const float2* tw16, const float2* tw512,
                                               const float2* twn, int lane) {
   float* c = reinterpret_cast<float*>(X);
   float2 v[16];
@@ -71,8 +72,8 @@ __device__ __forceinline__ void minimum_phase(const float* L, float2* z, float2*
 
 // Unnormalised inverse real FFT of the Hermitian half spectrum X[0 .. 512]: on return out[j] = (x[2 n], x[2 n + 1]) for
 // n = lane + 32 j, j < 16.  (A c2r transform ignores the imaginary parts of the DC and Nyquist bins: WORLD / FFTW semantics.)
-__device__ __forceinline__ void inverse_real(const float2* X, float2* z, const float2* tw16, const float2* tw512, const float2* twn,
-                                             int lane, float2 (&out)[16]) {
+__device__ __noinline__ void inverse_real_core(const float2* X, float2* z, const float2* tw16, const float2* tw512, const float2* twn,
+                                               int lane) {
   float2 v[16];
 #pragma unroll
   for (int q = 0; q < 16; ++q) {
@@ -92,6 +93,12 @@ __device__ __forceinline__ void inverse_real(const float2* X, float2* z, const f
     v[q] = float2{e.x - o.y, -(e.y + o.x)};
   }
   wfft512(z, v, tw16, tw512, lane);
+}
+// (the transform itself is out of line -- two calls per pulse --, only the sixteen result loads are inline: an array reference
+// through a real call would live in local memory)
+__device__ __forceinline__ void inverse_real(const float2* X, float2* z, const float2* tw16, const float2* tw512, const float2* twn,
+                                             int lane, float2 (&out)[16]) {
+  inverse_real_core(X, z, tw16, tw512, twn, lane);
   const float2* zi = z + lane + (lane >> 4);
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
@@ -180,45 +187,12 @@ render_fast_kernel(const void* __restrict__ sp, const void* __restrict__ ap, con
     double env0, ar0;
     env_ar(0, env0, ar0);
     const bool has_periodic = cur_vuv && !(ar0 > 0.999);
-    // The plane rows of the two frames around the pulse come from L2 / HBM: the loads of kBatch bins per lane are issued together
-    // (4 kBatch independent loads in flight per lane) before any of them is consumed -- one bin at a time the warp sat through 17
-    // dependent round trips per pulse (long-scoreboard stalls 31 % of the kernel).
-    constexpr int kBatch = sizeof(PT) == 4 ? 6 : 3;
-    const PT* sp0 = reinterpret_cast<const PT*>(sp) + r0;
-    const PT* ap0 = reinterpret_cast<const PT*>(ap) + r0;
-    const PT* sp1 = reinterpret_cast<const PT*>(sp) + r1;
-    const PT* ap1 = reinterpret_cast<const PT*>(ap) + r1;
-    const bool two_rows = fl != ce;
-#pragma unroll 1
-    for (int kb = lane; kb < kK; kb += 32 * kBatch) {
-      PT vs0[kBatch], va0[kBatch], vs1[kBatch], va1[kBatch];
-#pragma unroll
-      for (int b = 0; b < kBatch; ++b) {
-        const int k = min(kb + 32 * b, kK - 1);
-        vs0[b] = sp0[k];
-        va0[b] = ap0[k];
-        vs1[b] = two_rows ? sp1[k] : vs0[b];
-        va1[b] = two_rows ? ap1[k] : va0[b];
-      }
-#pragma unroll
-      for (int b = 0; b < kBatch; ++b) {
-        const int k = kb + 32 * b;
-        if (k < kK) {
-          const double s0 = fabs((double)vs0[b]);
-          double a0 = fmax(0.001, fmin(0.999999999999, (double)va0[b]));
-          a0 *= a0;
-          double env = s0, ar = a0;
-          if (two_rows) {
-            const double s1 = fabs((double)vs1[b]);
-            double a1 = fmax(0.001, fmin(0.999999999999, (double)va1[b]));
-            a1 *= a1;
-            env = (1.0 - w) * s0 + w * s1;
-            ar = (1.0 - w) * a0 + w * a1;
-          }
-          if (has_periodic) Lx[k] = 0.5f * __logf((float)(env * (1.0 - ar) + kMySafeGuardMinimum));
-          La[k] = 0.5f * __logf((float)(cur_vuv ? env * ar : env));
-        }
-      }
+#pragma unroll 1   // (unrolling by four to batch the plane loads was measured SLOWER: 6.0 against 5.6 ms per 345 k pulses)
+    for (int k = lane; k < kK; k += 32) {
+      double env, ar;
+      env_ar(k, env, ar);
+      if (has_periodic) Lx[k] = 0.5f * __logf((float)(env * (1.0 - ar) + kMySafeGuardMinimum));
+      La[k] = 0.5f * __logf((float)(cur_vuv ? env * ar : env));
     }
     __syncwarp();
 

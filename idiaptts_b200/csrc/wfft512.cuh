@@ -22,14 +22,12 @@ constexpr int kK = kM + 1; // bins
 
 // Forward complex FFT of 512 points by one warp.  v[q] = x[lane + 32 q] on entry; the spectrum ends up in z (natural order,
 // padded layout ZQ).  The caller guarantees that no lane still reads z.
-__device__ __forceinline__ void wfft512(float2* z, float2* v, const float2* tw16, const float2* tw512, int lane) {
-  f32::dft16(v);
-  {
-    float2* zo = z + 17 * lane;  // ZQ(16 lane + q)
-#pragma unroll
-    for (int q = 0; q < 16; ++q) zo[q] = v[q];
-  }
-  __syncwarp();
+// Passes two and three, out of line: the warp-per-unit kernels call the transform five to seven times per unit, and with a few
+// warps per sub-partition at different points of a 150 KB instruction stream they stall on instruction fetch (ncu: "no
+// instruction" 26 % of the stalls of render_fast_kernel).  One shared copy of the big block keeps the kernel inside the
+// instruction cache; only the register-fed first pass stays inline.
+static __device__ __noinline__ void wfft512_tail(float2* z, const float2* tw16, const float2* tw512, int lane) {
+  float2 v[16];
   float2* zi = z + lane + (lane >> 4);  // ZQ(lane)
 #pragma unroll
   for (int q = 0; q < 16; ++q) v[q] = zi[34 * q];  // ZQ(lane + 32 q)
@@ -52,6 +50,16 @@ __device__ __forceinline__ void wfft512(float2* z, float2* v, const float2* tw16
     pa[272] = csub(a, t);
   }
   __syncwarp();
+}
+__device__ __forceinline__ void wfft512(float2* z, float2* v, const float2* tw16, const float2* tw512, int lane) {
+  f32::dft16(v);
+  {
+    float2* zo = z + 17 * lane;  // ZQ(16 lane + q)
+#pragma unroll
+    for (int q = 0; q < 16; ++q) zo[q] = v[q];
+  }
+  __syncwarp();
+  wfft512_tail(z, tw16, tw512, lane);
 }
 
 // Walks the bins k = lane + 32 j <= 512 of the length-1024 REAL transform whose packed half-size transform sits in z:
