@@ -358,8 +358,11 @@ def run_b200(args):
         a = kernels[top]["algorithmic_GBps"]
         roofline = {"kernel": top, "bound": "hbm", "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": a / peaks["hbm_gbs"],
                     "traffic": traffic, "peak_source": peak_src, "binding": bound.get(top),
-                    "note": "the HBM fraction is what the metric asks for; this kernel is bound on chip (see `binding` and kernels.%s.ncu: "
-                            "pipe utilisation from the ncu capture under profiles/)" % top}
+                    "binding_frac": (max(pipes[top].get("issue_active_pct") or 0.0, pipes[top].get("l1_lsu_wavefronts_pct") or 0.0) / 100.0
+                                     if top in pipes else None),
+                    "note": "the HBM fraction is what the metric asks for; this kernel is bound on chip: `binding` names the pipes, "
+                            "`binding_frac` is the higher of issue-slot and L1 / shared-memory-pipe utilisation in the ncu capture under "
+                            "profiles/ (kernels.%s.ncu)" % top}
     roofline["share_of_step"] = kernels[top]["share_of_step"]
 
     # ---- timed region 2: end to end through host buffers ---------------------------------------------------------------

@@ -87,8 +87,9 @@ def test_layer_module_interface():
 @pytest.mark.parametrize("n,blocks,norm", [(60, 1, False), (60, 1, True), (20, 1, True), (60, 3, False), (32, 1, False)])
 def test_tensor_core_forward_vs_fp64_oracle(n, blocks, norm):
     """alpha constant over long runs of rows (one per speaker): tiles of 128 units that share alpha run on the tensor cores
-    (3xTF32), tiles that straddle a run boundary fall back to the recursion; both against the fp64 oracle, and the two
-    implementations against each other."""
+    (3xTF32); a tile with ONE run boundary is processed as two single-alpha segments, a tile with more than two runs falls back to
+    the recursion (the run lengths below produce all three cases); both against the fp64 oracle, and the two implementations against
+    each other."""
     from idiaptts_b200 import ops
     dev = torch.device("cuda", 0)
     rng = np.random.default_rng(100 + n + blocks)
@@ -115,8 +116,8 @@ def test_tensor_core_forward_vs_fp64_oracle(n, blocks, norm):
 
 @pytest.mark.parametrize("n,blocks,norm", [(60, 1, False), (60, 1, True), (20, 1, True), (60, 3, False)])
 def test_tensor_core_backward_vs_fp64_oracle(n, blocks, norm):
-    """Backward of the same configurations: grad_x through the transposed matrix, grad_alpha through the tangent matrix; tiles
-    with a run boundary take the recursion kernel."""
+    """Backward of the same configurations: grad_x through the transposed matrix, grad_alpha through the tangent matrix (tiles
+    with one run boundary as two segments, tiles with more runs through the recursion kernel)."""
     from idiaptts_b200 import ops
     dev = torch.device("cuda", 0)
     rng = np.random.default_rng(200 + n + blocks)
