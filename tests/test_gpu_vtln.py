@@ -84,7 +84,7 @@ def test_layer_module_interface():
     assert y2.shape == (1, T, n)
 
 
-@pytest.mark.parametrize("n,blocks,norm", [(60, 1, False), (60, 1, True), (20, 1, True), (60, 3, False), (32, 1, False)])
+@pytest.mark.parametrize("n,blocks,norm", [(60, 1, False), (60, 1, True), (20, 1, True), (60, 3, False), (32, 1, False), (64, 1, True), (4, 1, False)])
 def test_tensor_core_forward_vs_fp64_oracle(n, blocks, norm):
     """alpha constant over long runs of rows (one per speaker): tiles of 128 units that share alpha run on the tensor cores
     (3xTF32); a tile with ONE run boundary is processed as two single-alpha segments, a tile with more than two runs falls back to
@@ -114,7 +114,7 @@ def test_tensor_core_forward_vs_fp64_oracle(n, blocks, norm):
     assert np.abs(y_tc - y_cc).max() < 5e-5
 
 
-@pytest.mark.parametrize("n,blocks,norm", [(60, 1, False), (60, 1, True), (20, 1, True), (60, 3, False)])
+@pytest.mark.parametrize("n,blocks,norm", [(60, 1, False), (60, 1, True), (20, 1, True), (60, 3, False), (64, 1, True), (4, 1, False)])   # n = 64: two-stage ring
 def test_tensor_core_backward_vs_fp64_oracle(n, blocks, norm):
     """Backward of the same configurations: grad_x through the transposed matrix, grad_alpha through the tangent matrix (tiles
     with one run boundary as two segments, tiles with more runs through the recursion kernel)."""
