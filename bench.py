@@ -322,7 +322,7 @@ def run_b200(args):
         "render": 2 * 2 * 4 * K + 4 * N, "overlap_add": 4 * N + 4 * H_pulse(FS),                      # float32 responses
     }
     bound = {"lf0_vuv": "latency", "cheaptrick": "l1_shared_pipe", "mcep": "tensor", "d4c": "issue+l1_shared_pipe",
-             "bap_from_coarse": "latency", "stats": "hbm", "mc2sp": "fp32_fma+hbm", "decode_ap": "hbm", "synth_timebase": "latency",
+             "bap_from_coarse": "latency", "stats": "hbm", "mc2sp": "tensor+hbm (tcgen05 3xTF32, hand-overs per 32-bin chunk)", "decode_ap": "hbm", "synth_timebase": "latency",
              "render": "l1_shared_pipe+latency", "overlap_add": "hbm"}
     pipes = ncu_pipes()
     kernels = {}

@@ -47,6 +47,7 @@ _SIGNATURES = {
                               c_double, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_void_p]),
     "b2w_mc2sp": (c_int32, [c_void_p, c_int32, c_int64, c_int64, c_int32, c_int32, c_void_p, c_double, c_int32, c_void_p,
                             c_int32, c_void_p]),
+    "b2w_mc2sp_tc": (c_int32, [c_void_p, c_int32, c_int64, c_int64, c_int32, c_int32, c_void_p, c_double, c_int32, c_void_p, c_void_p]),
     "b2w_lf0_vuv": (c_int32, [c_void_p, c_void_p, c_int32, c_double, c_double, c_void_p, c_void_p, c_int64, c_void_p]),
     "b2w_deltas": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_int64,
                              c_void_p]),

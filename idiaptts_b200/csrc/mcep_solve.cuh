@@ -179,6 +179,11 @@ __host__ __device__ constexpr int rr_col_base(int NS, int j, bool want_end = fal
 __host__ __device__ constexpr int rr_workspace_floats(int NS) { return rr_col_base(NS, NS - 2, true) + 64 + 128; }
 
 __device__ __forceinline__ void ffma2(float2& c, const float2 a, const float2 b) {
+#ifdef B2W_SOLVE_SCALAR_FMA   // experiment: two scalar FMAs instead of one packed one (bit-identical results)
+  c.x = fmaf(a.x, b.x, c.x);
+  c.y = fmaf(a.y, b.y, c.y);
+  return;
+#endif
   unsigned long long cc = *reinterpret_cast<unsigned long long*>(&c);
   asm("fma.rn.f32x2 %0, %1, %2, %0;"
       : "+l"(cc)

@@ -559,9 +559,11 @@ def merlin_post_filter(mgc, alpha, fft_size=1024, coef=1.4):
     return out
 
 
-def mc2sp(mc, alpha, fft_size, scale=1.0, do_exp=True, out_dtype=torch.float32, order=None, mc_stride=None, square=False, out=None):
+def mc2sp(mc, alpha, fft_size, scale=1.0, do_exp=True, out_dtype=torch.float32, order=None, mc_stride=None, square=False, out=None,
+          impl=None):
     """(exp of) scale * Re FFT(freqt(mc, fft_size/2, -alpha)): log-amplitude / amplitude / power spectrum from mel-cepstra.
-    square=True (with do_exp, float64 output): the float32 amplitude squared in float64, i.e. world_features_to_raw's pow_sp."""
+    square=True (with do_exp): the float32 amplitude squared in float64, i.e. world_features_to_raw's pow_sp.
+    impl: "tc" = tcgen05 tensor-core kernel (default for a float32 plane and order <= 59), "cc" = CUDA-core kernel."""
     lib = _lib.load()
     dev = _need_cuda(mc)
     assert mc.dim() == 2 and mc.dtype in (torch.float32, torch.float64)
@@ -574,6 +576,15 @@ def mc2sp(mc, alpha, fft_size, scale=1.0, do_exp=True, out_dtype=torch.float32, 
     if out is None:
         out = torch.empty((F, fft_size // 2 + 1), dtype=out_dtype, device=dev)
     assert out.dtype == out_dtype and out.shape == (F, fft_size // 2 + 1) and out.is_contiguous()
+    if impl is None:
+        impl = "tc" if (out.dtype == torch.float32 and tab.stream1 is not None and order >= 1) else "cc"
+    if impl == "tc":
+        if out.dtype != torch.float32 or tab.stream1 is None:
+            raise ValueError("the tensor-core mc2sp kernel writes float32 planes for order <= 59")
+        with torch.cuda.device(dev):
+            check(lib.b2w_mc2sp_tc(mc.data_ptr(), _DT[mc.dtype], int(mc_stride), F, int(fft_size), int(order), tab.stream1.data_ptr(),
+                                   float(scale), (2 if square else 1) if do_exp else 0, out.data_ptr(), _stream(dev)), "b2w_mc2sp_tc")
+        return out
     with torch.cuda.device(dev):
         check(lib.b2w_mc2sp(mc.data_ptr(), _DT[mc.dtype], int(mc_stride), F, int(fft_size), int(order), tab.cmat.data_ptr(),
                             float(scale), (2 if square else 1) if do_exp else 0, out.data_ptr(), _DT[out.dtype], _stream(dev)),

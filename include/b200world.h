@@ -145,6 +145,11 @@ B2W_API int b2w_mcep_tc(const void* in, int32_t in_dtype, int32_t in_is_power, i
 B2W_API int b2w_mc2sp(const void* mc, int32_t mc_dtype, int64_t mc_stride, int64_t num_frames, int32_t fft_size,
               int32_t order, const float* cmat, double scale, int32_t do_exp, void* out, int32_t out_dtype,
               void* stream);
+/* Tensor-core version for order <= 59 and a float32 output plane (the batched synthesis path, Synthesiser.py:39-80 -> A:304-327):
+ * tiles of 128 frames as tcgen05.mma kind::tf32 GEMMs with the 3xTF32 split against the Cmat chunks of the pre-tiled Newton
+ * stream of b2w_mcep_tc_pretile (stream1, same order / alpha / fft_size). */
+B2W_API int b2w_mc2sp_tc(const void* mc, int32_t mc_dtype, int64_t mc_stride, int64_t num_frames, int32_t fft_size, int32_t order,
+                 const float* stream1, double scale, int32_t do_exp, float* out, void* stream);
 
 /* ---- label preparation: lf0 / vuv (W:798-802, U:40-86 interpolate_lin). -----------------------------------
  * One ragged batch; float32 arithmetic identical to the reference. lf0/vuv written with element stride

@@ -1,5 +1,11 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_analysis.py -m gpu -q -x -k "mcep or fused or padded" > gpurun_out/r02l_pytest.txt 2>&1; tail -3 gpurun_out/r02l_pytest.txt
-timeout 300 python scripts/gpu_kbench.py --utts 512 --kernels mcep > gpurun_out/r02l_kbench.txt 2>&1; cat gpurun_out/r02l_kbench.txt
-B2W_LIB=variants/libb200world_tccopy1.so timeout 300 python scripts/gpu_kbench.py --utts 512 --kernels mcep > gpurun_out/r02l_kbench_c1.txt 2>&1; cat gpurun_out/r02l_kbench_c1.txt
+timeout 600 python -m pytest tests/test_gpu_analysis.py tests/test_gpu_synthesis.py tests/test_gpu_pipeline.py -m gpu -q -x > gpurun_out/r02l_pytest.txt 2>&1; tail -12 gpurun_out/r02l_pytest.txt
+python bench.py --utts 2048 --steps 2 --warmup 1 --no-workloads --no-cpu-baseline > gpurun_out/r02l_bench.log 2>&1
+python - <<PY
+import json
+l=[x for x in open('gpurun_out/r02l_bench.log').read().splitlines() if x.startswith('{')]
+if l:
+    d=json.loads(l[-1]); print(d["value"], d["components"]["synthesis"]["audio_s_per_s"], d["parity"]["ok"], d["parity"]["resynthesis_snr_db_min"], {k:(v["avg_launch_ms"]) for k,v in d["kernels"].items()})
+else: print(open('gpurun_out/r02l_bench.log').read()[-1500:])
+PY

@@ -190,6 +190,32 @@ def test_mc2sp_and_reference_reconstruction_threshold(golden):
     assert (np.abs(p - sptk_np.mc2sp(mc60, 0.41, 1024)) / p).max() < 1e-4
 
 
+@pytest.mark.parametrize("order,fft_size,nframes", [(59, 1024, 1000), (59, 1024, 130), (24, 512, 77), (39, 2048, 300)])
+def test_tensor_core_mc2sp_vs_oracle_and_cuda_core_kernel(dev, order, fft_size, nframes):
+    """The tcgen05 mel-cepstrum -> spectrum kernel of the batched synthesis path (float32 plane, order <= 59) against the fp64 oracle
+    and against the CUDA-core kernel, for the three output forms (log amplitude, amplitude, float32 amplitude squared), float32 and
+    float64 coefficients, a padded row stride, and frame counts that are not multiples of the 128-frame tile."""
+    from idiaptts_b200 import ops
+    rng = np.random.default_rng(order + nframes)
+    mc = rng.standard_normal((nframes, order + 1)) * (0.6 ** np.arange(order + 1))[None, :]
+    mc[:, 0] -= 4.0
+    alpha = 0.455
+    ref = sptk_np.mgc2sp(mc, alpha, 0.0, fft_size).real                       # log amplitude
+    for dt in (torch.float32, torch.float64):
+        wide = torch.zeros((nframes, order + 5), dtype=dt, device=dev)         # row stride > order + 1
+        wide[:, :order + 1] = torch.from_numpy(mc).to(dev).to(dt)
+        for do_exp, square in ((False, False), (True, False), (True, True)):
+            kw = dict(scale=1.0, do_exp=do_exp, out_dtype=torch.float32, order=order, mc_stride=order + 5, square=square)
+            y_tc = ops.mc2sp(wide, alpha, fft_size, impl="tc", **kw).cpu().numpy().astype(np.float64)
+            y_cc = ops.mc2sp(wide, alpha, fft_size, impl="cc", **kw).cpu().numpy().astype(np.float64)
+            want = ref if not do_exp else (np.exp(ref) ** 2 if square else np.exp(ref))
+            assert np.isfinite(y_tc).all()
+            if do_exp:
+                assert (np.abs(y_tc - want) / want).max() < 5e-5 and (np.abs(y_tc - y_cc) / want).max() < 5e-5
+            else:
+                assert np.abs(y_tc - want).max() < 2e-5 and np.abs(y_tc - y_cc).max() < 2e-5
+
+
 def test_ragged_batch_equals_single_utterances_and_edge_cases(golden, dev):
     from idiaptts_b200 import ops, pipeline
     ids = ["LJ001-0002", "LJ001-0008", "LJ001-0004"]
