@@ -321,6 +321,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
         PROF_LAP(6);  // GEMM2 issue
         s = sn;
       }
+      if (pass > 0) {  // the D1 releases of the last two chunks (nothing depends on them: every completion gets a wait)
+        for (int c = (nch >= 2 ? nch - 2 : 0); c < nch; ++c) wait_slot(bar_d1free, 2, c, pass - 1);
+      }
     } else if (warp >= kTcEpiWarp0) {
       // ---- epilogue: P = per * exp(-2 D1) (pass 0: log per) -> hi / lo TF32 columns of A2 in tensor memory ---------------------
       // Twelve warps = three sets of four (one warp per TMEM lane quarter).  A work item is half a chunk (128 rows x 16 bins); the
@@ -381,6 +384,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) mcep_tc_kernel(McepTcParams p) 
         if (lane == 0) umma::mbar_arrive(&bar_a2[s]);
         PROF_LAP(12);  // epilogue: A2 stores + fence + arrive
       }
+      if (nch >= 2) wait_slot(bar_g2, kTcNST, nch - 2, pass);  // (observed by nobody else: keeps every completion waited for)
       wait_slot(bar_g2, kTcNST, nch - 1, pass);  // the last chunk's GEMM2 completes D2
     }
     umma::tc_fence_before_sync();

@@ -1,13 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for v in "" rb3 rb6; do
-  if [ -n "$v" ]; then export B2W_LIB=variants/libb200world_$v.so; fi
-  python bench.py --utts 1024 --steps 2 --warmup 1 --no-workloads --no-cpu-baseline > gpurun_out/r02l_bench_$v.log 2>&1
-  python - <<PY
-import json
-l=[x for x in open('gpurun_out/r02l_bench_$v.log').read().splitlines() if x.startswith('{')]
-if l:
-    d=json.loads(l[-1]); print("$v", d["components"]["synthesis"]["audio_s_per_s"], d["parity"]["ok"], d["kernels"]["render"]["avg_launch_ms"])
-else: print(open('gpurun_out/r02l_bench_$v.log').read()[-1000:])
-PY
-done
+timeout 900 compute-sanitizer --tool synccheck --print-limit 5 python -m pytest tests/test_gpu_vtln.py tests/test_gpu_analysis.py -m gpu -q -k "tensor_core or mcep_vs_oracle" > gpurun_out/r02r_synccheck_tc.log 2>&1; tail -4 gpurun_out/r02r_synccheck_tc.log
+timeout 300 python scripts/gpu_kbench.py --utts 512 --kernels mcep > gpurun_out/r02l_kbench.txt 2>&1; cat gpurun_out/r02l_kbench.txt
