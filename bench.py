@@ -189,7 +189,7 @@ def kernel_table(events, steps):
         d = per.setdefault(name, [0.0, 0, 0])
         d[0] += a.elapsed_time(b)
         d[1] += 1
-        d[2] += units
+        d[2] += units() if callable(units) else units
     return {k: {"ms_per_step": v[0] / steps, "launches_per_step": v[1] / steps, "units_per_launch": v[2] / max(v[1], 1),
                 "avg_launch_ms": v[0] / max(v[1], 1)} for k, v in per.items()}
 
@@ -373,17 +373,24 @@ def run_b200(args):
     d2h = feats_host.numel() * 4 + stats_pinned.numel() * 8 + y_host.numel() * 4
     e2e_state = {"buf": None}
 
+    e2e_marks = []
+
     def e2e_step():
         # the public end-to-end calls: pinned host corpus in, pinned host features + statistics out (WorldAnalyzer.extract_from_host),
         # then pinned host features in, pinned host waveforms out (WorldSynthesizer.synthesize_corpus); copies overlap the kernels
+        m0, m1, m2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        m0.record()
         stat_buf.zero_()
         _, _, _, e2e_state["buf"] = an.extract_from_host(host, feats_host, dev_buffers=e2e_state["buf"], sums=stat_buf[:2 * an.dim])
         stat_buf[2 * an.dim] = float(F)
         if world > 1:
             dist.all_reduce(stat_buf)
         stats_pinned.copy_(stat_buf, non_blocking=True)
+        m1.record()
         torch.cuda.current_stream().synchronize()   # the features must have landed in host memory before they are read back
         syn.synthesize_corpus(None, frame_off, batch_utts=args.synth_batch, feats_host=feats_host, out_host=y_host)
+        m2.record()
+        e2e_marks.append((m0, m1, m2))
 
     e2e_step()
     barrier()
@@ -397,6 +404,9 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = total_audio / (float(t2.item()) / args.steps / 1e3)
+    e2e_parts = {"analysis_ms": round(sum(a.elapsed_time(b) for a, b, _ in e2e_marks[1:]) / args.steps, 2),
+                 "synthesis_ms": round(sum(b.elapsed_time(c) for _, b, c in e2e_marks[1:]) / args.steps, 2),
+                 "what": "rank 0, host copies included; the resident-input passes take components.*.ms_per_step"}
     del e2e_state
 
     line = None
@@ -435,7 +445,7 @@ def run_b200(args):
                                             "what": "wav + cached F0 -> mcep60/lf0/vuv/bap + statistics all-reduce (rank 0)"},
                                "synthesis": {"audio_s_per_s": audio_s / (ms_synth / 1e3), "ms_per_step": ms_synth,
                                              "what": "features -> waveforms, batches of %d utterances (rank 0)" % args.synth_batch}},
-                "clocks": clocks, "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(h2d),
+                "clocks": clocks, "e2e_components": e2e_parts, "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(h2d),
                                           "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(args.steps * launches), "roofline": roofline, "kernels": kernels, "parity": parity,
                 "cpu_baseline": cpu, "workloads": workloads}

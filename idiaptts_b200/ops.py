@@ -716,22 +716,32 @@ class SynthPlan:
     pass
 
 
-def synth_timebase(f0, frame_off, fs, fft_size, frame_period=5.0, status=None, events=None):
+def synth_timebase(f0, frame_off, fs, fft_size, frame_period=5.0, status=None, events=None, frame_off_host=None):
     """Launches the pulse-placement kernels (sequential per utterance, a few hundred threads: they overlap well with other
-    work on a second stream).  f0 [F] f64, frame_off int64 [U+1] (device).  Returns a SynthPlan; nothing is synchronised."""
+    work on a second stream).  f0 [F] f64, frame_off int64 [U+1] (device).  Returns a SynthPlan.  frame_off_host: the same offsets
+    as host numpy; with them the call neither reads from nor (synchronously) writes to the device -- the sample / pulse-slab
+    offsets the kernels need are derived from frame_off on the device with the same arithmetic -- so batches can be queued back to
+    back (a small device-to-host read would otherwise wait behind the previous batch's waveform copy on the same copy engine)."""
     lib = _lib.load()
     dev = _need_cuda(f0, frame_off)
     assert f0.dtype == torch.float64
     p = SynthPlan()
-    foff = frame_off.cpu().numpy()
+    foff = frame_off.cpu().numpy() if frame_off_host is None else np.asarray(frame_off_host, np.int64)
     p.U = U = len(foff) - 1
     T = np.diff(foff)
     p.ylen = ylen = (T * frame_period * fs / 1000).astype(np.int64)  # int(T * frame_period * fs / 1000)
     p.out_off = out_off = np.concatenate(([0], np.cumsum(ylen)))
-    caps = np.array([lib.b2w_synth_max_pulses(int(v), int(fs)) for v in ylen], np.int64)
+    caps = (ylen.astype(np.float64) * 1200.0 / float(fs)).astype(np.int64) + 64   # = b2w_synth_max_pulses(ylen, fs)
     p.pulse_off = pulse_off = np.concatenate(([0], np.cumsum(caps)))
-    p.d_out_off = torch.from_numpy(out_off).to(dev)
-    p.d_pulse_off = torch.from_numpy(pulse_off).to(dev)
+    if frame_off_host is None:
+        p.d_out_off = torch.from_numpy(out_off).to(dev)
+        p.d_pulse_off = torch.from_numpy(pulse_off).to(dev)
+    else:  # same values, computed on the device (fp64 products of small integers, truncated: identical to the host arithmetic)
+        Td = (frame_off[1:] - frame_off[:-1]).double()
+        yl = (Td * frame_period * fs / 1000).long()
+        zero = torch.zeros(1, dtype=torch.int64, device=dev)
+        p.d_out_off = torch.cat((zero, torch.cumsum(yl, 0)))
+        p.d_pulse_off = torch.cat((zero, torch.cumsum((yl.double() * 1200.0 / float(fs)).long() + 64, 0)))
     total_cap = int(pulse_off[-1])
     p.pulse_index = torch.empty(max(total_cap, 1), dtype=torch.int32, device=dev)
     p.pulse_shift = torch.empty(max(total_cap, 1), dtype=torch.float64, device=dev)
@@ -754,7 +764,7 @@ def synth_timebase(f0, frame_off, fs, fft_size, frame_period=5.0, status=None, e
     return p
 
 
-def synth_render(p, sp, ap, deemphasis=0.0, out_dtype=torch.float64, debug=None, events=None, precision="f64"):
+def synth_render(p, sp, ap, deemphasis=0.0, out_dtype=torch.float64, debug=None, events=None, precision="f64", sync_counts=True):
     """Minimum-phase responses of every pulse of the plan + overlap-add.  sp, ap [F, K] (f64 or f32, same dtype).
     precision: "f64" = double precision throughout (pyworld-compatible calls); "fast" = one warp per pulse, single-precision
     transforms, float32 responses (the batched Synthesiser path; fft size 1024 only, other sizes fall back to "f64"): same pulse
@@ -772,14 +782,21 @@ def synth_render(p, sp, ap, deemphasis=0.0, out_dtype=torch.float64, debug=None,
         return y, out_off, p.status
     st = _stream(dev)
     with torch.cuda.device(dev):
-        # the response buffer is sized by the ACTUAL pulse counts (one small D2H of U ints)
-        npul = p.num_pulses.cpu().numpy()[:U].astype(np.int64)
-        max_p = int(npul.max()) if U else 0
-        # responses are addressed by the slab offsets, so allocate slab-sized storage only up to the last used row
-        last_row = int((pulse_off[:-1] + npul).max()) if U else 0
         fast = precision == "fast"
+        if sync_counts or not fast or debug is not None:
+            # the response buffer is sized by the ACTUAL pulse counts (one small D2H of U ints)
+            npul = p.num_pulses.cpu().numpy()[:U].astype(np.int64)
+            max_p = int(npul.max()) if U else 0
+            # responses are addressed by the slab offsets, so allocate slab-sized storage only up to the last used row
+            last_row = int((pulse_off[:-1] + npul).max()) if U else 0
+            total_p = int(npul.sum())
+        else:
+            # batched path: no read-back.  The slab (an upper bound of the pulse count per utterance) is allocated whole -- the last
+            # used row is within one utterance of its end anyway -- and the kernels take the actual counts from device memory.
+            npul, max_p, last_row = None, 1, int(pulse_off[-1])
+            counts = p.num_pulses
+            total_p = lambda: int(counts[:U].sum().item())   # (bench.py's per-kernel table evaluates it after the timed region)
         response = torch.empty((max(last_row, 1), fft_size), dtype=torch.float32 if fast else torch.float64, device=dev)
-        total_p = int(npul.sum())
         if max_p > 0 and fast:
             _timed(events, "render", total_p, lambda: check(lib.b2w_synth_render_f32(
                 sp.data_ptr(), ap.data_ptr(), _DT[sp.dtype], p.frame_off.data_ptr(),

@@ -196,7 +196,7 @@ class WorldSynthesizer:
         self.precision = precision
         ops.McepTables.get(self.num_coded_sps - 1, self.alpha, self.n_fft, self.device)
 
-    def synthesize(self, feats, frame_off, preemphasis=0.0, out_dtype=torch.float32, events=None):
+    def synthesize(self, feats, frame_off, preemphasis=0.0, out_dtype=torch.float32, events=None, frame_off_host=None):
         """feats [F, D + 2 + nap] float32 rows [coded_sp | lf0 | vuv | bap] on the device; frame_off int64 [U+1] on the device.
         Returns (y packed, out_off numpy int64 [U+1], status).  events: optional list that receives (kernel name, units, start
         event, end event) per launch (bench.py's per-kernel timing)."""
@@ -229,10 +229,12 @@ class WorldSynthesizer:
         ap = ops._timed(events, "decode_ap", F, lambda: ops.decode_aperiodicity(bap, self.fs, self.n_fft, out_dtype=plane_dtype))
         # (Measured: decoding the two planes on a side stream while the sequential pulse placement runs on this one is SLOWER,
         # 23.2 ms against 19.8 ms for 256 utterances -- scripts/gpu_synth_phases.py -- so the stages stay in one stream.)
-        plan = ops.synth_timebase(f0.contiguous(), frame_off, self.fs, self.n_fft, self.hop_size_ms, events=events)
+        # (frame_off_host given: nothing below reads back from the device, the host can queue the next batch right away)
+        plan = ops.synth_timebase(f0.contiguous(), frame_off, self.fs, self.n_fft, self.hop_size_ms, events=events,
+                                  frame_off_host=frame_off_host)
         de = float(preemphasis)
         y, out_off, status = ops.synth_render(plan, pow_sp, ap, deemphasis=de, out_dtype=torch.float64 if de != 0.0 else out_dtype,
-                                              events=events, precision=self.precision)
+                                              events=events, precision=self.precision, sync_counts=frame_off_host is None)
         return y, out_off, status
 
     def kernel_launches(self, num_utts, batch_utts=256):
@@ -260,6 +262,7 @@ class WorldSynthesizer:
         s_in.wait_stream(cur)
         s_out.wait_stream(cur)
         bounds = [(u0, min(U, u0 + batch_utts)) for u0 in range(0, U, batch_utts)]
+        fo_dev = torch.from_numpy(fo).to(dev)   # one upload; the per-batch offsets are slices of it
 
         def fetch(b):  # device rows of batch b (staged from the host one batch ahead)
             u0, u1 = bounds[b]
@@ -279,8 +282,8 @@ class WorldSynthesizer:
             if ev is not None:
                 cur.wait_event(ev)
                 rows.record_stream(cur)
-            off_b = torch.from_numpy(fo[u0:u1 + 1] - fo[u0]).to(dev)
-            y, _, st = self.synthesize(rows, off_b, events=events)
+            off_b = fo_dev[u0:u1 + 1] - fo_dev[u0]
+            y, _, st = self.synthesize(rows, off_b, events=events, frame_off_host=fo[u0:u1 + 1] - fo[u0])
             status |= st
             if out is not None:
                 out[out_off[u0]:out_off[u1]].copy_(y)
