@@ -20,7 +20,7 @@ for src, dst in (("bench_full_%s.log", "%s_bench_full.json"), ("bench_ref_%s.log
         json.dump(last_json(f), open(os.path.join(P, dst % tag), "w"))
 small = last_json(os.path.join(G, "bench_small_%s.log" % tag)) if os.path.exists(os.path.join(G, "bench_small_%s.log" % tag)) else None
 NAMES = {"cheaptrick_fast_kernel": "cheaptrick", "cheaptrick_kernel": "cheaptrick", "mcep_tc_kernel": "mcep", "d4c_fast_kernel": "d4c", "d4c_kernel": "d4c_f64_reeval", "render_fast_kernel": "render",
-         "overlap_add_kernel": "overlap_add", "mc2sp_kernel": "mc2sp", "decode_ap_kernel": "decode_ap", "lf0_vuv_kernel": "lf0_vuv",
+         "overlap_add_kernel": "overlap_add", "mc2sp_tc_kernel": "mc2sp", "mc2sp_kernel": "mc2sp", "decode_ap_kernel": "decode_ap", "lf0_vuv_kernel": "lf0_vuv",
          "bap_from_coarse_kernel": "bap_from_coarse", "stats_kernel": "stats", "phase_inc_kernel": "synth_timebase", "phase_scan_exact_kernel": "synth_timebase",
          "pulse_chunk_kernel": "synth_timebase", "allpass_tc_forward_kernel": "vtln_fwd", "allpass_tc_backward_kernel": "vtln_bwd"}
 
