@@ -218,3 +218,36 @@ def test_extract_from_host_matches_resident_extract():
         ops.raise_for_status(st2, "streamed")
         assert torch.equal(out, feats.cpu()) and torch.equal(f2, feats)
         assert torch.allclose(s2, sums, rtol=1e-12, atol=0.0)  # fp64 atomics: summation order may differ in the last bits
+
+
+def test_synthesize_corpus_without_round_trips_matches_single_calls():
+    """The corpus-level synthesis (batches queued back to back: offsets derived on the device, response slab allocated whole, no
+    pulse-count read-back; features from pinned host memory, waveforms to pinned host memory) returns exactly the samples of
+    per-batch calls that size everything from read-back counts, also when the last batch is ragged."""
+    from idiaptts_b200 import ops, pipeline, synthetic
+    dev = torch.device("cuda", 0)
+    fs = 22050
+    waves, f0s = synthetic.make_corpus(11, fs, seed=13, mean_dur=1.0, std_dur=0.4)
+    batch = ops.RaggedBatch.from_host([w.numpy() for w in waves], f0s, fs, device=dev)
+    an = pipeline.WorldAnalyzer(fs, 60, device=dev)
+    feats, _, st = an.extract(batch)
+    assert ops.raise_for_status(st, "extract") & ~8 == 0
+    fo = batch.frame_off.cpu().numpy()
+    syn = pipeline.WorldSynthesizer(fs, 60, device=dev)
+    # reference: one call per batch of 4 utterances through the read-back path
+    ref = []
+    for u0 in range(0, 11, 4):
+        u1 = min(11, u0 + 4)
+        off = torch.from_numpy(fo[u0:u1 + 1] - fo[u0]).to(dev)
+        y, _, s = syn.synthesize(feats[fo[u0]:fo[u1]], off)
+        assert ops.raise_for_status(s, "synth") == 0
+        ref.append(y)
+    ref = torch.cat(ref)
+    feats_host = feats.cpu().pin_memory()
+    y_host = torch.zeros(ref.numel(), dtype=torch.float32).pin_memory()
+    y_dev = torch.zeros(ref.numel(), dtype=torch.float32, device=dev)
+    out_off, s = syn.synthesize_corpus(None, fo, batch_utts=4, feats_host=feats_host, out_host=y_host, out=y_dev)
+    torch.cuda.synchronize()
+    assert ops.raise_for_status(s, "synthesize_corpus") == 0
+    assert int(out_off[-1]) == ref.numel()
+    assert torch.equal(y_dev, ref) and torch.equal(y_host, ref.cpu())
