@@ -378,6 +378,12 @@ pulse_chunk_kernel(const double* __restrict__ f0_all, const int64_t* __restrict_
                    int max_chunks, int* __restrict__ pulse_index, double* __restrict__ pulse_shift, uint8_t* __restrict__ pulse_vuv,
                    int* __restrict__ num_pulses, int* __restrict__ status) {
   __shared__ int sh_w[kTbThreads / 32];
+  // write pass: the pulses of the chunk are first collected (sample index + the two wrapped phases) and then finished by consecutive
+  // threads -- a pulse occurs once in ~100 samples, so finishing it where it is found ran the expensive part (three fp64 divisions,
+  // the frame search, the F0 / VUV interpolation) with one or two active lanes per warp, ~50 times per chunk
+  constexpr int kList = WRITE ? 640 : 1;   // >= kPulseChunk * 1200 / 8000: the slab bound of b2w_synth_max_pulses down to fs = 8 kHz
+  __shared__ int li[kList];
+  __shared__ double lw0[kList], lw1[kList];
   const int u = blockIdx.y, c = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = (int)(utt_frame_offset[u + 1] - utt_frame_offset[u]);
@@ -404,6 +410,7 @@ pulse_chunk_kernel(const double* __restrict__ f0_all, const int64_t* __restrict_
   const double fs = (double)fs_i;
   const double fp = frame_period_ms / 1000.0;
   const double lowest_f0 = (double)(fs_i / fft_size) + 1.0;
+  const int run0 = running;  // pulses of the utterance before this chunk
   int warp_total = 0;  // pass 1: pulses seen by this warp
   for (int s0 = j0; s0 < j1; s0 += kTbThreads) {
     const int i = s0 + tid;
@@ -427,22 +434,36 @@ pulse_chunk_kernel(const double* __restrict__ f0_all, const int64_t* __restrict_
       before += (w < warp) ? v : 0;
       slab += v;
     }
+    auto finish = [&](int slot, int i_, double w0_, double w1_) {
+      const double y1 = w0_ - two_pi;
+      const double x = -y1 / (w1_ - y1);
+      int k = max(1, min(T, (int)((double)i_ / fs / fp)));
+      while (k > 1 && (double)i_ / fs < __dmul_rn((double)(k - 1), fp)) --k;
+      double v;
+      sample_f0(f0, T, lowest_f0, fp, fs, i_, k, v);
+      pulse_index[poff + slot] = i_;
+      pulse_shift[poff + slot] = x / fs;
+      pulse_vuv[poff + slot] = v > 0.5 ? 1 : 0;
+    };
     if (is_pulse) {
       const int slot = running + before + __popc(ball & ((1u << lane) - 1u));
       if (slot < cap) {
-        const double y1 = w0 - two_pi;
-        const double x = -y1 / (w1 - y1);
-        int k = max(1, min(T, (int)((double)i / fs / fp)));
-        while (k > 1 && (double)i / fs < __dmul_rn((double)(k - 1), fp)) --k;
-        double v;
-        sample_f0(f0, T, lowest_f0, fp, fs, i, k, v);
-        pulse_index[poff + slot] = i;
-        pulse_shift[poff + slot] = x / fs;
-        pulse_vuv[poff + slot] = v > 0.5 ? 1 : 0;
+        const int loc = slot - run0;
+        if (loc < kList) {
+          li[loc] = i;
+          lw0[loc] = w0;
+          lw1[loc] = w1;
+        } else {
+          finish(slot, i, w0, w1);  // (more pulses in one chunk than the list holds: only with an F0 far above WORLD's range)
+        }
       }
     }
     running += slab;
-    __syncthreads();  // sh_w is rewritten by the next slab
+    __syncthreads();  // sh_w is rewritten by the next slab (and, after the last one, the list is complete)
+    if (s0 + kTbThreads >= j1) {
+      const int n_list = min(min(running, cap) - run0, kList);
+      for (int t = tid; t < n_list; t += kTbThreads) finish(run0 + t, li[t], lw0[t], lw1[t]);
+    }
   }
   if (!WRITE) {
     if (lane == 0) sh_w[warp] = warp_total;
