@@ -163,7 +163,9 @@ phase_inc_kernel(const double* __restrict__ f0_all, const int64_t* __restrict__ 
   const double fs = (double)fs_i;
   const double fp = frame_period_ms / 1000.0;
   const double lowest_f0 = (double)(fs_i / fft_size) + 1.0;
-  int k = max(1, min(T, (int)((double)n / fs / fp)));
+  // first guess of the frame interval by a multiplication (the two searches below and in sample_f0 correct it in either direction;
+  // they, the time and the interpolation weight keep WORLD's exact divisions)
+  int k = max(1, min(T, (int)((double)n * (1.0 / (fs * fp)))));
   while (k > 1 && (double)n / fs < __dmul_rn((double)(k - 1), fp)) --k;
   double v;
   const double f = sample_f0(f0, T, lowest_f0, fp, fs, n, k, v);
