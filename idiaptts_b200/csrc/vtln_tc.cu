@@ -26,7 +26,7 @@ constexpr uint32_t kVtcBBytes = kVtcNP * kVtcNP * 4;  // 16 KB, one of hi / lo
 // is, for a fixed row, a first-order linear recurrence over r with the CONSTANT coefficient a and a forcing term that only needs the
 // previous row: A[j][r] = a A[j][r-1] + g_r.  Lane l owns columns 2 l and 2 l + 1; a five-step warp scan over affine maps (the
 // multipliers are powers of a^2) resolves the recurrence, so a row costs ~40 instructions instead of a 119-step wavefront.
-// The unsplit fp32 values go to their final position in the hi tile; a second, fully parallel sweep splits them into hi / lo.
+// Every value is split into hi / lo TF32 as it is stored (side effects, off the dependent chain of the recurrence).
 __device__ __forceinline__ void vtc_build_matrix(float* b_hi, float* b_lo, float a, int n) {
   const int lane = threadIdx.x & 31;
   const int r0 = 2 * lane;
@@ -40,11 +40,11 @@ __device__ __forceinline__ void vtc_build_matrix(float* b_hi, float* b_lo, float
   float p1 = p0 * a;
   const uint32_t cb = (uint32_t)(r0 >> 2) * (kVtcNP * 4) + (r0 & 3);  // float offset of column r0 inside a row of the K-major tile
   const bool in = r0 < n;  // n is even: both columns of a lane are inside or outside
+  float left = __shfl_up_sync(0xffffffffu, p1, 1);            // A[j-1][r0 - 1] for the next row (0 for column -1)
+  if (lane == 0) left = 0.f;
   for (int j = 0; j < n; ++j) {
     if (j > 0) {
       const float cn = j == 1 ? 1.f - a * a : 1.f, cu = j == 1 ? 0.f : a;
-      float left = __shfl_up_sync(0xffffffffu, p1, 1);       // A[j-1][r0 - 1]
-      if (lane == 0) left = 0.f;
       const float g0 = lane == 0 ? 0.f : fmaf(cn, left, -cu * p0);   // column 0 of rows >= 1 is zero, and so is its forcing term
       const float g1 = fmaf(cn, p0, -cu * p1);
       // this lane's pair as an affine map of the incoming carry c = A[j][r0 - 1]:  A[j][r0] = a c + g0,  A[j][r1] = a^2 c + x
@@ -54,28 +54,23 @@ __device__ __forceinline__ void vtc_build_matrix(float* b_hi, float* b_lo, float
         const float t = __shfl_up_sync(0xffffffffu, x, 1 << i);
         if (lane >= (1 << i)) x = fmaf(pw[i], t, x);
       }
-      float carry = __shfl_up_sync(0xffffffffu, x, 1);        // A[j][r0 - 1]
+      float carry = __shfl_up_sync(0xffffffffu, x, 1);        // A[j][r0 - 1]: the carry of this row and `left` of the next one
       if (lane == 0) carry = 0.f;
       p0 = lane == 0 ? 0.f : fmaf(a, carry, g0);
       p1 = x;
+      left = carry;
     }
-    if (in) {
+    if (in) {  // split and store (off the dependent chain of the recurrence)
       const float s2 = j == 0 ? 2.f : 1.f;                    // S2; S1 halves column 0
       const uint32_t off = umma::tile_off(kVtcNP, j, 0) / 4 + cb;
-      *reinterpret_cast<float2*>(b_hi + off) = make_float2(p0 * s2 * (lane == 0 ? 0.5f : 1.f), p1 * s2);
+      float2 hi, lo;
+      umma::split_tf32(p0 * s2 * (lane == 0 ? 0.5f : 1.f), hi.x, lo.x);
+      umma::split_tf32(p1 * s2, hi.y, lo.y);
+      *reinterpret_cast<float2*>(b_hi + off) = hi;
+      *reinterpret_cast<float2*>(b_lo + off) = lo;
     }
   }
-  __syncwarp();
-  for (int e = lane; e < kVtcNP * kVtcNP / 4; e += 32) {  // (entries outside n x n stay zero: the buffers are cleared once)
-    const float4 v = reinterpret_cast<const float4*>(b_hi)[e];
-    float4 hi, lo;
-    umma::split_tf32(v.x, hi.x, lo.x);
-    umma::split_tf32(v.y, hi.y, lo.y);
-    umma::split_tf32(v.z, hi.z, lo.z);
-    umma::split_tf32(v.w, hi.w, lo.w);
-    reinterpret_cast<float4*>(b_hi)[e] = hi;
-    reinterpret_cast<float4*>(b_lo)[e] = lo;
-  }
+  __syncwarp();  // (entries outside n x n stay zero: the buffers are cleared once)
 }
 
 // ---- forward: a persistent, warp-specialised pipeline ------------------------------------------------------------------------
@@ -479,7 +474,7 @@ __device__ __forceinline__ void vtc_build_matrices_bwd(float* bb_hi, float* bb_l
   for (int i = 1; i < 5; ++i) pw[i] = pw[i - 1] * pw[i - 1];
   const float bcoef = 1.f - a * a;
   // v[r] = a v[r-1] + g[r] for this lane's two columns (v[-1] = 0): affine maps of the incoming carry, Kogge-Stone over the lanes
-  auto scan_row = [&](float g0, float g1, float& v0, float& v1) {
+  auto scan_row = [&](float g0, float g1, float& v0, float& v1, float& left) {  // left = v[r0 - 1] (0 for column -1)
     float x = fmaf(a, g0, g1);
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
@@ -490,24 +485,19 @@ __device__ __forceinline__ void vtc_build_matrices_bwd(float* bb_hi, float* bb_l
     if (lane == 0) carry = 0.f;
     v0 = fmaf(a, carry, g0);
     v1 = x;
+    left = carry;
   };
-  auto left_of = [&](float v1) {  // value of column r0 - 1 (0 for column -1)
-    const float l = __shfl_up_sync(0xffffffffu, v1, 1);
-    return lane == 0 ? 0.f : l;
-  };
-  float e0 = 0.f, e1 = 0.f, t0 = 0.f, t1 = 0.f;  // previous row
+  float e0 = 0.f, e1 = 0.f, t0 = 0.f, t1 = 0.f, el = 0.f, tl = 0.f;  // previous row: this lane's columns and the one to their left
   const bool in = r0 < n;
   const uint32_t cbt = (uint32_t)(r0 >> 2) * (kVtcNP * 4) + (r0 & 3);  // Bt[n = j][k = r]: float offset of column r0 inside row j
   for (int j = 0; j < n; ++j) {
-    float ne0, ne1, nt0, nt1;
+    float ne0, ne1, nt0, nt1, nel, ntl;
     if (j == 0) {
-      scan_row(lane == 0 ? 1.f : 0.f, 0.f, ne0, ne1);
-      scan_row(left_of(ne1), ne0, nt0, nt1);
+      scan_row(lane == 0 ? 1.f : 0.f, 0.f, ne0, ne1, nel);
+      scan_row(nel, ne0, nt0, nt1, ntl);
     } else {
-      const float el = left_of(e1), tl = left_of(t1);
       const float cn = j == 1 ? bcoef : 1.f, cu = j == 1 ? 0.f : a;
-      scan_row(lane == 0 ? 0.f : fmaf(cn, el, -cu * e0), fmaf(cn, e0, -cu * e1), ne0, ne1);
-      const float nel = left_of(ne1);  // E[j][r0 - 1]
+      scan_row(lane == 0 ? 0.f : fmaf(cn, el, -cu * e0), fmaf(cn, e0, -cu * e1), ne0, ne1, nel);
       float gt0, gt1;
       if (j == 1) {
         gt0 = fmaf(-2.f * a, el, fmaf(bcoef, tl, nel));
@@ -516,34 +506,30 @@ __device__ __forceinline__ void vtc_build_matrices_bwd(float* bb_hi, float* bb_l
         gt0 = (tl - a * t0) + (nel - e0);
         gt1 = (t0 - a * t1) + (ne0 - e1);
       }
-      scan_row(lane == 0 ? 0.f : gt0, gt1, nt0, nt1);
+      scan_row(lane == 0 ? 0.f : gt0, gt1, nt0, nt1, ntl);
     }
-    e0 = ne0; e1 = ne1; t0 = nt0; t1 = nt1;
-    if (in) {
+    e0 = ne0; e1 = ne1; t0 = nt0; t1 = nt1; el = nel; tl = ntl;
+    if (in) {  // split and store (off the dependent chain of the recurrences)
       const float s2 = j == 0 ? 2.f : 1.f, s1 = lane == 0 ? 0.5f : 1.f;
       // Bb[n = r][k = j]
       const uint32_t kb = (uint32_t)(j >> 2) * (kVtcNP * 4) + (j & 3);
-      bb_hi[umma::tile_off(kVtcNP, r0, 0) / 4 + kb] = e0 * s2 * s1;
-      bb_hi[umma::tile_off(kVtcNP, r0 + 1, 0) / 4 + kb] = e1 * s2;
-      *reinterpret_cast<float2*>(bt_hi + umma::tile_off(kVtcNP, j, 0) / 4 + cbt) = make_float2(t0 * s2 * s1, t1 * s2);
+      const uint32_t ob0 = umma::tile_off(kVtcNP, r0, 0) / 4 + kb, ob1 = umma::tile_off(kVtcNP, r0 + 1, 0) / 4 + kb;
+      float hi, lo;
+      umma::split_tf32(e0 * s2 * s1, hi, lo);
+      bb_hi[ob0] = hi;
+      bb_lo[ob0] = lo;
+      umma::split_tf32(e1 * s2, hi, lo);
+      bb_hi[ob1] = hi;
+      bb_lo[ob1] = lo;
+      float2 th, tlo;
+      umma::split_tf32(t0 * s2 * s1, th.x, tlo.x);
+      umma::split_tf32(t1 * s2, th.y, tlo.y);
+      const uint32_t ot = umma::tile_off(kVtcNP, j, 0) / 4 + cbt;
+      *reinterpret_cast<float2*>(bt_hi + ot) = th;
+      *reinterpret_cast<float2*>(bt_lo + ot) = tlo;
     }
   }
-  __syncwarp();
-  for (int e = lane; e < kVtcNP * kVtcNP / 4; e += 32) {  // (entries outside n x n stay zero: the buffers are cleared once)
-#pragma unroll
-    for (int m = 0; m < 2; ++m) {
-      float* ph = m ? bt_hi : bb_hi;
-      float* pl = m ? bt_lo : bb_lo;
-      const float4 v = reinterpret_cast<const float4*>(ph)[e];
-      float4 hi, lo;
-      umma::split_tf32(v.x, hi.x, lo.x);
-      umma::split_tf32(v.y, hi.y, lo.y);
-      umma::split_tf32(v.z, hi.z, lo.z);
-      umma::split_tf32(v.w, hi.w, lo.w);
-      reinterpret_cast<float4*>(ph)[e] = hi;
-      reinterpret_cast<float4*>(pl)[e] = lo;
-    }
-  }
+  __syncwarp();  // (entries outside n x n stay zero: the buffers are cleared once)
 }
 
 constexpr int kVtbThreads = 640;          // warp 0 issuer, 1 producer, 2 builder, 3 reduce, 4-19 converter / epilogue

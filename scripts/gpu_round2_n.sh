@@ -1,5 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_vtln.py -m gpu -q -x > gpurun_out/r02n_pytest.txt 2>&1; tail -4 gpurun_out/r02n_pytest.txt
+timeout 900 python -m pytest tests/test_gpu_vtln.py -m gpu -q -x > gpurun_out/r02n_pytest.txt 2>&1; tail -3 gpurun_out/r02n_pytest.txt
 timeout 300 python scripts/gpu_vtln_bench.py bwd > gpurun_out/r02n_vtln.txt 2>&1; cat gpurun_out/r02n_vtln.txt
-B2W_PROF_BWD=1 B2W_LIB=variants/libb200world_vtfprof.so timeout 300 python scripts/gpu_vtln_bench.py bwd > gpurun_out/r02n_vtln_prof.txt 2>&1; tail -17 gpurun_out/r02n_vtln_prof.txt
