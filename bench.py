@@ -417,7 +417,8 @@ def run_b200(args):
         workloads = None
         if not args.no_workloads:
             workloads = {"synth256": bench_synth256(args, dev, syn, feats, frame_off, stats_host, an, peaks, alpha),
-                         "vtln109": bench_vtln109(args, dev, peaks)}
+                         "vtln109": bench_vtln109(args, dev, peaks),
+                         "gen_data_files": bench_gen_data_files(args, host, sample_off, f0s, alpha)}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             # separate process: no fork of a CUDA-initialised interpreter
@@ -583,6 +584,85 @@ def bench_synth256(args, dev, syn, feats, frame_off, stats_host, an, peaks, alph
                              "sample": "%d utterances of the same rows" % ns}}
 
 
+def bench_gen_data_files(args, host, sample_off, f0s, alpha):
+    """WorldFeatLabelGen.gen_data FILES TO FILES -- wav files + cached F0 in, per-feature .npz archives and the
+    normalisation files out (WorldFeatLabelGen.py:947-1071) -- on the first --io-utts corpus utterances, wall clock (host IO is
+    the subject).  Beside it the reference's per-utterance IO loop alone (wave-module read + four numpy.savez per utterance, no
+    feature extraction at all) on the same files and arrays."""
+    import shutil
+    import tempfile
+    import wave
+    import torch
+    from idiaptts_b200.WorldFeatLabelGen import WorldFeatLabelGen
+    nu = min(args.io_utts, len(f0s))
+    if nu <= 0:
+        return None
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    root = tempfile.mkdtemp(prefix="b2w_io_", dir=base)
+    try:
+        wav_dir, ids, cache = os.path.join(root, "wav"), [], {}
+        os.makedirs(wav_dir)
+        x = host["x"].numpy()
+        for u in range(nu):
+            name = "utt%05d" % u
+            with wave.open(os.path.join(wav_dir, name + ".wav"), "wb") as w:
+                w.setnchannels(1)
+                w.setsampwidth(2)
+                w.setframerate(FS)
+                w.writeframes(x[sample_off[u]:sample_off[u + 1]].tobytes())
+            ids.append(name)
+            cache[name] = f0s[u]
+        audio = float(sample_off[nu]) / FS
+        gen = WorldFeatLabelGen(os.path.join(root, "out2"), num_coded_sps=NUM_CODED_SPS, num_bap=2, f0_cache=cache, mgc_alpha=alpha)
+        times = []
+        for it in range(3):  # the first pass warms the page cache and the allocator
+            out = os.path.join(root, "out%d" % it)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            gen.gen_data(wav_dir, out, file_id_list="train.txt", id_list=ids)
+            torch.cuda.synchronize()
+            times.append(time.perf_counter() - t0)
+            if it < 2:
+                shutil.rmtree(out)
+        t_native = min(times[1:])
+        # the batched reader protocol: archives -> one pinned packed matrix
+        t0 = time.perf_counter()
+        got, goff = gen.load_batch(ids, pin=True)
+        t_load = time.perf_counter() - t0
+        # the reference's IO loop alone, on the same data (what would remain if the extraction cost nothing)
+        feats_np = got.numpy()
+        cols = (("mcep", 0, NUM_CODED_SPS), ("lf0", NUM_CODED_SPS, 1), ("vuv", NUM_CODED_SPS + 1, 1), ("bap", NUM_CODED_SPS + 2, 2))
+        py_out = os.path.join(root, "py")
+        for k, _, _ in cols:
+            os.makedirs(os.path.join(py_out, k))
+        t0 = time.perf_counter()
+        for u, name in enumerate(ids):
+            with wave.open(os.path.join(wav_dir, name + ".wav"), "rb") as w:
+                np.frombuffer(w.readframes(w.getnframes()), dtype=np.int16)
+            rows = feats_np[goff[u]:goff[u + 1]]
+            for k, c0, c in cols:
+                np.savez(os.path.join(py_out, k, name), **{k: rows[:, c0:c0 + c]})
+        t_py_write = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for name in ids:
+            parts = []
+            for k, _, _ in cols:
+                with np.load(os.path.join(py_out, k, name + ".npz")) as arc:
+                    parts.append(arc[k])
+            np.concatenate(parts, axis=1)
+        t_py_load = time.perf_counter() - t0
+        return {"metric": "gen_data wav files + cached F0 -> npz feature files + normalisation files, wall clock",
+                "utts": nu, "audio_seconds": audio, "value": audio / t_native, "unit": "audio-s/s", "seconds": round(t_native, 3),
+                "first_call_seconds": round(times[0], 3), "filesystem": "tmpfs (/dev/shm)" if base else "tempfile default",
+                "bytes_read": int(sample_off[nu]) * 2, "bytes_written": int(feats_np.size) * 4,
+                "load_batch_seconds": round(t_load, 3), "load_batch_frames_per_s": float(goff[-1]) / t_load,
+                "python_io_loop_only": {"read_wav_savez_seconds": round(t_py_write, 3), "np_load_seconds": round(t_py_load, 3),
+                                        "what": "the reference's per-utterance wave read + 4 numpy.savez / 4 numpy.load, no extraction"},
+                "host_threads": os.cpu_count()}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
 def bench_vtln109(args, dev, peaks):
     """BASELINE.json configs[4]: Neural-VTLN all-pass warp forward + backward on VCTK-shaped mgc batches: 109 speakers x 4
     utterances x 1301 frames x 60 coefficients, one alpha ~ U[-0.2, 0.2] per speaker, grad_out ~ N(0, 1), seed 5."""
@@ -653,7 +733,8 @@ def main():
     ap.add_argument("--parity-utts", type=int, default=16)
     ap.add_argument("--synth-batch", type=int, default=SYNTH_BATCH, help="utterances per batched synthesis call of the corpus pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-workloads", action="store_true", help="skip the synth256 / vtln109 workloads")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the synth256 / vtln109 / gen_data_files workloads")
+    ap.add_argument("--io-utts", type=int, default=2048, help="utterances of the files-to-files gen_data workload (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

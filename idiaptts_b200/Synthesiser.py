@@ -9,7 +9,7 @@ import wave
 import numpy as np
 import torch
 
-from . import pipeline
+from . import corpus_io, pipeline
 from .WorldFeatLabelGen import WorldFeatLabelGen
 
 
@@ -19,6 +19,12 @@ class Synthesiser(object):
     @staticmethod
     def synth_batch(synth_output, hparams, has_deltas=False):
         """{id: [T, D]} -> {id: waveform float32}; the compute half of run_world_synth."""
+        ids, y, out_off = Synthesiser._synth_packed(synth_output, hparams, has_deltas)
+        return {ids[u]: y[out_off[u]:out_off[u + 1]] for u in range(len(ids))}
+
+    @staticmethod
+    def _synth_packed(synth_output, hparams, has_deltas=False):
+        """-> (ids, packed float32 waveforms on the host, sample offsets [U + 1])."""
         if not torch.cuda.is_available():
             raise RuntimeError("idiaptts_b200 needs a CUDA device; there is no CPU fallback")
         sp_type = getattr(hparams, "sp_type", "mcep")
@@ -34,7 +40,7 @@ class Synthesiser(object):
             lens.append(len(lf0))
             ids.append(id_name)
         if not rows:
-            return {}
+            return [], np.zeros(0, np.float32), np.zeros(1, np.int64)
         syn = pipeline.WorldSynthesizer(fs, D, getattr(hparams, "mgc_alpha", None),
                                         f0_silence_threshold=getattr(hparams, "f0_silence_threshold", WorldFeatLabelGen.f0_silence_threshold),
                                         lf0_zero=getattr(hparams, "lf0_zero", WorldFeatLabelGen.lf0_zero), device=dev,
@@ -46,19 +52,22 @@ class Synthesiser(object):
         y = y.cpu().numpy()
         from . import ops
         ops.raise_for_status(status, "run_world_synth")
-        return {ids[u]: y[out_off[u]:out_off[u + 1]] for u in range(len(ids))}
+        return ids, y, np.asarray(out_off, np.int64)
 
     @staticmethod
     def run_world_synth(synth_output, hparams, epoch=None, step=None, use_model_name=True, has_deltas=False):
         save_dir = Synthesiser._get_synth_dir(hparams, use_model_name, epoch=epoch, step=step)
-        waves = Synthesiser.synth_batch(synth_output, hparams, has_deltas)
-        for id_name, waveform in waves.items():
+        if getattr(hparams, "synth_ext", "wav").lower() != "wav":
+            raise NotImplementedError("only wav output is supported (pydub re-encoding is outside the path)")
+        ids, y, out_off = Synthesiser._synth_packed(synth_output, hparams, has_deltas)
+        paths = []
+        for id_name in ids:
             logging.info("Synthesise {} with the WORLD vocoder.".format(id_name))
             file_name = (os.path.basename(id_name) + getattr(hparams, "synth_file_suffix", "") + "_" + str(hparams.num_coded_sps)
                          + hparams.sp_type + "_WORLD")
-            Synthesiser.write_wav(os.path.join(save_dir, file_name + ".wav"), waveform, hparams.synth_fs)
-            if getattr(hparams, "synth_ext", "wav").lower() != "wav":
-                raise NotImplementedError("only wav output is supported (pydub re-encoding is outside the path)")
+            paths.append(os.path.join(save_dir, file_name + ".wav"))
+        # all files of the batch in one native call (a pool of host threads; same bytes as write_wav)
+        corpus_io.write_wavs_pcm16(paths, np.ascontiguousarray(y, np.float32), out_off, hparams.synth_fs)
 
     @staticmethod
     def write_wav(path, waveform, fs):

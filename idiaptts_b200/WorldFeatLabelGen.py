@@ -20,7 +20,7 @@ from collections import OrderedDict
 import numpy as np
 import torch
 
-from . import distributed, ops, pipeline
+from . import corpus_io, distributed, ops, pipeline
 from .AudioProcessing import AudioProcessing
 from .MeanCovarianceExtractor import MeanCovarianceExtractor
 from .MeanStdDevExtractor import MeanStdDevExtractor
@@ -109,9 +109,11 @@ class WorldFeatLabelGen(object):
     def __init__(self, *args, **kwargs):
         """Two forms, as in the reference (:140-228): WorldFeatLabelGen(config) with a WorldFeatLabelGen.Config, or the legacy
         WorldFeatLabelGen(dir_labels, add_deltas=..., num_coded_sps=..., ...) keyword form.  Extensions of this package (keyword
-        only): f0_cache (cached F0 tracks: dict / directory, north_star), mgc_alpha (override of fs_to_mgc_alpha)."""
+        only): f0_cache (cached F0 tracks: dict / directory, north_star), mgc_alpha (override of fs_to_mgc_alpha), io_threads
+        (host threads of the shard-at-a-time wav / npz file IO, corpus_io.py; 0 = one per hardware thread)."""
         self.f0_cache = kwargs.pop("f0_cache", None)
         self.mgc_alpha = kwargs.pop("mgc_alpha", None)
+        self.io_threads = int(kwargs.pop("io_threads", 0))
         if len(args) == 1 and isinstance(args[0], WorldFeatLabelGen.Config):
             config = args[0]
             fields = {k: getattr(config, k) for k in ("add_deltas", "preprocessing_fn", "preemphasis", "n_fft", "win_length_ms",
@@ -412,10 +414,9 @@ class WorldFeatLabelGen(object):
         dev = _device()
 
         # read this rank's shard
-        headers = []
-        for name in id_list:
-            with __import__("wave").open(os.path.join(dir_in, name + "." + file_ext), "rb") as w:
-                headers.append((w.getnframes(), w.getframerate()))
+        wav_paths = [os.path.join(dir_in, name + "." + file_ext) for name in id_list]
+        info = corpus_io.probe_wavs(wav_paths, threads=self.io_threads)  # all RIFF headers in one native call
+        headers = list(zip(info["num_samples"].tolist(), info["fs"].tolist()))
         if world > 1:
             mine = distributed.shard_utterances([h[0] for h in headers], world)[rank]
         else:
@@ -432,24 +433,31 @@ class WorldFeatLabelGen(object):
                            dtype=torch.float64, device=dev)
         feats_np, offs, failure = None, None, None
         try:
-            waves, f0s = [], []
-            for name in my_ids:
-                x, cur_fs = AudioProcessing.read_wav(os.path.join(dir_in, name + "." + file_ext))
-                if fs != cur_fs:
-                    raise ValueError("mixed sampling rates in one gen_data call ({} vs {})".format(fs, cur_fs))
+            if np.any(info["fs"][mine] != fs):
+                raise ValueError("mixed sampling rates in one gen_data call ({} vs {})".format(
+                    fs, int(info["fs"][mine][info["fs"][mine] != fs][0])))
+            f0s = []
+            for i, name in zip(mine, my_ids):
                 f0 = self._lookup_f0(f0_cache, name)
-                T = ops.num_frames(len(x), cur_fs, self.hop_size_ms)
+                T = ops.num_frames(int(info["num_samples"][i]), fs, self.hop_size_ms)
                 if f0 is None:
                     f0 = np.zeros(T)
                 if len(f0) != T:
                     raise ValueError("{}: cached F0 has {} frames, the waveform gives {}".format(name, len(f0), T))
-                waves.append(x)
                 f0s.append(f0)
-            if waves:
-                same = all(w.dtype == waves[0].dtype for w in waves)
-                if not same:
+            if len(my_ids):
+                my_paths = [wav_paths[i] for i in mine]
+                if np.all(info["bits"][mine] == 16) and np.all(info["channels"][mine] == 1):
+                    # the usual corpus: a pool of threads reads the PCM data straight into one pinned int16 buffer
+                    sub = {k: np.ascontiguousarray(v[mine]) for k, v in info.items()}
+                    samples, sample_off, _ = corpus_io.read_wavs_i16(my_paths, sub, pin=True, threads=self.io_threads)
+                    batch = ops.RaggedBatch.from_packed(samples, sample_off, f0s, fs, frame_period=self.hop_size_ms,
+                                                        preemphasis=self.preemphasis, device=dev)
+                else:  # other sample widths: per file, as float64
+                    waves = [AudioProcessing.read_wav(p)[0] for p in my_paths]
                     waves = [w.astype(np.float64) / 32768.0 if w.dtype == np.int16 else w.astype(np.float64) for w in waves]
-                batch = ops.RaggedBatch.from_host(waves, f0s, fs, frame_period=self.hop_size_ms, preemphasis=self.preemphasis, device=dev)
+                    batch = ops.RaggedBatch.from_host(waves, f0s, fs, frame_period=self.hop_size_ms, preemphasis=self.preemphasis,
+                                                      device=dev)
                 if f0_cache is None:
                     ops.estimate_f0(batch, frame_period=self.hop_size_ms)
                 an = pipeline.WorldAnalyzer(fs, D, alpha, self.hop_size_ms, self.n_fft, WorldFeatLabelGen.f0_silence_threshold,
@@ -496,27 +504,23 @@ class WorldFeatLabelGen(object):
 
         label_dict = OrderedDict()
         if feats_np is not None:
-            for u, name in enumerate(my_ids):
-                rows = feats_np[offs[u]:offs[u + 1]]
-                out_parts = []
-                base = os.path.basename(name)
+            if dir_out is not None:
+                # one native call per feature directory writes the archives of the whole shard (LabelGen.save_output's layout:
+                # <dir>/<feat>/<id>.npz with key <ext>[, <ext>_deltas, <ext>_double_deltas])
+                bases = [os.path.basename(name) for name in my_ids]
                 for key, load, fdir, fext, sl in groups:
                     if not load:
                         continue
-                    static = rows[:, cols(sl, 0)]
-                    if self.add_deltas and key != "vuv":
-                        dl, ddl = rows[:, cols(sl, 1)], rows[:, cols(sl, 2)]
-                        part = np.concatenate((static, dl, ddl), axis=1)
-                        if dir_out is not None:
-                            np.savez(os.path.join(dir_out, fdir, base), **{fext: static, fext + "_deltas": dl,
-                                                                          fext + "_double_deltas": ddl})
-                    else:
-                        part = static
-                        if dir_out is not None:
-                            np.savez(os.path.join(dir_out, fdir, base), **{fext: static})
-                    out_parts.append(part)
-                if return_dict:
-                    label_dict[name] = np.concatenate(out_parts, axis=1) if out_parts else None
+                    with_deltas = self.add_deltas and key != "vuv"
+                    keys = [fext, fext + "_deltas", fext + "_double_deltas"] if with_deltas else [fext]
+                    corpus_io.write_npz([os.path.join(dir_out, fdir, b + ".npz") for b in bases], keys,
+                                        [sl.start + blk * dim for blk in range(len(keys))], [sl.stop - sl.start] * len(keys),
+                                        offs, feats_np, threads=self.io_threads)
+            if return_dict:
+                sel = np.concatenate([np.concatenate([cols(sl, blk) for blk in range(3 if self.add_deltas and key != "vuv" else 1)])
+                                      for key, load, fdir, fext, sl in groups if load] or [np.zeros(0, np.int64)]).astype(np.int64)
+                for u, name in enumerate(my_ids):
+                    label_dict[name] = feats_np[offs[u]:offs[u + 1]][:, sel] if len(sel) else None
 
         # normalisation parameters from the (all-reduced) sums
         output_means, output_std_dev = [], []
@@ -620,6 +624,42 @@ class WorldFeatLabelGen(object):
             if self.load_bap:
                 out.append(lab[:, -3 * nap:])
         return np.concatenate(out, axis=1)
+
+    def load_batch(self, id_names, pin=True, verify_crc=True):
+        """The reader protocol for a whole mini-batch / shard: the rows `load` returns for every id, packed -- (feats, frame_off)
+        with feats a float32 CPU torch tensor [F, width] (pinned on request: the next stop is prepare_batch_device) and frame_off
+        int64 [U + 1].  One native call per feature directory reads all archives with a pool of threads (corpus_io.read_npz).
+        Archives the native reader refuses (compressed, other dtypes) and the legacy raw formats go through `load` per id."""
+        ids = [os.path.splitext(os.path.basename(i))[0] for i in id_names]
+        f3 = 3 if self.add_deltas else 1
+        feats_def = (("sp", self.load_sp, self.dir_coded_sps, self.sp_type, self.num_coded_sps),
+                     ("lf0", self.load_lf0, self.dir_lf0, self.ext_lf0, 1),
+                     ("vuv", self.load_vuv, self.dir_vuv, self.ext_vuv, 1),
+                     ("bap", self.load_bap, self.dir_bap, self.ext_bap, self.num_bap))
+        plan, width = [], 0
+        for key, load, fdir, fext, d in feats_def:
+            if not load:
+                continue
+            nblk = f3 if key != "vuv" else 1
+            keys = [fext, fext + "_deltas", fext + "_double_deltas"][:nblk]
+            plan.append((fdir, keys, [width + b * d for b in range(nblk)], [d] * nblk))
+            width += nblk * d
+        try:
+            if not plan or not ids:
+                raise ValueError("nothing to read natively")
+            paths0 = [os.path.join(self.dir_labels, plan[0][0], i + ".npz") for i in ids]
+            rows, _ = corpus_io.probe_npz(paths0, plan[0][1][0], threads=self.io_threads)
+            frame_off = np.concatenate(([0], np.cumsum(rows))).astype(np.int64)
+            feats = torch.empty((int(frame_off[-1]), width), dtype=torch.float32, pin_memory=bool(pin and frame_off[-1] > 0))
+            for fdir, keys, col_off, cols in plan:
+                corpus_io.read_npz([os.path.join(self.dir_labels, fdir, i + ".npz") for i in ids], keys, col_off, cols, frame_off,
+                                   feats, verify_crc=verify_crc, threads=self.io_threads)
+            return feats, frame_off
+        except ValueError:
+            parts = [self.load(i) for i in ids]
+            frame_off = np.concatenate(([0], np.cumsum([len(p) for p in parts]))).astype(np.int64)
+            feats = torch.from_numpy(np.ascontiguousarray(np.concatenate(parts, axis=0), np.float32)) if parts else torch.zeros((0, width))
+            return (feats.pin_memory() if pin and feats.numel() else feats), frame_off
 
     def __getitem__(self, id_name):
         """Load and normalise one sample (the reference's reader protocol, :290-300): the legacy constructor form returns the

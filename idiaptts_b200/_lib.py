@@ -97,6 +97,13 @@ _SIGNATURES = {
     "b2w_probe_fp64_fma": (c_int64, [c_int32, c_void_p, c_void_p]),
     "b2w_mcep_prof_read": (c_int32, [c_void_p]),
     "b2w_vtf_prof_read": (c_int32, [c_void_p]),
+    "b2w_wav_probe": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32]),
+    "b2w_wav_read_i16": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32]),
+    "b2w_wav_write_pcm16": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_int32]),
+    "b2w_npz_write_f32": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32]),
+    "b2w_npz_probe": (c_int32, [c_void_p, c_int32, ctypes.c_char_p, c_void_p, c_void_p, c_int32]),
+    "b2w_npz_read_f32": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
+                                   c_int32]),
     "b2w_cheaptrick_fft_size": (c_int32, [c_int32, c_double]),
     "b2w_num_aperiodicities": (c_int32, [c_int32]),
     "b2w_d4c_fft_size": (c_int32, [c_int32]),

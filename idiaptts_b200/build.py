@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libb200world.so")
-SOURCES = ["api.cu", "cheaptrick.cu", "cheaptrick_fast.cu", "d4c.cu", "d4c_fast.cu", "mcep.cu", "mgcep.cu", "mcep_tc.cu", "mc2sp_tc.cu", "labels.cu", "synth.cu", "synth_fast.cu", "vtln.cu", "vtln_tc.cu", "mlpg.cu", "metrics.cu", "dio.cu"]
+SOURCES = ["api.cu", "cheaptrick.cu", "cheaptrick_fast.cu", "d4c.cu", "d4c_fast.cu", "mcep.cu", "mgcep.cu", "mcep_tc.cu", "mc2sp_tc.cu", "labels.cu", "synth.cu", "synth_fast.cu", "vtln.cu", "vtln_tc.cu", "mlpg.cu", "metrics.cu", "dio.cu", "corpus_io.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

@@ -108,6 +108,27 @@ class RaggedBatch:
 
         return RaggedBatch(up(x), up(sample_off), up(f0), up(t), up(frame_off), up(frame_utt), fs, preemphasis)
 
+    @staticmethod
+    def from_packed(samples, sample_off, f0s, fs, frame_period=5.0, preemphasis=0.0, device="cuda"):
+        """The same batch from an already packed host waveform (corpus_io.read_wavs_i16: one pinned int16 tensor + offsets):
+        no per-utterance concatenation on the host.  f0s: list of float64 tracks, one value per frame."""
+        device = torch.device(device)
+        flens = np.array([len(f) for f in f0s], np.int64)
+        frame_off = np.concatenate(([0], np.cumsum(flens)))
+        f0 = np.concatenate([np.asarray(f, np.float64) for f in f0s]) if len(f0s) else np.zeros(0)
+        frame_utt = np.repeat(np.arange(len(f0s), dtype=np.int32), flens)
+        # i * frame_period / 1000 per utterance, on the device: the same two IEEE operations numpy does in from_host
+        fo_dev = torch.from_numpy(frame_off).to(device)
+        fu_dev = torch.from_numpy(frame_utt).to(device)
+        idx = torch.arange(int(frame_off[-1]), device=device, dtype=torch.int64) - fo_dev[:-1][fu_dev.long()]
+        t = idx.to(torch.float64) * frame_period / 1000.0
+
+        def up(a):
+            h = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+            return h.to(device, non_blocking=h.is_pinned())
+
+        return RaggedBatch(up(samples), up(np.asarray(sample_off, np.int64)), up(f0), t, fo_dev, fu_dev, fs, preemphasis)
+
     def c_struct(self, frame_lo=0, frame_hi=None):
         """struct b2w_batch for frames [frame_lo, frame_hi) (chunking keeps the intermediate planes bounded)."""
         if frame_hi is None:

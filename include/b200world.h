@@ -294,6 +294,43 @@ B2W_API int b2w_mgcep(const void* in, int32_t in_dtype, int32_t in_is_power, int
 B2W_API int b2w_mgc2sp(const void* mgc, int32_t mgc_dtype, int64_t mgc_stride, int64_t num_frames, int32_t fft_size, int32_t order,
                        double gamma, const float* fwd_cos, const float* fwd_sin, void* amp, int32_t amp_dtype, void* stream);
 
+/* ---- corpus file IO (host only, no device work, no stream): the formats on either side of the GPU batch, handled
+ * for a whole shard by a pool of `threads` host threads (0 = one per hardware thread, at most 64).  Errors: -1 and
+ * b2w_last_error() names the first file that failed; nothing is partially reported as success.
+ *
+ * wav in: replaces the per-utterance soundfile.read of AudioProcessing.get_raw (A:108-120) inside the gen_data loop (W:996-1013).
+ * b2w_wav_probe parses the RIFF headers (PCM, or extensible with PCM sub-format): per file the number of sample frames, sampling
+ * rate, bits per sample, channels and the byte offset of the data chunk.  b2w_wav_read_i16 reads 16-bit mono files into ONE packed
+ * buffer (samples of file i at utt_sample_offset[i] .. [i + 1]) -- the int16 waveform layout of b2w_batch, so the (pinned) buffer
+ * goes to the device as it is; the kernels scale by 1 / 32768 on load, which is the float64 soundfile returns.  Other widths /
+ * channel counts are the caller's general path.
+ *
+ * npz out / in: replaces numpy.savez per feature and utterance in LabelGen.save_output / WorldFeatLabelGen.save_output
+ * (LabelGen.py:63-101, W:1121-1172) and numpy.load in WorldFeatLabelGen.load_sample (W:459-567).  One call handles one feature
+ * directory: file i is a ZIP archive (stored) with one member "<keys[k]>.npy" per key, a C-ordered little-endian float32 matrix
+ * [utt_frame_offset[i + 1] - utt_frame_offset[i], cols[k]] = rows utt_frame_offset[i] .. of the packed host matrix `feats` (row
+ * stride feat_stride floats), columns col_offset[k] .. + cols[k].  Archives are byte-compatible with numpy (numpy.load reads
+ * them; the reader takes numpy.savez archives, ZIP64 headers included).  Compressed archives (savez_compressed) and other dtypes
+ * are refused with a message so that the caller can fall back to numpy.  b2w_npz_probe returns the shape of one key per file (1-D
+ * arrays report cols = 1); b2w_npz_read_f32 checks every shape against the offsets it was given and, with verify_crc, the CRC-32
+ * the way zipfile does. */
+B2W_API int b2w_wav_probe(const char* const* paths, int32_t num_files, int64_t* num_samples, int32_t* fs, int32_t* bits,
+                          int32_t* channels, int64_t* data_offset, int32_t threads);
+B2W_API int b2w_wav_read_i16(const char* const* paths, int32_t num_files, const int64_t* data_offset, const int64_t* utt_sample_offset,
+                             int16_t* samples, int32_t threads);
+/* wav out: the soundfile.write of Synthesiser.run_world_synth (idiaptts/src/Synthesiser.py:68-73) for a whole batch: file i gets the
+ * float32 samples [utt_sample_offset[i], utt_sample_offset[i + 1]) of the packed host buffer as 16-bit mono PCM,
+ * clip(round_half_even(32767 x), -32768, 32767). */
+B2W_API int b2w_wav_write_pcm16(const char* const* paths, int32_t num_files, const int64_t* utt_sample_offset, const float* samples,
+                                int32_t fs, int32_t threads);
+B2W_API int b2w_npz_write_f32(const char* const* paths, int32_t num_files, const char* const* keys, int32_t num_keys,
+                              const int32_t* col_offset, const int32_t* cols, const int64_t* utt_frame_offset, const float* feats,
+                              int64_t feat_stride, int32_t threads);
+B2W_API int b2w_npz_probe(const char* const* paths, int32_t num_files, const char* key, int64_t* rows, int32_t* cols, int32_t threads);
+B2W_API int b2w_npz_read_f32(const char* const* paths, int32_t num_files, const char* const* keys, int32_t num_keys,
+                             const int32_t* col_offset, const int32_t* cols, const int64_t* utt_frame_offset, float* feats,
+                             int64_t feat_stride, int32_t verify_crc, int32_t threads);
+
 /* ---- scalar helpers (host, pure functions): pyworld.get_cheaptrick_fft_size (A:60), get_num_aperiodicities
  * (A:71), and the D4C transform size. */
 B2W_API int32_t b2w_cheaptrick_fft_size(int32_t fs, double f0_floor);
