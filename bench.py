@@ -626,9 +626,13 @@ def bench_gen_data_files(args, host, sample_off, f0s, alpha):
                 shutil.rmtree(out)
         t_native = min(times[1:])
         # the batched reader protocol: archives -> one pinned packed matrix
-        t0 = time.perf_counter()
-        got, goff = gen.load_batch(ids, pin=True)
-        t_load = time.perf_counter() - t0
+        t_loads = []
+        for it in range(2):  # the first call also page-locks a new host block; later calls reuse it (torch's caching host allocator)
+            got = None
+            t0 = time.perf_counter()
+            got, goff = gen.load_batch(ids, pin=True)
+            t_loads.append(time.perf_counter() - t0)
+        t_load = t_loads[1]
         # the reference's IO loop alone, on the same data (what would remain if the extraction cost nothing)
         feats_np = got.numpy()
         cols = (("mcep", 0, NUM_CODED_SPS), ("lf0", NUM_CODED_SPS, 1), ("vuv", NUM_CODED_SPS + 1, 1), ("bap", NUM_CODED_SPS + 2, 2))
@@ -655,7 +659,7 @@ def bench_gen_data_files(args, host, sample_off, f0s, alpha):
                 "utts": nu, "audio_seconds": audio, "value": audio / t_native, "unit": "audio-s/s", "seconds": round(t_native, 3),
                 "first_call_seconds": round(times[0], 3), "filesystem": "tmpfs (/dev/shm)" if base else "tempfile default",
                 "bytes_read": int(sample_off[nu]) * 2, "bytes_written": int(feats_np.size) * 4,
-                "load_batch_seconds": round(t_load, 3), "load_batch_frames_per_s": float(goff[-1]) / t_load,
+                "load_batch_seconds": round(t_load, 3), "load_batch_first_call_seconds": round(t_loads[0], 3), "load_batch_frames_per_s": float(goff[-1]) / t_load,
                 "python_io_loop_only": {"read_wav_savez_seconds": round(t_py_write, 3), "np_load_seconds": round(t_py_load, 3),
                                         "what": "the reference's per-utterance wave read + 4 numpy.savez / 4 numpy.load, no extraction"},
                 "host_threads": os.cpu_count()}

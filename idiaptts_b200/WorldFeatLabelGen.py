@@ -110,10 +110,13 @@ class WorldFeatLabelGen(object):
         """Two forms, as in the reference (:140-228): WorldFeatLabelGen(config) with a WorldFeatLabelGen.Config, or the legacy
         WorldFeatLabelGen(dir_labels, add_deltas=..., num_coded_sps=..., ...) keyword form.  Extensions of this package (keyword
         only): f0_cache (cached F0 tracks: dict / directory, north_star), mgc_alpha (override of fs_to_mgc_alpha), io_threads
-        (host threads of the shard-at-a-time wav / npz file IO, corpus_io.py; 0 = one per hardware thread)."""
+        (host threads of the shard-at-a-time wav / npz file IO, corpus_io.py; 0 = one per hardware thread), io_chunk_seconds (audio
+        per piece of gen_data's read / extract / write pipeline)."""
         self.f0_cache = kwargs.pop("f0_cache", None)
         self.mgc_alpha = kwargs.pop("mgc_alpha", None)
         self.io_threads = int(kwargs.pop("io_threads", 0))
+        self.io_chunk_seconds = float(kwargs.pop("io_chunk_seconds", 4096.0))
+        self._io_slots = None
         if len(args) == 1 and isinstance(args[0], WorldFeatLabelGen.Config):
             config = args[0]
             fields = {k: getattr(config, k) for k in ("add_deltas", "preprocessing_fn", "preemphasis", "n_fft", "win_length_ms",
@@ -431,55 +434,24 @@ class WorldFeatLabelGen(object):
         alpha = self.mgc_alpha if self.mgc_alpha is not None else AudioProcessing.fs_to_mgc_alpha(fs)
         stat = torch.zeros(1 + 2 * dim * (3 if self.add_deltas else 1) + (3 * dim) ** 2 * (1 if self.add_deltas else 0) + 1,
                            dtype=torch.float64, device=dev)
-        feats_np, offs, failure = None, None, None
+        # per-feature column groups of the static block
+        groups = (("sp", self.load_sp, self.dir_coded_sps, self.sp_type, slice(0, D)),
+                  ("lf0", self.load_lf0, self.dir_lf0, self.ext_lf0, slice(D, D + 1)),
+                  ("vuv", self.load_vuv, self.dir_vuv, self.ext_vuv, slice(D + 1, D + 2)),
+                  ("bap", self.load_bap, self.dir_bap, self.ext_bap, slice(D + 2, D + 2 + nap)))
+
+        def cols(sl, block):  # columns of a feature in block 0 (static), 1 (delta), 2 (delta-delta)
+            return np.arange(sl.start, sl.stop) + block * dim
+
+        label_dict = OrderedDict()
+        failure = None
         try:
             if np.any(info["fs"][mine] != fs):
                 raise ValueError("mixed sampling rates in one gen_data call ({} vs {})".format(
                     fs, int(info["fs"][mine][info["fs"][mine] != fs][0])))
-            f0s = []
-            for i, name in zip(mine, my_ids):
-                f0 = self._lookup_f0(f0_cache, name)
-                T = ops.num_frames(int(info["num_samples"][i]), fs, self.hop_size_ms)
-                if f0 is None:
-                    f0 = np.zeros(T)
-                if len(f0) != T:
-                    raise ValueError("{}: cached F0 has {} frames, the waveform gives {}".format(name, len(f0), T))
-                f0s.append(f0)
             if len(my_ids):
-                my_paths = [wav_paths[i] for i in mine]
-                if np.all(info["bits"][mine] == 16) and np.all(info["channels"][mine] == 1):
-                    # the usual corpus: a pool of threads reads the PCM data straight into one pinned int16 buffer
-                    sub = {k: np.ascontiguousarray(v[mine]) for k, v in info.items()}
-                    samples, sample_off, _ = corpus_io.read_wavs_i16(my_paths, sub, pin=True, threads=self.io_threads)
-                    batch = ops.RaggedBatch.from_packed(samples, sample_off, f0s, fs, frame_period=self.hop_size_ms,
-                                                        preemphasis=self.preemphasis, device=dev)
-                else:  # other sample widths: per file, as float64
-                    waves = [AudioProcessing.read_wav(p)[0] for p in my_paths]
-                    waves = [w.astype(np.float64) / 32768.0 if w.dtype == np.int16 else w.astype(np.float64) for w in waves]
-                    batch = ops.RaggedBatch.from_host(waves, f0s, fs, frame_period=self.hop_size_ms, preemphasis=self.preemphasis,
-                                                      device=dev)
-                if f0_cache is None:
-                    ops.estimate_f0(batch, frame_period=self.hop_size_ms)
-                an = pipeline.WorldAnalyzer(fs, D, alpha, self.hop_size_ms, self.n_fft, WorldFeatLabelGen.f0_silence_threshold,
-                                            WorldFeatLabelGen.lf0_zero, device=dev, sp_type=self.sp_type,
-                                            mgc_gamma=AudioProcessing.mgc_gamma)
-                feats, sums, status = an.extract(batch)
-                F = batch.num_frames
-                if self.add_deltas:
-                    d, dd = ops.deltas(feats, batch.frame_off)
-                    full = torch.cat((feats, d, dd), dim=1).contiguous()  # [F, 3*dim] = [static | delta | delta-delta]
-                    sums3 = torch.zeros(2 * 3 * dim, dtype=torch.float64, device=dev)
-                    gram = torch.zeros((3 * dim) ** 2, dtype=torch.float64, device=dev)
-                    ops.stats_accumulate(full, sums3, gram)
-                    stat[1:1 + 6 * dim] = sums3
-                    stat[1 + 6 * dim:-1] = gram
-                    feats_np = full.cpu().numpy()
-                else:
-                    stat[1:1 + 2 * dim] = sums
-                    feats_np = feats.cpu().numpy()
-                stat[0] = float(F)
-                offs = batch.frame_off.cpu().numpy()
-                ops.raise_for_status(status, "gen_data")
+                self._extract_shard(dev, wav_paths, info, mine, my_ids, f0_cache, fs, alpha, dim, stat, groups, cols, dir_out,
+                                    label_dict if return_dict else None)
         except Exception as e:  # noqa: BLE001 -- re-raised below, after the collective
             failure = e
             stat.zero_()
@@ -492,35 +464,6 @@ class WorldFeatLabelGen(object):
             raise RuntimeError("gen_data failed on {} other rank(s); see their error".format(int(round(stat_np[-1]))))
         stat_np = stat_np[:-1]
         n_total = int(round(stat_np[0]))
-
-        # per-feature column groups of the static block
-        groups = (("sp", self.load_sp, self.dir_coded_sps, self.sp_type, slice(0, D)),
-                  ("lf0", self.load_lf0, self.dir_lf0, self.ext_lf0, slice(D, D + 1)),
-                  ("vuv", self.load_vuv, self.dir_vuv, self.ext_vuv, slice(D + 1, D + 2)),
-                  ("bap", self.load_bap, self.dir_bap, self.ext_bap, slice(D + 2, D + 2 + nap)))
-
-        def cols(sl, block):  # columns of a feature in block 0 (static), 1 (delta), 2 (delta-delta)
-            return np.arange(sl.start, sl.stop) + block * dim
-
-        label_dict = OrderedDict()
-        if feats_np is not None:
-            if dir_out is not None:
-                # one native call per feature directory writes the archives of the whole shard (LabelGen.save_output's layout:
-                # <dir>/<feat>/<id>.npz with key <ext>[, <ext>_deltas, <ext>_double_deltas])
-                bases = [os.path.basename(name) for name in my_ids]
-                for key, load, fdir, fext, sl in groups:
-                    if not load:
-                        continue
-                    with_deltas = self.add_deltas and key != "vuv"
-                    keys = [fext, fext + "_deltas", fext + "_double_deltas"] if with_deltas else [fext]
-                    corpus_io.write_npz([os.path.join(dir_out, fdir, b + ".npz") for b in bases], keys,
-                                        [sl.start + blk * dim for blk in range(len(keys))], [sl.stop - sl.start] * len(keys),
-                                        offs, feats_np, threads=self.io_threads)
-            if return_dict:
-                sel = np.concatenate([np.concatenate([cols(sl, blk) for blk in range(3 if self.add_deltas and key != "vuv" else 1)])
-                                      for key, load, fdir, fext, sl in groups if load] or [np.zeros(0, np.int64)]).astype(np.int64)
-                for u, name in enumerate(my_ids):
-                    label_dict[name] = feats_np[offs[u]:offs[u + 1]][:, sel] if len(sel) else None
 
         # normalisation parameters from the (all-reduced) sums
         output_means, output_std_dev = [], []
@@ -569,6 +512,191 @@ class WorldFeatLabelGen(object):
         if return_dict:
             return label_dict, output_means, output_std_dev
         return output_means, output_std_dev
+
+    def _extract_shard(self, dev, wav_paths, info, mine, my_ids, f0_cache, fs, alpha, dim, stat, groups, cols, dir_out, label_dict):
+        """The body of gen_data for this rank's shard, as a three-stage pipeline over pieces of about io_chunk_seconds of audio:
+            reader thread   wav files -> one pinned int16 buffer (native thread pool, corpus_io.read_wavs_i16)
+            this thread     pinned buffer -> device, the analysis kernels, statistics, feature rows -> pinned buffer (copy stream)
+            writer thread   pinned feature rows -> per-feature .npz archives (corpus_io.write_npz) [and the label dictionary]
+        with two buffers per hand-over, so the file reads of piece k + 1 and the file writes of piece k - 1 run while the GPU works
+        on piece k, and host memory is bounded by the piece size instead of the corpus.  The statistics accumulate on the device
+        across pieces (`stat` layout: [N | sums | (gram)] + failure flag)."""
+        import queue
+        import threading
+        D = self.num_coded_sps
+        width = dim * (3 if self.add_deltas else 1)
+        packed_ok = bool(np.all(info["bits"][mine] == 16) and np.all(info["channels"][mine] == 1))
+        # pieces of whole utterances, about io_chunk_seconds of audio each
+        budget = int(self.io_chunk_seconds * fs)
+        pieces, cur, acc = [], [], 0
+        for j, i in enumerate(mine):
+            n = int(info["num_samples"][i])
+            if cur and acc + n > budget:
+                pieces.append(cur)
+                cur, acc = [], 0
+            cur.append(j)
+            acc += n
+        if cur:
+            pieces.append(cur)
+        frames_of = [ops.num_frames(int(info["num_samples"][i]), fs, self.hop_size_ms) for i in mine]
+        max_samples = max(sum(int(info["num_samples"][mine[j]]) for j in pc) for pc in pieces)
+        max_frames = max(sum(frames_of[j] for j in pc) for pc in pieces)
+        want_rows = dir_out is not None or label_dict is not None
+        nslots = min(2, len(pieces))
+        slots = self._io_slots
+        if (slots is None or slots["in"][0].numel() < max_samples or slots["out"][0].shape[0] < max_frames
+                or slots["out"][0].shape[1] != width or len(slots["in"]) < nslots):
+            slots = {"in": [torch.empty(max_samples if packed_ok else 0, dtype=torch.int16, pin_memory=packed_ok and max_samples > 0)
+                            for _ in range(nslots)],
+                     "out": [torch.empty((max_frames if want_rows else 0, width), dtype=torch.float32,
+                                         pin_memory=want_rows and max_frames > 0) for _ in range(nslots)]}
+            self._io_slots = slots  # pinned allocations are expensive: kept for the next call
+        an = pipeline.WorldAnalyzer(fs, D, alpha, self.hop_size_ms, self.n_fft, WorldFeatLabelGen.f0_silence_threshold,
+                                    WorldFeatLabelGen.lf0_zero, device=dev, sp_type=self.sp_type, mgc_gamma=AudioProcessing.mgc_gamma)
+        status = ops.new_status(dev)
+        sums = torch.zeros(2 * dim, dtype=torch.float64, device=dev)
+        sums3 = torch.zeros(2 * 3 * dim, dtype=torch.float64, device=dev) if self.add_deltas else None
+        gram = torch.zeros((3 * dim) ** 2, dtype=torch.float64, device=dev) if self.add_deltas else None
+        copy_stream = torch.cuda.Stream(dev)
+        cur_stream = torch.cuda.current_stream(dev)
+        free_in, ready_in, free_out, ready_out = queue.Queue(), queue.Queue(), queue.Queue(), queue.Queue()
+        for k in range(nslots):
+            free_in.put((k, None))
+            free_out.put(k)
+        errors = []
+        stop = threading.Event()
+
+        def reader():
+            try:
+                for pc in pieces:
+                    if stop.is_set():
+                        break
+                    f0s = []
+                    for j in pc:
+                        name = my_ids[j]
+                        f0 = self._lookup_f0(f0_cache, name)
+                        if f0 is None:
+                            f0 = np.zeros(frames_of[j])
+                        if len(f0) != frames_of[j]:
+                            raise ValueError("{}: cached F0 has {} frames, the waveform gives {}".format(name, len(f0), frames_of[j]))
+                        f0s.append(f0)
+                    paths = [wav_paths[mine[j]] for j in pc]
+                    if packed_ok:
+                        slot, ev = free_in.get()
+                        if ev is not None:
+                            ev.synchronize()  # the previous piece in this buffer has reached the device
+                        idx = np.asarray([mine[j] for j in pc])
+                        sample_off = np.concatenate(([0], np.cumsum(info["num_samples"][idx]))).astype(np.int64)
+                        corpus_io._read_into(paths, np.ascontiguousarray(info["data_offset"][idx]), sample_off, slots["in"][slot],
+                                             self.io_threads)
+                        ready_in.put((pc, f0s, slot, sample_off, None))
+                    else:  # other sample widths: per file, as float64
+                        waves = [AudioProcessing.read_wav(p)[0] for p in paths]
+                        waves = [w.astype(np.float64) / 32768.0 if w.dtype == np.int16 else w.astype(np.float64) for w in waves]
+                        ready_in.put((pc, f0s, None, None, waves))
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+            finally:
+                ready_in.put(None)
+
+        sel = None
+        if label_dict is not None:
+            sel = np.concatenate([np.concatenate([cols(sl, blk) for blk in range(3 if self.add_deltas and key != "vuv" else 1)])
+                                  for key, load, fdir, fext, sl in groups if load] or [np.zeros(0, np.int64)]).astype(np.int64)
+
+        def writer():
+            while True:
+                item = ready_out.get()
+                if item is None:
+                    break
+                pc, slot, ev, offs = item
+                try:
+                    if errors:
+                        continue
+                    ev.synchronize()
+                    rows = slots["out"][slot]
+                    if dir_out is not None:
+                        # one native call per feature directory writes the archives of the piece (LabelGen.save_output's layout:
+                        # <dir>/<feat>/<id>.npz with key <ext>[, <ext>_deltas, <ext>_double_deltas])
+                        bases = [os.path.basename(my_ids[j]) for j in pc]
+                        for key, load, fdir, fext, sl in groups:
+                            if not load:
+                                continue
+                            with_deltas = self.add_deltas and key != "vuv"
+                            keys = [fext, fext + "_deltas", fext + "_double_deltas"] if with_deltas else [fext]
+                            corpus_io.write_npz([os.path.join(dir_out, fdir, b + ".npz") for b in bases], keys,
+                                                [sl.start + blk * dim for blk in range(len(keys))], [sl.stop - sl.start] * len(keys),
+                                                offs, rows, threads=self.io_threads)
+                    if label_dict is not None:
+                        rows_np = rows.numpy()
+                        for u, j in enumerate(pc):
+                            label_dict[my_ids[j]] = rows_np[offs[u]:offs[u + 1]][:, sel] if len(sel) else None  # fancy index: a copy
+                except Exception as e:  # noqa: BLE001
+                    errors.append(e)
+                    stop.set()
+                finally:
+                    free_out.put(slot)  # always handed back: the extraction loop may be waiting for it
+
+        threads = [threading.Thread(target=reader, name="b2w-wav-reader", daemon=True)]
+        if want_rows:
+            threads.append(threading.Thread(target=writer, name="b2w-npz-writer", daemon=True))
+        for t in threads:
+            t.start()
+        total_frames = 0
+        try:
+            while True:
+                item = ready_in.get()
+                if item is None or errors:
+                    break
+                pc, f0s, slot, sample_off, waves = item
+                if slot is not None:
+                    batch = ops.RaggedBatch.from_packed(slots["in"][slot][:int(sample_off[-1])], sample_off, f0s, fs,
+                                                        frame_period=self.hop_size_ms, preemphasis=self.preemphasis, device=dev)
+                    ev = torch.cuda.Event()
+                    ev.record(cur_stream)
+                    free_in.put((slot, ev))
+                else:
+                    batch = ops.RaggedBatch.from_host(waves, f0s, fs, frame_period=self.hop_size_ms, preemphasis=self.preemphasis,
+                                                      device=dev)
+                if f0_cache is None:
+                    ops.estimate_f0(batch, frame_period=self.hop_size_ms)
+                feats, _, _ = an.extract(batch, sums=sums, status=status)
+                F = batch.num_frames
+                total_frames += F
+                if self.add_deltas:
+                    d, dd = ops.deltas(feats, batch.frame_off)
+                    feats = torch.cat((feats, d, dd), dim=1).contiguous()  # [F, 3*dim] = [static | delta | delta-delta]
+                    ops.stats_accumulate(feats, sums3, gram)
+                if want_rows:
+                    oslot = free_out.get()  # blocks while the writer still holds both buffers
+                    done = torch.cuda.Event()
+                    done.record(cur_stream)
+                    copy_stream.wait_event(done)
+                    with torch.cuda.stream(copy_stream):
+                        slots["out"][oslot][:F].copy_(feats, non_blocking=True)
+                        copied = torch.cuda.Event()
+                        copied.record(copy_stream)
+                    feats.record_stream(copy_stream)
+                    offs = np.concatenate(([0], np.cumsum([frames_of[j] for j in pc]))).astype(np.int64)
+                    ready_out.put((pc, oslot, copied, offs))
+        finally:
+            stop.set()
+            if want_rows:
+                ready_out.put(None)
+            # unblock a reader that waits for a buffer, then collect the threads
+            free_in.put((0, None))
+            free_in.put((1, None))
+            for t in threads:
+                t.join()
+        if errors:
+            raise errors[0]
+        if self.add_deltas:
+            stat[1:1 + 6 * dim] = sums3
+            stat[1 + 6 * dim:-1] = gram
+        else:
+            stat[1:1 + 2 * dim] = sums
+        stat[0] = float(total_frames)
+        ops.raise_for_status(status, "gen_data")
 
     # ---- reading features back (SURVEY 8f N4: the on-disk formats at the boundary) ----------------------------------------
     @staticmethod

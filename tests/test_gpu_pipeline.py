@@ -251,3 +251,76 @@ def test_synthesize_corpus_without_round_trips_matches_single_calls():
     assert ops.raise_for_status(s, "synthesize_corpus") == 0
     assert int(out_off[-1]) == ref.numel()
     assert torch.equal(y_dev, ref) and torch.equal(y_host, ref.cpu())
+
+
+@pytest.mark.parametrize("add_deltas", [False, True])
+def test_gen_data_pieces_equal_one_piece(tmp_path, add_deltas):
+    """gen_data's read / extract / write pipeline: splitting the shard into pieces (here one or two utterances each, so the two
+    buffers of every hand-over are reused several times) leaves the same bytes on disk and the same statistics as one piece;
+    errors raised by the reader and writer threads reach the caller."""
+    import filecmp
+    from idiaptts_b200.WorldFeatLabelGen import WorldFeatLabelGen
+    fs = 22050
+    ids, cache, waves, f0s = _write_corpus(tmp_path, 7, fs, 0.6, seed=11)
+    one = WorldFeatLabelGen(str(tmp_path / "one"), add_deltas=add_deltas, num_coded_sps=60, num_bap=2, f0_cache=cache)
+    ld1, m1, s1 = one.gen_data(str(tmp_path / "wav"), str(tmp_path / "one"), file_id_list="train.txt", id_list=ids, return_dict=True)
+    many = WorldFeatLabelGen(str(tmp_path / "many"), add_deltas=add_deltas, num_coded_sps=60, num_bap=2, f0_cache=cache,
+                             io_chunk_seconds=1.0, io_threads=2)
+    for rep in range(2):                                       # the second call reuses the pinned buffers of the first
+        ld2, m2, s2 = many.gen_data(str(tmp_path / "wav"), str(tmp_path / "many"), file_id_list="train.txt", id_list=ids, return_dict=True)
+        assert list(ld2) == ids
+        for i in ids:
+            assert np.array_equal(ld1[i], ld2[i])
+            for d in ("mcep60", "lf0", "vuv", "bap"):
+                assert filecmp.cmp(str(tmp_path / "one" / d / (i + ".npz")), str(tmp_path / "many" / d / (i + ".npz")), shallow=False)
+        if add_deltas:
+            for a, b in zip(m1, m2):
+                np.testing.assert_allclose(a, b, rtol=1e-10, atol=1e-12)
+            for a, b in zip(s1, s2):
+                np.testing.assert_allclose(a, b, rtol=1e-8, atol=1e-10)
+        else:
+            np.testing.assert_allclose(m1, m2, rtol=1e-10, atol=1e-12)
+            np.testing.assert_allclose(s1, s2, rtol=1e-8, atol=1e-10)
+    # statistics only (no directory, no dictionary): nothing is copied back or written
+    m3, s3 = many.gen_data(str(tmp_path / "wav"), None, id_list=ids)
+    if not add_deltas:
+        np.testing.assert_allclose(m1, m3, rtol=1e-10, atol=1e-12)
+    # reader thread: a cached F0 of the wrong length; writer thread: an output directory that went away
+    bad = dict(cache)
+    bad[ids[4]] = cache[ids[4]][:-1]
+    with pytest.raises(ValueError, match="cached F0"):
+        many.gen_data(str(tmp_path / "wav"), str(tmp_path / "many"), id_list=ids, f0_cache=bad)
+    import shutil
+
+    class Vanishing(WorldFeatLabelGen):
+        def _create_directories(self, dir_out):
+            super()._create_directories(dir_out)
+            shutil.rmtree(os.path.join(dir_out, "bap"))
+    v = Vanishing(str(tmp_path / "gone"), add_deltas=add_deltas, num_coded_sps=60, num_bap=2, f0_cache=cache, io_chunk_seconds=1.0)
+    with pytest.raises(ValueError, match="cannot write"):
+        v.gen_data(str(tmp_path / "wav"), str(tmp_path / "gone"), id_list=ids)
+    # and the generator is usable afterwards
+    ld4, _, _ = many.gen_data(str(tmp_path / "wav"), None, id_list=ids[:2], return_dict=True)
+    assert np.array_equal(ld4[ids[1]], ld1[ids[1]])
+
+
+def test_gen_data_other_sample_widths(tmp_path):
+    """32-bit PCM files take the general per-file reader (float64 samples) through the same pipeline."""
+    import wave
+    from idiaptts_b200.WorldFeatLabelGen import WorldFeatLabelGen
+    fs = 16000
+    ids, cache, waves, f0s = _write_corpus(tmp_path, 3, fs, 0.5, seed=12)
+    os.makedirs(str(tmp_path / "wav32"))
+    for i, w in zip(ids, waves):
+        with wave.open(str(tmp_path / "wav32" / (i + ".wav")), "wb") as f:
+            f.setnchannels(1)
+            f.setsampwidth(4)
+            f.setframerate(fs)
+            f.writeframes((w.numpy().astype(np.int32) << 16).tobytes())
+    a, _, _ = WorldFeatLabelGen(None, num_coded_sps=60, f0_cache=cache, mgc_alpha=0.58).gen_data(str(tmp_path / "wav"), None, id_list=ids,
+                                                                                                 return_dict=True)
+    b, _, _ = WorldFeatLabelGen(None, num_coded_sps=60, f0_cache=cache, mgc_alpha=0.58, io_chunk_seconds=0.6).gen_data(
+        str(tmp_path / "wav32"), None, id_list=ids, return_dict=True)
+    for i in ids:
+        assert a[i].shape == b[i].shape and np.array_equal(a[i][:, 61], b[i][:, 61])
+        assert np.abs(a[i][:, :60] - b[i][:, :60]).max() < 1e-3
