@@ -207,6 +207,7 @@ def run_b200(args):
         raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpus_bound = distributed.bind_host_to_gpu(local)  # before any pinned allocation: host buffers on the GPU's own socket
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     alpha = float(mcepalpha(FS))
@@ -438,7 +439,7 @@ def run_b200(args):
                            "utts_this_rank": utts, "fs": FS, "utt_seconds": "N(%.1f, %.1f^2) clipped [1.1, 10.1]" % (DUR, DUR_STD)
                            if not args.fixed_dur else DUR, "audio_seconds_total": total_audio, "frames_this_rank": int(F),
                            "num_coded_sps": NUM_CODED_SPS, "mgc_alpha": alpha, "fft_size": an.n_fft, "num_bap": an.nap,
-                           "chunk_frames": an.chunk_frames, "synth_batch_utts": args.synth_batch, "shard_imbalance": round(imbalance, 4),
+                           "chunk_frames": an.chunk_frames, "synth_batch_utts": args.synth_batch, "shard_imbalance": round(imbalance, 4), "host_cpus_bound_to_gpu_socket": None if cpus_bound is None else len(cpus_bound),
                            "l2": "inputs (%.2f GB int16), features (%.2f GB) and waveforms (%.2f GB) exceed the 126 MB L2" % (
                                host["x"].numel() * 2 / 1e9, feats.numel() * 4 / 1e9, y_all.numel() * 4 / 1e9),
                            "corpus_gen_s": round(gen_s, 1), "mean_c0": float(mean[0]), "std_c0": float(std[0])},
