@@ -818,7 +818,7 @@ class WorldFeatLabelGen(object):
             return sample
         return np.float32((sample - mean) / std)
 
-    def prepare_batch_device(self, feats, frame_off, batch_first=False, norm_params=None, min_frames=None):
+    def prepare_batch_device(self, feats, frame_off, batch_first=False, norm_params=None, min_frames=None, lengths=None):
         """Device-side form of `preprocess_sample` on every utterance + `ModularModelHandlerPyTorch.prepare_batch` (:389-499) for
         feature rows that are already on the GPU (e.g. straight out of pipeline.WorldAnalyzer.extract): ragged [F, W] float32 +
         frame offsets -> (padded [T_max, B, W] | [B, T_max, W], mask, lengths).  One HBM pass (ops.pad_normalise)."""
@@ -826,7 +826,66 @@ class WorldFeatLabelGen(object):
         dev = feats.device
         m = None if mean is None else torch.from_numpy(np.ascontiguousarray(mean.reshape(-1))).to(dev)
         sd = None if std is None else torch.from_numpy(np.ascontiguousarray(std.reshape(-1))).to(dev)
-        return ops.pad_normalise(feats, frame_off, m, sd, batch_first=batch_first, min_frames=min_frames)
+        return ops.pad_normalise(feats, frame_off, m, sd, batch_first=batch_first, min_frames=min_frames, lengths=lengths)
+
+    def batches(self, id_list, batch_size, shuffle=False, seed=0, batch_first=False, drop_last=False, prefetch=2, device=None,
+                norm_params=None):
+        """The trainer-facing loader for this reader (the role of the reference's DataLoader over `__getitem__` +
+        `ModularModelHandlerPyTorch.prepare_batch`, :389-499): yields, per mini-batch, a dict with `ids`, `padded`
+        ([T_max, B, W] or [B, T_max, W] float32 on the device, normalised), `mask`, `lengths` (host int64 [B]) and `frame_off`
+        (device int64 [B + 1]).  A background thread reads the archives of the next `prefetch` mini-batches into pinned host
+        memory (load_batch: one native call per feature directory) while the caller trains on the current one; upload and
+        pad + normalise (one HBM pass) happen on the caller's stream.  Normalisation parameters must be loaded."""
+        import queue
+        import threading
+        if self.norm_params is None and norm_params is None:
+            raise RuntimeError("normalisation parameters are not loaded: call get_normalisation_params(dir_out, file_name) first")
+        dev = torch.device(device) if device is not None else _device()
+        ids = list(id_list)
+        if shuffle:
+            order = np.random.default_rng(seed).permutation(len(ids))
+            ids = [ids[i] for i in order]
+        groups = [ids[i:i + batch_size] for i in range(0, len(ids), batch_size)]
+        if drop_last and groups and len(groups[-1]) < batch_size:
+            groups.pop()
+        q = queue.Queue(maxsize=max(1, int(prefetch)))
+        stop = threading.Event()
+
+        def put(item):  # a bounded put that gives up when the consumer has gone away
+            while not stop.is_set():
+                try:
+                    q.put(item, timeout=0.1)
+                    return True
+                except queue.Full:
+                    continue
+            return False
+
+        def worker():
+            try:
+                for g in groups:
+                    if stop.is_set() or not put((g,) + self.load_batch(g, pin=dev.type == "cuda")):
+                        return
+                put(None)
+            except Exception as e:  # noqa: BLE001 -- re-raised in the consumer
+                put(e)
+
+        t = threading.Thread(target=worker, name="b2w-batch-loader", daemon=True)
+        t.start()
+        try:
+            while True:
+                item = q.get()
+                if item is None:
+                    break
+                if isinstance(item, Exception):
+                    raise item
+                g, feats, frame_off = item
+                fo_dev = torch.from_numpy(frame_off).to(dev)
+                padded, mask, lengths = self.prepare_batch_device(feats.to(dev, non_blocking=True), fo_dev, batch_first=batch_first,
+                                                                  norm_params=norm_params, lengths=np.diff(frame_off))
+                yield {"ids": g, "padded": padded, "mask": mask, "lengths": lengths, "frame_off": fo_dev}
+        finally:
+            stop.set()
+            t.join()
 
     def unprepare_batch_device(self, padded, frame_off, frame_utt, batch_first=False, norm_params=None):
         """Network output [T_max, B, W] | [B, T_max, W] -> de-normalised ragged rows [F, W] on the device (the first half of

@@ -57,3 +57,37 @@ def test_pad_normalise_strided_rows_and_corpus_scale():
     out60, _, _ = ops.pad_normalise(sub, off, batch_first=True)
     ref60, _, _ = glue_np.prepare_batch([s[:, :60] for s in samples], batch_first=True)
     assert np.array_equal(out60.cpu().numpy(), ref60)
+
+
+@pytest.mark.parametrize("add_deltas", [False, True])
+def test_prefetching_batch_loader_equals_the_per_sample_reader(tmp_path, add_deltas):
+    """WorldFeatLabelGen.batches (background load_batch into pinned memory + pad / normalise on the device) yields exactly what the
+    reference protocol gives sample by sample: reader[id] (load + preprocess_sample) padded by prepare_batch -- bit for bit."""
+    from test_host_logic import _write_world_label_dir
+    from idiaptts_b200.WorldFeatLabelGen import WorldFeatLabelGen
+    rng = np.random.default_rng(5)
+    ids = ["u%s" % ("x" * k) for k in range(11)]              # 11 utterances of different lengths
+    D, nap = 6, 2
+    root = str(tmp_path / "labels")
+    _write_world_label_dir(root, rng, ids, D, nap, add_deltas)
+    reader = WorldFeatLabelGen(root, add_deltas=add_deltas, num_coded_sps=D, num_bap=nap)
+    with pytest.raises(RuntimeError, match="get_normalisation_params"):
+        next(reader.batches(ids, 4))
+    reader.get_normalisation_params(root, "train")
+    for batch_first, shuffle in ((False, False), (True, True)):
+        seen = []
+        for b in reader.batches(ids, 4, shuffle=shuffle, seed=3, batch_first=batch_first, prefetch=2):
+            samples = [reader[i] for i in b["ids"]]           # the reference protocol, one sample at a time
+            ref, ref_mask, ref_lens = glue_np.prepare_batch(samples, batch_first=batch_first)
+            assert np.array_equal(b["lengths"], ref_lens)
+            assert np.array_equal(b["padded"].cpu().numpy(), ref) and np.array_equal(b["mask"].cpu().numpy(), ref_mask)
+            assert b["frame_off"].cpu().tolist() == np.concatenate(([0], np.cumsum(ref_lens))).tolist()
+            seen += b["ids"]
+        assert sorted(seen) == sorted(ids) and (seen != ids) == shuffle
+    assert [len(b["ids"]) for b in reader.batches(ids, 4, drop_last=True)] == [4, 4]
+    # abandoning the iterator stops the background thread; a missing archive surfaces in the consumer
+    it = reader.batches(ids, 2, prefetch=1)
+    next(it)
+    it.close()
+    with pytest.raises(FileNotFoundError):
+        list(reader.batches(ids[:3] + ["missing"], 2))
