@@ -418,8 +418,15 @@ def run_b200(args):
         workloads = None
         if not args.no_workloads:
             workloads = {"synth256": bench_synth256(args, dev, syn, feats, frame_off, stats_host, an, peaks, alpha),
-                         "vtln109": bench_vtln109(args, dev, peaks),
-                         "gen_data_files": bench_gen_data_files(args, host, sample_off, f0s, alpha)}
+                         "vtln109": bench_vtln109(args, dev, peaks)}
+            try:
+                workloads["postprocess256"] = bench_postprocess256(args, dev, feats, frame_off, stats_host, an, peaks)
+            except Exception as e:  # noqa: BLE001
+                workloads["postprocess256"] = {"failed": "%s: %s" % (type(e).__name__, str(e)[:300])}
+            try:  # host file systems differ from box to box: a failure here must not take the headline line with it
+                workloads["gen_data_files"] = bench_gen_data_files(args, host, sample_off, f0s, alpha)
+            except Exception as e:  # noqa: BLE001
+                workloads["gen_data_files"] = {"failed": "%s: %s" % (type(e).__name__, str(e)[:300])}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             # separate process: no fork of a CUDA-initialised interpreter
@@ -585,6 +592,54 @@ def bench_synth256(args, dev, syn, feats, frame_off, stats_host, an, peaks, alph
                              "sample": "%d utterances of the same rows" % ns}}
 
 
+def bench_postprocess256(args, dev, feats, frame_off, stats_host, an, peaks):
+    """The steps between the acoustic model and the vocoder on the features of the first 256 corpus
+    utterances: deltas (utils.py:103-105), the padded + normalised trainer batch and its inverse (ModularModelHandlerPyTorch
+    .prepare_batch, :389-499), MLPG of the 60 mel-cepstral trajectories (misc/mlpg.py:94-127) and the objective metrics
+    (Metrics.py:84-164); one CUDA-event time per operator, L2 flushed between iterations."""
+    import torch
+    from idiaptts_b200 import ops, pipeline
+    D = NUM_CODED_SPS
+    nu = min(256, len(frame_off) - 1)
+    f_end = int(frame_off[nu])
+    fo_np = np.asarray(frame_off[:nu + 1], np.int64)
+    fo = torch.from_numpy(fo_np).to(dev)
+    fu = torch.from_numpy(np.repeat(np.arange(nu, dtype=np.int32), np.diff(fo_np))).to(dev)
+    sub = feats[:f_end].contiguous()
+    W = sub.shape[1]
+    n = float(stats_host[2 * an.dim])
+    mean, std = pipeline.mean_std_from_sums(stats_host, n, an.dim)
+    m_dev = torch.from_numpy(mean.astype(np.float32)).to(dev)
+    s_dev = torch.from_numpy(np.maximum(std, 1e-6).astype(np.float32)).to(dev)
+    flush = L2Flusher(dev)
+    lengths = np.diff(fo_np)
+    out = {}
+
+    def timed(name, fn, bytes_moved=None):
+        ms = timed_steps(fn, args.steps, args.warmup, flush)
+        out[name] = {"ms": round(ms, 4), "frames_per_s": f_end / (ms / 1e3)}
+        if bytes_moved:
+            gbs = bytes_moved / (ms / 1e3) / 1e9
+            out[name].update({"algorithmic_GBps": round(gbs, 1), "hbm_frac": round(gbs / peaks["hbm_gbs"], 4)})
+
+    d, dd = ops.deltas(sub, fo)
+    timed("deltas", lambda: ops.deltas(sub, fo), 3 * f_end * W * 4)
+    padded, mask, _ = ops.pad_normalise(sub, fo, m_dev, s_dev, lengths=lengths)
+    t_max = int(lengths.max())
+    timed("pad_normalise", lambda: ops.pad_normalise(sub, fo, m_dev, s_dev, lengths=lengths),
+          f_end * W * 4 + nu * t_max * (W + 1) * 4)
+    timed("unpad_denormalise", lambda: ops.unpad_denormalise(padded, fo, fu, m_dev, s_dev), 2 * f_end * W * 4)
+    tri = torch.cat((sub[:, :D], d[:, :D], dd[:, :D]), dim=1).contiguous()
+    var3 = torch.ones(3 * D, dtype=torch.float64, device=dev)
+    timed("mlpg_60_trajectories", lambda: ops.mlpg(tri, var3, fo, D))
+    gen = torch.Generator(device=dev).manual_seed(6)
+    noisy = sub + 0.05 * torch.randn(sub.shape, generator=gen, device=dev) * s_dev
+    noisy[:, D + 1] = sub[:, D + 1]
+    timed("world_metrics", lambda: ops.world_metrics(sub, noisy, fu, nu, D, an.nap), 2 * f_end * W * 4)
+    return {"workload": "post-network steps on %d utterances (%d frames x %d features)" % (nu, f_end, W), "operators": out,
+            "l2": "flushed between timed iterations (256 MB write)", "steps": args.steps, "warmup": args.warmup}
+
+
 def bench_gen_data_files(args, host, sample_off, f0s, alpha):
     """WorldFeatLabelGen.gen_data FILES TO FILES -- wav files + cached F0 in, per-feature .npz archives and the
     normalisation files out (WorldFeatLabelGen.py:947-1071) -- on the first --io-utts corpus utterances, wall clock (host IO is
@@ -598,7 +653,11 @@ def bench_gen_data_files(args, host, sample_off, f0s, alpha):
     nu = min(args.io_utts, len(f0s))
     if nu <= 0:
         return None
-    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    need = 6 * int(sample_off[nu]) * 2  # wav + up to two feature sets + the numpy copies, with margin
+    base = "/dev/shm" if (os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK)
+                          and shutil.disk_usage("/dev/shm").free > need) else None
+    if base is None and shutil.disk_usage(tempfile.gettempdir()).free < need:
+        return {"skipped": "no file system with %.1f GB free for the files-to-files workload" % (need / 1e9)}
     root = tempfile.mkdtemp(prefix="b2w_io_", dir=base)
     try:
         wav_dir, ids, cache = os.path.join(root, "wav"), [], {}
