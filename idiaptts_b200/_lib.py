@@ -78,7 +78,7 @@ _SIGNATURES = {
     "b2w_allpass_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2w_mlpg_workspace_doubles": (c_int64, [c_int64, c_int32]),
-    "b2w_mlpg": (c_int32, [c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_void_p]),
+    "b2w_mlpg": (c_int32, [c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int64, c_void_p, c_void_p, c_int64, c_void_p]),
     "b2w_world_metrics": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "b2w_pad_normalise": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p,
                                     c_void_p, c_void_p]),

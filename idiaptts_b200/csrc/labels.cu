@@ -116,6 +116,82 @@ __global__ void deltas_kernel(const float* __restrict__ feats, int64_t fstride, 
   }
 }
 
+// Vectorised form of the same arithmetic for rows that can be read as float4 (dim, both strides multiples of 4, 16-byte aligned
+// pointers): a thread owns four columns and kDeltaRows consecutive frames and slides a five-row window x[i-2 .. i+2] down the
+// utterance, so a feature row is read once (plus a two-row halo per thread) instead of up to nine times, the utterance is looked
+// up once per thread instead of once per element, and a warp moves whole 256-byte row segments.  Same float32 operations in the
+// same order as grad_at: bit-identical results.
+constexpr int kDeltaRows = 16;
+
+__device__ __forceinline__ float grad5(const float (&x)[5], int k, int i, int n) {  // gradient at row i + k, x = rows i-2 .. i+2
+  const int j = i + k;
+  if (n < 2) return 0.f;
+  if (j == 0) return __fsub_rn(x[k + 3], x[k + 2]);
+  if (j == n - 1) return __fsub_rn(x[k + 2], x[k + 1]);
+  return __fmul_rn(__fsub_rn(x[k + 3], x[k + 1]), 0.5f);
+}
+
+__device__ __forceinline__ void delta_pair(const float (&x)[5], int i, int n, float& d, float& dd) {
+  d = grad5(x, 0, i, n);
+  dd = 0.f;
+  if (n >= 2) {
+    if (i == 0) dd = __fsub_rn(grad5(x, 1, i, n), d);
+    else if (i == n - 1) dd = __fsub_rn(d, grad5(x, -1, i, n));
+    else dd = __fmul_rn(__fsub_rn(grad5(x, 1, i, n), grad5(x, -1, i, n)), 0.5f);
+  }
+}
+
+__global__ void __launch_bounds__(256) deltas_rows_kernel(const float* __restrict__ feats, int64_t fstride, int dim4,
+                                                          const int64_t* __restrict__ utt_frame_offset, int num_utts,
+                                                          int64_t total_frames, float* __restrict__ deltas,
+                                                          float* __restrict__ ddeltas, int64_t ostride) {
+  const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int cv = (int)(gid % dim4);
+  const int64_t r0 = (gid / dim4) * kDeltaRows;
+  if (r0 >= total_frames) return;
+  const int64_t r1 = min(total_frames, r0 + kDeltaRows);
+  int u = find_utt(utt_frame_offset, num_utts, r0);
+  int64_t beg = utt_frame_offset[u], end = utt_frame_offset[u + 1];
+  int n = (int)(end - beg), i = (int)(r0 - beg);
+  const float* base = feats + 4 * cv;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 w[5];
+  auto row = [&](int idx) { return (idx >= 0 && idx < n) ? *reinterpret_cast<const float4*>(base + (beg + idx) * fstride) : zero; };
+#pragma unroll
+  for (int k = 0; k < 5; ++k) w[k] = row(i - 2 + k);
+  for (int64_t frame = r0; frame < r1; ++frame) {
+    if (frame == end) {  // next (non-empty) utterance: restart the window
+      do {
+        ++u;
+        beg = utt_frame_offset[u];
+        end = utt_frame_offset[u + 1];
+      } while (end == beg);
+      n = (int)(end - beg);
+      i = 0;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) w[k] = row(i - 2 + k);
+    }
+    const float4 nxt = row(i + 3);  // in flight while this row is finished
+    float4 d, dd;
+    {
+      const float x0[5] = {w[0].x, w[1].x, w[2].x, w[3].x, w[4].x}, x1[5] = {w[0].y, w[1].y, w[2].y, w[3].y, w[4].y};
+      const float x2[5] = {w[0].z, w[1].z, w[2].z, w[3].z, w[4].z}, x3[5] = {w[0].w, w[1].w, w[2].w, w[3].w, w[4].w};
+      delta_pair(x0, i, n, d.x, dd.x);
+      delta_pair(x1, i, n, d.y, dd.y);
+      delta_pair(x2, i, n, d.z, dd.z);
+      delta_pair(x3, i, n, d.w, dd.w);
+    }
+    if (deltas) *reinterpret_cast<float4*>(deltas + frame * ostride + 4 * cv) = d;
+    if (ddeltas) *reinterpret_cast<float4*>(ddeltas + frame * ostride + 4 * cv) = dd;
+    w[0] = w[1];
+    w[1] = w[2];
+    w[2] = w[3];
+    w[3] = w[4];
+    w[4] = nxt;
+    ++i;
+  }
+}
+
 // sums[c] += sum_t x[t][c]; sums[dim + c] += sum_t x[t][c]^2 (fp64).  blockDim.x = columns handled per pass (<= 256),
 // blockDim.y row lanes; one fp64 atomic per column and block.
 __global__ void stats_kernel(const float* __restrict__ feats, int64_t fstride, int dim, int64_t num_frames,
@@ -398,6 +474,14 @@ extern "C" int b2w_deltas(const float* feats, int64_t feat_stride, int32_t dim, 
   B2W_REQUIRE(feats && utt_frame_offset && (deltas || ddeltas), "b2w_deltas: null argument");
   B2W_REQUIRE(dim >= 1 && feat_stride >= dim && out_stride >= dim, "b2w_deltas: bad dim/stride");
   if (num_utts == 0 || num_frames == 0) return 0;
+  const auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (dim % 4 == 0 && feat_stride % 4 == 0 && out_stride % 4 == 0 && al16(feats) && al16(deltas) && al16(ddeltas)) {
+    const int dim4 = dim / 4;
+    const int64_t threads = ((num_frames + kDeltaRows - 1) / kDeltaRows) * dim4;
+    deltas_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        feats, feat_stride, dim4, utt_frame_offset, num_utts, num_frames, deltas, ddeltas, out_stride);
+    return check_launch("deltas_rows_kernel");
+  }
   const int64_t total = num_frames * dim;
   int64_t g = (total + 255) / 256;
   if (g > 148 * 32) g = 148 * 32;

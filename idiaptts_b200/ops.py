@@ -928,7 +928,7 @@ def mlpg(feats, var3, frame_off, D):
     ws = torch.empty(int(lib.b2w_mlpg_workspace_doubles(F, int(D))), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
         check(lib.b2w_mlpg(feats.data_ptr(), _DT[feats.dtype], int(feats.stride(0)) if F > 1 else feats.shape[1], var3.data_ptr(),
-                           frame_off.data_ptr(), frame_off.numel() - 1, int(D), ws.data_ptr(), out.data_ptr(), int(D), _stream(dev)),
+                           frame_off.data_ptr(), frame_off.numel() - 1, int(D), int(F), ws.data_ptr(), out.data_ptr(), int(D), _stream(dev)),
               "b2w_mlpg")
     return out
 

@@ -231,15 +231,14 @@ B2W_API int b2w_allpass_backward(const float* grad_y, const float* x, const floa
                          int32_t blocks, const float* mean, const float* std_dev, float* grad_x, float* grad_alpha,
                          float* unit_workspace /* [rows * blocks] */, void* stream);
 
-/* ---- self-test of the tcgen05 (UMMA) building blocks used by the tensor-core mel-cepstrum kernel: one CTA computes
- * d[128, n] = a[128, k] . bt[n, k]^T with the 3xTF32 split (n % 16 == 0, n <= 256, k % 8 == 0); b_tiled_ws: 2*n*k floats. */
 /* ---- MLPG: replaces MLPG.generation (idiaptts/misc/mlpg.py:94-127) as called from
  * WorldFeatLabelGen._postprocess_world (W:357-415).  feats [F, >= 3 D] rows [static(D) | delta(D) | delta-delta(D)] (F64|F32, row stride
- * feat_stride), var3 [3 D] = the diagonal of the covariance, frame_off [num_utts + 1]; out [F, D] fp64 (row stride out_stride);
- * workspace: b2w_mlpg_workspace_doubles(F, D) doubles. */
+ * feat_stride), var3 [3 D] = the diagonal of the covariance, frame_off [num_utts + 1], num_frames = F = frame_off[num_utts] (the
+ * host knows it); out [F, D] fp64 (row stride out_stride); workspace: b2w_mlpg_workspace_doubles(F, D) doubles (the intermediate
+ * vector [F][D] and the factor table shared by all utterances of a dimension, csrc/mlpg.cu). */
 B2W_API int64_t b2w_mlpg_workspace_doubles(int64_t num_frames, int32_t D);
 B2W_API int b2w_mlpg(const void* feats, int32_t feats_dtype, int64_t feat_stride, const double* var3, const int64_t* frame_off,
-                     int32_t num_utts, int32_t D, double* workspace, double* out, int64_t out_stride, void* stream);
+                     int32_t num_utts, int32_t D, int64_t num_frames, double* workspace, double* out, int64_t out_stride, void* stream);
 /* ---- trainer-facing batch: for feature rows that are already on the device, replaces
  * WorldFeatLabelGen.preprocess_sample ((x - mean) / std_dev, W:279-336) + ModularModelHandlerPyTorch.prepare_batch
  * (idiaptts/src/neural_networks/pytorch/ModularModelHandlerPyTorch.py:389-499: pad_sequence to the longest utterance with

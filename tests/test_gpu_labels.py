@@ -66,3 +66,29 @@ def test_deltas_bit_exact_and_stats(golden):
     np.testing.assert_allclose(sums.cpu().numpy()[:60], 2 * f64.sum(0), rtol=1e-12, atol=1e-9)
     np.testing.assert_allclose(sums.cpu().numpy()[60:], 2 * (f64 ** 2).sum(0), rtol=1e-12)
     np.testing.assert_allclose(gram.cpu().numpy().reshape(60, 60), 2 * f64.T @ f64, rtol=1e-11, atol=1e-9)
+
+
+@pytest.mark.parametrize("dim", [64, 20, 4, 7, 1])
+def test_deltas_ragged_edge_cases_match_numpy_gradient(dim):
+    """Both delta kernels (float4 rows with a sliding window for dim % 4 == 0, element-wise otherwise) against
+    utils.compute_deltas = np.gradient in float32 (idiaptts/misc/utils.py:103-105) on utterances of 1, 2, 3, 4, 5 frames, empty
+    utterances, lengths around the rows-per-thread boundary and a long one; bit-exact."""
+    from idiaptts_b200 import ops
+    from oracle import glue_np
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(dim)
+    lengths = [0, 1, 0, 0, 2, 3, 4, 5, 15, 16, 17, 0, 31, 32, 33, 1301, 1, 0]
+    xs = [(rng.standard_normal((n, dim)) * 3).astype(np.float32) for n in lengths]
+    x = torch.from_numpy(np.concatenate(xs)).to(dev)
+    off = torch.from_numpy(np.concatenate(([0], np.cumsum(lengths))).astype(np.int64)).to(dev)
+    d, dd = ops.deltas(x, off)
+
+    def grad(a):
+        if len(a) < 2:
+            return np.zeros_like(a)
+        return glue_np.compute_deltas(a)
+    ref_d = np.concatenate([grad(a) for a in xs])
+    ref_dd = np.concatenate([grad(grad(a)) for a in xs])
+    assert np.array_equal(d.cpu().numpy(), ref_d) and np.array_equal(dd.cpu().numpy(), ref_dd)
+    d_only, none = ops.deltas(x, off, want_double=False)
+    assert none is None and np.array_equal(d_only.cpu().numpy(), ref_d)

@@ -90,3 +90,30 @@ def test_postprocess_world_applies_mlpg_per_feature():
     assert np.abs(out[:, D + 2:] - mlpg_np.generation(sample[:, -3 * nap:], gen.covs[3], nap)).max() < 1e-9
     plain = gen._postprocess_world(sample.copy(), apply_mlpg=False)
     assert np.array_equal(plain[:, :D], sample[:, :D]) and np.array_equal(plain[:, D + 2:], sample[:, -3 * nap:][:, :nap])
+
+
+@pytest.mark.gpu
+def test_gpu_mlpg_shared_factor_table_edges():
+    """The factor table shared by all utterances of a dimension (rows 0 .. T - 3 do not depend on T; the recurrence is cut off once
+    its state repeats): utterance lengths on both sides of the in-place / tabulated switch (T < 6), lengths around the chunk size,
+    and lengths far beyond the point where the factors become stationary, in one ragged batch, against the oracle."""
+    from idiaptts_b200 import ops
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(8)
+    D = 5
+    lens = [5, 6, 7, 8, 9, 15, 16, 17, 1, 700, 2, 1301, 3, 64]
+    var = rng.uniform(0.01, 5.0, 3 * D)
+    var[0], var[D], var[2 * D] = 1e-4, 10.0, 10.0      # a sharply peaked static expert: factors stationary almost at once
+    var[1], var[D + 1], var[2 * D + 1] = 10.0, 1e-3, 1e-3  # dominated by the dynamic experts: slow convergence
+    feats = [rng.standard_normal((T, 3 * D)) for T in lens]
+    ref = np.concatenate([mlpg_np.generation(f, np.diag(var), D) for f in feats])
+    off = torch.tensor(np.concatenate(([0], np.cumsum(lens))), dtype=torch.int64, device=dev)
+    x = torch.from_numpy(np.concatenate(feats)).to(dev)
+    out = ops.mlpg(x, torch.from_numpy(var).to(dev), off, D).cpu().numpy()
+    scale = np.abs(ref).max(axis=0)
+    assert (np.abs(out - ref) / scale).max() < 1e-9
+    # the same utterance alone and inside the batch: identical bits (the table does not depend on the batch composition)
+    for u in (0, 3, 9):
+        lo, hi = int(off[u]), int(off[u + 1])
+        alone = ops.mlpg(x[lo:hi].contiguous(), torch.from_numpy(var).to(dev), torch.tensor([0, hi - lo], dtype=torch.int64, device=dev), D)
+        assert np.array_equal(alone.cpu().numpy(), out[lo:hi])
