@@ -122,14 +122,32 @@ __global__ void __launch_bounds__(128) mlpg_solve_kernel(const FT* __restrict__ 
       }
     }
   };
+  // factors of the rows beyond the table's last row (the recurrence is stationary there): kept in registers
+  const double sl1 = tab[(int64_t)lastrow * D4], sl2 = tab[(int64_t)lastrow * D4 + D], sd = tab[(int64_t)lastrow * D4 + 2 * D],
+               srd = tab[(int64_t)lastrow * D4 + 3 * D];
   // forward: y = L^-1 b, z = D^-1 y
   double d1 = 0.0, d2 = 0.0, l1p = 0.0;  // d_{i-1}, d_{i-2}, l1_{i-1}
   double y1 = 0.0, y2 = 0.0;             // y_{i-1}, y_{i-2}
   double m1m = 0.0, m1c = (double)col[D] * ta.tau1(0), m2m = 0.0, m2c = (double)col[2 * D] * ta.tau2(0);  // (tau mu) at i-1 and i
-  double c0[kCh], c1[kCh], c2[kCh], n0[kCh], n1[kCh], n2[kCh];
-  load_fwd(0, c0, c1, c2);
-  for (int i0 = 0; i0 < T; i0 += kCh) {
-    load_fwd(i0 + kCh, n0, n1, n2);
+  auto fwd_chunk = [&](int i0, const double (&c0)[kCh], const double (&c1)[kCh], const double (&c2)[kCh]) {
+    double* zp = zcol + (int64_t)i0 * D;
+    const bool interior = i0 >= 2 && i0 + kCh <= first_own;  // every expert of rows i - 1 .. i + 1 switched on, factors tabulated
+    if (interior && i0 > lastrow) {
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) {
+        const double m1n = c1[k] * ta.t1i, m2n = c2[k] * ta.t2i;
+        const double bi = ta.t0 * c0[k] + 0.5 * m1m - 0.5 * m1n + m2m - 2.0 * m2c + m2n;
+        const double yi = bi - sl1 * y1 - sl2 * y2;
+        zp[0] = yi * srd;
+        zp += D;
+        y2 = y1; y1 = yi;
+        m1m = m1c; m1c = m1n; m2m = m2c; m2c = m2n;
+      }
+      d2 = sd;
+      d1 = sd;
+      l1p = sl1;
+      return;
+    }
     double tl1[kCh], tl2[kCh], td[kCh], trd[kCh];
     if (i0 + kCh - 1 <= lastrow) {  // tabulated factors of this chunk (shared by all utterances: cache hits)
       const double* w = tab + (int64_t)i0 * D4;
@@ -151,9 +169,7 @@ __global__ void __launch_bounds__(128) mlpg_solve_kernel(const FT* __restrict__ 
         trd[k] = w[3 * D];
       }
     }
-    double* zp = zcol + (int64_t)i0 * D;
-    if (i0 >= 2 && i0 + kCh <= first_own) {
-      // interior chunk: every expert of rows i - 1 .. i + 1 is switched on and the factors are tabulated
+    if (interior) {
 #pragma unroll
       for (int k = 0; k < kCh; ++k) {
         const double m1n = c1[k] * ta.t1i, m2n = c2[k] * ta.t2i;
@@ -167,34 +183,51 @@ __global__ void __launch_bounds__(128) mlpg_solve_kernel(const FT* __restrict__ 
       d2 = td[kCh - 2];
       d1 = td[kCh - 1];
       l1p = tl1[kCh - 1];
-    } else {
-#pragma unroll
-      for (int k = 0; k < kCh; ++k) {
-        const int i = i0 + k;
-        if (i < T) {
-          const double m1n = c1[k] * ta.tau1(i + 1), m2n = c2[k] * ta.tau2(i + 1);
-          const double bi = ta.t0 * c0[k] + 0.5 * m1m - 0.5 * m1n + m2m - 2.0 * m2c + m2n;
-          double l1 = tl1[k], l2 = tl2[k], di = td[k], rdi = trd[k];
-          if (i >= first_own) {
-            factor_row(ta, i, d1, d2, l1p, l1, l2, di);
-            rdi = 1.0 / di;
-            el1[i - first_own] = l1;
-            el2[i - first_own] = l2;
-          }
-          const double yi = bi - l1 * y1 - l2 * y2;
-          zp[0] = yi * rdi;
-          d2 = d1; d1 = di; l1p = l1; y2 = y1; y1 = yi;
-          m1m = m1c; m1c = m1n; m2m = m2c; m2c = m2n;
-        }
-        zp += D;
-      }
+      return;
     }
 #pragma unroll
-    for (int k = 0; k < kCh; ++k) { c0[k] = n0[k]; c1[k] = n1[k]; c2[k] = n2[k]; }
+    for (int k = 0; k < kCh; ++k) {
+      const int i = i0 + k;
+      if (i < T) {
+        const double m1n = c1[k] * ta.tau1(i + 1), m2n = c2[k] * ta.tau2(i + 1);
+        const double bi = ta.t0 * c0[k] + 0.5 * m1m - 0.5 * m1n + m2m - 2.0 * m2c + m2n;
+        double l1 = tl1[k], l2 = tl2[k], di = td[k], rdi = trd[k];
+        if (i >= first_own) {
+          factor_row(ta, i, d1, d2, l1p, l1, l2, di);
+          rdi = 1.0 / di;
+          el1[i - first_own] = l1;
+          el2[i - first_own] = l2;
+        }
+        const double yi = bi - l1 * y1 - l2 * y2;
+        zp[0] = yi * rdi;
+        d2 = d1; d1 = di; l1p = l1; y2 = y1; y1 = yi;
+        m1m = m1c; m1c = m1n; m2m = m2c; m2c = m2n;
+      }
+      zp += D;
+    }
+  };
+  double pa0[kCh], pa1[kCh], pa2[kCh], pb0[kCh], pb1[kCh], pb2[kCh];  // two chunk buffers, used alternately (no copies)
+  load_fwd(0, pa0, pa1, pa2);
+  for (int i0 = 0; i0 < T; i0 += 2 * kCh) {
+    load_fwd(i0 + kCh, pb0, pb1, pb2);
+    fwd_chunk(i0, pa0, pa1, pa2);
+    if (i0 + kCh < T) {
+      load_fwd(i0 + 2 * kCh, pa0, pa1, pa2);
+      fwd_chunk(i0 + kCh, pb0, pb1, pb2);
+    }
   }
   // backward: x_i = z_i - l1_{i+1} x_{i+1} - l2_{i+2} x_{i+2}; chunks of rows i0 - k, k < kCh, loaded one chunk ahead
+  // (a0, a1 = tabulated l1, l2 of the rows -- not loaded for chunks that lie wholly in the stationary part)
+  auto bwd_stationary = [&](int i0) { return i0 < first_own && i0 - kCh + 1 > lastrow; };
   auto load_bwd = [&](int i0, double (&a0)[kCh], double (&a1)[kCh], double (&a2)[kCh]) {
-    if (i0 - kCh + 1 >= 0 && i0 <= lastrow) {
+    if (bwd_stationary(i0)) {
+      const double* z = zcol + (int64_t)i0 * D;
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) {
+        a2[k] = z[0];
+        z -= D;
+      }
+    } else if (i0 - kCh + 1 >= 0 && i0 <= lastrow) {
       const double* w = tab + (int64_t)i0 * D4;
       const double* z = zcol + (int64_t)i0 * D;
 #pragma unroll
@@ -218,11 +251,20 @@ __global__ void __launch_bounds__(128) mlpg_solve_kernel(const FT* __restrict__ 
     }
   };
   double x1 = 0.0, x2 = 0.0, l1n = 0.0, l2n = 0.0, l2nn = 0.0;  // x_{i+1}, x_{i+2}, l1_{i+1}, l2_{i+1}, l2_{i+2}
-  load_bwd(T - 1, c0, c1, c2);
-  for (int i0 = T - 1; i0 >= 0; i0 -= kCh) {
-    load_bwd(i0 - kCh, n0, n1, n2);
+  auto bwd_chunk = [&](int i0, const double (&c0)[kCh], const double (&c1)[kCh], const double (&c2)[kCh]) {
     double* op = ocol + (int64_t)i0 * out_stride;
-    if (i0 < first_own && i0 - kCh + 1 >= 0) {
+    if (bwd_stationary(i0)) {
+#pragma unroll
+      for (int k = 0; k < kCh; ++k) {
+        const double xi = c2[k] - l1n * x1 - l2nn * x2;
+        op[0] = xi;
+        op -= out_stride;
+        x2 = x1; x1 = xi;
+        l2nn = l2n;
+        l1n = sl1;
+        l2n = sl2;
+      }
+    } else if (i0 < first_own && i0 - kCh + 1 >= 0) {
 #pragma unroll
       for (int k = 0; k < kCh; ++k) {
         const double xi = c2[k] - l1n * x1 - l2nn * x2;
@@ -248,8 +290,15 @@ __global__ void __launch_bounds__(128) mlpg_solve_kernel(const FT* __restrict__ 
         op -= out_stride;
       }
     }
-#pragma unroll
-    for (int k = 0; k < kCh; ++k) { c0[k] = n0[k]; c1[k] = n1[k]; c2[k] = n2[k]; }
+  };
+  load_bwd(T - 1, pa0, pa1, pa2);
+  for (int i0 = T - 1; i0 >= 0; i0 -= 2 * kCh) {
+    load_bwd(i0 - kCh, pb0, pb1, pb2);
+    bwd_chunk(i0, pa0, pa1, pa2);
+    if (i0 - kCh >= 0) {
+      load_bwd(i0 - 2 * kCh, pa0, pa1, pa2);
+      bwd_chunk(i0 - kCh, pb0, pb1, pb2);
+    }
   }
 }
 
