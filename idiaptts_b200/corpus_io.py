@@ -60,7 +60,7 @@ def read_wavs_i16(paths, info=None, pin=False, threads=DEFAULT_THREADS):
 
 def _read_into(paths, data_offset, sample_off, samples, threads=DEFAULT_THREADS):
     """read_wavs_i16 into a caller-owned int16 tensor (gen_data's reusable pinned buffers); the caller has probed the files."""
-    assert samples.dtype == __import__("torch").int16 and samples.numel() >= int(sample_off[-1])
+    assert str(samples.dtype) == "torch.int16" and samples.numel() >= int(sample_off[-1])
     arr, _keep = _paths(paths)
     _lib.check(_lib.load().b2w_wav_read_i16(arr, len(paths), _ptr(np.ascontiguousarray(data_offset, np.int64)),
                                             _ptr(np.ascontiguousarray(sample_off, np.int64)), samples.data_ptr(), threads), "read_wavs_i16")

@@ -331,3 +331,17 @@ def test_trainer_call_sequence_on_a_fresh_reader(tmp_path, add_deltas):
     with pytest.raises(TypeError):
         WorldFeatLabelGen(root, not_an_option=1)
     WorldFeatLabelGen(root, f0_cache={}, mgc_alpha=0.5)
+
+
+def test_bind_host_to_gpu_is_harmless_without_nvml_or_gpu(monkeypatch):
+    """distributed.bind_host_to_gpu is an optimisation only: without a GPU / NVML, or when switched off, it changes nothing."""
+    from idiaptts_b200 import distributed
+    before = os.sched_getaffinity(0)
+    monkeypatch.setenv("B2W_NUMA_BIND", "0")
+    assert distributed.bind_host_to_gpu(0) is None
+    monkeypatch.setenv("B2W_NUMA_BIND", "1")
+    got = distributed.bind_host_to_gpu(0)
+    assert got is None or got <= before
+    if got is None:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
