@@ -117,3 +117,52 @@ def test_gpu_mlpg_shared_factor_table_edges():
         lo, hi = int(off[u]), int(off[u + 1])
         alone = ops.mlpg(x[lo:hi].contiguous(), torch.from_numpy(var).to(dev), torch.tensor([0, hi - lo], dtype=torch.int64, device=dev), D)
         assert np.array_equal(alone.cpu().numpy(), out[lo:hi])
+
+
+def _ldl_rows(T, t0, t1, t2, rows):
+    """The factor recurrence of csrc/mlpg.cu in numpy: (l1, l2, d) of the first `rows` rows of the pentadiagonal precision matrix of
+    an utterance of T frames (T = None: no final frame in sight)."""
+    te = 1.0 / 100000000000.0
+    end = (lambda t: False) if T is None else (lambda t: t == T - 1)
+    out_of = (lambda t: t < 0) if T is None else (lambda t: t < 0 or t >= T)
+    tau1 = lambda t: 0.0 if out_of(t) else (te if (t == 0 or end(t)) else t1)  # noqa: E731
+    tau2 = lambda t: 0.0 if out_of(t) else (te if (t == 0 or end(t)) else t2)  # noqa: E731
+    d1 = d2 = l1p = 0.0
+    res = []
+    for i in range(rows):
+        pii = t0 + 0.25 * (tau1(i - 1) + tau1(i + 1)) + tau2(i - 1) + 4.0 * tau2(i) + tau2(i + 1)
+        pi1 = -2.0 * (tau2(i - 1) + tau2(i)) if i >= 1 else 0.0
+        pi2 = tau2(i - 1) - 0.25 * tau1(i - 1) if i >= 2 else 0.0
+        l2 = pi2 / d2 if i >= 2 else 0.0
+        l1 = (pi1 - l2 * d2 * l1p) / d1 if i >= 1 else 0.0
+        di = pii - l1 * l1 * d1 - l2 * l2 * d2
+        res.append((l1, l2, di))
+        d2, d1, l1p = d1, di, l1
+    return res
+
+
+@pytest.mark.parametrize("taus", [(1.0, 1.0, 1.0), (10.0, 0.3, 2.0), (0.1, 100.0, 100.0)])
+def test_factor_rows_before_the_last_two_do_not_depend_on_the_length(taus):
+    """The claim the CUDA solver's shared factor table rests on: rows 0 .. T - 3 of the L D L^T factorisation are the same for every
+    utterance length (bit for bit), and once the recurrence state repeats it stays put; the factors agree with a dense LDL^T of the
+    oracle's precision matrix."""
+    t0, t1, t2 = taus
+    free = _ldl_rows(None, t0, t1, t2, 400)
+    for T in (6, 7, 9, 40, 400):
+        own = _ldl_rows(T, t0, t1, t2, T)
+        assert own[:T - 2] == free[:T - 2]                         # exact equality of Python floats (IEEE doubles)
+        assert own[T - 2:] != free[T - 2:T]                        # ... and the last two rows really do differ
+    # stationarity: the first row whose state equals the previous row's fixes all later rows
+    fixed = next((i for i in range(4, 400) if free[i][2] == free[i - 1][2] == free[i - 2][2] and free[i][0] == free[i - 1][0]), None)
+    if fixed is not None:
+        assert all(r == free[fixed] for r in free[fixed:])
+    # against the dense factorisation of the oracle's matrix (T = 12)
+    T = 12
+    cov = np.diag([1.0 / t0, 1.0 / t1, 1.0 / t2])
+    _, tf = mlpg_np._frames_params(np.zeros((T, 3)), cov, 1, 0)
+    P = sum(W.T @ (tf[:, w][:, None] * W) for w, W in enumerate(mlpg_np._win_dense(T)))
+    L = np.linalg.cholesky(P)
+    own = _ldl_rows(T, t0, t1, t2, T)
+    np.testing.assert_allclose([r[2] for r in own], np.diag(L) ** 2, rtol=1e-9)                    # d_i
+    np.testing.assert_allclose([r[0] for r in own[1:]], np.diag(L, -1) / np.diag(L)[:-1], rtol=1e-8, atol=1e-12)   # l1_i
+    np.testing.assert_allclose([r[1] for r in own[2:]], np.diag(L, -2) / np.diag(L)[:-2], rtol=1e-8, atol=1e-12)   # l2_i
