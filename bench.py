@@ -673,7 +673,9 @@ def bench_gen_data_files(args, host, sample_off, f0s, alpha):
             ids.append(name)
             cache[name] = f0s[u]
         audio = float(sample_off[nu]) / FS
-        gen = WorldFeatLabelGen(os.path.join(root, "out2"), num_coded_sps=NUM_CODED_SPS, num_bap=2, f0_cache=cache, mgc_alpha=alpha)
+        # (only rank 0 runs the workloads: the generator must neither shard the list nor enter the statistics all-reduce)
+        gen = WorldFeatLabelGen(os.path.join(root, "out2"), num_coded_sps=NUM_CODED_SPS, num_bap=2, f0_cache=cache, mgc_alpha=alpha,
+                                use_distributed=False)
         times = []
         for it in range(3):  # the first pass warms the page cache and the allocator
             out = os.path.join(root, "out%d" % it)

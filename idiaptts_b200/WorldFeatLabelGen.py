@@ -111,11 +111,13 @@ class WorldFeatLabelGen(object):
         WorldFeatLabelGen(dir_labels, add_deltas=..., num_coded_sps=..., ...) keyword form.  Extensions of this package (keyword
         only): f0_cache (cached F0 tracks: dict / directory, north_star), mgc_alpha (override of fs_to_mgc_alpha), io_threads
         (host threads of the shard-at-a-time wav / npz file IO, corpus_io.py; 0 = one per hardware thread), io_chunk_seconds (audio
-        per piece of gen_data's read / extract / write pipeline)."""
+        per piece of gen_data's read / extract / write pipeline), use_distributed (False: gen_data treats the process as the only rank
+        even when torch.distributed is initialised -- no sharding, no collective)."""
         self.f0_cache = kwargs.pop("f0_cache", None)
         self.mgc_alpha = kwargs.pop("mgc_alpha", None)
         self.io_threads = int(kwargs.pop("io_threads", 0))
         self.io_chunk_seconds = float(kwargs.pop("io_chunk_seconds", 4096.0))
+        self.use_distributed = bool(kwargs.pop("use_distributed", True))
         self._io_slots = None
         if len(args) == 1 and isinstance(args[0], WorldFeatLabelGen.Config):
             config = args[0]
@@ -411,7 +413,7 @@ class WorldFeatLabelGen(object):
         and the statistics are all-reduced (files are written by the owning rank, statistics by rank 0)."""
         id_list, file_id_list_name = self._get_id_list(dir_in, file_id_list, id_list, file_ext)
         f0_cache = f0_cache if f0_cache is not None else self.f0_cache
-        rank, world = distributed.world_info()
+        rank, world = distributed.world_info() if self.use_distributed else (0, 1)
         if dir_out is not None:
             self._create_directories(dir_out)
         dev = _device()
@@ -456,7 +458,8 @@ class WorldFeatLabelGen(object):
             failure = e
             stat.zero_()
             stat[-1] = 1.0
-        distributed.allreduce_stats(stat)
+        if world > 1:
+            distributed.allreduce_stats(stat)
         stat_np = stat.cpu().numpy()
         if failure is not None:
             raise failure
