@@ -66,8 +66,12 @@ class Synthesiser(object):
             file_name = (os.path.basename(id_name) + getattr(hparams, "synth_file_suffix", "") + "_" + str(hparams.num_coded_sps)
                          + hparams.sp_type + "_WORLD")
             paths.append(os.path.join(save_dir, file_name + ".wav"))
-        # all files of the batch in one native call (a pool of host threads; same bytes as write_wav)
-        corpus_io.write_wavs_pcm16(paths, np.ascontiguousarray(y, np.float32), out_off, hparams.synth_fs)
+        if y.dtype == np.float32:
+            # all files of the batch in one native call (a pool of host threads; same bytes as write_wav)
+            corpus_io.write_wavs_pcm16(paths, np.ascontiguousarray(y), out_off, hparams.synth_fs)
+        else:  # float64 samples (de-emphasis): quantised from the doubles, file by file
+            for u, path in enumerate(paths):
+                Synthesiser.write_wav(path, y[out_off[u]:out_off[u + 1]], hparams.synth_fs)
 
     @staticmethod
     def write_wav(path, waveform, fs):
