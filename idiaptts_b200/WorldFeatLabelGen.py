@@ -408,9 +408,10 @@ class WorldFeatLabelGen(object):
 
     # ---- corpus extraction -------------------------------------------------------------------------------------------------
     def gen_data(self, dir_in, dir_out=None, file_id_list="", file_ext="wav", id_list=None, return_dict=False, f0_cache=None):
-        """Prepare acoustic features of all utterances in id_list as ONE GPU batch; save them per feature / utterance as
-        .npz; return ([label_dict,] means, std_devs).  With torch.distributed initialised each rank extracts its shard
-        and the statistics are all-reduced (files are written by the owning rank, statistics by rank 0)."""
+        """Prepare acoustic features of all utterances in id_list in ragged GPU batches (pieces of io_chunk_seconds of audio, read,
+        extracted and written by a three-stage pipeline: _extract_shard); save them per feature / utterance as .npz; return
+        ([label_dict,] means, std_devs).  With torch.distributed initialised each rank extracts its shard and the statistics are
+        all-reduced (files are written by the owning rank, statistics by rank 0)."""
         id_list, file_id_list_name = self._get_id_list(dir_in, file_id_list, id_list, file_ext)
         f0_cache = f0_cache if f0_cache is not None else self.f0_cache
         rank, world = distributed.world_info() if self.use_distributed else (0, 1)
