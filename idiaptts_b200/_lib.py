@@ -104,6 +104,7 @@ _SIGNATURES = {
     "b2w_npz_probe": (c_int32, [c_void_p, c_int32, ctypes.c_char_p, c_void_p, c_void_p, c_int32]),
     "b2w_npz_read_f32": (c_int32, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
                                    c_int32]),
+    "b2w_crc32": (ctypes.c_uint32, [c_void_p, c_int64, c_int32]),
     "b2w_cheaptrick_fft_size": (c_int32, [c_int32, c_double]),
     "b2w_num_aperiodicities": (c_int32, [c_int32]),
     "b2w_d4c_fft_size": (c_int32, [c_int32]),

@@ -14,11 +14,15 @@
 //     true sizes in the central directory; the reader takes sizes and offsets from the central directory (ZIP64 extra fields
 //     included), so both kinds load.  Compressed members (savez_compressed) are refused with a message: the caller falls back.
 #include <fcntl.h>
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#endif
 #include <string.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
 #include <atomic>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -136,10 +140,98 @@ const CrcTables& crc_tables() {
   static const CrcTables tables;
   return tables;
 }
-uint32_t crc32_update(uint32_t crc, const void* data, size_t n) {
+#if defined(__x86_64__) && defined(__GNUC__)
+#define B2W_CRC_CLMUL 1
+// Carry-less-multiplication folding (V. Gopal et al., "Fast CRC Computation for Generic Polynomials Using PCLMULQDQ Instruction",
+// Intel 2009; constants of the reflected CRC-32 polynomial as zlib-family libraries use them): folds 64 bytes per step.
+// `state` is the running (inverted) register; n >= 64 and a multiple of 16.  Checked against the table code in the tests.
+__attribute__((target("pclmul,sse4.1"))) uint32_t crc32_clmul(uint32_t state, const unsigned char* buf, size_t n) {
+  alignas(16) static const uint64_t k1k2[2] = {0x0154442bd4ull, 0x01c6e41596ull};
+  alignas(16) static const uint64_t k3k4[2] = {0x01751997d0ull, 0x00ccaa009eull};
+  alignas(16) static const uint64_t k5k0[2] = {0x0163cd6124ull, 0x0000000000ull};
+  alignas(16) static const uint64_t poly[2] = {0x01db710641ull, 0x01f7011641ull};
+  __m128i x0, x1, x2, x3, x4, x5, x6, x7, x8, y5, y6, y7, y8;
+  x1 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(buf + 0x00));
+  x2 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(buf + 0x10));
+  x3 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(buf + 0x20));
+  x4 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(buf + 0x30));
+  x1 = _mm_xor_si128(x1, _mm_cvtsi32_si128((int)state));
+  x0 = _mm_load_si128(reinterpret_cast<const __m128i*>(k1k2));
+  buf += 64;
+  n -= 64;
+  while (n >= 64) {  // four independent 128-bit lanes
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+    x6 = _mm_clmulepi64_si128(x2, x0, 0x00);
+    x7 = _mm_clmulepi64_si128(x3, x0, 0x00);
+    x8 = _mm_clmulepi64_si128(x4, x0, 0x00);
+    x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+    x2 = _mm_clmulepi64_si128(x2, x0, 0x11);
+    x3 = _mm_clmulepi64_si128(x3, x0, 0x11);
+    x4 = _mm_clmulepi64_si128(x4, x0, 0x11);
+    y5 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(buf + 0x00));
+    y6 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(buf + 0x10));
+    y7 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(buf + 0x20));
+    y8 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(buf + 0x30));
+    x1 = _mm_xor_si128(_mm_xor_si128(x1, x5), y5);
+    x2 = _mm_xor_si128(_mm_xor_si128(x2, x6), y6);
+    x3 = _mm_xor_si128(_mm_xor_si128(x3, x7), y7);
+    x4 = _mm_xor_si128(_mm_xor_si128(x4, x8), y8);
+    buf += 64;
+    n -= 64;
+  }
+  x0 = _mm_load_si128(reinterpret_cast<const __m128i*>(k3k4));  // four lanes into one
+  x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+  x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+  x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
+  x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+  x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+  x1 = _mm_xor_si128(_mm_xor_si128(x1, x3), x5);
+  x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+  x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+  x1 = _mm_xor_si128(_mm_xor_si128(x1, x4), x5);
+  while (n >= 16) {  // remaining whole 16-byte blocks
+    x2 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(buf));
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+    x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+    x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
+    buf += 16;
+    n -= 16;
+  }
+  x2 = _mm_clmulepi64_si128(x1, x0, 0x10);  // 128 -> 64 bits
+  x3 = _mm_setr_epi32(~0, 0, ~0, 0);
+  x1 = _mm_srli_si128(x1, 8);
+  x1 = _mm_xor_si128(x1, x2);
+  x0 = _mm_loadl_epi64(reinterpret_cast<const __m128i*>(k5k0));
+  x2 = _mm_srli_si128(x1, 4);
+  x1 = _mm_and_si128(x1, x3);
+  x1 = _mm_clmulepi64_si128(x1, x0, 0x00);
+  x1 = _mm_xor_si128(x1, x2);
+  x0 = _mm_load_si128(reinterpret_cast<const __m128i*>(poly));  // Barrett reduction to 32 bits
+  x2 = _mm_and_si128(x1, x3);
+  x2 = _mm_clmulepi64_si128(x2, x0, 0x10);
+  x2 = _mm_and_si128(x2, x3);
+  x2 = _mm_clmulepi64_si128(x2, x0, 0x00);
+  x1 = _mm_xor_si128(x1, x2);
+  return (uint32_t)_mm_extract_epi32(x1, 1);
+}
+bool have_clmul() {
+  static const bool ok = __builtin_cpu_supports("pclmul") && __builtin_cpu_supports("sse4.1");
+  return ok;
+}
+#endif
+
+uint32_t crc32_update(uint32_t crc, const void* data, size_t n, bool allow_clmul = true) {
   const CrcTables& T = crc_tables();
   const unsigned char* p = static_cast<const unsigned char*>(data);
   crc = ~crc;
+#ifdef B2W_CRC_CLMUL
+  if (allow_clmul && n >= 64 && have_clmul()) {
+    const size_t body = n & ~(size_t)15;
+    crc = crc32_clmul(crc, p, body);
+    p += body;
+    n -= body;
+  }
+#endif
   while (n >= 8) {
     uint32_t a, b;
     memcpy(&a, p, 4);
@@ -527,47 +619,75 @@ int b2w_npz_write_f32(const char* const* paths, int32_t num_files, const char* c
       msg = "negative row count";
       return false;
     }
-    // the whole archive is assembled in memory (a few hundred KB) and written with one call
-    std::vector<unsigned char> out;
-    std::vector<unsigned char> central;
-    size_t reserve = 22;
-    for (int k = 0; k < num_keys; ++k) reserve += 256 + 2 * strlen(keys[k]) + (size_t)rows * cols[k] * 4;
-    out.reserve(reserve);
+    // the whole archive is assembled in memory (a few hundred KB, uninitialised buffer sized up front) and written with one call
+    std::vector<std::string> heads(num_keys), names(num_keys);
+    size_t total = 22;
     for (int k = 0; k < num_keys; ++k) {
-      const std::string name = std::string(keys[k]) + ".npy";
-      const std::string head = npy_header(rows, cols[k]);
-      const uint64_t size = head.size() + (uint64_t)rows * cols[k] * 4;
-      if (size >= 0xffffffffull || out.size() + size >= 0xffffffffull) {
+      names[k] = std::string(keys[k]) + ".npy";
+      heads[k] = npy_header(rows, cols[k]);
+      const uint64_t size = heads[k].size() + (uint64_t)rows * cols[k] * 4;
+      total += 30 + 46 + 2 * names[k].size() + (size_t)size;
+      if (size >= 0xffffffffull || total >= 0xffffffffull) {
         msg = std::string(paths[i]) + ": arrays of 4 GiB and more need ZIP64";
         return false;
       }
-      const uint32_t local_off = (uint32_t)out.size();
-      wr32(out, 0x04034b50u);
-      wr16(out, 20);
-      wr16(out, 0);
-      wr16(out, 0);
-      wr16(out, 0);
-      wr16(out, 0x21);  // 1980-01-01
-      const size_t crc_pos = out.size();
-      wr32(out, 0);
-      wr32(out, (uint32_t)size);
-      wr32(out, (uint32_t)size);
-      wr16(out, (uint32_t)name.size());
-      wr16(out, 0);
-      out.insert(out.end(), name.begin(), name.end());
-      const size_t data_pos = out.size();
-      out.insert(out.end(), head.begin(), head.end());
-      const size_t body = out.size();
-      out.resize(body + (size_t)rows * cols[k] * 4);
+    }
+    std::unique_ptr<unsigned char[]> buf(new unsigned char[total]);
+    unsigned char* const out = buf.get();
+    size_t pos = 0;
+    auto put16 = [&](uint32_t x) {
+      out[pos++] = (unsigned char)(x & 255);
+      out[pos++] = (unsigned char)((x >> 8) & 255);
+    };
+    auto put32 = [&](uint32_t x) {
+      put16(x & 0xffff);
+      put16(x >> 16);
+    };
+    auto put = [&](const void* p, size_t n) {
+      memcpy(out + pos, p, n);
+      pos += n;
+    };
+    std::vector<unsigned char> central;
+    for (int k = 0; k < num_keys; ++k) {
+      const std::string& name = names[k];
+      const std::string& head = heads[k];
+      const size_t bytes = (size_t)rows * cols[k] * 4;
+      const uint32_t size = (uint32_t)(head.size() + bytes);
+      const uint32_t local_off = (uint32_t)pos;
+      put32(0x04034b50u);
+      put16(20);
+      put16(0);
+      put16(0);
+      put16(0);
+      put16(0x21);  // 1980-01-01
+      const size_t crc_pos = pos;
+      put32(0);
+      put32(size);
+      put32(size);
+      put16((uint32_t)name.size());
+      put16(0);
+      put(name.data(), name.size());
+      const size_t data_pos = pos;
+      put(head.data(), head.size());
       const float* src = feats + r0 * feat_stride + col_offset[k];
       if (cols[k] == feat_stride) {
-        memcpy(&out[body], src, (size_t)rows * cols[k] * 4);
+        put(src, bytes);
+      } else if (cols[k] <= 4) {  // narrow column blocks (lf0, vuv, bap): element loop instead of a memcpy call per row
+        float* dst = reinterpret_cast<float*>(out + pos);  // (the member's offset in the archive need not be a multiple of 4)
+        const int c = cols[k];
+        if ((reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
+          for (int64_t r = 0; r < rows; ++r)
+            for (int e = 0; e < c; ++e) dst[r * c + e] = src[r * feat_stride + e];
+        } else {
+          for (int64_t r = 0; r < rows; ++r) memcpy(out + pos + (size_t)r * c * 4, src + r * feat_stride, (size_t)c * 4);
+        }
+        pos += bytes;
       } else {
-        unsigned char* dst = &out[body];
         const size_t rb = (size_t)cols[k] * 4;
-        for (int64_t r = 0; r < rows; ++r) memcpy(dst + r * rb, src + r * feat_stride, rb);
+        for (int64_t r = 0; r < rows; ++r) memcpy(out + pos + r * rb, src + r * feat_stride, rb);
+        pos += bytes;
       }
-      const uint32_t crc = crc32_update(0, &out[data_pos], (size_t)size);
+      const uint32_t crc = crc32_update(0, out + data_pos, (size_t)size);
       out[crc_pos] = (unsigned char)(crc & 255);
       out[crc_pos + 1] = (unsigned char)((crc >> 8) & 255);
       out[crc_pos + 2] = (unsigned char)((crc >> 16) & 255);
@@ -580,8 +700,8 @@ int b2w_npz_write_f32(const char* const* paths, int32_t num_files, const char* c
       wr16(central, 0);
       wr16(central, 0x21);
       wr32(central, crc);
-      wr32(central, (uint32_t)size);
-      wr32(central, (uint32_t)size);
+      wr32(central, size);
+      wr32(central, size);
       wr16(central, (uint32_t)name.size());
       wr16(central, 0);
       wr16(central, 0);
@@ -591,19 +711,19 @@ int b2w_npz_write_f32(const char* const* paths, int32_t num_files, const char* c
       wr32(central, local_off);
       central.insert(central.end(), name.begin(), name.end());
     }
-    const uint32_t cd_off = (uint32_t)out.size();
-    out.insert(out.end(), central.begin(), central.end());
-    wr32(out, 0x06054b50u);
-    wr16(out, 0);
-    wr16(out, 0);
-    wr16(out, (uint32_t)num_keys);
-    wr16(out, (uint32_t)num_keys);
-    wr32(out, (uint32_t)central.size());
-    wr32(out, cd_off);
-    wr16(out, 0);
+    const uint32_t cd_off = (uint32_t)pos;
+    put(central.data(), central.size());
+    put32(0x06054b50u);
+    put16(0);
+    put16(0);
+    put16((uint32_t)num_keys);
+    put16((uint32_t)num_keys);
+    put32((uint32_t)central.size());
+    put32(cd_off);
+    put16(0);
     Fd f;
     f.fd = ::open(paths[i], O_WRONLY | O_CREAT | O_TRUNC, 0644);
-    if (f.fd < 0 || !write_all(f.fd, out.data(), out.size())) {
+    if (f.fd < 0 || pos != total || !write_all(f.fd, out, pos)) {
       msg = std::string("cannot write ") + paths[i];
       return false;
     }
@@ -706,5 +826,9 @@ int b2w_npz_read_f32(const char* const* paths, int32_t num_files, const char* co
     return true;
   });
 }
+
+/* development aid (tests): CRC-32 of a host buffer by the table code (variant 0) or with carry-less folding where the CPU has it
+ * (variant 1) */
+uint32_t b2w_crc32(const void* data, int64_t n, int32_t variant) { return crc32_update(0, data, (size_t)n, variant != 0); }
 
 }  // extern "C"

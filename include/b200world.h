@@ -330,6 +330,10 @@ B2W_API int b2w_npz_read_f32(const char* const* paths, int32_t num_files, const 
                              const int32_t* col_offset, const int32_t* cols, const int64_t* utt_frame_offset, float* feats,
                              int64_t feat_stride, int32_t verify_crc, int32_t threads);
 
+/* development aid (tests): the archives' CRC-32 of a host buffer; variant 0 = table code, 1 = carry-less-multiplication folding
+ * where the CPU has it (what the writers / readers use) */
+B2W_API uint32_t b2w_crc32(const void* data, int64_t n, int32_t variant);
+
 /* ---- scalar helpers (host, pure functions): pyworld.get_cheaptrick_fft_size (A:60), get_num_aperiodicities
  * (A:71), and the D4C transform size. */
 B2W_API int32_t b2w_cheaptrick_fft_size(int32_t fs, double f0_floor);

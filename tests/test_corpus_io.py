@@ -192,3 +192,18 @@ def test_round_trip_and_load_batch_equal_the_per_sample_reader(tmp_path):
         assert goff3.tolist() == off.tolist() and np.array_equal(got3.numpy(), feats[:, expect])
         with pytest.raises(FileNotFoundError):
             reader.load_batch(["a", "missing"], pin=False)
+
+
+def test_crc32_variants_equal_zlib():
+    """The archives' CRC-32: the table code and the carry-less-multiplication folding (taken where the CPU has PCLMULQDQ) against
+    zlib, for every length around the 16 / 64-byte block boundaries and unaligned starts."""
+    import zlib
+    from idiaptts_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(9)
+    for n in list(range(0, 200)) + [255, 256, 257, 1023, 4096, 65537, 1000003]:
+        b = rng.integers(0, 256, n + 3, dtype=np.uint8)
+        for off in (0, 1, 3):
+            v = b[off:off + n]
+            want = zlib.crc32(v.tobytes())
+            assert lib.b2w_crc32(v.ctypes.data, n, 0) == want and lib.b2w_crc32(v.ctypes.data, n, 1) == want, (n, off)
